@@ -1,0 +1,334 @@
+// Fused QK^T - softmax - PV attention in fp32 (flash-style: no T x T matrix in HBM).
+//
+// Two kernels:
+//  * attn_mma_kernel<D>  : head dim D in {32,40,64,80}: warp-level tensor-core MMAs
+//    (m16n8k8 tf32) with 3-pass hi/lo error compensation so the result is fp32-accurate.
+//    The tcgen05/TMEM version of this kernel is the next step.
+//  * attn_generic_kernel<G> : any head dim (CIFAR d=256, cin d=384..960): G lanes share one
+//    query, FFMA only.
+#include "ctx.h"
+
+namespace tfmq {
+
+struct AttnP {
+  tfmq_attn_desc a;
+  int tk_tile;
+};
+
+// ------------------------------------------------------------------ generic FFMA kernel
+template <int G>
+__global__ void __launch_bounds__(128) attn_generic_kernel(const AttnP P) {
+  extern __shared__ float sm[];
+  const tfmq_attn_desc& a = P.a;
+  const int d = a.d, TK = P.tk_tile;
+  const int dp = d / G;  // dims per lane, <= 32, lane g owns dims g + G*i
+  float* Ks = sm;
+  float* Vs = sm + (size_t)TK * d;
+  const int bh = blockIdx.y, b = bh / a.heads, h = bh % a.heads;
+  constexpr int QPC = 128 / G;
+  const int qi = blockIdx.x * QPC + threadIdx.x / G;
+  const int g = threadIdx.x % G;
+  const bool qvalid = qi < a.tq;
+  const float* qp = a.q + (long long)b * a.q_sb + (long long)h * a.q_sh + (long long)(qvalid ? qi : 0) * a.q_st;
+  const float* kp = a.k + (long long)b * a.k_sb + (long long)h * a.k_sh;
+  const float* vp = a.v + (long long)b * a.v_sb + (long long)h * a.v_sh;
+  float q[32], o[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    q[i] = (i < dp) ? qp[g + G * i] : 0.f;
+    o[i] = 0.f;
+  }
+  float m = -INFINITY, l = 0.f;
+  for (int k0 = 0; k0 < a.tk; k0 += TK) {
+    __syncthreads();
+    const int kn = min(TK, a.tk - k0);
+    for (int i = threadIdx.x; i < TK * d; i += 128) {
+      const int j = i / d, c = i - j * d;
+      float kv = 0.f, vv = 0.f;
+      if (j < kn) {
+        kv = kp[(long long)(k0 + j) * a.k_st + c];
+        vv = vp[(long long)(k0 + j) * a.v_st + c];
+      }
+      Ks[i] = kv;
+      Vs[i] = vv;
+    }
+    __syncthreads();
+    for (int j0 = 0; j0 < kn; j0 += 4) {
+      float s[4];
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const float* kr = Ks + (size_t)min(j0 + jj, TK - 1) * d + g;
+        float acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (i < dp) acc = fmaf(q[i], kr[G * i], acc);
+#pragma unroll
+        for (int off = G / 2; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+        s[jj] = (j0 + jj < kn) ? acc * a.scale : -INFINITY;
+      }
+      const float mnew = fmaxf(fmaxf(fmaxf(s[0], s[1]), fmaxf(s[2], s[3])), m);
+      const float corr = expf(m - mnew);
+      float p[4];
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) p[jj] = expf(s[jj] - mnew);
+      l = l * corr + ((p[0] + p[1]) + (p[2] + p[3]));
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        if (i < dp) {
+          float acc = o[i] * corr;
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) acc = fmaf(p[jj], Vs[(size_t)min(j0 + jj, TK - 1) * d + g + G * i], acc);
+          o[i] = acc;
+        }
+      }
+      m = mnew;
+    }
+  }
+  if (qvalid) {
+    float* op = a.o + (long long)b * a.o_sb + (long long)h * a.o_sh + (long long)qi * a.o_st;
+    const float inv = 1.f / l;
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (i < dp) op[g + G * i] = o[i] * inv;
+  }
+}
+
+// ------------------------------------------------------------------ tensor-core kernel
+// CTA = 4 warps x 16 queries; K/V tiles of 64 keys staged in smem as tf32 hi / lo planes with
+// row pitch D+4 floats (conflict-free fragment reads).  S = Q K^T and O += P V each as
+// hi*hi + lo*hi + hi*lo.  The softmax probabilities come out of the S accumulator fragment in
+// columns (2t, 2t+1); the PV MMA wants k-indices (t, t+4), so key (2t) is presented as k-index t
+// and key (2t+1) as k-index t+4 -- a permutation of the summation order only.
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void split_hi_lo(float v, uint32_t& hi, uint32_t& lo) {
+  hi = __float_as_uint(v) & 0xFFFFE000u;
+  lo = __float_as_uint(v - __uint_as_float(hi)) & 0xFFFFE000u;
+}
+
+constexpr int ATT_TK = 64;
+
+template <int D>
+__global__ void __launch_bounds__(128) attn_mma_kernel(const AttnP P) {
+  constexpr int PITCH = D + 4;
+  constexpr int KS = D / 8;   // k-steps of QK^T, n-tiles of PV
+  extern __shared__ float sm[];
+  float* Khi = sm;
+  float* Klo = Khi + ATT_TK * PITCH;
+  float* Vhi = Klo + ATT_TK * PITCH;
+  float* Vlo = Vhi + ATT_TK * PITCH;
+  const tfmq_attn_desc& a = P.a;
+  const int bh = blockIdx.y, b = bh / a.heads, h = bh % a.heads;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int q0 = blockIdx.x * 64 + warp * 16;
+  const float* qb = a.q + (long long)b * a.q_sb + (long long)h * a.q_sh;
+  const float* kb = a.k + (long long)b * a.k_sb + (long long)h * a.k_sh;
+  const float* vb = a.v + (long long)b * a.v_sb + (long long)h * a.v_sh;
+
+  // Q fragments (A operand, rows g / g+8, cols t / t+4 of each 8-wide k-step), pre-scaled
+  uint32_t qh[KS][4], ql[KS][4];
+  {
+    const int r0 = min(q0 + g, a.tq - 1), r1 = min(q0 + g + 8, a.tq - 1);
+    const float* p0 = qb + (long long)r0 * a.q_st;
+    const float* p1 = qb + (long long)r1 * a.q_st;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      split_hi_lo(p0[ks * 8 + t] * a.scale, qh[ks][0], ql[ks][0]);
+      split_hi_lo(p1[ks * 8 + t] * a.scale, qh[ks][1], ql[ks][1]);
+      split_hi_lo(p0[ks * 8 + t + 4] * a.scale, qh[ks][2], ql[ks][2]);
+      split_hi_lo(p1[ks * 8 + t + 4] * a.scale, qh[ks][3], ql[ks][3]);
+    }
+  }
+  float o[KS][4];
+#pragma unroll
+  for (int i = 0; i < KS; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+
+  for (int k0 = 0; k0 < a.tk; k0 += ATT_TK) {
+    __syncthreads();
+    const int kn = min(ATT_TK, a.tk - k0);
+    for (int i = threadIdx.x; i < ATT_TK * (D / 4); i += 128) {
+      const int j = i / (D / 4), c4 = (i - j * (D / 4)) * 4;
+      float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
+      if (j < kn) {
+        kv = *reinterpret_cast<const float4*>(kb + (long long)(k0 + j) * a.k_st + c4);
+        vv = *reinterpret_cast<const float4*>(vb + (long long)(k0 + j) * a.v_st + c4);
+      }
+      uint32_t hh[4], ll[4];
+      split_hi_lo(kv.x, hh[0], ll[0]), split_hi_lo(kv.y, hh[1], ll[1]);
+      split_hi_lo(kv.z, hh[2], ll[2]), split_hi_lo(kv.w, hh[3], ll[3]);
+      *reinterpret_cast<uint4*>(Khi + j * PITCH + c4) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+      *reinterpret_cast<uint4*>(Klo + j * PITCH + c4) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+      split_hi_lo(vv.x, hh[0], ll[0]), split_hi_lo(vv.y, hh[1], ll[1]);
+      split_hi_lo(vv.z, hh[2], ll[2]), split_hi_lo(vv.w, hh[3], ll[3]);
+      *reinterpret_cast<uint4*>(Vhi + j * PITCH + c4) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+      *reinterpret_cast<uint4*>(Vlo + j * PITCH + c4) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+    }
+    __syncthreads();
+
+    // ---- S = Q K^T : 8 n-tiles of 8 keys
+    float s[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+      const uint32_t* kh = reinterpret_cast<const uint32_t*>(Khi) + (nt * 8 + g) * PITCH + t;
+      const uint32_t* kl = reinterpret_cast<const uint32_t*>(Klo) + (nt * 8 + g) * PITCH + t;
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        const uint32_t bh0 = kh[ks * 8], bh1 = kh[ks * 8 + 4];
+        const uint32_t bl0 = kl[ks * 8], bl1 = kl[ks * 8 + 4];
+        mma_tf32(s[nt], ql[ks], bh0, bh1);
+        mma_tf32(s[nt], qh[ks], bl0, bl1);
+        mma_tf32(s[nt], qh[ks], bh0, bh1);
+      }
+    }
+    // ---- mask the tail, online softmax (rows g and g+8; columns 2t, 2t+1 of each n-tile)
+    float mx0 = m0, mx1 = m1;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const int c = nt * 8 + 2 * t;
+      if (c >= kn) s[nt][0] = -INFINITY, s[nt][2] = -INFINITY;
+      if (c + 1 >= kn) s[nt][1] = -INFINITY, s[nt][3] = -INFINITY;
+      mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+      mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float c0 = expf(m0 - mx0), c1 = expf(m1 - mx1);
+    m0 = mx0, m1 = mx1;
+    float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      s[nt][0] = expf(s[nt][0] - mx0);
+      s[nt][1] = expf(s[nt][1] - mx0);
+      s[nt][2] = expf(s[nt][2] - mx1);
+      s[nt][3] = expf(s[nt][3] - mx1);
+      rs0 += s[nt][0] + s[nt][1];
+      rs1 += s[nt][2] + s[nt][3];
+    }
+    l0 = l0 * c0 + rs0;
+    l1 = l1 * c1 + rs1;
+#pragma unroll
+    for (int i = 0; i < KS; ++i) {
+      o[i][0] *= c0, o[i][1] *= c0;
+      o[i][2] *= c1, o[i][3] *= c1;
+    }
+    // ---- O += P V : k-step = one n-tile of S (8 keys), n-tiles over D
+#pragma unroll
+    for (int kt = 0; kt < 8; ++kt) {
+      uint32_t ph[4], pl[4];
+      // A fragment: a0=(row g, k t) a1=(row g+8, k t) a2=(row g, k t+4) a3=(row g+8, k t+4)
+      // with k-index t <-> key 2t and k-index t+4 <-> key 2t+1
+      split_hi_lo(s[kt][0], ph[0], pl[0]);
+      split_hi_lo(s[kt][2], ph[1], pl[1]);
+      split_hi_lo(s[kt][1], ph[2], pl[2]);
+      split_hi_lo(s[kt][3], ph[3], pl[3]);
+      const uint32_t* vh = reinterpret_cast<const uint32_t*>(Vhi) + (kt * 8 + 2 * t) * PITCH + g;
+      const uint32_t* vl = reinterpret_cast<const uint32_t*>(Vlo) + (kt * 8 + 2 * t) * PITCH + g;
+#pragma unroll
+      for (int nt = 0; nt < KS; ++nt) {
+        const uint32_t bh0 = vh[nt * 8], bh1 = vh[PITCH + nt * 8];
+        const uint32_t bl0 = vl[nt * 8], bl1 = vl[PITCH + nt * 8];
+        mma_tf32(o[nt], pl, bh0, bh1);
+        mma_tf32(o[nt], ph, bl0, bl1);
+        mma_tf32(o[nt], ph, bh0, bh1);
+      }
+    }
+  }
+  // ---- normalise and store: C fragment rows g / g+8, cols 2t, 2t+1 of each 8-wide n-tile
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float i0 = 1.f / l0, i1 = 1.f / l1;
+  float* ob = a.o + (long long)b * a.o_sb + (long long)h * a.o_sh;
+  const int r0 = q0 + g, r1 = q0 + g + 8;
+#pragma unroll
+  for (int nt = 0; nt < KS; ++nt) {
+    if (r0 < a.tq)
+      *reinterpret_cast<float2*>(ob + (long long)r0 * a.o_st + nt * 8 + 2 * t) =
+          make_float2(o[nt][0] * i0, o[nt][1] * i0);
+    if (r1 < a.tq)
+      *reinterpret_cast<float2*>(ob + (long long)r1 * a.o_st + nt * 8 + 2 * t) =
+          make_float2(o[nt][2] * i1, o[nt][3] * i1);
+  }
+}
+
+template <int D>
+static int launch_mma(tfmq_ctx* ctx, const AttnP& P, cudaStream_t st) {
+  const size_t smem = (size_t)4 * ATT_TK * (D + 4) * sizeof(float);
+  auto kern = attn_mma_kernel<D>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return tfmq_fail(ctx, TFMQ_ERR_CUDA, "attention: smem attr: %s", cudaGetErrorString(e));
+  dim3 grid((P.a.tq + 63) / 64, P.a.b * P.a.heads);
+  kern<<<grid, 128, smem, st>>>(P);
+  TFMQ_LAUNCH_CHECK("attention_mma");
+  return TFMQ_OK;
+}
+
+template <int G>
+static int launch_generic(tfmq_ctx* ctx, AttnP& P, cudaStream_t st) {
+  int tk = 12288 / P.a.d;
+  if (tk > 32) tk = 32;
+  if (tk < 4) tk = 4;
+  tk &= ~3;
+  P.tk_tile = tk;
+  const size_t smem = (size_t)2 * tk * P.a.d * sizeof(float);
+  auto kern = attn_generic_kernel<G>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return tfmq_fail(ctx, TFMQ_ERR_CUDA, "attention: smem attr: %s", cudaGetErrorString(e));
+  constexpr int QPC = 128 / G;
+  dim3 grid((P.a.tq + QPC - 1) / QPC, P.a.b * P.a.heads);
+  kern<<<grid, 128, smem, st>>>(P);
+  TFMQ_LAUNCH_CHECK("attention_generic");
+  return TFMQ_OK;
+}
+
+}  // namespace tfmq
+
+using namespace tfmq;
+
+extern "C" int tfmq_attention(tfmq_ctx* ctx, const tfmq_attn_desc* d, void* stream) {
+  if (!ctx) return TFMQ_ERR_ARG;
+  TFMQ_REQUIRE(d && d->q && d->k && d->v && d->o, TFMQ_ERR_ARG, "attention: null pointer");
+  TFMQ_REQUIRE(d->d > 0 && d->d <= 1024, TFMQ_ERR_SHAPE, "attention: head dim %d", d->d);
+  if (d->b == 0 || d->heads == 0 || d->tq == 0) return TFMQ_OK;
+  TFMQ_REQUIRE(d->tk > 0, TFMQ_ERR_SHAPE, "attention: empty key set");
+  TFMQ_REQUIRE((long long)d->b * d->heads <= 65535, TFMQ_ERR_SHAPE, "attention: b*heads > 65535");
+  AttnP P;
+  P.a = *d;
+  P.tk_tile = ATT_TK;
+  cudaStream_t st = tfmq_stream(stream);
+  auto al16 = [](const void* p, int64_t s0, int64_t s1, int64_t s2) {
+    return (((uintptr_t)p & 15) == 0) && s0 % 4 == 0 && s1 % 4 == 0 && s2 % 4 == 0;
+  };
+  const bool vec_ok = al16(d->k, d->k_sb, d->k_sh, d->k_st) && al16(d->v, d->v_sb, d->v_sh, d->v_st) &&
+                      (((uintptr_t)d->o & 7) == 0) && d->o_sb % 2 == 0 && d->o_sh % 2 == 0 && d->o_st % 2 == 0;
+  if (vec_ok) {
+    switch (d->d) {
+      case 32: return launch_mma<32>(ctx, P, st);
+      case 40: return launch_mma<40>(ctx, P, st);
+      case 64: return launch_mma<64>(ctx, P, st);
+      case 80: return launch_mma<80>(ctx, P, st);
+      default: break;
+    }
+  }
+  int G = 1;
+  while (G <= 32 && !(d->d % G == 0 && d->d / G <= 32)) G <<= 1;
+  TFMQ_REQUIRE(G <= 32, TFMQ_ERR_SHAPE, "attention: head dim %d not supported", d->d);
+  switch (G) {
+    case 1: return launch_generic<1>(ctx, P, st);
+    case 2: return launch_generic<2>(ctx, P, st);
+    case 4: return launch_generic<4>(ctx, P, st);
+    case 8: return launch_generic<8>(ctx, P, st);
+    case 16: return launch_generic<16>(ctx, P, st);
+    default: return launch_generic<32>(ctx, P, st);
+  }
+}

@@ -1,0 +1,307 @@
+// HBM-bound producer / consumer kernels around the tcgen05 GEMMs:
+// GroupNorm statistics, the fused GN-apply + SiLU + activation-quantise producer,
+// DDIM update, classifier-free-guidance combine, timestep embedding.
+#include "ctx.h"
+
+namespace tfmq {
+
+// ---------------------------------------------------------------- GN statistics
+// grid (chunks, n); each CTA reduces a run of pixels, threads own float4 channel
+// vectors (coalesced rows), fp32 partials over <= a few hundred pixels, then
+// double per channel -> per group -> one atomicAdd(double) pair per group.
+constexpr int GN_THREADS = 256;
+constexpr int GN_MAXVEC = 2;  // c <= 2048
+
+__global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const float* __restrict__ x, long long ld, int hw, int c,
+                                                              int groups, int pix_per_cta,
+                                                              double* __restrict__ stats) {
+  extern __shared__ double sm[];  // [c] sum, [c] sumsq
+  const int n = blockIdx.y;
+  const int p0 = blockIdx.x * pix_per_cta;
+  int p1 = p0 + pix_per_cta;
+  if (p1 > hw) p1 = hw;
+  const int nvec = c >> 2;
+  float s[GN_MAXVEC][4], ss[GN_MAXVEC][4];
+#pragma unroll
+  for (int v = 0; v < GN_MAXVEC; ++v)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s[v][j] = ss[v][j] = 0.f;
+  const float* base = x + ((long long)n * hw) * ld;
+  for (int p = p0; p < p1; ++p) {
+    const float4* row = reinterpret_cast<const float4*>(base + (long long)p * ld);
+#pragma unroll
+    for (int v = 0; v < GN_MAXVEC; ++v) {
+      const int iv = threadIdx.x + v * GN_THREADS;
+      if (iv < nvec) {
+        const float4 f = row[iv];
+        s[v][0] += f.x, s[v][1] += f.y, s[v][2] += f.z, s[v][3] += f.w;
+        ss[v][0] += f.x * f.x, ss[v][1] += f.y * f.y, ss[v][2] += f.z * f.z, ss[v][3] += f.w * f.w;
+      }
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < GN_MAXVEC; ++v) {
+    const int iv = threadIdx.x + v * GN_THREADS;
+    if (iv < nvec) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        sm[iv * 4 + j] = (double)s[v][j];
+        sm[c + iv * 4 + j] = (double)ss[v][j];
+      }
+    }
+  }
+  __syncthreads();
+  const int cpg = c / groups;
+  for (int g = threadIdx.x; g < groups; g += GN_THREADS) {
+    double a = 0, b = 0;
+    for (int j = 0; j < cpg; ++j) {
+      a += sm[g * cpg + j];
+      b += sm[c + g * cpg + j];
+    }
+    atomicAdd(&stats[((long long)n * groups + g) * 2], a);
+    atomicAdd(&stats[((long long)n * groups + g) * 2 + 1], b);
+  }
+}
+
+// ------------------------------------------------- GN-apply + SiLU + quantise
+constexpr int ACT_THREADS = 256;
+
+struct ActParams {
+  tfmq_act_desc d;
+  int out_h, out_w;     // destination interior extent
+  int pix_per_cta;      // destination pixels (incl. halo) per CTA
+};
+
+__device__ __forceinline__ float silu_f(float v) { return v * (1.f / (1.f + expf(-v))); }
+
+__global__ void __launch_bounds__(ACT_THREADS) act_prepare_kernel(const ActParams P) {
+  extern __shared__ float sp[];  // [c] a = rstd*gamma, [c] b = beta - a*mean
+  const tfmq_act_desc& d = P.d;
+  const int n = blockIdx.y;
+  const int c = d.c;
+  if (d.gn_stats) {
+    const int cpg = c / d.groups;
+    const double cnt = (double)cpg * d.h * d.w;
+    for (int ch = threadIdx.x; ch < c; ch += ACT_THREADS) {
+      const int g = ch / cpg;
+      const double su = d.gn_stats[((long long)n * d.groups + g) * 2];
+      const double sq = d.gn_stats[((long long)n * d.groups + g) * 2 + 1];
+      const double mean = su / cnt;
+      double var = sq / cnt - mean * mean;
+      if (var < 0) var = 0;
+      const float rstd = (float)(1.0 / sqrt(var + (double)d.eps));
+      const float a = rstd * d.gamma[ch];
+      sp[ch] = a;
+      sp[c + ch] = -a * (float)mean + d.beta[ch];
+    }
+    __syncthreads();
+  }
+  float delta = 1.f, zp = 0.f;
+  if (d.dst_u8) {
+    delta = d.aq[0];
+    zp = d.aq[1];
+  }
+  const int halo = d.dst_u8 ? d.halo : 0;
+  const int Wp = P.out_w + 2 * halo, Hp = P.out_h + 2 * halo;
+  const int npix = Wp * Hp;
+  const int nvec = c >> 2;
+  const int p0 = blockIdx.x * P.pix_per_cta;
+  int p1 = p0 + P.pix_per_cta;
+  if (p1 > npix) p1 = npix;
+  const int total = (p1 - p0) * nvec;
+  for (int i = threadIdx.x; i < total; i += ACT_THREADS) {
+    const int pp = p0 + i / nvec;
+    const int v = i - (i / nvec) * nvec;
+    const int yy = pp / Wp, xx = pp - yy * Wp;
+    const int y = yy - halo, x = xx - halo;
+    const bool border = (y < 0) | (x < 0) | (y >= P.out_h) | (x >= P.out_w);
+    if (border) {
+      const uint32_t z = (uint32_t)zp;
+      uint32_t* o = reinterpret_cast<uint32_t*>(d.dst_u8 + ((long long)n * npix + pp) * d.dst_c + d.dst_c_off);
+      o[v] = z * 0x01010101u;
+      continue;
+    }
+    const int sy = d.upsample ? (y >> 1) : y, sx = d.upsample ? (x >> 1) : x;
+    const float4 f =
+        reinterpret_cast<const float4*>(d.src + (((long long)n * d.h + sy) * d.w + sx) * d.src_ld)[v];
+    float t[4] = {f.x, f.y, f.z, f.w};
+    if (d.gn_stats) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) t[j] = fmaf(t[j], sp[v * 4 + j], sp[c + v * 4 + j]);
+    }
+    if (d.silu) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) t[j] = silu_f(t[j]);
+    }
+    if (d.dst_u8) {
+      uint32_t pk = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float q = rintf(__fdiv_rn(t[j], delta)) + zp;
+        q = fminf(fmaxf(q, 0.f), 255.f);
+        pk |= ((uint32_t)q) << (8 * j);
+      }
+      uint32_t* o = reinterpret_cast<uint32_t*>(d.dst_u8 + ((long long)n * npix + pp) * d.dst_c + d.dst_c_off);
+      o[v] = pk;
+    } else {
+      float4* o = reinterpret_cast<float4*>(d.dst_f32 + ((long long)n * npix + pp) * d.dst_ld);
+      o[v] = make_float4(t[0], t[1], t[2], t[3]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- DDIM update
+__global__ void ddim_update_kernel(const float* __restrict__ x, const float* __restrict__ e,
+                                   const float* __restrict__ noise, const float* __restrict__ coef, long long count,
+                                   float* __restrict__ x_prev, float* __restrict__ x0_out) {
+  const float sa = coef[0], s1ma = coef[1], sap = coef[2], c2 = coef[3];
+  const float c1 = noise ? coef[4] : 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float ev = e[i];
+    // (x - e*sqrt(1-a)) / sqrt(a), then sqrt(a')*x0 + c1*noise + c2*e : same operation order as
+    // ddim/functions/denoising.py:31-37 so the fp32 roundings agree; no FMA contraction
+    const float x0 = __fdiv_rn(__fsub_rn(x[i], __fmul_rn(ev, s1ma)), sa);
+    float r = __fmul_rn(sap, x0);
+    if (noise) r = __fadd_rn(r, __fmul_rn(c1, noise[i]));
+    r = __fadd_rn(r, __fmul_rn(c2, ev));
+    x_prev[i] = r;
+    if (x0_out) x0_out[i] = x0;
+  }
+}
+
+__global__ void cfg_combine_kernel(const float* __restrict__ eu, const float* __restrict__ ec, float s, long long count,
+                                   float* __restrict__ out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count;
+       i += (long long)gridDim.x * blockDim.x)
+    out[i] = __fadd_rn(eu[i], __fmul_rn(s, __fsub_rn(ec[i], eu[i])));
+}
+
+__global__ void timestep_embedding_kernel(const float* __restrict__ t, int m, int dim, int style,
+                                          float* __restrict__ out) {
+  const int half = dim / 2;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m * half) return;
+  const int r = i / half, j = i - r * half;
+  float freq;
+  if (style == 0)
+    freq = expf((float)j * -(logf(10000.f) / (float)(half - 1)));
+  else
+    freq = expf(-logf(10000.f) * (float)j / (float)half);
+  const float a = t[r] * freq;
+  float* o = out + (long long)r * dim;
+  if (style == 0) {
+    o[j] = sinf(a);
+    o[half + j] = cosf(a);
+  } else {
+    o[j] = cosf(a);
+    o[half + j] = sinf(a);
+  }
+  if ((dim & 1) && j == 0) o[dim - 1] = 0.f;
+}
+
+}  // namespace tfmq
+
+using namespace tfmq;
+
+extern "C" int tfmq_fill_zero(tfmq_ctx* ctx, void* p, size_t bytes, void* stream) {
+  if (!ctx) return TFMQ_ERR_ARG;
+  TFMQ_REQUIRE(p || bytes == 0, TFMQ_ERR_ARG, "fill_zero: null pointer");
+  cudaError_t e = cudaMemsetAsync(p, 0, bytes, tfmq_stream(stream));
+  if (e != cudaSuccess) return tfmq_fail(ctx, TFMQ_ERR_CUDA, "fill_zero: %s", cudaGetErrorString(e));
+  return TFMQ_OK;
+}
+
+extern "C" int tfmq_gn_stats(tfmq_ctx* ctx, const float* x, int64_t ld, int n, int hw, int c, int groups,
+                             double* stats, void* stream) {
+  if (!ctx) return TFMQ_ERR_ARG;
+  TFMQ_REQUIRE(x && stats, TFMQ_ERR_ARG, "gn_stats: null pointer");
+  TFMQ_REQUIRE(c % 4 == 0 && ld % 4 == 0 && c <= 4 * GN_THREADS * GN_MAXVEC && c % groups == 0, TFMQ_ERR_SHAPE,
+               "gn_stats: c=%d groups=%d ld=%lld", c, groups, (long long)ld);
+  TFMQ_REQUIRE(((uintptr_t)x & 15) == 0, TFMQ_ERR_ARG, "gn_stats: x must be 16-byte aligned");
+  if (n == 0 || hw == 0) return TFMQ_OK;
+  int chunks = (ctx->sm_count * 4 + n - 1) / n;
+  if (chunks > hw) chunks = hw;
+  if (chunks < 1) chunks = 1;
+  const int ppc = (hw + chunks - 1) / chunks;
+  chunks = (hw + ppc - 1) / ppc;
+  gn_stats_kernel<<<dim3(chunks, n), GN_THREADS, 2 * c * sizeof(double), tfmq_stream(stream)>>>(x, ld, hw, c, groups,
+                                                                                                ppc, stats);
+  TFMQ_LAUNCH_CHECK("gn_stats");
+  return TFMQ_OK;
+}
+
+extern "C" int tfmq_act_prepare(tfmq_ctx* ctx, const tfmq_act_desc* d, void* stream) {
+  if (!ctx) return TFMQ_ERR_ARG;
+  TFMQ_REQUIRE(d && d->src, TFMQ_ERR_ARG, "act_prepare: null pointer");
+  TFMQ_REQUIRE((d->dst_u8 != nullptr) != (d->dst_f32 != nullptr), TFMQ_ERR_ARG,
+               "act_prepare: exactly one of dst_u8 / dst_f32");
+  TFMQ_REQUIRE(d->c % 4 == 0 && d->src_ld % 4 == 0, TFMQ_ERR_SHAPE, "act_prepare: c/ld not multiple of 4");
+  TFMQ_REQUIRE(((uintptr_t)d->src & 15) == 0, TFMQ_ERR_ARG, "act_prepare: src must be 16-byte aligned");
+  if (d->dst_u8) {
+    TFMQ_REQUIRE(d->aq, TFMQ_ERR_ARG, "act_prepare: aq required for u8 output");
+    TFMQ_REQUIRE(d->dst_c % 4 == 0 && d->dst_c_off % 4 == 0 && d->dst_c_off + d->c <= d->dst_c, TFMQ_ERR_SHAPE,
+                 "act_prepare: bad dst channel window");
+    TFMQ_REQUIRE(d->halo == 0 || d->halo == 1, TFMQ_ERR_ARG, "act_prepare: halo");
+    TFMQ_REQUIRE(((uintptr_t)d->dst_u8 & 3) == 0, TFMQ_ERR_ARG, "act_prepare: dst must be 4-byte aligned");
+  } else {
+    TFMQ_REQUIRE(d->dst_ld % 4 == 0 && ((uintptr_t)d->dst_f32 & 15) == 0, TFMQ_ERR_SHAPE, "act_prepare: dst_ld/align");
+  }
+  if (d->gn_stats) {
+    TFMQ_REQUIRE(d->gamma && d->beta && d->groups > 0 && d->c % d->groups == 0, TFMQ_ERR_ARG,
+                 "act_prepare: GroupNorm parameters");
+    TFMQ_REQUIRE(!d->upsample, TFMQ_ERR_ARG, "act_prepare: GN with upsample unsupported");
+  }
+  if (d->n == 0) return TFMQ_OK;
+  ActParams P;
+  P.d = *d;
+  P.out_h = d->upsample ? 2 * d->h : d->h;
+  P.out_w = d->upsample ? 2 * d->w : d->w;
+  const int halo = d->dst_u8 ? d->halo : 0;
+  const int npix = (P.out_h + 2 * halo) * (P.out_w + 2 * halo);
+  int chunks = (ctx->sm_count * 8 + d->n - 1) / d->n;
+  if (chunks > npix) chunks = npix;
+  const int ppc = (npix + chunks - 1) / chunks;
+  chunks = (npix + ppc - 1) / ppc;
+  P.pix_per_cta = ppc;
+  const size_t smem = d->gn_stats ? 2 * (size_t)d->c * sizeof(float) : 0;
+  act_prepare_kernel<<<dim3(chunks, d->n), ACT_THREADS, smem, tfmq_stream(stream)>>>(P);
+  TFMQ_LAUNCH_CHECK("act_prepare");
+  return TFMQ_OK;
+}
+
+extern "C" int tfmq_ddim_update(tfmq_ctx* ctx, const float* x, const float* e, const float* noise, const float* coef,
+                                int64_t count, float* x_prev, float* x0_out, void* stream) {
+  if (!ctx) return TFMQ_ERR_ARG;
+  TFMQ_REQUIRE(x && e && coef && x_prev, TFMQ_ERR_ARG, "ddim_update: null pointer");
+  if (count == 0) return TFMQ_OK;
+  int blocks = (int)((count + 255) / 256);
+  if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
+  ddim_update_kernel<<<blocks, 256, 0, tfmq_stream(stream)>>>(x, e, noise, coef, count, x_prev, x0_out);
+  TFMQ_LAUNCH_CHECK("ddim_update");
+  return TFMQ_OK;
+}
+
+extern "C" int tfmq_cfg_combine(tfmq_ctx* ctx, const float* e_uncond, const float* e_cond, float s, int64_t count,
+                                float* out, void* stream) {
+  if (!ctx) return TFMQ_ERR_ARG;
+  TFMQ_REQUIRE(e_uncond && e_cond && out, TFMQ_ERR_ARG, "cfg_combine: null pointer");
+  if (count == 0) return TFMQ_OK;
+  int blocks = (int)((count + 255) / 256);
+  if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
+  cfg_combine_kernel<<<blocks, 256, 0, tfmq_stream(stream)>>>(e_uncond, e_cond, s, count, out);
+  TFMQ_LAUNCH_CHECK("cfg_combine");
+  return TFMQ_OK;
+}
+
+extern "C" int tfmq_timestep_embedding(tfmq_ctx* ctx, const float* t, int m, int dim, int style, float* out,
+                                       void* stream) {
+  if (!ctx) return TFMQ_ERR_ARG;
+  TFMQ_REQUIRE(t && out, TFMQ_ERR_ARG, "timestep_embedding: null pointer");
+  TFMQ_REQUIRE(dim >= 4 && (style == 0 || style == 1), TFMQ_ERR_ARG, "timestep_embedding: dim/style");
+  if (m == 0) return TFMQ_OK;
+  const int total = m * (dim / 2);
+  timestep_embedding_kernel<<<(total + 127) / 128, 128, 0, tfmq_stream(stream)>>>(t, m, dim, style, out);
+  TFMQ_LAUNCH_CHECK("timestep_embedding");
+  return TFMQ_OK;
+}

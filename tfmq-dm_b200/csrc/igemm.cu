@@ -1,0 +1,526 @@
+// tcgen05 implicit-GEMM convolution kernels + their C-ABI launchers.
+// See igemm.cuh for the pipeline description and DESIGN.md for the roofline.
+#include "igemm.cuh"
+
+#include "ctx.h"
+#include "ptx.cuh"
+
+namespace tfmq {
+
+// ---------------------------------------------------------------------------
+// kernel
+// ---------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(IGEMM_THREADS, 1)
+igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+             const __grid_constant__ CUtensorMap tmB2, const IgemmParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // dynamic smem is only guaranteed 16-B aligned: round up to the 1024 B the 128B swizzle needs
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int S = p.stages;
+
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S * p.stage_bytes);
+  uint64_t* full_tma = bars;           // [S] TMA bytes landed
+  uint64_t* full_xf = bars + S;        // [S] transform warps done
+  uint64_t* empty = bars + 2 * S;      // [S] UMMAs that read the stage retired
+  uint64_t* acc_full = bars + 3 * S;   // accumulator complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * S + 1);
+
+  // ---- tile coordinates
+  const int tiles_x = p.W / p.tw;
+  const int tiles_y = p.H / p.th;
+  int mt = blockIdx.x;
+  const int tx = mt % tiles_x;
+  mt /= tiles_x;
+  const int ty = mt % tiles_y;
+  const int ng = mt / tiles_y;
+  const int n0 = ng * p.tn, y0 = ty * p.th, x0 = tx * p.tw;
+  const int c_out0 = blockIdx.y * p.tile_n;
+
+  const int kchunks = (p.cin + p.kchunk - 1) / p.kchunk;
+  const int taps = p.ksize * p.ksize;
+  const int nkb = taps * kchunks;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&full_tma[s], 1);
+      mbar_init(&full_xf[s], 4);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(acc_full, 1);
+    mbar_fence_init();
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    if (MODE == MODE_TF32) tma_prefetch_desc(&tmB2);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const bool need_a_lo = (MODE == MODE_TF32) && (p.pass_flags & PASS_LO_HI);
+  const bool need_b_lo = (MODE == MODE_TF32) && (p.pass_flags & PASS_HI_LO);
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (lane == 0) {
+      uint32_t tx_bytes = IGEMM_A_BYTES;
+      if (MODE == MODE_W4A8) tx_bytes += (uint32_t)p.tile_n * 64u;
+      if (MODE == MODE_I8) tx_bytes += (uint32_t)p.tile_n * 128u;
+      if (MODE == MODE_TF32) tx_bytes += (uint32_t)p.tile_n * 128u * (need_b_lo ? 2u : 1u);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % S;
+        const uint32_t par = (uint32_t)(kb / S) & 1u;
+        mbar_wait(&empty[s], par ^ 1u);
+        uint8_t* st = smem + (size_t)s * p.stage_bytes;
+        const int tap = kb / kchunks, kc = kb - tap * kchunks;
+        const int ky = tap / p.ksize, kx = tap - ky * p.ksize;
+        mbar_expect_tx(&full_tma[s], tx_bytes);
+        tma_load_4d(st, &tmA, &full_tma[s], kc * p.kchunk, x0 * p.stride + kx + p.off, y0 * p.stride + ky + p.off,
+                    n0);
+        if (MODE == MODE_W4A8) {
+          // packed bytes: column = (tap*cin + kc*128)/2
+          tma_load_2d(st + p.offP, &tmB, &full_tma[s], (tap * p.cin + kc * p.kchunk) >> 1, c_out0);
+        } else {
+          tma_load_2d(st + p.offB, &tmB, &full_tma[s], tap * p.cin + kc * p.kchunk, c_out0);
+          if (need_b_lo) tma_load_2d(st + p.offB_lo, &tmB2, &full_tma[s], tap * p.cin + kc * p.kchunk, c_out0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== UMMA issuer
+    const uint32_t idesc = (MODE == MODE_TF32) ? idesc_tf32(128, (uint32_t)p.tile_n)
+                                               : idesc_i8_u8s8(128, (uint32_t)p.tile_n);
+    uint32_t accumulate = 0;
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % S;
+      const uint32_t par = (uint32_t)(kb / S) & 1u;
+      mbar_wait(&full_tma[s], par);
+      mbar_wait(&full_xf[s], par);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t st = smem_u32(smem + (size_t)s * p.stage_bytes);
+        const int kc = kb % kchunks;
+        int rem = p.cin - kc * p.kchunk;
+        if (rem > p.kchunk) rem = p.kchunk;
+        const int nslice = rem / p.kslice;  // valid 32-byte K slices in this k-block
+        const uint64_t a_hi = smem_desc_sw128(st);
+        const uint64_t b_hi = smem_desc_sw128(st + p.offB);
+        if (MODE == MODE_TF32) {
+          const uint64_t a_lo = smem_desc_sw128(st + p.offA_lo);
+          const uint64_t b_lo = smem_desc_sw128(st + p.offB_lo);
+          // small terms first, then the main product
+          if (need_a_lo)
+            for (int k = 0; k < nslice; ++k) {
+              umma_tf32(tmem_base, a_lo + 2 * k, b_hi + 2 * k, idesc, accumulate);
+              accumulate = 1;
+            }
+          if (need_b_lo)
+            for (int k = 0; k < nslice; ++k) {
+              umma_tf32(tmem_base, a_hi + 2 * k, b_lo + 2 * k, idesc, accumulate);
+              accumulate = 1;
+            }
+          for (int k = 0; k < nslice; ++k) {
+            umma_tf32(tmem_base, a_hi + 2 * k, b_hi + 2 * k, idesc, accumulate);
+            accumulate = 1;
+          }
+        } else {
+          for (int k = 0; k < nslice; ++k) {
+            umma_i8(tmem_base, a_hi + 2 * k, b_hi + 2 * k, idesc, accumulate);
+            accumulate = 1;
+          }
+        }
+        umma_commit(&empty[s]);
+        if (kb == nkb - 1) umma_commit(acc_full);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===================================================== transform warps (2..5)
+    const int t = threadIdx.x - 64;  // 0..127
+    if (MODE == MODE_W4A8) {
+      // this thread always unpacks the same rows: row_i = (t + 128*i) >> 2, K slice = t & 3
+      const int sub = t & 3;
+      uint32_t zc[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int row = (t + 128 * i) >> 2;
+        uint32_t z = 0;
+        if (row < p.tile_n && c_out0 + row < p.cout) z = p.wzp[c_out0 + row];
+        zc[i] = 0x80808080u - z * 0x01010101u;
+      }
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % S;
+        const uint32_t par = (uint32_t)(kb / S) & 1u;
+        mbar_wait(&full_tma[s], par);
+        uint8_t* st = smem + (size_t)s * p.stage_bytes;
+        const int kc = kb % kchunks;
+        int rem = p.cin - kc * p.kchunk;
+        if (rem > p.kchunk) rem = p.kchunk;
+        const int nslice = rem >> 5;
+        if (sub < nslice) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int row = (t + 128 * i) >> 2;
+            if (row < p.tile_n) {
+              const uint4 pk = *reinterpret_cast<const uint4*>(st + p.offP + row * 64 + sub * 16);
+              uint4 lo, hi;
+              lo.x = ((pk.x & 0x0F0F0F0Fu) + zc[i]) ^ 0x80808080u;
+              lo.y = ((pk.y & 0x0F0F0F0Fu) + zc[i]) ^ 0x80808080u;
+              lo.z = ((pk.z & 0x0F0F0F0Fu) + zc[i]) ^ 0x80808080u;
+              lo.w = ((pk.w & 0x0F0F0F0Fu) + zc[i]) ^ 0x80808080u;
+              hi.x = (((pk.x >> 4) & 0x0F0F0F0Fu) + zc[i]) ^ 0x80808080u;
+              hi.y = (((pk.y >> 4) & 0x0F0F0F0Fu) + zc[i]) ^ 0x80808080u;
+              hi.z = (((pk.z >> 4) & 0x0F0F0F0Fu) + zc[i]) ^ 0x80808080u;
+              hi.w = (((pk.w >> 4) & 0x0F0F0F0Fu) + zc[i]) ^ 0x80808080u;
+              uint8_t* brow = st + p.offB + row * 128;
+              const int sw = row & 7;
+              *reinterpret_cast<uint4*>(brow + (((2 * sub) ^ sw) << 4)) = lo;
+              *reinterpret_cast<uint4*>(brow + (((2 * sub + 1) ^ sw) << 4)) = hi;
+            }
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full_xf[s]);
+      }
+    } else if (MODE == MODE_TF32) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % S;
+        const uint32_t par = (uint32_t)(kb / S) & 1u;
+        mbar_wait(&full_tma[s], par);
+        if (need_a_lo) {
+          uint8_t* st = smem + (size_t)s * p.stage_bytes;
+          uint4* a = reinterpret_cast<uint4*>(st);
+          uint4* al = reinterpret_cast<uint4*>(st + p.offA_lo);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int idx = t + 128 * i;
+            uint4 v = a[idx], h, l;
+            h.x = v.x & 0xFFFFE000u;
+            h.y = v.y & 0xFFFFE000u;
+            h.z = v.z & 0xFFFFE000u;
+            h.w = v.w & 0xFFFFE000u;
+            l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x));
+            l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y));
+            l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z));
+            l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w));
+            a[idx] = h;
+            al[idx] = l;
+          }
+          fence_proxy_async_smem();
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full_xf[s]);
+      }
+    } else {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % S;
+        const uint32_t par = (uint32_t)(kb / S) & 1u;
+        mbar_wait(&full_tma[s], par);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full_xf[s]);
+      }
+    }
+
+    // ===================================================== epilogue (same 4 warps)
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    const int q = warp & 3;             // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;        // accumulator row = pixel within the tile
+    const int hw_t = p.th * p.tw;
+    const int n = n0 + r / hw_t;
+    const int y = y0 + (r / p.tw) % p.th;
+    const int x = x0 + r % p.tw;
+    const bool valid = n < p.n_img;
+    const long long pix = ((long long)n * p.H + y) * p.W + x;
+
+    float a_scale = 1.f;
+    int za = 0;
+    if (MODE == MODE_W4A8) {
+      a_scale = p.aq[0];
+      za = (int)p.aq[1];
+    }
+    for (int c0 = 0; c0 < p.tile_n; c0 += 16) {
+      uint32_t v[16];
+      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      tmem_ld_wait();
+      const int c = c_out0 + c0;
+      if (valid && c < p.cout) {
+        if (MODE == MODE_I8) {
+          int4* o = reinterpret_cast<int4*>(p.out_i32 + pix * p.cout + c);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            o[j] = make_int4((int)v[4 * j], (int)v[4 * j + 1], (int)v[4 * j + 2], (int)v[4 * j + 3]);
+        } else {
+          float f[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            if (MODE == MODE_W4A8) {
+              const int acc = (int)v[j] - za * p.wsum[c + j];
+              f[j] = (float)acc * (a_scale * p.wscale[c + j]);
+            } else {
+              f[j] = __uint_as_float(v[j]);
+              if (p.wscale) f[j] *= p.wscale[c + j];
+            }
+            if (p.bias) f[j] += p.bias[c + j];
+          }
+          if (p.emb) {
+            const float* e = p.emb + (long long)n * p.emb_ld + c;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] += e[j];
+          }
+          if (p.res) {
+            const float4* rp = reinterpret_cast<const float4*>(p.res + pix * p.res_ld + c);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 rv = rp[j];
+              f[4 * j] += rv.x;
+              f[4 * j + 1] += rv.y;
+              f[4 * j + 2] += rv.z;
+              f[4 * j + 3] += rv.w;
+            }
+          }
+          float4* o = reinterpret_cast<float4*>(p.out + pix * p.out_ld + c);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) o[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+// largest multiple of 16 that divides cout and is <= 256 (prefer >= 64)
+static int pick_tile_n(int cout) {
+  for (int t = 256; t >= 16; t -= 16)
+    if (cout % t == 0) return t;
+  return 0;
+}
+
+struct TileGeom {
+  int th, tw, tn;
+};
+static bool pick_geom(int H, int W, TileGeom* g) {
+  if (!is_pow2(W) || !is_pow2(H)) return false;
+  if (W >= 128) {
+    g->tw = 128, g->th = 1, g->tn = 1;
+  } else {
+    g->tw = W;
+    int th = 128 / W;
+    if (th > H) th = H;
+    g->th = th;
+    g->tn = 128 / (g->tw * g->th);
+  }
+  return g->tw * g->th * g->tn == 128;
+}
+
+static int encode(tfmq_ctx* ctx, CUtensorMap* m, CUtensorMapDataType dt, int rank, const void* base,
+                  const cuuint64_t* dims, const cuuint64_t* strides, const cuuint32_t* box, const cuuint32_t* estr,
+                  CUtensorMapSwizzle sw) {
+  CUresult r = ctx->encode_tiled(m, dt, (cuuint32_t)rank, const_cast<void*>(base), dims, strides, box, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return tfmq_fail(ctx, TFMQ_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return TFMQ_OK;
+}
+
+template <int MODE>
+static int launch_igemm(tfmq_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmB2,
+                        IgemmParams& p, cudaStream_t stream, const char* name) {
+  // shared-memory plan
+  const uint32_t bB = (uint32_t)p.tile_n * 128u;
+  uint32_t off = IGEMM_A_BYTES;
+  p.offA_lo = p.offB_lo = p.offP = 0;
+  if (MODE == MODE_TF32 && (p.pass_flags & PASS_LO_HI)) {
+    p.offA_lo = off;
+    off += IGEMM_A_BYTES;
+  }
+  p.offB = off;
+  off += bB;
+  if (MODE == MODE_TF32 && (p.pass_flags & PASS_HI_LO)) {
+    p.offB_lo = off;
+    off += bB;
+  }
+  if (MODE == MODE_W4A8) {
+    p.offP = off;
+    off += (uint32_t)p.tile_n * 64u;
+  }
+  p.stage_bytes = (off + 1023u) & ~1023u;
+  const uint32_t extra = 1024u /*alignment slack*/ + 256u /*barriers*/;
+  const int kchunks = (p.cin + p.kchunk - 1) / p.kchunk;
+  const int nkb = p.ksize * p.ksize * kchunks;
+  int stages = (int)(((uint32_t)ctx->max_smem_optin - extra) / p.stage_bytes);
+  // two CTAs per SM (epilogue of one overlaps the main loop of the other) when >= 2 stages still fit
+  const int half = (int)(((uint32_t)ctx->max_smem_optin / 2 - 1024u - extra) / p.stage_bytes);
+  if (half >= 2) stages = half;
+  if (stages > 6) stages = 6;
+  if (stages > nkb) stages = nkb;
+  if (stages < 1) return tfmq_fail(ctx, TFMQ_ERR_SHAPE, "%s: tile does not fit shared memory", name);
+  p.stages = stages;
+  p.tmem_cols = p.tile_n <= 32 ? 32 : p.tile_n <= 64 ? 64 : p.tile_n <= 128 ? 128 : 256;
+  const size_t smem = (size_t)stages * p.stage_bytes + extra;
+
+  auto kern = igemm_kernel<MODE>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return tfmq_fail(ctx, TFMQ_ERR_CUDA, "%s: smem attr: %s", name, cudaGetErrorString(e));
+  const int tiles_m = (p.W / p.tw) * (p.H / p.th) * ((p.n_img + p.tn - 1) / p.tn);
+  dim3 grid((unsigned)tiles_m, (unsigned)(p.cout / p.tile_n));
+  kern<<<grid, IGEMM_THREADS, smem, stream>>>(tmA, tmB, tmB2, p);
+  TFMQ_LAUNCH_CHECK(name);
+  return TFMQ_OK;
+}
+
+}  // namespace tfmq
+
+using namespace tfmq;
+
+extern "C" int tfmq_conv_w4a8(tfmq_ctx* ctx, const tfmq_conv_w4a8_desc* d, void* stream) {
+  if (!ctx) return TFMQ_ERR_ARG;
+  TFMQ_REQUIRE(d && d->act && d->packed && d->wzp && d->wdelta && d->wsum && d->aq && d->out, TFMQ_ERR_ARG,
+               "conv_w4a8: null pointer");
+  TFMQ_REQUIRE(d->ksize == 1 || d->ksize == 3, TFMQ_ERR_SHAPE, "conv_w4a8: ksize %d", d->ksize);
+  TFMQ_REQUIRE(d->cin % 32 == 0 && d->cin >= 32, TFMQ_ERR_SHAPE, "conv_w4a8: cin %d not a multiple of 32", d->cin);
+  TFMQ_REQUIRE(d->cout % 16 == 0, TFMQ_ERR_SHAPE, "conv_w4a8: cout %d not a multiple of 16", d->cout);
+  TFMQ_REQUIRE(d->out_ld % 4 == 0 && (!d->res || d->res_ld % 4 == 0), TFMQ_ERR_SHAPE, "conv_w4a8: ld not multiple of 4");
+  TFMQ_REQUIRE(((uintptr_t)d->out & 15) == 0 && ((uintptr_t)d->act & 15) == 0 && ((uintptr_t)d->packed & 15) == 0 &&
+                   (!d->res || ((uintptr_t)d->res & 15) == 0),
+               TFMQ_ERR_ARG, "conv_w4a8: pointers must be 16-byte aligned");
+  TileGeom g;
+  TFMQ_REQUIRE(pick_geom(d->h, d->w, &g), TFMQ_ERR_SHAPE, "conv_w4a8: unsupported spatial %dx%d", d->h, d->w);
+  IgemmParams p{};
+  p.n_img = d->n, p.H = d->h, p.W = d->w, p.cin = d->cin, p.cout = d->cout;
+  p.ksize = d->ksize, p.stride = 1, p.off = 0;
+  p.th = g.th, p.tw = g.tw, p.tn = g.tn;
+  p.tile_n = pick_tile_n(d->cout);
+  p.kchunk = 128, p.kslice = 32;
+  p.out = d->out, p.out_ld = d->out_ld, p.bias = d->bias, p.wscale = d->wdelta, p.wsum = d->wsum, p.wzp = d->wzp;
+  p.aq = d->aq, p.emb = d->emb, p.emb_ld = d->emb_ld, p.res = d->res, p.res_ld = d->res_ld;
+
+  const int halo = d->ksize == 3 ? 1 : 0;
+  const cuuint64_t Hp = d->h + 2 * halo, Wp = d->w + 2 * halo;
+  CUtensorMap tmA, tmB;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)d->cin, Wp, Hp, (cuuint64_t)d->n};
+    cuuint64_t str[3] = {(cuuint64_t)d->cin, Wp * d->cin, Hp * Wp * d->cin};
+    cuuint32_t box[4] = {128, (cuuint32_t)g.tw, (cuuint32_t)g.th, (cuuint32_t)g.tn};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    int rc = encode(ctx, &tmA, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, d->act, dims, str, box, es,
+                    CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  {
+    const cuuint64_t kbytes = (cuuint64_t)d->ksize * d->ksize * d->cin / 2;
+    cuuint64_t dims[2] = {kbytes, (cuuint64_t)d->cout};
+    cuuint64_t str[1] = {kbytes};
+    cuuint32_t box[2] = {64, (cuuint32_t)p.tile_n};
+    cuuint32_t es[2] = {1, 1};
+    int rc = encode(ctx, &tmB, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, d->packed, dims, str, box, es,
+                    CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (rc) return rc;
+  }
+  return launch_igemm<MODE_W4A8>(ctx, tmA, tmB, tmB, p, tfmq_stream(stream), "conv_w4a8");
+}
+
+extern "C" int tfmq_conv_fp(tfmq_ctx* ctx, const tfmq_conv_fp_desc* d, void* stream) {
+  if (!ctx) return TFMQ_ERR_ARG;
+  TFMQ_REQUIRE(d && d->x && d->w_hi && d->out, TFMQ_ERR_ARG, "conv_fp: null pointer");
+  TFMQ_REQUIRE(d->ksize == 1 || d->ksize == 3, TFMQ_ERR_SHAPE, "conv_fp: ksize %d", d->ksize);
+  TFMQ_REQUIRE(d->stride == 1 || d->stride == 2, TFMQ_ERR_SHAPE, "conv_fp: stride %d", d->stride);
+  TFMQ_REQUIRE(d->cin % 8 == 0 && d->cin >= 8, TFMQ_ERR_SHAPE, "conv_fp: cin %d not a multiple of 8", d->cin);
+  TFMQ_REQUIRE(d->cout % 16 == 0, TFMQ_ERR_SHAPE, "conv_fp: cout %d not a multiple of 16", d->cout);
+  TFMQ_REQUIRE(d->x_ld % 4 == 0 && d->out_ld % 4 == 0 && (!d->res || d->res_ld % 4 == 0), TFMQ_ERR_SHAPE,
+               "conv_fp: ld not multiple of 4");
+  TFMQ_REQUIRE(((uintptr_t)d->out & 15) == 0 && ((uintptr_t)d->x & 15) == 0 && ((uintptr_t)d->w_hi & 15) == 0 &&
+                   (!d->w_lo || ((uintptr_t)d->w_lo & 15) == 0) && (!d->res || ((uintptr_t)d->res & 15) == 0),
+               TFMQ_ERR_ARG, "conv_fp: pointers must be 16-byte aligned");
+  TFMQ_REQUIRE(d->passes == 1 || d->passes == 3, TFMQ_ERR_ARG, "conv_fp: passes %d", d->passes);
+  TileGeom g;
+  TFMQ_REQUIRE(pick_geom(d->out_h, d->out_w, &g), TFMQ_ERR_SHAPE, "conv_fp: unsupported spatial %dx%d", d->out_h,
+               d->out_w);
+  TFMQ_REQUIRE(g.tw * d->stride <= 256 && g.th * d->stride <= 256, TFMQ_ERR_SHAPE, "conv_fp: box too large");
+  IgemmParams p{};
+  p.n_img = d->n, p.H = d->out_h, p.W = d->out_w, p.cin = d->cin, p.cout = d->cout;
+  p.ksize = d->ksize, p.stride = d->stride, p.off = d->ksize == 3 ? -d->pad_lo : 0;
+  p.th = g.th, p.tw = g.tw, p.tn = g.tn;
+  p.tile_n = pick_tile_n(d->cout);
+  p.kchunk = 32, p.kslice = 8;
+  p.pass_flags = PASS_HI_HI;
+  if (d->passes == 3) p.pass_flags |= PASS_LO_HI | (d->w_lo ? PASS_HI_LO : 0);
+  p.out = d->out, p.out_ld = d->out_ld, p.bias = d->bias, p.wscale = d->wscale;
+  p.res = d->res, p.res_ld = d->res_ld;
+
+  CUtensorMap tmA, tmB, tmB2;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)d->cin, (cuuint64_t)d->w, (cuuint64_t)d->h, (cuuint64_t)d->n};
+    cuuint64_t str[3] = {(cuuint64_t)d->x_ld * 4, (cuuint64_t)d->w * d->x_ld * 4,
+                         (cuuint64_t)d->h * d->w * d->x_ld * 4};
+    cuuint32_t box[4] = {32, (cuuint32_t)(g.tw * d->stride), (cuuint32_t)(g.th * d->stride), (cuuint32_t)g.tn};
+    cuuint32_t es[4] = {1, (cuuint32_t)d->stride, (cuuint32_t)d->stride, 1};
+    // a box dimension of extent 1 must not carry a traversal stride
+    if (g.tw == 1) box[1] = 1, es[1] = 1;
+    if (g.th == 1) box[2] = 1, es[2] = 1;
+    int rc = encode(ctx, &tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, d->x, dims, str, box, es,
+                    CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  const cuuint64_t kk = (cuuint64_t)d->ksize * d->ksize * d->cin;
+  for (int i = 0; i < 2; ++i) {
+    const float* w = i ? d->w_lo : d->w_hi;
+    if (!w) {
+      tmB2 = tmB;
+      continue;
+    }
+    cuuint64_t dims[2] = {kk, (cuuint64_t)d->cout};
+    cuuint64_t str[1] = {kk * 4};
+    cuuint32_t box[2] = {32, (cuuint32_t)p.tile_n};
+    cuuint32_t es[2] = {1, 1};
+    int rc = encode(ctx, i ? &tmB2 : &tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, w, dims, str, box, es,
+                    CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  return launch_igemm<MODE_TF32>(ctx, tmA, tmB, tmB2, p, tfmq_stream(stream), "conv_fp");
+}
+
+extern "C" int tfmq_gemm_i8_peak(tfmq_ctx* ctx, const uint8_t* a, const int8_t* b, int m, int n, int k, int32_t* out,
+                                 void* stream) {
+  if (!ctx) return TFMQ_ERR_ARG;
+  TFMQ_REQUIRE(a && b && out, TFMQ_ERR_ARG, "gemm_i8_peak: null pointer");
+  TFMQ_REQUIRE(m % 128 == 0 && k % 128 == 0 && n % 16 == 0, TFMQ_ERR_SHAPE, "gemm_i8_peak: m%%128, k%%128, n%%16");
+  IgemmParams p{};
+  p.n_img = m, p.H = 1, p.W = 1, p.cin = k, p.cout = n, p.ksize = 1, p.stride = 1, p.off = 0;
+  p.th = 1, p.tw = 1, p.tn = 128;
+  p.tile_n = pick_tile_n(n);
+  p.kchunk = 128, p.kslice = 32;
+  p.out_i32 = out;
+  CUtensorMap tmA, tmB;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)k, 1, 1, (cuuint64_t)m};
+    cuuint64_t str[3] = {(cuuint64_t)k, (cuuint64_t)k, (cuuint64_t)k};
+    cuuint32_t box[4] = {128, 1, 1, 128};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    int rc = encode(ctx, &tmA, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, a, dims, str, box, es, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)n};
+    cuuint64_t str[1] = {(cuuint64_t)k};
+    cuuint32_t box[2] = {128, (cuuint32_t)p.tile_n};
+    cuuint32_t es[2] = {1, 1};
+    int rc = encode(ctx, &tmB, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, b, dims, str, box, es, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  return launch_igemm<MODE_I8>(ctx, tmA, tmB, tmB, p, tfmq_stream(stream), "gemm_i8_peak");
+}

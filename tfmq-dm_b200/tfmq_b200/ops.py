@@ -1,0 +1,263 @@
+"""Tensor-level wrappers over the C ABI (torch is only the owner of device memory here).
+
+Every function launches on torch's current CUDA stream and is graph-capturable.
+Activations are NHWC views: a 4-D tensor [N, H, W, C] whose last dim is contiguous and whose
+pixel pitch (`stride(2)`) may exceed C (a window into a concat buffer).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import ActDesc, AttnDesc, ConvFpDesc, ConvW4A8Desc, LinearDesc
+
+
+def _ctx(t: torch.Tensor) -> _lib.Context:
+    if not t.is_cuda:
+        raise RuntimeError("tfmq_b200 kernels need CUDA tensors on an sm_100 device; there is no CPU path")
+    return _lib.context(t.device.index or 0)
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _nhwc(t: torch.Tensor):
+    """(N, H, W, C, ld) of an NHWC view; checks the layout the kernels assume."""
+    assert t.dim() == 4 and t.stride(3) == 1, "expected NHWC view with contiguous channels"
+    n, h, w, c = t.shape
+    ld = t.stride(2)
+    assert t.stride(1) == w * ld and t.stride(0) == h * w * ld, "NHWC view must be pixel-contiguous"
+    return n, h, w, c, ld
+
+
+# --------------------------------------------------------------------------- weights
+def pack_w4(w2d: torch.Tensor, delta: torch.Tensor, zp: torch.Tensor, alpha: torch.Tensor | None = None):
+    """w2d: [cout, k] fp32 in (tap, cin) order. Returns (codes u8 [cout,k], packed u8 [cout,k/2], wsum i32 [cout])."""
+    ctx = _ctx(w2d)
+    cout, k = w2d.shape
+    w2d = w2d.contiguous().float()
+    delta = delta.reshape(-1).contiguous().float()
+    zp = zp.reshape(-1).contiguous().float()
+    assert delta.numel() == cout and zp.numel() == cout
+    if alpha is not None:
+        alpha = alpha.reshape(cout, k).contiguous().float()
+    codes = torch.empty((cout, k), dtype=torch.uint8, device=w2d.device)
+    packed = torch.empty((cout, k // 2), dtype=torch.uint8, device=w2d.device)
+    wsum = torch.empty((cout,), dtype=torch.int32, device=w2d.device)
+    ctx.call("tfmq_pack_w4", _p(w2d), _p(delta), _p(zp), _p(alpha), cout, k, _p(codes), _p(packed), _p(wsum), _stream())
+    return codes, packed, wsum
+
+
+# --------------------------------------------------------------------------- GroupNorm + producer
+def gn_stats(x: torch.Tensor, groups: int, stats: torch.Tensor | None = None) -> torch.Tensor:
+    ctx = _ctx(x)
+    n, h, w, c, ld = _nhwc(x)
+    if stats is None:
+        stats = torch.zeros((n, groups, 2), dtype=torch.float64, device=x.device)
+    ctx.call("tfmq_gn_stats", _p(x), ld, n, h * w, c, groups, _p(stats), _stream())
+    return stats
+
+
+def fill_zero(t: torch.Tensor):
+    _ctx(t).call("tfmq_fill_zero", _p(t), t.numel() * t.element_size(), _stream())
+
+
+def act_prepare(src: torch.Tensor, *, aq: torch.Tensor | None = None, dst_u8: torch.Tensor | None = None,
+                halo: int = 0, dst_c_off: int = 0, dst_f32: torch.Tensor | None = None,
+                gn_stats_t: torch.Tensor | None = None, gamma=None, beta=None, groups: int = 32,
+                eps: float = 1e-5, silu: bool = False, upsample: bool = False):
+    """[GN] -> [SiLU] -> u8 codes into a halo-padded NHWC buffer, or fp32 NHWC."""
+    ctx = _ctx(src)
+    n, h, w, c, ld = _nhwc(src)
+    d = ActDesc()
+    d.src, d.src_ld = src.data_ptr(), ld
+    d.n, d.h, d.w, d.c = n, h, w, c
+    d.upsample = int(upsample)
+    d.gn_stats = gn_stats_t.data_ptr() if gn_stats_t is not None else None
+    d.gamma = gamma.data_ptr() if gamma is not None else None
+    d.beta = beta.data_ptr() if beta is not None else None
+    d.groups, d.eps, d.silu = groups, eps, int(silu)
+    oh, ow = (2 * h, 2 * w) if upsample else (h, w)
+    if dst_u8 is not None:
+        assert dst_u8.dtype == torch.uint8 and dst_u8.is_contiguous()
+        assert tuple(dst_u8.shape[:3]) == (n, oh + 2 * halo, ow + 2 * halo), (dst_u8.shape, (n, oh, ow, halo))
+        d.aq = aq.data_ptr()
+        d.dst_u8 = dst_u8.data_ptr()
+        d.halo, d.dst_c, d.dst_c_off = halo, dst_u8.shape[3], dst_c_off
+    else:
+        dn, dh, dw, dc, dld = _nhwc(dst_f32)
+        assert (dn, dh, dw, dc) == (n, oh, ow, c)
+        d.dst_f32, d.dst_ld = dst_f32.data_ptr(), dld
+    ctx.call("tfmq_act_prepare", C.byref(d), _stream())
+
+
+# --------------------------------------------------------------------------- tensor-core convs
+def conv_w4a8(act: torch.Tensor, ksize: int, packed, wzp_u8, wdelta, wsum, bias, aq, out: torch.Tensor,
+              emb: torch.Tensor | None = None, res: torch.Tensor | None = None):
+    """act: u8 [N, H+2h, W+2h, Cin] (h = 1 for 3x3, 0 for 1x1); out: fp32 NHWC view [N,H,W,Cout]."""
+    ctx = _ctx(out)
+    n, h, w, cout, out_ld = _nhwc(out)
+    halo = 1 if ksize == 3 else 0
+    assert act.dtype == torch.uint8 and act.is_contiguous()
+    assert tuple(act.shape[:3]) == (n, h + 2 * halo, w + 2 * halo)
+    d = ConvW4A8Desc()
+    d.act = act.data_ptr()
+    d.n, d.h, d.w, d.cin, d.cout, d.ksize = n, h, w, act.shape[3], cout, ksize
+    d.packed, d.wzp, d.wdelta, d.wsum = packed.data_ptr(), wzp_u8.data_ptr(), wdelta.data_ptr(), wsum.data_ptr()
+    d.bias = bias.data_ptr() if bias is not None else None
+    d.aq = aq.data_ptr()
+    if emb is not None:
+        assert emb.stride(-1) == 1
+        d.emb, d.emb_ld = emb.data_ptr(), (emb.stride(0) if emb.dim() == 2 and emb.shape[0] > 1 else 0)
+    if res is not None:
+        rn, rh, rw, rc, rld = _nhwc(res)
+        assert (rn, rh, rw, rc) == (n, h, w, cout)
+        d.res, d.res_ld = res.data_ptr(), rld
+    d.out, d.out_ld = out.data_ptr(), out_ld
+    ctx.call("tfmq_conv_w4a8", C.byref(d), _stream())
+
+
+def conv_fp(x: torch.Tensor, ksize: int, stride: int, pad_lo: int, w_hi, w_lo, out: torch.Tensor, bias=None,
+            wscale=None, res=None, passes: int = 3):
+    ctx = _ctx(out)
+    n, h, w, cin, x_ld = _nhwc(x)
+    on, oh, ow, cout, out_ld = _nhwc(out)
+    assert on == n
+    d = ConvFpDesc()
+    d.x, d.x_ld = x.data_ptr(), x_ld
+    d.n, d.h, d.w, d.cin, d.cout = n, h, w, cin, cout
+    d.ksize, d.stride, d.pad_lo, d.out_h, d.out_w = ksize, stride, pad_lo, oh, ow
+    d.w_hi = w_hi.data_ptr()
+    d.w_lo = w_lo.data_ptr() if w_lo is not None else None
+    d.wscale = wscale.data_ptr() if wscale is not None else None
+    d.bias = bias.data_ptr() if bias is not None else None
+    if res is not None:
+        rn, rh, rw, rc, rld = _nhwc(res)
+        assert (rn, rh, rw, rc) == (n, oh, ow, cout)
+        d.res, d.res_ld = res.data_ptr(), rld
+    d.out, d.out_ld = out.data_ptr(), out_ld
+    d.passes = passes
+    ctx.call("tfmq_conv_fp", C.byref(d), _stream())
+
+
+def split_tf32(w2d: torch.Tensor):
+    """w = hi + lo with hi exactly representable in tf32 (low 13 mantissa bits zero)."""
+    w2d = w2d.contiguous().float()
+    hi = (w2d.view(torch.int32) & -8192).view(torch.float32)
+    lo = w2d - hi
+    return hi.contiguous(), lo.contiguous()
+
+
+def gemm_i8_peak(a_u8: torch.Tensor, b_s8: torch.Tensor, out_i32: torch.Tensor):
+    ctx = _ctx(out_i32)
+    m, k = a_u8.shape
+    n = b_s8.shape[0]
+    ctx.call("tfmq_gemm_i8_peak", _p(a_u8), _p(b_s8), m, n, k, _p(out_i32), _stream())
+
+
+# --------------------------------------------------------------------------- small kernels
+def conv_in(x_nchw: torch.Tensor, w, bias, out: torch.Tensor):
+    ctx = _ctx(out)
+    n, cin, h, wd = x_nchw.shape
+    on, oh, ow, cout, ld = _nhwc(out)
+    assert x_nchw.is_contiguous() and (on, oh, ow) == (n, h, wd)
+    ctx.call("tfmq_conv_in", _p(x_nchw), _p(w), _p(bias), n, h, wd, cin, cout, _p(out), ld, _stream())
+
+
+def conv_out(x: torch.Tensor, w, bias, out_nchw: torch.Tensor):
+    ctx = _ctx(x)
+    n, h, wd, cin, ld = _nhwc(x)
+    cout = out_nchw.shape[1]
+    assert out_nchw.is_contiguous()
+    ctx.call("tfmq_conv_out", _p(x), ld, _p(w), _p(bias), n, h, wd, cin, cout, _p(out_nchw), _stream())
+
+
+def linear_small(x: torch.Tensor, out: torch.Tensor, *, w_f32=None, codes=None, wzp_f=None, wdelta=None, bias=None,
+                 aq=None, silu_in: bool = False):
+    ctx = _ctx(out)
+    m, in_f = x.shape
+    d = LinearDesc()
+    d.x, d.x_ld = x.data_ptr(), x.stride(0)
+    d.m, d.in_f, d.out_f = m, in_f, out.shape[1]
+    d.silu_in = int(silu_in)
+    d.aq = aq.data_ptr() if aq is not None else None
+    d.w_f32 = w_f32.data_ptr() if w_f32 is not None else None
+    d.codes = codes.data_ptr() if codes is not None else None
+    d.wzp_f = wzp_f.data_ptr() if wzp_f is not None else None
+    d.wdelta = wdelta.data_ptr() if wdelta is not None else None
+    d.bias = bias.data_ptr() if bias is not None else None
+    d.out, d.out_ld = out.data_ptr(), out.stride(0)
+    ctx.call("tfmq_linear_small", C.byref(d), _stream())
+
+
+def timestep_embedding(t: torch.Tensor, dim: int, style: int, out: torch.Tensor):
+    _ctx(out).call("tfmq_timestep_embedding", _p(t), t.numel(), dim, style, _p(out), _stream())
+
+
+def attention(q, k, v, o, b: int, heads: int, tq: int, tk: int, d: int, scale: float, strides):
+    """strides: dict name -> (sb, sh, st) in elements for q, k, v, o."""
+    ctx = _ctx(o)
+    a = AttnDesc()
+    for name, t in (("q", q), ("k", k), ("v", v), ("o", o)):
+        sb, sh, st = strides[name]
+        setattr(a, name, t.data_ptr())
+        setattr(a, name + "_sb", sb)
+        setattr(a, name + "_sh", sh)
+        setattr(a, name + "_st", st)
+    a.b, a.heads, a.tq, a.tk, a.d, a.scale = b, heads, tq, tk, d, scale
+    ctx.call("tfmq_attention", C.byref(a), _stream())
+
+
+def ddim_update(x, e, coef, x_prev, x0_out=None, noise=None):
+    _ctx(x).call("tfmq_ddim_update", _p(x), _p(e), _p(noise), _p(coef), x.numel(), _p(x_prev), _p(x0_out), _stream())
+
+
+def cfg_combine(e_u, e_c, s: float, out):
+    _ctx(out).call("tfmq_cfg_combine", _p(e_u), _p(e_c), C.c_float(s), out.numel(), _p(out), _stream())
+
+
+# --------------------------------------------------------------------------- calibration
+def minmax_rows(x2d: torch.Tensor) -> torch.Tensor:
+    rows, cols = x2d.shape
+    mm = torch.empty((rows, 2), dtype=torch.float32, device=x2d.device)
+    _ctx(x2d).call("tfmq_minmax_rows", _p(x2d), rows, cols, _p(mm), _stream())
+    return mm
+
+
+def mse_scale_search(x2d: torch.Tensor, level: int):
+    rows, cols = x2d.shape
+    delta = torch.empty((rows,), dtype=torch.float32, device=x2d.device)
+    zp = torch.empty((rows,), dtype=torch.float32, device=x2d.device)
+    _ctx(x2d).call("tfmq_mse_scale_search", _p(x2d), rows, cols, level, _p(delta), _p(zp), _stream())
+    return delta, zp
+
+
+def act_range_update(x: torch.Tensor, state: torch.Tensor, aq: torch.Tensor, momentum: float = 0.95,
+                     level: int = 256):
+    x2 = x.reshape(-1, x.shape[-1]) if x.stride(-1) == 1 else x.contiguous().reshape(-1, x.shape[-1])
+    assert x2.stride(1) == 1
+    _ctx(x).call("tfmq_act_range_update", _p(x2), x2.stride(0), x2.shape[0], x2.shape[1], C.c_float(momentum), level,
+                 _p(state), _p(aq), _stream())
+
+
+def adaround_soft(w2d, delta, zp, alpha, level: int, out):
+    cout, k = w2d.shape
+    _ctx(w2d).call("tfmq_adaround_soft", _p(w2d), _p(delta), _p(zp), _p(alpha), cout, k, level, _p(out), _stream())
+
+
+def adaround_step(w2d, delta, zp, alpha, grad_w, adam_m, adam_v, level: int, step: int, lr: float, b: float,
+                  lam: float, round_loss):
+    cout, k = w2d.shape
+    _ctx(w2d).call("tfmq_adaround_step", _p(w2d), _p(delta), _p(zp), _p(alpha), _p(grad_w), _p(adam_m), _p(adam_v),
+                   cout, k, level, step, C.c_float(lr), C.c_float(b), C.c_float(lam), _p(round_loss), _stream())
+
+
+def rec_loss(pred, tgt, batch: int, loss, grad=None):
+    _ctx(pred).call("tfmq_rec_loss", _p(pred), _p(tgt), pred.numel(), batch, _p(loss), _p(grad), _stream())
