@@ -254,8 +254,9 @@ int tfmq_adaround_soft(tfmq_ctx* ctx, const float* w, const float* delta, const 
 int tfmq_adaround_step(tfmq_ctx* ctx, const float* w, const float* delta, const float* zp, float* alpha,
                        const float* grad_w, float* adam_m, float* adam_v, int cout, int64_t k, int level, int step,
                        float lr, float b, float lambda, float* round_loss, void* stream);
-/* rec = sum over all elements of |pred-tgt|^2 / batch   (lp_loss p=2, quant_layer.py:146-156),
- * and grad = 2*(pred-tgt)/batch.  loss[0] accumulated (caller zeroes). */
+/* rec = sum over all elements of |pred-tgt|^2 / batch   (lp_loss p=2, quant_layer.py:146-156:
+ * .sum(1).mean(), so `batch` = numel / shape[1]), and grad = 2*(pred-tgt)/batch.
+ * loss[0] accumulated (caller zeroes). */
 int tfmq_rec_loss(tfmq_ctx* ctx, const float* pred, const float* tgt, int64_t count, int batch, float* loss,
                   float* grad_or_null, void* stream);
 

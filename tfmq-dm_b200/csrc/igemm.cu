@@ -95,7 +95,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     // ===================================================== UMMA issuer
     const uint32_t idesc = (MODE == MODE_TF32) ? idesc_tf32(128, (uint32_t)p.tile_n)
                                                : idesc_i8_u8s8(128, (uint32_t)p.tile_n);
-    uint32_t accumulate = 0;
+    uint32_t accumulate = 0, accumulate_lo = 0;
+    // tf32: the two small cross terms accumulate in their own TMEM columns so the (truncating)
+    // tensor-core accumulator adds them to a small running sum, not to the large main one
+    const uint32_t tmem_lo = tmem_base + (uint32_t)p.tile_n;
     for (int kb = 0; kb < nkb; ++kb) {
       const int s = kb % S;
       const uint32_t par = (uint32_t)(kb / S) & 1u;
@@ -116,13 +119,13 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           // small terms first, then the main product
           if (need_a_lo)
             for (int k = 0; k < nslice; ++k) {
-              umma_tf32(tmem_base, a_lo + 2 * k, b_hi + 2 * k, idesc, accumulate);
-              accumulate = 1;
+              umma_tf32(tmem_lo, a_lo + 2 * k, b_hi + 2 * k, idesc, accumulate_lo);
+              accumulate_lo = 1;
             }
           if (need_b_lo)
             for (int k = 0; k < nslice; ++k) {
-              umma_tf32(tmem_base, a_hi + 2 * k, b_lo + 2 * k, idesc, accumulate);
-              accumulate = 1;
+              umma_tf32(tmem_lo, a_hi + 2 * k, b_lo + 2 * k, idesc, accumulate_lo);
+              accumulate_lo = 1;
             }
           for (int k = 0; k < nslice; ++k) {
             umma_tf32(tmem_base, a_hi + 2 * k, b_hi + 2 * k, idesc, accumulate);
@@ -248,6 +251,13 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     for (int c0 = 0; c0 < p.tile_n; c0 += 16) {
       uint32_t v[16];
       tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      if (MODE == MODE_TF32 && (need_a_lo || need_b_lo)) {
+        uint32_t v2[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(p.tile_n + c0), v2);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
+      }
       tmem_ld_wait();
       const int c = c_out0 + c0;
       if (valid && c < p.cout) {
@@ -370,7 +380,9 @@ static int launch_igemm(tfmq_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap
   if (stages > nkb) stages = nkb;
   if (stages < 1) return tfmq_fail(ctx, TFMQ_ERR_SHAPE, "%s: tile does not fit shared memory", name);
   p.stages = stages;
-  p.tmem_cols = p.tile_n <= 32 ? 32 : p.tile_n <= 64 ? 64 : p.tile_n <= 128 ? 128 : 256;
+  int acc_cols = p.tile_n;
+  if (MODE == MODE_TF32 && (p.pass_flags & (PASS_LO_HI | PASS_HI_LO))) acc_cols *= 2;
+  p.tmem_cols = acc_cols <= 32 ? 32 : acc_cols <= 64 ? 64 : acc_cols <= 128 ? 128 : acc_cols <= 256 ? 256 : 512;
   const size_t smem = (size_t)stages * p.stage_bytes + extra;
 
   auto kern = igemm_kernel<MODE>;
