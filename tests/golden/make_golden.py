@@ -1,0 +1,271 @@
+"""Generate the golden fixtures by running the REFERENCE's own code (ModelTC/TFMQ-DM at
+/root/reference) on CPU.  Run once in the build container:  python tests/golden/make_golden.py
+The fixtures are small (.pt, outputs + quantiser parameters only; weights are re-created from the
+seeded fill in synth.py) and are what tests/test_oracle_golden.py and the GPU parity tests check."""
+import os
+import sys
+import tempfile
+import time
+import types
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.environ.get("TFMQ_REFERENCE", "/root/reference")
+sys.path[:0] = [REF, os.path.join(REF, "stable-diffusion"), HERE]
+
+# ---- environment shims (type-only imports and hard-coded .cuda()) -------------------------------
+pl = types.ModuleType("pytorch_lightning")
+pl.LightningModule = torch.nn.Module
+pl.seed_everything = lambda s: torch.manual_seed(s)
+plu = types.ModuleType("pytorch_lightning.utilities")
+plud = types.ModuleType("pytorch_lightning.utilities.distributed")
+plud.rank_zero_only = lambda f: f
+sys.modules.update({"pytorch_lightning": pl, "pytorch_lightning.utilities": plu,
+                    "pytorch_lightning.utilities.distributed": plud})
+ddpm_stub = types.ModuleType("ldm.models.diffusion.ddpm")
+ddpm_stub.LatentDiffusion = torch.nn.Module
+sys.modules["ldm.models.diffusion.ddpm"] = ddpm_stub
+torch.Tensor.cuda = lambda self, *a, **k: self
+torch.nn.Module.cuda = lambda self, *a, **k: self
+_orig_to = torch.Tensor.to
+
+
+def _to(self, *a, **k):
+    a = tuple("cpu" if (isinstance(x, str) and x.startswith("cuda")) else x for x in a)
+    if isinstance(k.get("device"), str) and k["device"].startswith("cuda"):
+        k["device"] = "cpu"
+    return _orig_to(self, *a, **k)
+
+
+torch.Tensor.to = _to
+torch.set_flush_denormal(True)
+torch.set_num_threads(8)
+
+import synth  # noqa: E402
+from quant.quant_layer import QMODE, QuantLayer, Scaler, UniformAffineQuantizer, minmax, mse  # noqa: E402
+from quant.adaptive_rounding import AdaRoundQuantizer, RMODE  # noqa: E402
+from quant.quant_model import QuantModel  # noqa: E402
+from quant.calibration import load_cali_model  # noqa: E402
+from quant import quant_block as rqb  # noqa: E402
+
+SEED = 1234
+
+
+def wq_aq(scaler=Scaler.MINMAX):
+    wq = dict(bits=4, channel_wise=True, scaler=scaler)
+    aq = dict(bits=8, channel_wise=False, scaler=Scaler.MINMAX, leaf_param=True)
+    return wq, aq
+
+
+# ---------------------------------------------------------------------------- G1/G2/G4 KATs
+def quantizer_kats():
+    out = {}
+    g = torch.Generator().manual_seed(7)
+    w = torch.randn(24, 16, 3, 3, generator=g) * 0.07
+    x = torch.randn(4, 16, 12, 12, generator=g) * 1.7 + 0.2
+    # G2 scalers
+    d, z = minmax(x, False, 256, False)
+    out["minmax_x"] = (d.clone(), torch.as_tensor(z).clone())
+    d, z = mse(x, False, 256, False)
+    out["mse_x"] = (d.clone(), torch.as_tensor(z).clone())
+    q = UniformAffineQuantizer(bits=4, channel_wise=True, scaler=Scaler.MINMAX)
+    wdq = q(w)
+    out["w_minmax"] = (q.delta.clone(), q.zero_point.clone(), wdq.clone())
+    q2 = UniformAffineQuantizer(bits=4, channel_wise=True, scaler=Scaler.MSE)
+    wdq2 = q2(w)
+    out["w_mse"] = (q2.delta.clone(), q2.zero_point.clone(), wdq2.clone())
+    # G1 act quantiser incl. running-stat update
+    qa = UniformAffineQuantizer(bits=8, channel_wise=False, scaler=Scaler.MSE, leaf_param=True)
+    xdq = qa(x)
+    out["x_mse_fq"] = (qa.delta.detach().clone(), torch.as_tensor(qa.zero_point).clone(), xdq.detach().clone())
+    qa.running_stat = True
+    trace = []
+    for i in range(3):
+        xi = torch.randn(4, 16, 12, 12, generator=g) * (1.0 + 0.5 * i)
+        qa(xi)
+        trace.append((xi, qa.x_min.clone(), qa.x_max.clone(), qa.delta.detach().clone(), qa.zero_point.clone()))
+    out["running_stat"] = trace
+    qs = UniformAffineQuantizer(bits=8, channel_wise=False, scaler=Scaler.MINMAX, always_zero=True)
+    p = torch.softmax(torch.randn(2, 8, 8, generator=g), -1)
+    out["softmax_always_zero"] = (p, qs(p).clone(), qs.delta.clone())
+    # G4 AdaRound
+    ar = AdaRoundQuantizer(q, w, RMODE.LEARNED_HARD_SIGMOID)
+    alpha0 = ar.alpha.detach().clone()
+    hard0 = ar(w).detach().clone()
+    ar.alpha.data += torch.randn(w.shape, generator=g)
+    hard1 = ar(w).detach().clone()
+    ar.soft_tgt = True
+    soft1 = ar(w).detach().clone()
+    out["adaround"] = dict(alpha0=alpha0, hard0=hard0, alpha1=ar.alpha.detach().clone(), hard1=hard1, soft1=soft1)
+    out["inputs"] = dict(w=w, x=x)
+    # G3 QuantLayer KATs: conv3x3, conv1x1, linear
+    layers = {}
+    for name, mod, inp in (("conv3", torch.nn.Conv2d(16, 24, 3, padding=1), x),
+                           ("conv1", torch.nn.Conv2d(16, 8, 1), x),
+                           ("lin", torch.nn.Linear(32, 12), torch.randn(5, 32, generator=g))):
+        synth.fill_state_dict(mod, 5)
+        wq, aq = wq_aq()
+        ql = QuantLayer(mod, wq, aq)
+        ql.set_quant_state(True, True)
+        y = ql(inp)
+        layers[name] = dict(x=inp, y=y.detach().clone(), wd=ql.wqtizer.delta.clone(), wz=ql.wqtizer.zero_point.clone(),
+                            ad=ql.aqtizer.delta.detach().clone(), az=torch.as_tensor(ql.aqtizer.zero_point).clone())
+    out["quant_layer"] = layers
+    torch.save(out, os.path.join(HERE, "kats.pt"))
+    print("kats.pt written")
+
+
+# ---------------------------------------------------------------------------- model goldens
+def build_ref_qnn(kind):
+    if kind == "cifar":
+        from ddim.models.diffusion import Model
+        sys.path.insert(0, os.path.join(HERE, "..", "..", "tfmq-dm_b200"))
+        from tfmq_b200.host.ddim_unet import cifar10_config
+        fp = Model(cifar10_config())
+        x = synth.latents((1, 3, 32, 32), 11)
+    else:
+        from ldm.modules.diffusionmodules.openaimodel import UNetModel
+        sys.path.insert(0, os.path.join(HERE, "..", "..", "tfmq-dm_b200"))
+        from tfmq_b200.host.ldm_unet import celebahq_ldm4_config
+        fp = UNetModel(**celebahq_ldm4_config())
+        x = synth.latents((1, 3, 64, 64), 12)
+    fp.eval()
+    synth.fill_state_dict(fp, SEED)
+    wq, aq = wq_aq()
+    qnn = QuantModel(fp, wq, aq, cali=False, softmax_a_bit=8, aq_mode=[QMODE.NORMAL.value, QMODE.QDIFF.value])
+    qnn.eval()
+    return qnn, x
+
+
+def attach_alpha(qnn, init):
+    """Run the reference's load_cali_model on a synthetic AdaRound checkpoint."""
+    # first pass: initialise weight quantisers to learn delta (needed for the synthetic alpha)
+    qnn.set_quant_state(True, False)
+    with torch.no_grad():
+        qnn(*init)
+    weight = {}
+    for name, m in qnn.model.named_modules():
+        if isinstance(m, QuantLayer):
+            weight[f"model.{name}.wqtizer.alpha"] = synth.synth_alpha(name, m.original_w, m.wqtizer.delta, SEED)
+    for m in qnn.model.modules():           # undo the init so load_cali_model starts from scratch
+        if isinstance(m, QuantLayer):
+            m.wqtizer.init = False
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "ckpt.pth")
+        torch.save({"weight": weight}, path)
+        with torch.no_grad():
+            load_cali_model(qnn, init, use_aq=True, path=path)
+    qnn.set_quant_state(True, True)
+
+
+def reset_aq(qnn):
+    for name, module in qnn.model.named_modules():
+        if "aqtizer" in name and isinstance(module, UniformAffineQuantizer):
+            if module.delta is not None:   # registered Parameters must be deleted first (calibration.py:115-121)
+                del module.delta
+                del module.zero_point
+            module.delta = None
+            module.zero_point = None
+            module.init = False
+
+
+def collect_aq(qnn):
+    d = {}
+    for name, module in qnn.model.named_modules():
+        if "aqtizer" in name and isinstance(module, UniformAffineQuantizer) and module.delta is not None:
+            d["model." + name + ".delta"] = module.delta.detach().clone().reshape(())
+            d["model." + name + ".zero_point"] = torch.as_tensor(module.zero_point).detach().clone().reshape(())
+    return d
+
+
+def pack_act(act):
+    """list of act_k dicts -> (sorted layer names, float tensor [steps, layers, 2]) to keep the fixture small."""
+    names = sorted({k[len("model."):-len(".aqtizer.delta")] for k in act[0] if k.endswith(".aqtizer.delta")})
+    tab = torch.zeros(len(act), len(names), 2)
+    for k, a in enumerate(act):
+        for i, n in enumerate(names):
+            tab[k, i, 0] = a[f"model.{n}.aqtizer.delta"]
+            tab[k, i, 1] = a[f"model.{n}.aqtizer.zero_point"]
+    return names, tab
+
+
+def promote_zero_points(qnn):
+    for module in qnn.model.modules():
+        if isinstance(module, UniformAffineQuantizer) and module.delta is not None and \
+                not isinstance(module.zero_point, torch.nn.Parameter):
+            module.zero_point = torch.nn.Parameter(torch.as_tensor(module.zero_point).float())
+
+
+def cifar_golden(steps=50):
+    from ddim.functions.denoising import generalized_steps
+    t0 = time.time()
+    qnn, x = build_ref_qnn("cifar")
+    seq = list(range(0, 1000, 1000 // steps))
+    betas = synth.ddim_betas()
+    attach_alpha(qnn, (x, torch.tensor([float(seq[-1])])))
+    print("cifar: load_cali_model done", time.time() - t0)
+    # pass 1: FSC tables -- at every step re-initialise the activation quantisers on the current latent
+    act, xt = [], x
+    seq_next = [-1] + seq[:-1]
+    with torch.no_grad():
+        for i, j in zip(reversed(seq), reversed(seq_next)):
+            reset_aq(qnn)
+            t = torch.ones(1) * i
+            et = qnn(xt, t)
+            act.append(collect_aq(qnn))
+            at = (1 - betas).cumprod(0)[i]
+            an = (1 - betas).cumprod(0)[j] if j >= 0 else torch.tensor(1.0)
+            x0 = (xt - et * (1 - at).sqrt()) / at.sqrt()
+            xt = an.sqrt() * x0 + (1 - an).sqrt() * et
+    print("cifar: pass 1 done", time.time() - t0)
+    promote_zero_points(qnn)
+    ckpt = {f"act_{k}": a for k, a in enumerate(act)}
+    # pass 2: the reference sampler with the FSC switch
+    eps = {}
+    hook_k = [0]
+    orig_fwd = qnn.forward
+
+    def rec_fwd(xx, tt=None, context=None):
+        out = orig_fwd(xx, tt) if context is None else orig_fwd(xx, tt, context)
+        if hook_k[0] in (0, 25, 49):
+            eps[hook_k[0]] = (xx.clone(), tt.clone(), out.clone())
+        hook_k[0] += 1
+        return out
+    qnn.forward = rec_fwd
+    xs, x0_preds, _, _ = generalized_steps(x, seq, qnn, betas, eta=0.0, tot=1000 // steps, cali_ckpt=ckpt,
+                                           t_max=steps - 1)
+    qnn.forward = orig_fwd
+    print("cifar: pass 2 done", time.time() - t0)
+    names, tab = pack_act(act)
+    torch.save(dict(seed=SEED, steps=steps, seq=seq, x_T=x, act_names=names, act_table=tab, eps=eps, xs_last=xs[-1], x_mid=xs[25],
+                    x0_last=x0_preds[-1]), os.path.join(HERE, "cifar_w4a8.pt"))
+    print("cifar_w4a8.pt written")
+
+
+def ldm_golden():
+    t0 = time.time()
+    qnn, x = build_ref_qnn("ldm")
+    t = torch.tensor([501.0])
+    attach_alpha(qnn, (x, t))
+    print("ldm: load_cali_model done", time.time() - t0)
+    with torch.no_grad():
+        reset_aq(qnn)
+        e = qnn(x, t)
+        act = collect_aq(qnn)
+        e2 = qnn(x, t)     # second call with frozen parameters = what sampling sees
+    print("ldm: forward done", time.time() - t0)
+    names, tab = pack_act([act])
+    torch.save(dict(seed=SEED, x=x, t=t, act_names=names, act_table=tab, eps=e2, eps_init=e),
+               os.path.join(HERE, "ldm4_w4a8.pt"))
+    print("ldm4_w4a8.pt written")
+
+
+if __name__ == "__main__":
+    what = sys.argv[1:] or ["kats", "cifar", "ldm"]
+    if "kats" in what:
+        quantizer_kats()
+    if "cifar" in what:
+        cifar_golden()
+    if "ldm" in what:
+        ldm_golden()

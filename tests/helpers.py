@@ -1,0 +1,35 @@
+"""Shared test fixtures: seeded FP models (product host classes + tests/golden/synth.py), oracle specs."""
+import os
+import sys
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLDEN = os.path.join(HERE, "golden")
+if GOLDEN not in sys.path:
+    sys.path.insert(0, GOLDEN)
+import synth  # noqa: E402
+
+CIFAR_CFG = dict(ch=128, ch_mult=[1, 2, 2, 2], num_res_blocks=2)
+LDM4_CFG = dict(model_channels=224, num_head_channels=32)
+
+
+def load_golden(name):
+    return torch.load(os.path.join(GOLDEN, name), map_location="cpu", weights_only=False)
+
+
+def fp_model(kind: str, seed: int = 1234):
+    if kind == "cifar":
+        from tfmq_b200.host.ddim_unet import Model, cifar10_config
+        m = Model(cifar10_config())
+    else:
+        from tfmq_b200.host.ldm_unet import UNetModel, celebahq_ldm4_config
+        m = UNetModel(**celebahq_ldm4_config())
+    m.eval()
+    synth.fill_state_dict(m, seed)
+    return m
+
+
+def oracle_spec(sd, seed: int = 1234):
+    from oracle import unet_ref
+    return unet_ref.build_spec(sd, alpha_fn=lambda n, w, d: synth.synth_alpha(n, w, d, seed))

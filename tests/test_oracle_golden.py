@@ -1,0 +1,114 @@
+"""CPU: pin the oracle (oracle/*.py) against fixtures produced by the reference itself
+(tests/golden/make_golden.py).  No GPU, no product compute."""
+import torch
+
+from helpers import CIFAR_CFG, LDM4_CFG, fp_model, load_golden, oracle_spec, synth
+from oracle import quant_ref as Q
+from oracle import unet_ref as U
+
+torch.set_flush_denormal(True)   # the goldens were generated with FTZ (make_golden.py)
+
+
+def test_scaler_kats_bit_exact():
+    k = load_golden("kats.pt")
+    w, x = k["inputs"]["w"], k["inputs"]["x"]
+    d, z = Q.minmax_scale(x, 256)
+    assert d.item() == k["minmax_x"][0].item() and z.item() == k["minmax_x"][1].item()
+    d, z = Q.mse_scale(x, 256)
+    assert d.item() == k["mse_x"][0].item() and z.item() == k["mse_x"][1].item()
+    d, z = Q.channel_wise(Q.minmax_scale, w, 16)
+    assert torch.equal(d, k["w_minmax"][0]) and torch.equal(z, k["w_minmax"][1])
+    assert torch.equal(Q.uaq_fake_quant(w, d, z, 16), k["w_minmax"][2])
+    d, z = Q.channel_wise(Q.mse_scale, w, 16)
+    assert torch.equal(d, k["w_mse"][0]) and torch.equal(z, k["w_mse"][1])
+    assert torch.equal(Q.uaq_fake_quant(w, d, z, 16), k["w_mse"][2])
+
+
+def test_act_quantizer_and_running_stat_bit_exact():
+    k = load_golden("kats.pt")
+    x = k["inputs"]["x"]
+    d, z, xdq = k["x_mse_fq"]
+    d2, z2 = Q.mse_scale(x, 256)
+    assert d2.item() == d.item() and z2.item() == z.item()
+    assert torch.equal(Q.uaq_fake_quant(x, d, z, 256), xdq)
+    x_min, x_max = x.min(), x.max()
+    for xi, gmin, gmax, gd, gz in k["running_stat"]:
+        x_min, x_max, dd, zz = Q.act_momentum_update(xi, x_min, x_max)
+        assert x_min.item() == gmin.item() and x_max.item() == gmax.item()
+        assert dd.item() == gd.item() and zz.item() == gz.item()
+    p, pq, pd = k["softmax_always_zero"]
+    d, z = Q.minmax_scale(p, 256, always_zero=True)
+    assert d.item() == pd.item() and torch.equal(Q.uaq_fake_quant(p, d, z, 256), pq)
+
+
+def test_adaround_kats():
+    k = load_golden("kats.pt")
+    w = k["inputs"]["w"]
+    d, z = Q.channel_wise(Q.minmax_scale, w, 16)
+    a = k["adaround"]
+    assert torch.equal(Q.adaround_init_alpha(w, d), a["alpha0"])
+    assert torch.equal(Q.adaround_fake_quant(w, d, z, a["alpha0"], 16), a["hard0"])
+    assert torch.equal(Q.adaround_fake_quant(w, d, z, a["alpha1"], 16), a["hard1"])
+    assert torch.equal(Q.adaround_fake_quant(w, d, z, a["alpha1"], 16, soft=True), a["soft1"])
+    # hard rounding at the analytic initialisation is round-to-nearest
+    assert torch.equal(a["hard0"], Q.uaq_fake_quant(w, d, z, 16))
+
+
+def test_quant_layer_kats():
+    k = load_golden("kats.pt")["quant_layer"]
+    for name, mod, conv in (("conv3", torch.nn.Conv2d(16, 24, 3, padding=1), dict(padding=1)),
+                            ("conv1", torch.nn.Conv2d(16, 8, 1), dict(padding=0)),
+                            ("lin", torch.nn.Linear(32, 12), None)):
+        synth.fill_state_dict(mod, 5)
+        g = k[name]
+        wd, wz = Q.channel_wise(Q.minmax_scale, mod.weight.data, 16)
+        ad, az = Q.minmax_scale(g["x"], 256)
+        assert torch.equal(wd, g["wd"]) and torch.equal(wz, g["wz"])
+        assert ad.item() == g["ad"].item() and az.item() == g["az"].item()
+        y = Q.quant_layer_forward(g["x"], mod.weight.data, mod.bias.data, wq=(wd, wz), aq=(ad, az), conv=conv)
+        assert torch.equal(y, g["y"])
+
+
+def test_cifar_unet_step_and_trajectory():
+    g = load_golden("cifar_w4a8.pt")
+    sd = fp_model("cifar", g["seed"]).state_dict()
+    spec = oracle_spec(sd, g["seed"])
+    names, tab = g["act_names"], g["act_table"]
+    assert len(U.wrapped_layer_names(sd)) == 97
+    assert sorted(n for n, s in spec.items() if s["aq"]) == names      # which layers carry act-quant state
+    with torch.no_grad():
+        for k, (x, t, eps) in g["eps"].items():
+            e = U.ddim_unet_forward(sd, CIFAR_CFG, x, t, spec, U.ActParams(names, tab[k]))
+            assert (e - eps).abs().max().item() < 2e-5, k
+        betas = synth.ddim_betas()
+        fn = lambda xt, t, k: U.ddim_unet_forward(sd, CIFAR_CFG, xt, t, spec, U.ActParams(names, tab[k]))  # noqa: E731
+        xs, x0 = U.generalized_steps(g["x_T"], g["seq"], fn, betas, eta=0.0)
+    assert (xs[25] - g["x_mid"]).abs().max().item() < 1e-3
+    assert (xs[-1] - g["xs_last"]).abs().max().item() < 1e-3
+    assert (x0[-1] - g["x0_last"]).abs().max().item() < 1e-3
+
+
+def test_ldm4_unet_step():
+    g = load_golden("ldm4_w4a8.pt")
+    sd = fp_model("ldm", g["seed"]).state_dict()
+    spec = oracle_spec(sd, g["seed"])
+    assert len(U.wrapped_layer_names(sd)) == 73
+    assert sorted(n for n, s in spec.items() if s["aq"]) == g["act_names"]
+    with torch.no_grad():
+        e = U.ldm_unet_forward(sd, LDM4_CFG, g["x"], g["t"], spec, U.ActParams(g["act_names"], g["act_table"][0]))
+    assert (e - g["eps"]).abs().max().item() < 2e-5
+
+
+def test_ddim_coef_table_matches_sampler():
+    betas = synth.ddim_betas()
+    seq = list(range(0, 1000, 20))
+    rows = U.ddim_coef_table(seq, betas)
+    x = synth.latents((1, 3, 8, 8), 3)
+    e = synth.latents((1, 3, 8, 8), 4)
+    xs, _ = U.generalized_steps(x, seq[-1:], lambda xt, t, k: e, betas)   # one step from t=980
+    sa, s1, sn, c2, c1 = rows[0]
+    # the last element of seq with seq_next=-1: rebuild by hand from the first row of a 1-step schedule
+    rows1 = U.ddim_coef_table(seq[-1:], betas)
+    sa, s1, sn, c2, c1 = (torch.tensor(v) for v in rows1[0])
+    x0 = (x - e * s1) / sa
+    assert torch.equal(sn * x0 + c2 * e, xs[-1])

@@ -265,8 +265,12 @@ template <int D>
 static int launch_mma(tfmq_ctx* ctx, const AttnP& P, cudaStream_t st) {
   const size_t smem = (size_t)4 * ATT_TK * (D + 4) * sizeof(float);
   auto kern = attn_mma_kernel<D>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return tfmq_fail(ctx, TFMQ_ERR_CUDA, "attention: smem attr: %s", cudaGetErrorString(e));
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return tfmq_fail(ctx, TFMQ_ERR_CUDA, "attention: smem attr: %s", cudaGetErrorString(e));
+    smem_set = smem;
+  }
   dim3 grid((P.a.tq + 63) / 64, P.a.b * P.a.heads);
   kern<<<grid, 128, smem, st>>>(P);
   TFMQ_LAUNCH_CHECK("attention_mma");
@@ -282,8 +286,12 @@ static int launch_generic(tfmq_ctx* ctx, AttnP& P, cudaStream_t st) {
   P.tk_tile = tk;
   const size_t smem = (size_t)2 * tk * P.a.d * sizeof(float);
   auto kern = attn_generic_kernel<G>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return tfmq_fail(ctx, TFMQ_ERR_CUDA, "attention: smem attr: %s", cudaGetErrorString(e));
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return tfmq_fail(ctx, TFMQ_ERR_CUDA, "attention: smem attr: %s", cudaGetErrorString(e));
+    smem_set = smem;
+  }
   constexpr int QPC = 128 / G;
   dim3 grid((P.a.tq + QPC - 1) / QPC, P.a.b * P.a.heads);
   kern<<<grid, 128, smem, st>>>(P);

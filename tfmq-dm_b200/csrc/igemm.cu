@@ -386,8 +386,12 @@ static int launch_igemm(tfmq_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap
   const size_t smem = (size_t)stages * p.stage_bytes + extra;
 
   auto kern = igemm_kernel<MODE>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return tfmq_fail(ctx, TFMQ_ERR_CUDA, "%s: smem attr: %s", name, cudaGetErrorString(e));
+  static size_t smem_set = 0;  // per template instance; one device per process
+  if (smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return tfmq_fail(ctx, TFMQ_ERR_CUDA, "%s: smem attr: %s", name, cudaGetErrorString(e));
+    smem_set = smem;
+  }
   const int tiles_m = (p.W / p.tw) * (p.H / p.th) * ((p.n_img + p.tn - 1) / p.tn);
   dim3 grid((unsigned)tiles_m, (unsigned)(p.cout / p.tile_n));
   kern<<<grid, IGEMM_THREADS, smem, stream>>>(tmA, tmB, tmB2, p);

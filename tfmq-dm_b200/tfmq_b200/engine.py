@@ -1,0 +1,548 @@
+"""Fused step engine: the per-timestep w4a8 UNet forward (+ DDIM update) as one static program of
+the library's sm_100a kernels, replayed through a CUDA graph.
+
+Replaces, for sampling, the module-by-module execution of QuantModel.forward
+(reference quant/quant_model.py:94-101 -> ddim/models/diffusion.py:306-354 /
+ldm/modules/diffusionmodules/openaimodel.py:744-780) and the per-step host work of the samplers
+(ddim/functions/denoising.py:18-39; ldm/models/diffusion/ddpm.py:1402-1405):
+
+* weights are quantised ONCE (hard AdaRound / nearest) and stored packed int4 + per-channel
+  (delta, zero_point, sum(q - z)); the reference re-quantises all weights every forward;
+* activations live in HBM as fp32 NHWC; every QuantLayer input is produced by one fused
+  GroupNorm-apply + SiLU + quantise kernel writing u8 codes with a zero-point halo;
+* conv / linear run on tcgen05 (int8 for w4a8 layers, 3-pass tf32 for the layers the reference keeps
+  in floating point) with bias / time-embedding / residual fused in the epilogue; skip
+  concatenations are free (producers write into windows of the concat buffer);
+* the Finite-Set-Calibration switch is one device-to-device copy of a parameter row per step
+  (activation (delta, zp) of every layer, the sinusoidal embedding, the DDIM coefficients) instead of
+  ~184 `load_state_dict` tensor copies and a `.item()` sync.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .quant.quant_block import QuantAttentionBlock, QuantAttnBlock, QuantResBlock, QuantResnetBlock
+from .quant.quant_layer import QuantLayer
+
+
+class T:
+    """Symbolic fp32 NHWC tensor; storage is assigned after the whole program is known so that
+    skip concatenations can alias their parts."""
+
+    def __init__(self, n, h, w, c):
+        self.n, self.h, self.w, self.c = n, h, w, c
+        self.parent: Optional["T"] = None
+        self.c_off = 0
+        self.buf: Optional[torch.Tensor] = None
+        self._view = None
+
+    def root(self):
+        t, off = self, 0
+        while t.parent is not None:
+            off += t.c_off
+            t = t.parent
+        return t, off
+
+    @property
+    def view(self) -> torch.Tensor:
+        if self._view is None:
+            r, off = self.root()
+            self._view = r.buf[..., off:off + self.c]
+        return self._view
+
+
+def _cat(a: T, b: T) -> T:
+    assert a.parent is None and b.parent is None and (a.n, a.h, a.w) == (b.n, b.h, b.w)
+    p = T(a.n, a.h, a.w, a.c + b.c)
+    a.parent, a.c_off = p, 0
+    b.parent, b.c_off = p, a.c
+    return p
+
+
+class _QL:
+    """Device-side constants of one QuantLayer, frozen in its current quant state."""
+
+    def __init__(self, name: str, layer: QuantLayer, dev, aq_index: Optional[int]):
+        self.name, self.layer = name, layer
+        w = layer.w.detach() if layer.use_wq else layer.original_w
+        b = layer.b if layer.use_wq else layer.original_b
+        self.is_conv = w.dim() == 4
+        self.cout = w.shape[0]
+        self.ksize = w.shape[2] if self.is_conv else 1
+        self.cin = w.shape[1]
+        self.stride = layer.fwd_kwargs.get("stride", (1, 1))[0] if self.is_conv else 1
+        self.bias = b.detach().float().contiguous().to(dev) if b is not None else None
+        self.aq_index = aq_index
+        self.quant_w = bool(layer.use_wq)
+        w2d = (w.permute(0, 2, 3, 1).reshape(self.cout, -1) if self.is_conv else w).float().contiguous().to(dev)
+        self.w_oihw = w.float().contiguous().to(dev)    # conv_in / conv_out kernels read torch's layout
+        if self.quant_w:
+            wq = layer.wqtizer
+            delta = wq.delta.detach().reshape(-1).float().to(dev)
+            zp = wq.zero_point
+            zp = zp.detach().reshape(-1).float().to(dev) if torch.is_tensor(zp) else torch.full_like(delta, float(zp))
+            if zp.numel() == 1 and delta.numel() > 1:
+                zp = zp.expand_as(delta).contiguous()
+            alpha = getattr(wq, "alpha", None)
+            if alpha is not None:
+                a = alpha.detach()
+                alpha = (a.permute(0, 2, 3, 1).reshape(self.cout, -1) if self.is_conv else a).float().contiguous().to(dev)
+            self.codes, self.packed, self.wsum = ops.pack_w4(w2d, delta, zp, alpha)
+            self.wdelta, self.wzp_f = delta.contiguous(), zp.contiguous()
+            self.wzp_u8 = zp.to(torch.uint8).contiguous()
+            if aq_index is None and self.is_conv:
+                # weight-only quantised conv with fp activations: exact integer weights on the tf32 path
+                self.w_hi = (self.codes.float() - zp[:, None]).contiguous()
+                self.w_lo = None
+        else:
+            self.w_f32 = w2d
+            if self.is_conv and self.cin > 4 and self.cout > 4:
+                self.w_hi, self.w_lo = ops.split_tf32(w2d)
+
+
+class StepEngine:
+    def __init__(self, qnn, batch: int, act_tables: Optional[Sequence[Dict[str, torch.Tensor]]] = None,
+                 timesteps: Optional[Sequence[int]] = None, fp_passes: int = 3, device=None, use_graph: bool = True):
+        model = qnn.model
+        self.dev = torch.device(device) if device is not None else next(model.parameters()).device
+        if self.dev.type != "cuda":
+            raise RuntimeError("StepEngine needs the model on an sm_100a GPU (no CPU path)")
+        self.batch, self.fp_passes, self.use_graph = batch, fp_passes, use_graph
+        self.kind = "ddim" if hasattr(model, "temb") else "ldm"
+        self.model = model
+        self.ops: List = []
+        self.tensors: List[T] = []
+        self._gn_slots = 0
+        self._u8_bufs: List = []
+        self.graph = None
+
+        # ---- quantised-layer table; activation-quantised layers get a slot in the per-step row
+        self.ql: Dict[int, _QL] = {}
+        self.aq_names: List[str] = []
+        with torch.cuda.device(self.dev):
+            for name, m in model.named_modules():
+                if isinstance(m, QuantLayer):
+                    idx = None
+                    if m.use_aq and not m.disable_aq:
+                        idx = len(self.aq_names)
+                        self.aq_names.append(name)
+                    self.ql[id(m)] = _QL(name, m, self.dev, idx)
+        L = len(self.aq_names)
+        self.emb_dim = model.ch if self.kind == "ddim" else model.model_channels
+        self.off_coef = 2 * L
+        self.off_emb = 2 * L + 8
+        self.row = self.off_emb + self.emb_dim
+        self.cur = torch.zeros(self.row, dtype=torch.float32, device=self.dev)
+        self.cur[0:2 * L:2] = 1.0
+        self.table = None
+        self.timesteps = None
+
+        # ---- trace the program
+        N = batch
+        res = model.resolution if self.kind == "ddim" else model.image_size
+        self.x_in = torch.zeros((N, model.in_channels, res, res), dtype=torch.float32, device=self.dev)
+        self.t_in = torch.zeros((N,), dtype=torch.float32, device=self.dev)
+        self.noise = None
+        if self.kind == "ddim":
+            self._trace_ddim(model, N, res)
+        else:
+            self._trace_ldm(model, N, res)
+        self._allocate()
+        self._load_current_aq()
+        if act_tables is not None or timesteps is not None:
+            self.set_schedule(timesteps, act_tables)
+
+    # ================================================================ per-step parameter rows
+    def _aq_ptr(self, q: _QL) -> torch.Tensor:
+        return self.cur[2 * q.aq_index:2 * q.aq_index + 2]
+
+    def _load_current_aq(self):
+        """Take (delta, zp) from the live aqtizers (after load_cali_model / a calibration forward)."""
+        mods = dict(self.model.named_modules())
+        for i, name in enumerate(self.aq_names):
+            aqt = mods[name].aqtizer
+            if aqt.delta is not None:
+                self.cur[2 * i] = float(aqt.delta)
+                self.cur[2 * i + 1] = float(aqt.zero_point)
+
+    def timestep_embedding_cpu(self, t: torch.Tensor) -> torch.Tensor:
+        """Bit-identical to the reference's CPU embedding (same torch ops, on the host)."""
+        if self.kind == "ddim":
+            from .host.ddim_unet import get_timestep_embedding
+            return get_timestep_embedding(t.float().cpu(), self.emb_dim)
+        from .host.ldm_unet import timestep_embedding
+        return timestep_embedding(t.float().cpu(), self.emb_dim)
+
+    def set_schedule(self, timesteps: Optional[Sequence[int]], act_tables=None, ddim_coefs=None):
+        """Build the [steps, row] device table: per-step activation quant params (FSC), the timestep
+        embedding, and the DDIM update coefficients.
+
+        timesteps[k]: the t fed to the UNet at sampling step k.  act_tables[k]: the reference's
+        `act_k` dict ('model.<layer>.aqtizer.delta' / '.zero_point', quant/calibration.py:147-152) or
+        None to keep the current values.  ddim_coefs[k] = (sqrt(a_t), sqrt(1-a_t), sqrt(a_prev), c2, c1)."""
+        steps = len(timesteps) if timesteps is not None else len(act_tables)
+        tab = self.cur.detach().cpu().repeat(steps, 1)
+        if act_tables is not None:
+            assert len(act_tables) >= steps
+            for k in range(steps):
+                d = act_tables[k]
+                for i, name in enumerate(self.aq_names):
+                    kd = f"model.{name}.aqtizer.delta"
+                    if kd in d:
+                        tab[k, 2 * i] = float(d[kd])
+                        tab[k, 2 * i + 1] = float(d[f"model.{name}.aqtizer.zero_point"])
+        if timesteps is not None:
+            ts = torch.tensor([float(t) for t in timesteps])
+            tab[:, self.off_emb:self.off_emb + self.emb_dim] = self.timestep_embedding_cpu(ts)
+            self.timesteps = [float(t) for t in timesteps]
+        if ddim_coefs is not None:
+            tab[:, self.off_coef:self.off_coef + 5] = torch.tensor(ddim_coefs, dtype=torch.float64).float()
+        self.table = tab.to(self.dev)
+        self.select_step(0)
+
+    def select_step(self, k: int):
+        self.cur.copy_(self.table[k], non_blocking=True)
+
+    # ================================================================ op emission
+    def _new(self, n, h, w, c) -> T:
+        t = T(n, h, w, c)
+        self.tensors.append(t)
+        return t
+
+    def _gn(self, x: T, norm: nn.GroupNorm):
+        slot = self._gn_slots
+        self._gn_slots += 1
+        g = norm.num_groups
+        self.ops.append(lambda: ops.gn_stats(x.view, g, self.gn_ws[slot]))
+        return (norm, slot)
+
+    def _gn_args(self, gn):
+        if gn is None:
+            return {}
+        norm, slot = gn
+        return dict(gn_stats_t=self.gn_ws[slot], gamma=self._const(norm.weight), beta=self._const(norm.bias),
+                    groups=norm.num_groups, eps=float(norm.eps))
+
+    def _const(self, p: torch.Tensor) -> torch.Tensor:
+        key = id(p)
+        if key not in self._consts:
+            self._consts[key] = p.detach().float().contiguous().to(self.dev)
+        return self._consts[key]
+
+    _consts: Dict[int, torch.Tensor]
+
+    def _qconv(self, layer: QuantLayer, x: T, gn=None, silu=False, upsample=False, emb: Optional[torch.Tensor] = None,
+               res: Optional[T] = None, out: Optional[T] = None) -> T:
+        """One QuantLayer conv with its input transform and fused epilogue."""
+        q = self.ql[id(layer)]
+        oh, ow = (2 * x.h, 2 * x.w) if upsample else (x.h, x.w)
+        if out is None:
+            out = self._new(x.n, oh, ow, q.cout)
+        if q.quant_w and q.aq_index is not None:
+            halo = 1 if q.ksize == 3 else 0
+            u8 = torch.empty((x.n, oh + 2 * halo, ow + 2 * halo, q.cin), dtype=torch.uint8, device=self.dev)
+            self._u8_bufs.append(u8)
+            aq = self._aq_ptr(q)
+
+            def run():
+                ops.act_prepare(x.view, aq=aq, dst_u8=u8, halo=halo, silu=silu, upsample=upsample, **self._gn_args(gn))
+                ops.conv_w4a8(u8, q.ksize, q.packed, q.wzp_u8, q.wdelta, q.wsum, q.bias, aq, out.view, emb=emb,
+                              res=res.view if res is not None else None)
+            self.ops.append(run)
+        else:
+            assert emb is None and not upsample
+            src = x
+            if gn is not None or silu:
+                src = self._new(x.n, x.h, x.w, x.c)
+                self.ops.append(lambda: ops.act_prepare(x.view, dst_f32=src.view, silu=silu, **self._gn_args(gn)))
+            self._fp_conv(q, src, out, res, pad_lo=q.ksize // 2)
+        return out
+
+    def _fp_conv(self, q: _QL, src: T, out: T, res: Optional[T], pad_lo: int, stride: int = 1):
+        wscale = q.wdelta if q.quant_w else None
+        passes = self.fp_passes
+
+        def run():
+            ops.conv_fp(src.view, q.ksize, stride, pad_lo, q.w_hi, q.w_lo, out.view, bias=q.bias, wscale=wscale,
+                        res=res.view if res is not None else None, passes=passes)
+        self.ops.append(run)
+
+    def _plain_conv(self, conv: nn.Module, src: T, out: T, res: Optional[T], pad_lo: int, stride: int):
+        """An nn.Conv2d / nn.Conv1d the reference never wraps (skip / op / shortcut / qkv / proj_out)."""
+        key = id(conv)
+        if key not in self._plain:
+            w = conv.weight.detach().float()
+            if w.dim() == 3:
+                w = w[..., None]
+            cout, k = w.shape[0], w.shape[2]
+            w2d = w.permute(0, 2, 3, 1).reshape(cout, -1).contiguous().to(self.dev)
+            hi, lo = ops.split_tf32(w2d)
+            b = conv.bias.detach().float().contiguous().to(self.dev) if conv.bias is not None else None
+            self._plain[key] = (hi, lo, b, k)
+        hi, lo, b, k = self._plain[key]
+        passes = self.fp_passes
+        self.ops.append(lambda: ops.conv_fp(src.view, k, stride, pad_lo, hi, lo, out.view, bias=b,
+                                            res=res.view if res is not None else None, passes=passes))
+
+    def _linear(self, layer: QuantLayer, x: torch.Tensor, x_ld_zero: bool, silu_in: bool) -> torch.Tensor:
+        """Time-embedding MLP layer on [batch, in] rows (row pitch 0 = the same row for every sample)."""
+        q = self.ql[id(layer)]
+        out = torch.empty((self.batch, q.cout), dtype=torch.float32, device=self.dev)
+        self._emb_bufs.append(out)
+        xin = x if not x_ld_zero else x.reshape(1, -1).expand(self.batch, -1)
+        aq = self._aq_ptr(q) if (q.quant_w and q.aq_index is not None) else None
+        if q.quant_w:
+            self.ops.append(lambda: ops.linear_small(xin, out, codes=q.codes, wzp_f=q.wzp_f, wdelta=q.wdelta,
+                                                     bias=q.bias, aq=aq, silu_in=silu_in))
+        else:
+            self.ops.append(lambda: ops.linear_small(xin, out, w_f32=q.w_f32, bias=q.bias, silu_in=silu_in))
+        return out
+
+    def _attention(self, q_t, k_t, v_t, o: T, heads: int, d: int, scale: float, strides):
+        b, tq = o.n, o.h * o.w
+        self.ops.append(lambda: ops.attention(q_t(), k_t(), v_t(), o.view, b, heads, tq, tq, d, scale, strides()))
+
+    # ================================================================ DDIM UNet program
+    def _trace_ddim(self, m, N, res):
+        self._consts, self._plain, self._emb_bufs = {}, {}, []
+        emb_in = self.cur[self.off_emb:self.off_emb + self.emb_dim]
+        self.emb_rows = torch.zeros((N, self.emb_dim), dtype=torch.float32, device=self.dev)
+        t1 = self._linear(m.temb.dense[0], self.emb_rows, False, silu_in=False)
+        temb = self._linear(m.temb.dense[1], t1, False, silu_in=True)
+
+        def resblock(blk: QuantResnetBlock, x: T) -> T:
+            e = self._linear(blk.temb_proj, temb, False, silu_in=True)
+            h = self._qconv(blk.conv1, x, gn=self._gn(x, blk.norm1), silu=True, emb=e)
+            out = self._new(x.n, x.h, x.w, blk.out_channels)
+            r = x
+            if blk.in_channels != blk.out_channels:
+                if blk.use_conv_shortcut:
+                    self._plain_conv(blk.conv_shortcut, x, out, None, pad_lo=1, stride=1)
+                else:
+                    self._plain_conv(blk.nin_shortcut, x, out, None, pad_lo=0, stride=1)
+                r = out
+            self._qconv(blk.conv2, h, gn=self._gn(h, blk.norm2), silu=True, res=r, out=out)
+            return out
+
+        def attnblock(blk: QuantAttnBlock, x: T) -> T:
+            gn = self._gn(x, blk.norm)
+            q = self._qconv(blk.q, x, gn=gn)
+            k = self._qconv(blk.k, x, gn=gn)
+            v = self._qconv(blk.v, x, gn=gn)
+            o = self._new(x.n, x.h, x.w, x.c)
+            c, tq = x.c, x.h * x.w
+
+            def strides():
+                return {name: (t.view.stride(0), 0, t.view.stride(2)) for name, t in
+                        (("q", q), ("k", k), ("v", v), ("o", o))}
+            self._attention(lambda: q.view, lambda: k.view, lambda: v.view, o, 1, c, float(int(c) ** -0.5), strides)
+            return self._qconv(blk.proj_out, o, res=x)
+
+        x0 = self._new(N, res, res, m.ch)
+        ci = self.ql[id(m.conv_in)]
+        self.ops.append(lambda: ops.conv_in(self.x_in, ci.w_oihw, ci.bias, x0.view))
+        hs = [x0]
+        for lvl in range(m.num_resolutions):
+            st = m.down[lvl]
+            for j in range(m.num_res_blocks):
+                h = resblock(st.block[j], hs[-1])
+                if len(st.attn) > 0:
+                    h = attnblock(st.attn[j], h)
+                hs.append(h)
+            if lvl != m.num_resolutions - 1:
+                src = hs[-1]
+                ds = st.downsample
+                out = self._new(N, src.h // 2, src.w // 2, src.c)
+                if ds.with_conv:
+                    self._plain_conv(ds.conv, src, out, None, pad_lo=0, stride=2)
+                else:
+                    raise NotImplementedError("avg-pool downsample (resamp_with_conv=False)")
+                hs.append(out)
+        h = resblock(m.mid.block_1, hs[-1])
+        h = attnblock(m.mid.attn_1, h)
+        h = resblock(m.mid.block_2, h)
+        for lvl in reversed(range(m.num_resolutions)):
+            st = m.up[lvl]
+            for j in range(m.num_res_blocks + 1):
+                h = resblock(st.block[j], _cat(h, hs.pop()))
+                if len(st.attn) > 0:
+                    h = attnblock(st.attn[j], h)
+            if lvl != 0:
+                h = self._qconv(st.upsample.conv, h, upsample=True)
+        self._final(m.norm_out, m.conv_out, h)
+
+    def _final(self, norm, conv_out_layer, h: T):
+        gn = self._gn(h, norm)
+        f = self._new(h.n, h.h, h.w, h.c)
+        self.ops.append(lambda: ops.act_prepare(h.view, dst_f32=f.view, silu=True, **self._gn_args(gn)))
+        co = self.ql[id(conv_out_layer)]
+        self.eps = torch.zeros((h.n, co.cout, h.h, h.w), dtype=torch.float32, device=self.dev)
+        self.ops.append(lambda: ops.conv_out(f.view, co.w_oihw, co.bias, self.eps))
+
+    # ================================================================ LDM UNet program
+    def _trace_ldm(self, m, N, res):
+        self._consts, self._plain, self._emb_bufs = {}, {}, []
+        self.emb_rows = torch.zeros((N, self.emb_dim), dtype=torch.float32, device=self.dev)
+        t1 = self._linear(m.time_embed[0], self.emb_rows, False, silu_in=False)
+        emb = self._linear(m.time_embed[2], t1, False, silu_in=True)
+
+        def resblock(blk: QuantResBlock, x: T) -> T:
+            e = self._linear(blk.emb_layers[1], emb, False, silu_in=True)
+            n1, c1 = blk.in_layers[0], blk.in_layers[2]
+            n2, c2 = blk.out_layers[0], blk.out_layers[3]
+            h = self._qconv(c1, x, gn=self._gn(x, n1), silu=True, emb=e)
+            out = self._new(x.n, x.h, x.w, blk.out_channels)
+            r = x
+            if not isinstance(blk.skip_connection, nn.Identity):
+                self._plain_conv(blk.skip_connection, x, out, None, pad_lo=0, stride=1)
+                r = out
+            self._qconv(c2, h, gn=self._gn(h, n2), silu=True, res=r, out=out)
+            return out
+
+        def attnblock(blk: QuantAttentionBlock, x: T) -> T:
+            gn = self._gn(x, blk.norm)
+            xn = self._new(x.n, x.h, x.w, x.c)
+            self.ops.append(lambda: ops.act_prepare(x.view, dst_f32=xn.view, silu=False, **self._gn_args(gn)))
+            qkv = self._new(x.n, x.h, x.w, 3 * x.c)
+            self._plain_conv(blk.qkv, xn, qkv, None, pad_lo=0, stride=1)
+            heads = blk.num_heads
+            d = x.c // heads
+            o = self._new(x.n, x.h, x.w, x.c)
+            tq = x.h * x.w
+
+            def strides():
+                s = (qkv.view.stride(0), 3 * d, qkv.view.stride(2))
+                return dict(q=s, k=s, v=s, o=(o.view.stride(0), d, o.view.stride(2)))
+
+            def part(i):
+                # per head the qkv conv writes (q | k | v) blocks of d channels (legacy order,
+                # openaimodel.py:386-389); q / k / v of head 0 start at channel 0 / d / 2d
+                return lambda: qkv.view.reshape(-1)[i * d:]
+            self._attention(part(0), part(1), part(2), o, heads, d, 1.0 / math.sqrt(d), strides)
+            out = self._new(x.n, x.h, x.w, x.c)
+            self._plain_conv(blk.proj_out, o, out, x, pad_lo=0, stride=1)
+            return out
+
+        def run_seq(seq, h: T) -> T:
+            for layer in seq:
+                name = layer.__class__.__name__
+                if isinstance(layer, QuantResBlock):
+                    h = resblock(layer, h)
+                elif isinstance(layer, QuantAttentionBlock):
+                    h = attnblock(layer, h)
+                elif name == "Downsample":
+                    out = self._new(h.n, h.h // 2, h.w // 2, layer.out_channels)
+                    if not isinstance(layer.op, nn.Conv2d):
+                        raise NotImplementedError("avg-pool downsample")
+                    self._plain_conv(layer.op, h, out, None, pad_lo=layer.op.padding[0], stride=2)
+                    h = out
+                elif name == "Upsample":
+                    h = self._qconv(layer.conv, h, upsample=True)
+                elif isinstance(layer, QuantLayer):   # input_blocks.0.0
+                    q = self.ql[id(layer)]
+                    out = self._new(N, res, res, q.cout)
+                    self.ops.append(lambda q=q, out=out: ops.conv_in(self.x_in, q.w_oihw, q.bias, out.view))
+                    h = out
+                else:
+                    raise NotImplementedError(f"engine: unsupported module {name}")
+            return h
+
+        hs, h = [], None
+        for blk in m.input_blocks:
+            h = run_seq(blk, h)
+            hs.append(h)
+        h = run_seq(m.middle_block, h)
+        for blk in m.output_blocks:
+            h = run_seq(blk, _cat(h, hs.pop()))
+        self._final(m.out[0], m.out[2], h)
+
+    # ================================================================ allocation / execution
+    def _allocate(self):
+        for t in self.tensors:
+            r, _ = t.root()
+            if r.buf is None:
+                r.buf = torch.zeros((r.n, r.h, r.w, r.c), dtype=torch.float32, device=self.dev)
+        self.gn_ws = torch.zeros((max(self._gn_slots, 1), self.batch, 32, 2), dtype=torch.float64, device=self.dev)
+        self.coef = self.cur[self.off_coef:self.off_coef + 5]
+        self.x_next = torch.zeros_like(self.x_in)
+        self.x0_pred = torch.zeros_like(self.x_in)
+
+    def _emb_rows_from_cur(self):
+        src = self.cur[self.off_emb:self.off_emb + self.emb_dim]
+        self.emb_rows.copy_(src.reshape(1, -1).expand(self.batch, -1))
+
+    def _run_program(self, with_update: bool):
+        if with_update:          # sampling step: embedding comes from the selected schedule row
+            self._emb_rows_from_cur()
+        ops.fill_zero(self.gn_ws)
+        for op in self.ops:
+            op()
+        if with_update:
+            ops.ddim_update(self.x_in, self.eps, self.coef, self.x_in, self.x0_pred, noise=self.noise)
+
+    def _launch(self, with_update: bool):
+        if not self.use_graph:
+            self._run_program(with_update)
+            return
+        key = "g_upd" if with_update else "g_fwd"
+        g = getattr(self, key, None)
+        if g is None:
+            # warm-up on a side stream (module loading, smem attribute calls), then capture
+            s = torch.cuda.Stream(self.dev)
+            s.wait_stream(torch.cuda.current_stream(self.dev))
+            saved = (self.x_in.clone(), self.cur.clone())
+            with torch.cuda.stream(s):
+                self._run_program(with_update)
+            torch.cuda.current_stream(self.dev).wait_stream(s)
+            self.x_in.copy_(saved[0])
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._run_program(with_update)
+            setattr(self, key, g)
+            self.x_in.copy_(saved[0])
+        g.replay()
+
+    @property
+    def launches_per_step(self) -> int:
+        """Kernels of this library in one captured step (counted by the C-ABI launch counter)."""
+        from . import _lib
+        ctx = _lib.context(self.dev.index or 0)
+        before = ctx.launches
+        saved = self.x_in.clone()
+        self._run_program(True)
+        torch.cuda.synchronize(self.dev)
+        self.x_in.copy_(saved)
+        return ctx.launches - before
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor, t=None) -> torch.Tensor:
+        """eps = UNet(x, t) with the currently selected activation-quant row (QuantModel.forward)."""
+        self.x_in.copy_(x)
+        if t is not None:
+            t = torch.as_tensor(t, dtype=torch.float32, device=self.dev).reshape(-1)
+            t = t.expand(self.batch) if t.numel() == 1 else t
+            tc = t.detach().cpu()
+            self.emb_rows.copy_(self.timestep_embedding_cpu(tc).to(self.dev))
+        else:
+            self._emb_rows_from_cur()
+        self._launch(with_update=False)
+        return self.eps.clone()
+
+    @torch.no_grad()
+    def step(self, k: int) -> None:
+        """One sampling step on the resident latent: FSC row k, UNet, DDIM update in place."""
+        self.select_step(k)
+        self._launch(with_update=True)
+
+    @torch.no_grad()
+    def sample(self, x_T: torch.Tensor, steps: Optional[int] = None) -> torch.Tensor:
+        assert self.table is not None, "call set_schedule() first"
+        self.x_in.copy_(x_T)
+        for k in range(steps if steps is not None else self.table.shape[0]):
+            self.step(k)
+        return self.x_in.clone()
