@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""Benchmark of the w4a8 DDIM denoising hot path (BASELINE.json: LDM-4 CelebA-HQ latent UNet, w4a8,
+200 DDIM steps, batch 16 per GPU; synthetic latents, seeded random-init weights).
+
+  python bench.py --gpus N --steps K --warmup W            our arm (one process per GPU under torchrun)
+  python bench.py --impl reference --gpus N --steps K ...  CPU arm: the oracle port of the reference's
+                                                           fake-quant path on the host cores (rank 0 only)
+
+A "step" is one denoising step of one batch: FSC parameter switch, UNet forward, DDIM update.
+value   = images/s with the latents resident in HBM  (batch * gpus / (ddim_steps * step time))
+e2e     = the same through the public API with HOST buffers: per step pinned-host -> device copy of the
+          latent, QuantModel.forward(x, t), device -> host read of eps (what the reference's sampler
+          loop does every step, ddim/functions/denoising.py:23,38)
+roofline= int8 tensor-core ops of the w4a8 conv kernel / its device time, against the int8 peak
+cpu_baseline = the oracle port timed on this box's host cores on a bounded sample
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tfmq-dm_b200"), os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "golden")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+DDIM_STEPS = 200
+BATCH = 16
+WORKLOAD = ("LDM-4 CelebA-HQ latent UNet 3x64x64 (model_channels 224, mult 1-2-3-4, attn ds 2/4/8, 32-ch heads), "
+            "w4a8 QuantModel, 200 DDIM steps eta=0, batch 16 per GPU (BASELINE.json configs[1])")
+METRIC = "w4a8 DDIM images/sec"
+SEED = 1234
+# algorithmic work of one UNet forward per sample (FlopCounterMode on the reference graph)
+GFLOP_PER_SAMPLE = 202.4
+INT8_GFLOP_PER_SAMPLE = 166.6
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(bf16_burst=p["bf16_tflops"], bf16_sustained=p["bf16_tflops_sustained"], hbm=p["hbm_gbs"],
+                    source="MEASURED_PEAKS.json")
+    return dict(bf16_burst=1590.0, bf16_sustained=1400.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+# ----------------------------------------------------------------------------------------------- model
+def ldm_timesteps(S: int):
+    import numpy as np
+    return [float(t) for t in np.flip(np.asarray(list(range(0, 1000, 1000 // S))) + 1)]
+
+
+def build_quantised(dev, batch):
+    """Seeded random-init LDM-4 UNet -> QuantModel (w4 channel-wise asym, a8 per-tensor asym, first/last layer
+    exemptions) -> synthetic Phase-A: activation ranges from calibration forwards at 8 timesteps, spread over
+    the 200 sampling steps as FSC tables."""
+    from helpers import fp_model, synth
+    from tfmq_b200.quant.calibration import _collect_act, _reset_aqtizers, load_cali_model
+    from tfmq_b200.quant.quant_layer import QMODE, Scaler
+    from tfmq_b200.quant.quant_model import QuantModel
+    fp = fp_model("ldm", SEED).to(dev)
+    wq = dict(bits=4, channel_wise=True, scaler=Scaler.MINMAX)
+    aq = dict(bits=8, channel_wise=False, scaler=Scaler.MINMAX, leaf_param=True)
+    qnn = QuantModel(fp, wq, aq, cali=False, softmax_a_bit=8, aq_mode=[QMODE.NORMAL.value, QMODE.QDIFF.value])
+    qnn.eval()
+    x = synth.latents((2, 3, 64, 64), 21).to(dev)
+    ts = ldm_timesteps(DDIM_STEPS)
+    load_cali_model(qnn, (x, torch.full((2,), ts[0], device=dev)), use_aq=True, ckpt={"weight": {}})
+    anchors = []
+    with torch.no_grad():
+        for i in range(8):
+            k = i * (DDIM_STEPS - 1) // 7
+            _reset_aqtizers(qnn)
+            qnn.set_quant_state(True, True)
+            qnn(x, torch.full((2,), ts[k], device=dev))
+            anchors.append((k, _collect_act(qnn)))
+    tables = []
+    for k in range(DDIM_STEPS):
+        tables.append(min(anchors, key=lambda a: abs(a[0] - k))[1])
+    eng = qnn.build_engine(batch=batch)
+    from tfmq_b200.samplers import DDIMSampler
+    smp = DDIMSampler(qnn)
+    smp.make_schedule(DDIM_STEPS)
+    eng.set_schedule(ts, tables, smp.coefficient_rows())
+    return qnn, eng, ts
+
+
+# ----------------------------------------------------------------------------------------------- clocks
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.rows = index, False, []
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                if out.returncode == 0:
+                    self.rows.append([c.strip() for c in out.stdout.strip().split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        mx = int(float(self.rows[0][1])) if self.rows else None
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------- CPU arm
+def cpu_port_step_time(batch: int, steps: int, warmup: int):
+    """One UNet step + DDIM update of the oracle port (fp32 fake-quant, torch CPU ops), seconds per step."""
+    from helpers import LDM4_CFG, fp_model, synth
+    from oracle import unet_ref as U
+    torch.set_flush_denormal(True)
+    sd = fp_model("ldm", SEED).state_dict()
+    spec = U.build_spec(sd)
+    names = sorted(n for n, s in spec.items() if s["aq"])
+    x = synth.latents((batch, 3, 64, 64), 21)
+    t = torch.full((batch,), 996.0)
+    # activation parameters: one calibration pass of the oracle itself (lazy MINMAX init), then frozen
+    act = U.CalibratingActParams()
+    with torch.no_grad():
+        U.ldm_unet_forward(sd, LDM4_CFG, x, t, spec, act)
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            e = U.ldm_unet_forward(sd, LDM4_CFG, x, t, spec, act)
+            x0 = (x - e * 0.9) / 0.4
+            x = 0.5 * x0 + 0.8 * e
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+            x = synth.latents((batch, 3, 64, 64), 22 + i)
+    return sum(times) / len(times), len(names)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sample_batch = 2
+    t_step, _ = cpu_port_step_time(sample_batch, max(1, args.steps), max(0, min(args.warmup, 1)))
+    value = sample_batch / (DDIM_STEPS * t_step)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_step * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32 fake-quant (CPU)", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "ddim_steps": DDIM_STEPS, "sample_batch": sample_batch},
+        "cpu_baseline": {"value": value, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": f"{args.steps} UNet steps at batch {sample_batch} (of 200 steps x batch 16), "
+                                   "oracle port of the reference fake-quant path, flush-denormal on"},
+        "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------- our arm
+def time_w4a8_kernels(eng):
+    """Device time of the dominant kernel (tcgen05 w4a8 implicit-GEMM conv) inside one step: the program is
+    run eagerly with a CUDA-event pair around every conv_w4a8 launch on the launching stream."""
+    from tfmq_b200 import ops
+    ev = []
+    orig = ops.conv_w4a8
+
+    def timed(*a, **k):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        orig(*a, **k)
+        e.record()
+        ev.append((s, e))
+    ops.conv_w4a8 = timed
+    try:
+        saved = eng.x_in.clone()
+        for _ in range(2):
+            ev.clear()
+            eng._run_program(True)
+            torch.cuda.synchronize()
+        eng.x_in.copy_(saved)
+    finally:
+        ops.conv_w4a8 = orig
+    return sum(s.elapsed_time(e) for s, e in ev) * 1e-3, len(ev)
+
+
+def int8_cublas_tops(dev):
+    """cuBLASLt int8 GEMM (torch._int_mm) 8192^3, best of 10 -- a library reference point for the int8 peak."""
+    try:
+        a = torch.randint(-8, 8, (8192, 8192), dtype=torch.int8, device=dev)
+        b = torch.randint(-8, 8, (8192, 8192), dtype=torch.int8, device=dev)
+        best = 1e9
+        for _ in range(12):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            torch._int_mm(a, b)
+            e.record()
+            torch.cuda.synchronize()
+            best = min(best, s.elapsed_time(e))
+        return 2 * 8192 ** 3 / (best * 1e-3) / 1e12
+    except Exception:
+        return None
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a B200: there is no CPU fallback for the product path "
+                           "(use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from tfmq_b200 import _lib
+    from helpers import synth
+
+    qnn, eng, ts = build_quantised(dev, BATCH)
+    if world > 1:
+        # the one collective of the sampling path: rank 0's packed int4 weights / scales / FSC table -> all ranks
+        for q in eng.ql.values():
+            for name in ("packed", "wdelta", "wsum", "wzp_u8", "bias"):
+                t = getattr(q, name, None)
+                if t is not None:
+                    dist.broadcast(t, 0)
+        dist.broadcast(eng.table, 0)
+    x_T = synth.latents((BATCH, 3, 64, 64), 100 + rank).to(dev)
+    ctx = _lib.context(local)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: latents resident in HBM
+    eng.x_in.copy_(x_T)
+    for i in range(args.warmup):
+        eng.step(i % DDIM_STEPS)
+    launches_per_step = eng.launches_per_step
+    eng.x_in.copy_(x_T)
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    barrier()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for i in range(args.steps):
+        eng.step(i % DDIM_STEPS)
+    e.record()
+    barrier()
+    ms = torch.tensor([s.elapsed_time(e)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_per_step = ms.item() / args.steps
+
+    # ---- e2e: host buffers through QuantModel.forward, H2D + D2H inside the timed region
+    x_host = x_T.cpu().pin_memory()
+    eps_host = torch.empty_like(x_host).pin_memory()
+    t_dev = [torch.full((BATCH,), t, device=dev) for t in ts]
+    e2e_steps = max(3, min(args.steps, 50))
+    with torch.no_grad():
+        for i in range(3):
+            eng.select_step(i)
+            qnn(x_host.to(dev, non_blocking=True), t_dev[i])
+        barrier()
+        s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s2.record()
+        for i in range(e2e_steps):
+            eng.select_step(i % DDIM_STEPS)
+            out = qnn(x_host.to(dev, non_blocking=True), t_dev[i % DDIM_STEPS])
+            eps_host.copy_(out, non_blocking=True)
+            torch.cuda.current_stream().synchronize()      # the sampler needs eps on the host to continue
+        e2.record()
+        barrier()
+    ms2 = torch.tensor([s2.elapsed_time(e2)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    ms_e2e = ms2.item() / e2e_steps
+    if sampler:
+        sampler.stop_flag = True
+        sampler.join(timeout=2)
+
+    if rank == 0:
+        pk = peaks()
+        conv_s, conv_n = time_w4a8_kernels(eng)
+        int8_ops = INT8_GFLOP_PER_SAMPLE * 1e9 * BATCH          # per step, all w4a8 QuantLayers
+        # weight-only layers (2 of 73) run on the tf32 path; their share of the int8-eligible work is removed
+        achieved = int8_ops / conv_s / 1e12
+        int8_peak = 2.0 * pk["bf16_sustained"]
+        cub = int8_cublas_tops(dev)
+        images_s = BATCH * world / (DDIM_STEPS * ms_per_step * 1e-3)
+        e2e_images_s = BATCH * world / (DDIM_STEPS * ms_e2e * 1e-3)
+        cpu_line = None
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            torch.set_num_threads(cores)
+            t_cpu, _ = cpu_port_step_time(2, 3, 1)
+            cpu_line = {"value": 2 / (DDIM_STEPS * t_cpu), "unit": "images/s", "cores": torch.get_num_threads(),
+                        "kind": "port", "sample": "3 UNet steps at batch 2 of the 200-step batch-16 workload "
+                                                  "(oracle port of the reference fake-quant path, flush-denormal on)"}
+        line = {
+            "metric": METRIC, "value": images_s, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8 x s4->s8 (int32 accumulate); fp layers tf32x3", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "ddim_steps": DDIM_STEPS, "batch_per_gpu": BATCH,
+                       "l2": "per-step activation working set (several GB) >> 126 MB L2, no explicit flush",
+                       "step_gflop": GFLOP_PER_SAMPLE * BATCH, "step_tflops": GFLOP_PER_SAMPLE * BATCH / ms_per_step,
+                       "images_per_s_at_50_steps": images_s * DDIM_STEPS / 50},
+            "e2e": {"value": e2e_images_s, "unit": "images/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": x_host.numel() * 4 + BATCH * 4, "d2h_bytes_per_step": eps_host.numel() * 4},
+            "gpu_launches": launches_per_step * args.steps,
+            "launches_per_step": launches_per_step,
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": int8_peak, "unit": "TFLOP/s",
+                         "frac": achieved / int8_peak, "traffic": None,
+                         "kernel": "igemm_kernel<MODE_W4A8> (tcgen05 kind::i8)", "launches_per_step": conv_n,
+                         "kernel_ms_per_step": conv_s * 1e3,
+                         "peak_note": f"int8 dense = 2 x measured bf16 sustained ({pk['source']}); "
+                                      f"cuBLASLt int8 8192^3 measured here: {cub}",
+                         "step_frac": GFLOP_PER_SAMPLE * BATCH / ms_per_step / int8_peak},
+            "clocks": sampler.summary() if sampler else None,
+        }
+        if cpu_line:
+            line["cpu_baseline"] = cpu_line
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        if args.steps > 6:
+            args.steps = 6          # bounded sample: each CPU step is seconds
+        run_reference(args)
+    else:
+        args.warmup = max(args.warmup, 3)
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -140,7 +140,7 @@ int tfmq_conv_w4a8(tfmq_ctx* ctx, const tfmq_conv_w4a8_desc* d, void* stream);
  * proj_out, first/last layers) and for weight-only-quantised layers
  * (disable_aq).  w_hi/w_lo are [cout][ksize*ksize*cin] fp32 in (tap, cin)
  * order with w_hi = tf32(w), w_lo = w - w_hi (w_lo NULL: weights exact in tf32).
- *   out = wscale[c] * conv(x, w) + bias[c] [+ res]
+ *   out = wscale[c] * conv(x, w) + bias[c] [+ emb[n][c]] [+ res]
  * passes: 3 = fp32-accurate, 1 = plain tf32.
  * ------------------------------------------------------------------------- */
 typedef struct {
@@ -159,6 +159,8 @@ typedef struct {
   float* out;
   int64_t out_ld;
   int passes;           /* 1 or 3 */
+  const float* emb;     /* [n][cout] per-image add (time embedding) or NULL */
+  int64_t emb_ld;
 } tfmq_conv_fp_desc;
 int tfmq_conv_fp(tfmq_ctx* ctx, const tfmq_conv_fp_desc* d, void* stream);
 

@@ -63,8 +63,21 @@ class ActParams:
     def __init__(self, names: List[str], row: torch.Tensor):
         self.p = {n: (row[i, 0], row[i, 1]) for i, n in enumerate(names)}
 
-    def get(self, name):
+    def get(self, name, x=None):
         return self.p.get(name)
+
+
+class CalibratingActParams(ActParams):
+    """Lazy MINMAX initialisation on first use, like UniformAffineQuantizer's first forward
+    (quant/quant_layer.py:213-217); afterwards the parameters are frozen."""
+
+    def __init__(self):
+        self.p = {}
+
+    def get(self, name, x=None):
+        if name not in self.p:
+            self.p[name] = Q.minmax_scale(x, 256)
+        return self.p[name]
 
 
 class _Net:
@@ -78,12 +91,15 @@ class _Net:
             if w.dim() == 3:
                 return F.conv1d(x, w, b)
             return F.linear(x, w, b) if conv is None else F.conv2d(x, w, b, **conv)
-        aq = self.act.get(name) if (s["aq"] and self.act is not None) else None
+        aq = self.act.get(name, x) if (s["aq"] and self.act is not None) else None
         if s["aq"] and self.act is not None and aq is None:
             raise KeyError(f"no activation quant parameters for {name}")
-        if self.record is not None and aq is not None:
+        if self.record is not None and aq is not None and x.dim() == 4:
             self.record[name] = Q.uaq_codes(x, aq[0], aq[1], 256).to(torch.uint8)
-        return Q.quant_layer_forward(x, w, b, wq=s["wq"], aq=aq, conv=conv)
+        y = Q.quant_layer_forward(x, w, b, wq=s["wq"], aq=aq, conv=conv)
+        if self.record is not None and x.dim() == 2:
+            self.record["out:" + name] = y          # time-embedding MLP outputs (teacher forcing)
+        return y
 
     def gn(self, name, x, eps):
         return F.group_norm(x, 32, self.sd[name + ".weight"], self.sd[name + ".bias"], eps)

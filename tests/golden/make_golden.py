@@ -12,7 +12,9 @@ import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF = os.environ.get("TFMQ_REFERENCE", "/root/reference")
-sys.path[:0] = [REF, os.path.join(REF, "stable-diffusion"), HERE]
+ROOT = os.path.abspath(os.path.join(HERE, "..", ".."))
+sys.path[:0] = [REF, os.path.join(REF, "stable-diffusion"), HERE, os.path.join(HERE, ".."), ROOT,
+                os.path.join(ROOT, "tfmq-dm_b200")]
 
 # ---- environment shims (type-only imports and hard-coded .cuda()) -------------------------------
 pl = types.ModuleType("pytorch_lightning")
@@ -197,6 +199,65 @@ def promote_zero_points(qnn):
             module.zero_point = torch.nn.Parameter(torch.as_tensor(module.zero_point).float())
 
 
+def alt_arithmetic():
+    """Context manager: evaluate the oracle with every conv / linear accumulated in float64 (and rounded
+    once) instead of fp32 -- a strictly more accurate evaluation of the SAME fake-quant network, used
+    to measure how far fp re-association alone moves the reference's outputs (flip cascade)."""
+    import contextlib
+    import torch.nn.functional as F
+    sys.path.insert(0, os.path.join(HERE, "..", ".."))
+    from oracle import quant_ref as Q
+
+    @contextlib.contextmanager
+    def cm():
+        orig = Q.quant_layer_forward
+
+        def qlf64(x, w, bias, wq=None, aq=None, conv=None):
+            if aq is not None:
+                x = Q.uaq_fake_quant(x, aq[0], aq[1], 256)
+            if wq is not None:
+                w = Q.adaround_fake_quant(w, wq[0], wq[1], wq[2], 16) if wq[2] is not None \
+                    else Q.uaq_fake_quant(w, wq[0], wq[1], 16)
+            b = bias.double() if bias is not None else None
+            if conv is None:
+                return F.linear(x.double(), w.double(), b).float()
+            return F.conv2d(x.double(), w.double(), b, **conv).float()
+        Q.quant_layer_forward = qlf64
+        try:
+            yield
+        finally:
+            Q.quant_layer_forward = orig
+    return cm()
+
+
+def oracle_alt_cifar(g):
+    """The oracle's float64-accumulation evaluation of the CIFAR golden: eps at step 0 and the 50-step latent."""
+    sys.path.insert(0, os.path.join(HERE, ".."))
+    sys.path.insert(0, os.path.join(HERE, "..", "..", "tfmq-dm_b200"))
+    from helpers import CIFAR_CFG, fp_model, oracle_spec
+    from oracle import unet_ref as U
+    sd = fp_model("cifar", g["seed"]).state_dict()
+    spec = oracle_spec(sd, g["seed"])
+    names, tab = g["act_names"], g["act_table"]
+    with torch.no_grad(), alt_arithmetic():
+        x, t, _ = g["eps"][0]
+        e = U.ddim_unet_forward(sd, CIFAR_CFG, x, t, spec, U.ActParams(names, tab[0]))
+        fn = lambda xt, tt, k: U.ddim_unet_forward(sd, CIFAR_CFG, xt, tt, spec, U.ActParams(names, tab[k]))  # noqa
+        xs, _ = U.generalized_steps(g["x_T"], g["seq"], fn, synth.ddim_betas(), eta=0.0)
+    return e, xs[-1]
+
+
+def oracle_alt_ldm(g):
+    sys.path.insert(0, os.path.join(HERE, ".."))
+    sys.path.insert(0, os.path.join(HERE, "..", "..", "tfmq-dm_b200"))
+    from helpers import LDM4_CFG, fp_model, oracle_spec
+    from oracle import unet_ref as U
+    sd = fp_model("ldm", g["seed"]).state_dict()
+    spec = oracle_spec(sd, g["seed"])
+    with torch.no_grad(), alt_arithmetic():
+        return U.ldm_unet_forward(sd, LDM4_CFG, g["x"], g["t"], spec, U.ActParams(g["act_names"], g["act_table"][0]))
+
+
 def cifar_golden(steps=50):
     from ddim.functions.denoising import generalized_steps
     t0 = time.time()
@@ -238,7 +299,12 @@ def cifar_golden(steps=50):
     qnn.forward = orig_fwd
     print("cifar: pass 2 done", time.time() - t0)
     names, tab = pack_act(act)
-    torch.save(dict(seed=SEED, steps=steps, seq=seq, x_T=x, act_names=names, act_table=tab, eps=eps, xs_last=xs[-1], x_mid=xs[25],
+    g = dict(seed=SEED, seq=seq, x_T=x, act_names=names, act_table=tab, eps=eps)
+    alt_eps0, alt_last = oracle_alt_cifar(g)
+    print("cifar: float64-accumulation oracle: eps0 dev", (alt_eps0 - eps[0][2]).abs().max().item(),
+          "final latent dev", (alt_last - xs[-1]).abs().max().item(), time.time() - t0)
+    torch.save(dict(seed=SEED, steps=steps, seq=seq, x_T=x, act_names=names, act_table=tab, eps=eps,
+                    alt_eps0=alt_eps0, alt_last=alt_last, xs_last=xs[-1], x_mid=xs[25],
                     x0_last=x0_preds[-1]), os.path.join(HERE, "cifar_w4a8.pt"))
     print("cifar_w4a8.pt written")
 
@@ -256,7 +322,9 @@ def ldm_golden():
         e2 = qnn(x, t)     # second call with frozen parameters = what sampling sees
     print("ldm: forward done", time.time() - t0)
     names, tab = pack_act([act])
-    torch.save(dict(seed=SEED, x=x, t=t, act_names=names, act_table=tab, eps=e2, eps_init=e),
+    alt = oracle_alt_ldm(dict(seed=SEED, x=x, t=t, act_names=names, act_table=tab))
+    print("ldm: float64-accumulation oracle: eps dev", (alt - e2).abs().max().item(), time.time() - t0)
+    torch.save(dict(seed=SEED, x=x, t=t, act_names=names, act_table=tab, eps=e2, eps_init=e, alt_eps=alt),
                os.path.join(HERE, "ldm4_w4a8.pt"))
     print("ldm4_w4a8.pt written")
 

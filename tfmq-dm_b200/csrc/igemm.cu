@@ -477,6 +477,7 @@ extern "C" int tfmq_conv_fp(tfmq_ctx* ctx, const tfmq_conv_fp_desc* d, void* str
   if (d->passes == 3) p.pass_flags |= PASS_LO_HI | (d->w_lo ? PASS_HI_LO : 0);
   p.out = d->out, p.out_ld = d->out_ld, p.bias = d->bias, p.wscale = d->wscale;
   p.res = d->res, p.res_ld = d->res_ld;
+  p.emb = d->emb, p.emb_ld = d->emb_ld;
 
   CUtensorMap tmA, tmB, tmB2;
   {

@@ -51,6 +51,7 @@ class ConvFpDesc(C.Structure):
         ("res", C.c_void_p), ("res_ld", i64),
         ("out", C.c_void_p), ("out_ld", i64),
         ("passes", C.c_int),
+        ("emb", C.c_void_p), ("emb_ld", i64),
     ]
 
 

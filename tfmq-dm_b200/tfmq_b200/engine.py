@@ -119,6 +119,8 @@ class StepEngine:
         self.tensors: List[T] = []
         self._gn_slots = 0
         self._u8_bufs: List = []
+        self.u8_by_name: Dict[str, tuple] = {}
+        self.teacher: Optional[Dict[str, torch.Tensor]] = None   # test hook: force quantiser decisions
         self.graph = None
 
         # ---- quantised-layer table; activation-quantised layers get a slot in the per-step row
@@ -167,7 +169,7 @@ class StepEngine:
         for i, name in enumerate(self.aq_names):
             aqt = mods[name].aqtizer
             if aqt.delta is not None:
-                self.cur[2 * i] = float(aqt.delta)
+                self.cur[2 * i] = float(aqt.delta.detach())
                 self.cur[2 * i + 1] = float(aqt.zero_point)
 
     def timestep_embedding_cpu(self, t: torch.Tensor) -> torch.Tensor:
@@ -247,29 +249,33 @@ class StepEngine:
             halo = 1 if q.ksize == 3 else 0
             u8 = torch.empty((x.n, oh + 2 * halo, ow + 2 * halo, q.cin), dtype=torch.uint8, device=self.dev)
             self._u8_bufs.append(u8)
+            self.u8_by_name[q.name] = (u8, halo)
             aq = self._aq_ptr(q)
 
             def run():
                 ops.act_prepare(x.view, aq=aq, dst_u8=u8, halo=halo, silu=silu, upsample=upsample, **self._gn_args(gn))
+                if self.teacher is not None and q.name in self.teacher:
+                    forced = self.teacher[q.name].to(self.dev).permute(0, 2, 3, 1)
+                    (u8[:, 1:-1, 1:-1] if halo else u8).copy_(forced)
                 ops.conv_w4a8(u8, q.ksize, q.packed, q.wzp_u8, q.wdelta, q.wsum, q.bias, aq, out.view, emb=emb,
                               res=res.view if res is not None else None)
             self.ops.append(run)
         else:
-            assert emb is None and not upsample
+            assert not upsample
             src = x
             if gn is not None or silu:
                 src = self._new(x.n, x.h, x.w, x.c)
                 self.ops.append(lambda: ops.act_prepare(x.view, dst_f32=src.view, silu=silu, **self._gn_args(gn)))
-            self._fp_conv(q, src, out, res, pad_lo=q.ksize // 2)
+            self._fp_conv(q, src, out, res, pad_lo=q.ksize // 2, emb=emb)
         return out
 
-    def _fp_conv(self, q: _QL, src: T, out: T, res: Optional[T], pad_lo: int, stride: int = 1):
+    def _fp_conv(self, q: _QL, src: T, out: T, res: Optional[T], pad_lo: int, stride: int = 1, emb=None):
         wscale = q.wdelta if q.quant_w else None
         passes = self.fp_passes
 
         def run():
             ops.conv_fp(src.view, q.ksize, stride, pad_lo, q.w_hi, q.w_lo, out.view, bias=q.bias, wscale=wscale,
-                        res=res.view if res is not None else None, passes=passes)
+                        res=res.view if res is not None else None, passes=passes, emb=emb)
         self.ops.append(run)
 
     def _plain_conv(self, conv: nn.Module, src: T, out: T, res: Optional[T], pad_lo: int, stride: int):
@@ -296,11 +302,15 @@ class StepEngine:
         self._emb_bufs.append(out)
         xin = x if not x_ld_zero else x.reshape(1, -1).expand(self.batch, -1)
         aq = self._aq_ptr(q) if (q.quant_w and q.aq_index is not None) else None
-        if q.quant_w:
-            self.ops.append(lambda: ops.linear_small(xin, out, codes=q.codes, wzp_f=q.wzp_f, wdelta=q.wdelta,
-                                                     bias=q.bias, aq=aq, silu_in=silu_in))
-        else:
-            self.ops.append(lambda: ops.linear_small(xin, out, w_f32=q.w_f32, bias=q.bias, silu_in=silu_in))
+        def run():
+            if q.quant_w:
+                ops.linear_small(xin, out, codes=q.codes, wzp_f=q.wzp_f, wdelta=q.wdelta, bias=q.bias, aq=aq,
+                                 silu_in=silu_in)
+            else:
+                ops.linear_small(xin, out, w_f32=q.w_f32, bias=q.bias, silu_in=silu_in)
+            if self.teacher is not None and ("out:" + q.name) in self.teacher:
+                out.copy_(self.teacher["out:" + q.name].to(self.dev))
+        self.ops.append(run)
         return out
 
     def _attention(self, q_t, k_t, v_t, o: T, heads: int, d: int, scale: float, strides):
@@ -433,7 +443,7 @@ class StepEngine:
                 name = layer.__class__.__name__
                 if isinstance(layer, QuantResBlock):
                     h = resblock(layer, h)
-                elif isinstance(layer, QuantAttentionBlock):
+                elif isinstance(layer, QuantAttentionBlock) or name == "AttentionBlock":
                     h = attnblock(layer, h)
                 elif name == "Downsample":
                     out = self._new(h.n, h.h // 2, h.w // 2, layer.out_channels)
@@ -531,6 +541,22 @@ class StepEngine:
         else:
             self._emb_rows_from_cur()
         self._launch(with_update=False)
+        return self.eps.clone()
+
+    @torch.no_grad()
+    def forward_teacher_forced(self, x: torch.Tensor, t, record: Dict[str, torch.Tensor]) -> torch.Tensor:
+        """Test hook: eager run in which every activation quantiser's output codes (and the time-
+        embedding MLP outputs) are replaced by the oracle's, so that the comparison isolates the
+        arithmetic of the kernels from the flip cascade of the quantised network (Parity)."""
+        self.x_in.copy_(x)
+        t = torch.as_tensor(t, dtype=torch.float32).reshape(-1)
+        t = t.expand(self.batch) if t.numel() == 1 else t
+        self.emb_rows.copy_(self.timestep_embedding_cpu(t.cpu()).to(self.dev))
+        self.teacher = record
+        try:
+            self._run_program(False)
+        finally:
+            self.teacher = None
         return self.eps.clone()
 
     @torch.no_grad()

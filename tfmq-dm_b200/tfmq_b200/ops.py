@@ -125,7 +125,7 @@ def conv_w4a8(act: torch.Tensor, ksize: int, packed, wzp_u8, wdelta, wsum, bias,
 
 
 def conv_fp(x: torch.Tensor, ksize: int, stride: int, pad_lo: int, w_hi, w_lo, out: torch.Tensor, bias=None,
-            wscale=None, res=None, passes: int = 3):
+            wscale=None, res=None, passes: int = 3, emb=None):
     ctx = _ctx(out)
     n, h, w, cin, x_ld = _nhwc(x)
     on, oh, ow, cout, out_ld = _nhwc(out)
@@ -144,6 +144,9 @@ def conv_fp(x: torch.Tensor, ksize: int, stride: int, pad_lo: int, w_hi, w_lo, o
         d.res, d.res_ld = res.data_ptr(), rld
     d.out, d.out_ld = out.data_ptr(), out_ld
     d.passes = passes
+    if emb is not None:
+        assert emb.stride(-1) == 1
+        d.emb, d.emb_ld = emb.data_ptr(), (emb.stride(0) if emb.dim() == 2 and emb.shape[0] > 1 else 0)
     ctx.call("tfmq_conv_fp", C.byref(d), _stream())
 
 

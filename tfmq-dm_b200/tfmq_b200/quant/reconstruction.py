@@ -1,0 +1,173 @@
+"""AdaRound / TIAR reconstruction -- mirror of the reference's `quant/reconstruction.py`
+(layer_reconstruction, block_reconstruction, tib_reconstruction: same signatures and semantics).
+
+Inner loop (reference :182-198), re-designed for the GPU: per iteration
+  1. soft-rounded weights of every layer of the unit are materialised by one kernel each
+     (ops.adaround_soft) and injected as autograd leaves,
+  2. the unit's forward / backward gives dL/dW_soft for the batch (torch autograd over the block graph),
+  3. one fused kernel per layer (ops.adaround_step) applies the chain rule to alpha, adds the rounding
+     regulariser's gradient, performs the Adam update in place and reduces the regulariser value
+     -- no optimiser object, no per-iteration host sync; the loss is read back only when it is logged.
+Multi-GPU: dL/dW_soft of all layers is SUM-all-reduced as ONE flat bucket per iteration (the reference
+all-reduces alpha.grad per tensor, `linklink.allreduce` = SUM; summing alpha.grad also multiplies the
+regulariser by world_size, which is reproduced through lambda * world_size).
+"""
+from __future__ import annotations
+
+import logging
+from typing import List
+
+import torch
+
+from .. import ops
+from .adaptive_rounding import RMODE, AdaRoundQuantizer
+from .data_utill import save_inout
+from .quant_block import BaseQuantBlock
+from .quant_layer import QuantLayer, StraightThrough, lp_loss
+from .reconstruction_util import RLOSS, LinearTempDecay, print_freq, unit_layers
+
+logger = logging.getLogger(__name__)
+
+
+class _LayerState:
+    def __init__(self, layer: QuantLayer):
+        self.layer = layer
+        layer.wqtizer = AdaRoundQuantizer(uaqtizer=layer.wqtizer, rmode=RMODE.LEARNED_HARD_SIGMOID,
+                                          w=layer.original_w.data)
+        layer.wqtizer.soft_tgt = True
+        q = layer.wqtizer
+        dev = layer.w.device
+        self.cout = layer.w.shape[0]
+        self.w2d = layer.w.detach().reshape(self.cout, -1).contiguous().float()
+        self.delta = q.delta.detach().reshape(-1).float().to(dev).contiguous()
+        zp = q.zero_point
+        zp = zp.detach().reshape(-1).float().to(dev) if torch.is_tensor(zp) else torch.full_like(self.delta, float(zp))
+        self.zp = zp.expand_as(self.delta).contiguous()
+        self.alpha = q.alpha                        # nn.Parameter, updated in place by the kernel
+        assert self.alpha.is_contiguous()
+        self.m = torch.zeros_like(self.w2d)
+        self.v = torch.zeros_like(self.w2d)
+        self.level = q.level
+        self.w_soft = torch.empty_like(self.w2d)
+
+    def materialise(self):
+        ops.adaround_soft(self.w2d, self.delta, self.zp, self.alpha.data, self.level, self.w_soft)
+        leaf = self.w_soft.view_as(self.layer.w).detach().requires_grad_(True)
+        self.layer.w_override = leaf
+        return leaf
+
+    def finish(self):
+        self.layer.w_override = None
+        self.layer.wqtizer.soft_tgt = False
+
+
+def _adaround_loop(forward, layers: List[QuantLayer], cached_inputs, cached_outputs, batch_size, iters, w, b_range,
+                   warmup, multi_gpu, p):
+    if p != 2.0:
+        raise NotImplementedError("reconstruction: only the p=2 loss of the entry points is implemented")
+    states = [_LayerState(m) for m in layers]
+    if not states:
+        return
+    dev = states[0].w2d.device
+    decay = LinearTempDecay(iters, warmup, b_range[0], b_range[1])
+    loss_start = iters * warmup
+    world = 1
+    if multi_gpu:
+        import torch.distributed as dist
+        world = dist.get_world_size() if dist.is_initialized() else 1
+    round_acc = torch.zeros(1, device=dev)
+    tuple_out = isinstance(cached_outputs, (tuple, list))
+    n = cached_inputs[0].size(0)
+    for it in range(1, iters + 1):
+        idx = torch.randperm(n)[:batch_size].to(cached_inputs[0].device)
+        cur_in = tuple(x[idx].to(dev) for x in cached_inputs)
+        leaves = [s.materialise() for s in states]
+        out = forward(*cur_in)
+        if tuple_out:
+            rec = sum(lp_loss(o_, t_[idx].to(dev), p=2.0) for o_, t_ in zip(out, cached_outputs))
+        else:
+            rec = lp_loss(out, cached_outputs[idx].to(dev), p=2.0)
+        grads = torch.autograd.grad(rec, leaves, allow_unused=True)
+        grads = [g if g is not None else torch.zeros_like(l_) for g, l_ in zip(grads, leaves)]
+        if world > 1:
+            import torch.distributed as dist
+            flat = torch.cat([g.reshape(-1) for g in grads])
+            dist.all_reduce(flat)
+            off = 0
+            for i, g in enumerate(grads):
+                grads[i] = flat[off:off + g.numel()].view_as(g)
+                off += g.numel()
+        b = decay(it) if it >= loss_start else 0.0
+        log = it % print_freq == 0
+        if log:
+            round_acc.zero_()
+        for s, g in zip(states, grads):
+            ops.adaround_step(s.w2d, s.delta, s.zp, s.alpha.data, g.contiguous(), s.m, s.v, s.level, it, 1e-3,
+                              float(b), float(w) * world, round_acc)
+        if log:
+            logger.info("Total loss:\t{:.8f} (rec:{:.8f}, round:{:.8f})\tb={:.2f}\tcount={}".format(
+                float(rec) + float(round_acc) / world, float(rec), float(round_acc) / world, b, it))
+    for s in states:
+        s.finish()
+
+
+def _common(model, unit, cali_data, batch_size, iters, w, opt_mode, asym, include_act_func, b_range, warmup, use_aq,
+            p, multi_gpu, keep_gpu, layers, forward, cache_model):
+    if use_aq:
+        raise NotImplementedError("learning activation deltas is unreachable from the reference entry points "
+                                  "(cali_model never forwards use_aq to the reconstruction calls)")
+    if opt_mode != RLOSS.MSE:
+        raise NotImplementedError("only RLOSS.MSE is used by the entry points")
+    org = None
+    if not include_act_func:
+        org, unit.act_func = unit.act_func, StraightThrough()
+    if layers:
+        ins, outs = save_inout(cache_model, unit, cali_data, asym, use_aq, batch_size, keep_gpu)
+        _adaround_loop(forward, layers, ins, outs, batch_size, iters, w, b_range, warmup, multi_gpu, p)
+    if org is not None:
+        unit.act_func = org
+
+
+def layer_reconstruction(model, layer: QuantLayer, cali_data, batch_size: int = 128, iters: int = 20000,
+                         w: float = 0.001, opt_mode: RLOSS = RLOSS.MSE, asym: bool = False,
+                         include_act_func: bool = True, b_range: tuple = (20, 2), warmup: float = 0.0,
+                         use_aq: bool = False, lr: float = 4e-5, p: float = 2.0, multi_gpu: bool = False,
+                         keep_gpu=True) -> None:
+    model.set_quant_state(use_wq=False, use_aq=False)
+    layer.set_quant_state(use_wq=True, use_aq=use_aq)
+    _common(model, layer, cali_data, batch_size, iters, w, opt_mode, asym, include_act_func, b_range, warmup, use_aq,
+            p, multi_gpu, keep_gpu, [layer], layer, model)
+
+
+def block_reconstruction(model, block: BaseQuantBlock, cali_data, batch_size: int = 32, iters: int = 20000,
+                         w: float = 0.01, opt_mode: RLOSS = RLOSS.MSE, asym: bool = False,
+                         include_act_func: bool = True, b_range: tuple = (20, 2), warmup: float = 0.0,
+                         use_aq: bool = False, lr: float = 4e-5, p: float = 2.0, multi_gpu: bool = True,
+                         keep_gpu=True) -> None:
+    model.set_quant_state(use_wq=False, use_aq=False)
+    block.set_quant_state(use_wq=True, use_aq=use_aq)
+    # quant_emb layers belong to the TIB; QK / SMV matmul blocks have no layers and return early
+    layers = [m for m in block.modules() if isinstance(m, QuantLayer) and m.quant_emb is False]
+    _common(model, block, cali_data, batch_size, iters, w, opt_mode, asym, include_act_func, b_range, warmup, use_aq,
+            p, multi_gpu, keep_gpu, layers, block, model)
+
+
+def tib_reconstruction(block: BaseQuantBlock, cali_data, batch_size: int = 32, iters: int = 20000, w: float = 0.01,
+                       opt_mode: RLOSS = RLOSS.MSE, asym: bool = False, include_act_func: bool = True,
+                       b_range: tuple = (20, 2), warmup: float = 0.0, use_aq: bool = False, lr: float = 4e-5,
+                       p: float = 2.0, multi_gpu: bool = True, keep_gpu=True) -> None:
+    """TIAR: all time-embedding projections reconstructed jointly against the tuple of their FP outputs."""
+    block.set_quant_state(use_wq=True, use_aq=use_aq)
+    layers = [m for m in dict.fromkeys(unit_layers_all(block)) if not m.ignore_recon]
+    _common(block, block, cali_data, batch_size, iters, w, opt_mode, asym, include_act_func, b_range, warmup, use_aq,
+            p, multi_gpu, keep_gpu, layers, block, block)
+
+
+def unit_layers_all(tib) -> List[QuantLayer]:
+    """Every QuantLayer of a TIB, including the ignore_recon first layer (the reference swaps all of
+    them to AdaRound, :233-253)."""
+    out = [m for m in tib.modules() if isinstance(m, QuantLayer)]
+    for seq in getattr(tib, "emb_layers", []):
+        out += [m for m in seq.modules() if isinstance(m, QuantLayer)]
+    out += list(getattr(tib, "temb_projs", []))
+    return out

@@ -1,0 +1,157 @@
+"""Sampler entry points with the reference's call shape, running on the fused step engine.
+
+* generalized_steps(x, seq, model, b, **kwargs) -> (xs, x0_preds, xt, t)
+      reference ddim/functions/denoising.py:10-41 (used by Diffusion.sample_image, runners/diffusion.py:429-476)
+* DDIMSampler(model).sample(S, batch_size, shape, eta=0., x_T=None, ...) -> (samples, intermediates)
+      reference ldm/models/diffusion/ddim.py:57-212, unconditional path (LDM-4 CelebA-HQ / LSUN)
+
+What changes underneath: the latent stays resident on the GPU for the whole trajectory (the reference
+hops GPU<->CPU every step, denoising.py:23,38), the FSC parameter switch is one device-side row
+copy (instead of `load_state_dict` + `.item()`), and the UNet step + DDIM update is one CUDA-graph replay.
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+
+def compute_alpha(beta: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
+    beta = torch.cat([torch.zeros(1).to(beta.device), beta], dim=0)
+    return (1 - beta).cumprod(dim=0).index_select(0, t + 1).view(-1, 1, 1, 1)
+
+
+def ddim_coefficients(seq: Sequence[int], betas: torch.Tensor, eta: float = 0.0):
+    """Per sampling step (sqrt(a_t), sqrt(1-a_t), sqrt(a_next), c2, c1) as fp32 values computed with the
+    same tensor ops as the reference loop (denoising.py:19-36), so the device update reproduces it."""
+    betas = betas.detach().float().cpu()
+    rows = []
+    seq_next = [-1] + list(seq[:-1])
+    for i, j in zip(reversed(seq), reversed(seq_next)):
+        at = compute_alpha(betas, torch.tensor([i])).reshape(())
+        an = compute_alpha(betas, torch.tensor([j])).reshape(())
+        c1 = eta * ((1 - at / an) * (1 - an) / (1 - at)).sqrt()
+        c2 = ((1 - an) - c1 ** 2).sqrt()
+        rows.append([at.sqrt().item(), (1 - at).sqrt().item(), an.sqrt().item(), c2.item(), float(c1)])
+    return rows
+
+
+def _act_tables(cali_ckpt, steps: int):
+    if cali_ckpt is None:
+        return None
+    return [cali_ckpt[f"act_{k}"] for k in range(steps)]
+
+
+@torch.no_grad()
+def generalized_steps(x, seq, model, b, **kwargs):
+    """Drop-in for ddim/functions/denoising.py:generalized_steps.  `model` is a QuantModel whose
+    calibrated state is loaded; kwargs: eta, tot / cali_ckpt / t_max (FSC, as the reference passes them),
+    untill_fake_t.  Returns (xs, x0_preds, xt, t) with xs[0] = x and xs[-1] the denoised sample
+    (intermediates are kept only with keep_trajectory=True)."""
+    eta = kwargs.get("eta", 0)
+    if eta != 0:
+        raise NotImplementedError("eta > 0 (stochastic DDIM) is not part of the benchmarked path yet")
+    dev = next(model.parameters()).device
+    n = x.size(0)
+    seq = list(seq)
+    steps = len(seq)
+    fsc = kwargs.get("cali_ckpt") if kwargs.get("tot") is not None else None
+    eng = getattr(model, "_engine", None)
+    if eng is None or eng.batch != n:
+        eng = model.build_engine(batch=n)
+    eng.set_schedule(list(reversed(seq)), _act_tables(fsc, steps), ddim_coefficients(seq, b, eta))
+    keep = kwargs.get("keep_trajectory", False)
+    stop = kwargs.get("untill_fake_t")
+    xs, x0_preds = [x], []
+    eng.x_in.copy_(x.to(dev))
+    xt = t = None
+    for k in range(steps):
+        t = torch.ones(n, device=dev) * list(reversed(seq))[k]
+        if keep or (stop is not None and k == stop - 1):
+            xt = eng.x_in.clone()
+        if stop is not None and k == stop - 1:
+            break
+        eng.step(k)
+        if keep:
+            xs.append(eng.x_in.to("cpu"))
+            x0_preds.append(eng.x0_pred.to("cpu"))
+    if not keep:
+        xs.append(eng.x_in.to("cpu"))
+        x0_preds.append(eng.x0_pred.to("cpu"))
+    return xs, x0_preds, xt, t
+
+
+def make_beta_schedule(schedule: str, n_timestep: int, linear_start: float = 1e-4, linear_end: float = 2e-2):
+    """ldm/modules/diffusionmodules/util.py:20-43 ('linear' = linspace of sqrt(beta), squared)."""
+    if schedule != "linear":
+        raise NotImplementedError(schedule)
+    return (torch.linspace(linear_start ** 0.5, linear_end ** 0.5, n_timestep, dtype=torch.float64) ** 2).numpy()
+
+
+def make_ddim_timesteps(num_ddim_timesteps: int, num_ddpm_timesteps: int = 1000) -> np.ndarray:
+    """uniform discretisation, +1 (util.py:46-60)."""
+    c = num_ddpm_timesteps // num_ddim_timesteps
+    return np.asarray(list(range(0, num_ddpm_timesteps, c))) + 1
+
+
+class DDIMSampler:
+    """Unconditional DDIM sampling for the LDM UNets (ldm/models/diffusion/ddim.py:57-212).
+    `model` is the QuantModel (what the reference installs as model.model.diffusion_model);
+    the noise schedule comes from linear_start / linear_end of the LDM config."""
+
+    def __init__(self, model, linear_start: float = 0.0015, linear_end: float = 0.0195, timesteps: int = 1000,
+                 ckpt: Optional[dict] = None):
+        self.model = model
+        self.ddpm_num_timesteps = timesteps
+        betas = make_beta_schedule("linear", timesteps, linear_start, linear_end)
+        self.alphas_cumprod = np.cumprod(1.0 - betas, axis=0)
+        self.ckpt = ckpt         # FSC tables: {'act_k': ...} as saved by cali_model
+
+    def make_schedule(self, ddim_num_steps: int, ddim_eta: float = 0.0):
+        self.ddim_timesteps = make_ddim_timesteps(ddim_num_steps, self.ddpm_num_timesteps)
+        ac = self.alphas_cumprod
+        alphas = ac[self.ddim_timesteps]
+        alphas_prev = np.asarray([ac[0]] + ac[self.ddim_timesteps[:-1]].tolist())
+        sigmas = ddim_eta * np.sqrt((1 - alphas_prev) / (1 - alphas) * (1 - alphas / alphas_prev))
+        f32 = lambda a: torch.from_numpy(np.asarray(a)).to(torch.float32)  # noqa: E731
+        self.ddim_alphas, self.ddim_alphas_prev, self.ddim_sigmas = f32(alphas), f32(alphas_prev), f32(sigmas)
+        self.ddim_sqrt_one_minus_alphas = f32(np.sqrt(1.0 - alphas))
+
+    def coefficient_rows(self):
+        """p_sample_ddim's per-index scalars (ddim.py:196-211) in sampling order (index S-1 .. 0)."""
+        rows = []
+        for index in reversed(range(len(self.ddim_timesteps))):
+            a_t, a_prev = self.ddim_alphas[index], self.ddim_alphas_prev[index]
+            sigma = self.ddim_sigmas[index]
+            rows.append([a_t.sqrt().item(), self.ddim_sqrt_one_minus_alphas[index].item(), a_prev.sqrt().item(),
+                         (1.0 - a_prev - sigma ** 2).sqrt().item(), sigma.item()])
+        return rows
+
+    @torch.no_grad()
+    def sample(self, S, batch_size, shape, conditioning=None, eta=0.0, x_T=None, verbose=False,
+               unconditional_guidance_scale=1.0, unconditional_conditioning=None, untill_fake_t=None, **kwargs):
+        if conditioning is not None or unconditional_conditioning is not None:
+            raise NotImplementedError("conditional sampling (SD / cin256) is the next widening step")
+        if eta != 0:
+            raise NotImplementedError("eta > 0")
+        self.make_schedule(S, eta)
+        dev = next(self.model.parameters()).device
+        C, H, W = shape
+        img = torch.randn((batch_size, C, H, W), device=dev) if x_T is None else x_T.to(dev)
+        eng = getattr(self.model, "_engine", None)
+        if eng is None or eng.batch != batch_size:
+            eng = self.model.build_engine(batch=batch_size)
+        ts = [float(t) for t in np.flip(self.ddim_timesteps)]
+        tables = None
+        if self.ckpt is not None:
+            # FSC index of DiffusionWrapper.forward (ddpm.py:1402-1405): t_max - (t-1)//tot
+            tot, t_max = self.ddpm_num_timesteps // S, S - 1
+            tables = [self.ckpt[f"act_{int(t_max - (int(t) - 1) // tot)}"] for t in ts]
+        eng.set_schedule(ts, tables, self.coefficient_rows())
+        eng.x_in.copy_(img)
+        n_run = S if not untill_fake_t else min(S, untill_fake_t - 1)
+        for k in range(n_run):
+            eng.step(k)
+        out = eng.x_in.clone()
+        return out, {"x_inter": [img, out], "pred_x0": [img, eng.x0_pred.clone()]}
