@@ -101,6 +101,11 @@ class _Net:
             self.record["out:" + name] = y          # time-embedding MLP outputs (teacher forcing)
         return y
 
+    def mark(self, name, y):
+        if self.record is not None:
+            self.record["blk:" + name] = y
+        return y
+
     def gn(self, name, x, eps):
         return F.group_norm(x, 32, self.sd[name + ".weight"], self.sd[name + ".bias"], eps)
 
@@ -132,7 +137,7 @@ def ddim_unet_forward(sd, cfg, x, t, spec, act: Optional[ActParams] = None, reco
         h = net.layer(p + ".conv2", Q.silu(net.gn(p + ".norm2", h, 1e-6)), P1)
         if has(p + ".nin_shortcut"):
             x = net.layer(p + ".nin_shortcut", x, P0)
-        return x + h
+        return net.mark(p, x + h)
 
     def attn(p, x):
         hn = net.gn(p + ".norm", x, 1e-6)
@@ -142,11 +147,11 @@ def ddim_unet_forward(sd, cfg, x, t, spec, act: Optional[ActParams] = None, reco
         k = k.reshape(b, c, h * w)
         w_ = torch.softmax(torch.bmm(q, k) * (int(c) ** (-0.5)), dim=2)
         h_ = torch.bmm(v.reshape(b, c, h * w), w_.permute(0, 2, 1)).reshape(b, c, h, w)
-        return x + net.layer(p + ".proj_out", h_, P0)
+        return net.mark(p, x + net.layer(p + ".proj_out", h_, P0))
 
     temb = net.layer("temb.dense.0", ddim_timestep_embedding(t, ch))
     temb = net.layer("temb.dense.1", Q.silu(temb))
-    hs = [net.layer("conv_in", x, P1)]
+    hs = [net.mark("conv_in", net.layer("conv_in", x, P1))]
     for l in range(nres):
         for j in range(nrb):
             h = resblock(f"down.{l}.block.{j}", hs[-1], temb)
@@ -154,7 +159,8 @@ def ddim_unet_forward(sd, cfg, x, t, spec, act: Optional[ActParams] = None, reco
                 h = attn(f"down.{l}.attn.{j}", h)
             hs.append(h)
         if l != nres - 1:
-            hs.append(net.layer(f"down.{l}.downsample.conv", F.pad(hs[-1], (0, 1, 0, 1)), dict(stride=2, padding=0)))
+            hs.append(net.mark(f"down.{l}.downsample", net.layer(f"down.{l}.downsample.conv",
+                                                                 F.pad(hs[-1], (0, 1, 0, 1)), dict(stride=2, padding=0))))
     h = resblock("mid.block_1", hs[-1], temb)
     h = attn("mid.attn_1", h)
     h = resblock("mid.block_2", h, temb)
@@ -164,8 +170,9 @@ def ddim_unet_forward(sd, cfg, x, t, spec, act: Optional[ActParams] = None, reco
             if has(f"up.{l}.attn.{j}.q"):
                 h = attn(f"up.{l}.attn.{j}", h)
         if l != 0:
-            h = net.layer(f"up.{l}.upsample.conv", F.interpolate(h, scale_factor=2.0, mode="nearest"), P1)
-    return net.layer("conv_out", Q.silu(net.gn("norm_out", h, 1e-6)), P1)
+            h = net.mark(f"up.{l}.upsample", net.layer(f"up.{l}.upsample.conv",
+                                                       F.interpolate(h, scale_factor=2.0, mode="nearest"), P1))
+    return net.layer("conv_out", net.mark("final_act", Q.silu(net.gn("norm_out", h, 1e-6))), P1)
 
 
 # --------------------------------------------------------------------------- LDM UNet
@@ -191,7 +198,7 @@ def ldm_unet_forward(sd, cfg, x, t, spec, act: Optional[ActParams] = None, recor
         h = net.layer(p + ".out_layers.3", F.silu(net.gn(p + ".out_layers.0", h, 1e-5)), P1)
         if has(p + ".skip_connection"):
             x = net.layer(p + ".skip_connection", x, P0)
-        return x + h
+        return net.mark(p, x + h)
 
     def attn(p, x, heads_ch):
         b, c, hh, ww = x.shape
@@ -204,7 +211,7 @@ def ldm_unet_forward(sd, cfg, x, t, spec, act: Optional[ActParams] = None, recor
         scale = 1 / math.sqrt(math.sqrt(chd))
         w = torch.softmax(torch.einsum("bct,bcs->bts", q * scale, k * scale), dim=-1)
         a = torch.einsum("bts,bcs->bct", w, v).reshape(bs, -1, length)
-        return (xf + net.layer(p + ".proj_out", a)).reshape(b, c, hh, ww)
+        return net.mark(p, (xf + net.layer(p + ".proj_out", a)).reshape(b, c, hh, ww))
 
     def run_block(p, h, emb):
         j = 0
@@ -215,11 +222,11 @@ def ldm_unet_forward(sd, cfg, x, t, spec, act: Optional[ActParams] = None, recor
             elif has(q + ".qkv"):
                 h = attn(q, h, cfg["num_head_channels"])
             elif has(q + ".op"):
-                h = net.layer(q + ".op", h, dict(stride=2, padding=1))
+                h = net.mark(q, net.layer(q + ".op", h, dict(stride=2, padding=1)))
             elif has(q + ".conv"):
-                h = net.layer(q + ".conv", F.interpolate(h, scale_factor=2, mode="nearest"), P1)
+                h = net.mark(q, net.layer(q + ".conv", F.interpolate(h, scale_factor=2, mode="nearest"), P1))
             elif has(q):
-                h = net.layer(q, h, P1)           # input_blocks.0.0
+                h = net.mark(q, net.layer(q, h, P1))           # input_blocks.0.0
             else:
                 return h
             j += 1
@@ -236,7 +243,7 @@ def ldm_unet_forward(sd, cfg, x, t, spec, act: Optional[ActParams] = None, recor
     while has(f"output_blocks.{i}.0.in_layers.2"):
         h = run_block(f"output_blocks.{i}", torch.cat([h, hs.pop()], dim=1), emb)
         i += 1
-    return net.layer("out.2", F.silu(net.gn("out.0", h, 1e-5)), P1)
+    return net.layer("out.2", net.mark("final_act", F.silu(net.gn("out.0", h, 1e-5))), P1)
 
 
 # --------------------------------------------------------------------------- DDIM sampler

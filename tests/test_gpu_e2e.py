@@ -75,6 +75,17 @@ def _flip_report(eng, record, tag, verbose=False):
     return diff / max(tot, 1)
 
 
+def _block_report(eng, record, tag):
+    print(f"[{tag}] teacher-forced block outputs vs oracle (max-abs):")
+    for name, t in eng.block_out.items():
+        ref = record.get("blk:" + name)
+        if ref is None:
+            print(f"    {name:36s} (no oracle record)")
+            continue
+        got = t.view.cpu().permute(0, 3, 1, 2)
+        print(f"    {name:36s} {(got - ref).abs().max().item():.3e}   |ref| max {ref.abs().max().item():.2f}")
+
+
 def test_cifar_unet_step_and_ddim_trajectory(dev):
     from oracle import unet_ref as U
     g = load_golden("cifar_w4a8.pt")
@@ -92,10 +103,14 @@ def test_cifar_unet_step_and_ddim_trajectory(dev):
         err = (e - eps).abs().max().item()
         rec = {}
         with torch.no_grad():
-            U.ddim_unet_forward(sd, CIFAR_CFG, x, t, spec, U.ActParams(g["act_names"], g["act_table"][k]), rec)
+            e_orc = U.ddim_unet_forward(sd, CIFAR_CFG, x, t, spec, U.ActParams(g["act_names"], g["act_table"][k]), rec)
         flips = _flip_report(eng, rec, f"cifar step {k}")
-        tf = (eng.forward_teacher_forced(x.to(dev), t, rec).cpu() - eps).abs().max().item()
-        first = next(iter(eng.u8_by_name))
+        # the oracle on THIS host vs the golden made on another CPU: the same flip cascade (different
+        # oneDNN accumulation order), so teacher forcing is judged against the oracle run that made `rec`
+        print(f"[cifar] step {k}: oracle on this host vs golden (other CPU): {(e_orc - eps).abs().max():.3e}")
+        tf = (eng.forward_teacher_forced(x.to(dev), t, rec).cpu() - e_orc).abs().max().item()
+        if tf >= TOL_EPS and k == 0:
+            _block_report(eng, rec, "cifar")
         print(f"[cifar] step {k}: eps max-abs err vs reference: teacher-forced {tf:.3e}, free-running {err:.3e} "
               f"(reference's own fp64-accumulation sensitivity {(g['alt_eps0'] - g['eps'][0][2]).abs().max():.3e}; "
               f"|eps| max {eps.abs().max():.3f})")
@@ -130,9 +145,13 @@ def test_ldm4_unet_step(dev):
     spec = oracle_spec(sd, g["seed"])
     rec = {}
     with torch.no_grad():
-        U.ldm_unet_forward(sd, LDM4_CFG, g["x"], g["t"], spec, U.ActParams(g["act_names"], g["act_table"][0]), rec)
+        e_orc = U.ldm_unet_forward(sd, LDM4_CFG, g["x"], g["t"], spec,
+                                   U.ActParams(g["act_names"], g["act_table"][0]), rec)
     flips = _flip_report(eng, rec, "ldm4")
-    tf = (eng.forward_teacher_forced(g["x"].to(dev), g["t"], rec).cpu() - g["eps"]).abs().max().item()
+    print(f"[ldm4] oracle on this host vs golden (other CPU): {(e_orc - g['eps']).abs().max():.3e}")
+    tf = (eng.forward_teacher_forced(g["x"].to(dev), g["t"], rec).cpu() - e_orc).abs().max().item()
+    if tf >= TOL_EPS:
+        _block_report(eng, rec, "ldm4")
     sens = (g["alt_eps"] - g["eps"]).abs().max().item()
     print(f"[ldm4] eps max-abs err vs reference: teacher-forced {tf:.3e}, free-running {err:.3e} "
           f"(reference's own fp64-accumulation sensitivity {sens:.3e}; |eps| max {g['eps'].abs().max():.3f})")

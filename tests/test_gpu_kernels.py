@@ -276,6 +276,19 @@ def test_conv_in_out(dev):
     assert (o2.cpu() - F.conv2d(h, w2, b2, padding=1)).abs().max().item() < 1e-5
 
 
+def test_conv_out_model_shapes(dev):
+    ops = _ops()
+    for n, c, hw in ((1, 128, 32), (2, 224, 64)):
+        g = torch.Generator().manual_seed(c)
+        h = torch.randn(n, c, hw, hw, generator=g)
+        w2 = torch.randn(3, c, 3, 3, generator=g) * 0.05
+        b2 = torch.randn(3, generator=g)
+        o2 = torch.empty((n, 3, hw, hw), device=dev)
+        ops.conv_out(nhwc(h).to(dev), w2.to(dev), b2.to(dev), o2)
+        err = (o2.cpu() - F.conv2d(h, w2, b2, padding=1)).abs().max().item()
+        assert err < 2e-5, (n, c, hw, err)
+
+
 def test_ddim_update_and_embedding(dev):
     ops, q = _ops(), _qref()
     g = torch.Generator().manual_seed(4)

@@ -121,6 +121,8 @@ class StepEngine:
         self._u8_bufs: List = []
         self.u8_by_name: Dict[str, tuple] = {}
         self.teacher: Optional[Dict[str, torch.Tensor]] = None   # test hook: force quantiser decisions
+        self.block_out: Dict[str, T] = {}                          # test hook: block name -> output tensor
+        self._names = {id(m): n for n, m in model.named_modules()}
         self.graph = None
 
         # ---- quantised-layer table; activation-quantised layers get a slot in the per-step row
@@ -337,6 +339,7 @@ class StepEngine:
                     self._plain_conv(blk.nin_shortcut, x, out, None, pad_lo=0, stride=1)
                 r = out
             self._qconv(blk.conv2, h, gn=self._gn(h, blk.norm2), silu=True, res=r, out=out)
+            self.block_out[self._names[id(blk)]] = out
             return out
 
         def attnblock(blk: QuantAttnBlock, x: T) -> T:
@@ -351,11 +354,14 @@ class StepEngine:
                 return {name: (t.view.stride(0), 0, t.view.stride(2)) for name, t in
                         (("q", q), ("k", k), ("v", v), ("o", o))}
             self._attention(lambda: q.view, lambda: k.view, lambda: v.view, o, 1, c, float(int(c) ** -0.5), strides)
-            return self._qconv(blk.proj_out, o, res=x)
+            out = self._qconv(blk.proj_out, o, res=x)
+            self.block_out[self._names[id(blk)]] = out
+            return out
 
         x0 = self._new(N, res, res, m.ch)
         ci = self.ql[id(m.conv_in)]
         self.ops.append(lambda: ops.conv_in(self.x_in, ci.w_oihw, ci.bias, x0.view))
+        self.block_out["conv_in"] = x0
         hs = [x0]
         for lvl in range(m.num_resolutions):
             st = m.down[lvl]
@@ -370,6 +376,7 @@ class StepEngine:
                 out = self._new(N, src.h // 2, src.w // 2, src.c)
                 if ds.with_conv:
                     self._plain_conv(ds.conv, src, out, None, pad_lo=0, stride=2)
+                    self.block_out[self._names[id(ds)]] = out
                 else:
                     raise NotImplementedError("avg-pool downsample (resamp_with_conv=False)")
                 hs.append(out)
@@ -384,12 +391,14 @@ class StepEngine:
                     h = attnblock(st.attn[j], h)
             if lvl != 0:
                 h = self._qconv(st.upsample.conv, h, upsample=True)
+                self.block_out[self._names[id(st.upsample)]] = h
         self._final(m.norm_out, m.conv_out, h)
 
     def _final(self, norm, conv_out_layer, h: T):
         gn = self._gn(h, norm)
         f = self._new(h.n, h.h, h.w, h.c)
         self.ops.append(lambda: ops.act_prepare(h.view, dst_f32=f.view, silu=True, **self._gn_args(gn)))
+        self.block_out["final_act"] = f
         co = self.ql[id(conv_out_layer)]
         self.eps = torch.zeros((h.n, co.cout, h.h, h.w), dtype=torch.float32, device=self.dev)
         self.ops.append(lambda: ops.conv_out(f.view, co.w_oihw, co.bias, self.eps))
@@ -412,6 +421,7 @@ class StepEngine:
                 self._plain_conv(blk.skip_connection, x, out, None, pad_lo=0, stride=1)
                 r = out
             self._qconv(c2, h, gn=self._gn(h, n2), silu=True, res=r, out=out)
+            self.block_out[self._names[id(blk)]] = out
             return out
 
         def attnblock(blk: QuantAttentionBlock, x: T) -> T:
@@ -436,6 +446,7 @@ class StepEngine:
             self._attention(part(0), part(1), part(2), o, heads, d, 1.0 / math.sqrt(d), strides)
             out = self._new(x.n, x.h, x.w, x.c)
             self._plain_conv(blk.proj_out, o, out, x, pad_lo=0, stride=1)
+            self.block_out[self._names[id(blk)]] = out
             return out
 
         def run_seq(seq, h: T) -> T:
@@ -451,13 +462,16 @@ class StepEngine:
                         raise NotImplementedError("avg-pool downsample")
                     self._plain_conv(layer.op, h, out, None, pad_lo=layer.op.padding[0], stride=2)
                     h = out
+                    self.block_out[self._names[id(layer)]] = out
                 elif name == "Upsample":
                     h = self._qconv(layer.conv, h, upsample=True)
+                    self.block_out[self._names[id(layer)]] = h
                 elif isinstance(layer, QuantLayer):   # input_blocks.0.0
                     q = self.ql[id(layer)]
                     out = self._new(N, res, res, q.cout)
                     self.ops.append(lambda q=q, out=out: ops.conv_in(self.x_in, q.w_oihw, q.bias, out.view))
                     h = out
+                    self.block_out[self._names[id(layer)]] = out
                 else:
                     raise NotImplementedError(f"engine: unsupported module {name}")
             return h
