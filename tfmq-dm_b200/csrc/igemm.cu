@@ -10,10 +10,18 @@ namespace tfmq {
 // ---------------------------------------------------------------------------
 // kernel
 // ---------------------------------------------------------------------------
+// Persistent: grid = min(#tiles, #SMs); each CTA walks tiles t = blockIdx.x, +gridDim.x, ... with the
+// M index fastest, so CTAs running together share one weight tile in L2.
+//   warp 0      TMA producer
+//   warp 1      UMMA issuer (owns TMEM: 1 or 2 accumulator stages)
+//   warps 2-5   operand transform (int4 unpack / tf32 hi-lo split)
+//   warps 6-9   epilogue: TMEM -> registers -> per-warp smem transpose -> coalesced global I/O,
+//               overlapped with the next tile's main loop through the second accumulator stage
 template <int MODE>
 __global__ void __launch_bounds__(IGEMM_THREADS, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-             const __grid_constant__ CUtensorMap tmB2, const IgemmParams p) {
+             const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmOut,
+             const __grid_constant__ CUtensorMap tmRes, const IgemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // dynamic smem is only guaranteed 16-B aligned: round up to the 1024 B the 128B swizzle needs
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -21,25 +29,24 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int S = p.stages;
+  const int ACC = p.acc_stages;
 
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S * p.stage_bytes);
-  uint64_t* full_tma = bars;           // [S] TMA bytes landed
-  uint64_t* full_xf = bars + S;        // [S] transform warps done
-  uint64_t* empty = bars + 2 * S;      // [S] UMMAs that read the stage retired
-  uint64_t* acc_full = bars + 3 * S;   // accumulator complete
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * S + 1);
+  uint8_t* ebuf = smem + (size_t)S * p.stage_bytes;                       // 2 epilogue chunks [128][chunk_w] f32
+  float4* chp = reinterpret_cast<float4*>(ebuf + 2 * 128 * 32 * 4);        // [tile_n] per-channel constants
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ebuf + 2 * 128 * 32 * 4 + 256 * 16);
+  uint64_t* full_tma = bars;            // [S] TMA bytes landed
+  uint64_t* full_xf = bars + S;         // [S] transform warps done
+  uint64_t* empty = bars + 2 * S;       // [S] UMMAs that read the stage retired
+  uint64_t* acc_full = bars + 3 * S;    // [2] accumulator stage complete
+  uint64_t* acc_empty = bars + 3 * S + 2;  // [2] accumulator stage drained by the epilogue
+  uint64_t* res_full = bars + 3 * S + 4;   // [2] residual chunk landed in the epilogue buffer
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * S + 6);
 
-  // ---- tile coordinates
   const int tiles_x = p.W / p.tw;
   const int tiles_y = p.H / p.th;
-  int mt = blockIdx.x;
-  const int tx = mt % tiles_x;
-  mt /= tiles_x;
-  const int ty = mt % tiles_y;
-  const int ng = mt / tiles_y;
-  const int n0 = ng * p.tn, y0 = ty * p.th, x0 = tx * p.tw;
-  const int c_out0 = blockIdx.y * p.tile_n;
-
+  const int tiles_m = tiles_x * tiles_y * ((p.n_img + p.tn - 1) / p.tn);
+  const int tiles_n = p.cout / p.tile_n;
+  const int total_tiles = tiles_m * tiles_n;
   const int kchunks = (p.cin + p.kchunk - 1) / p.kchunk;
   const int taps = p.ksize * p.ksize;
   const int nkb = taps * kchunks;
@@ -50,11 +57,17 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       mbar_init(&full_xf[s], 4);
       mbar_init(&empty[s], 1);
     }
-    mbar_init(acc_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], 4);
+      mbar_init(&res_full[s], 1);
+    }
     mbar_fence_init();
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     if (MODE == MODE_TF32) tma_prefetch_desc(&tmB2);
+    tma_prefetch_desc(&tmOut);
+    if (p.res) tma_prefetch_desc(&tmRes);
   }
   if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
   tc_fence_before();
@@ -64,6 +77,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 
   const bool need_a_lo = (MODE == MODE_TF32) && (p.pass_flags & PASS_LO_HI);
   const bool need_b_lo = (MODE == MODE_TF32) && (p.pass_flags & PASS_HI_LO);
+  const bool two_acc = need_a_lo || need_b_lo;                 // tf32: separate accumulator for the small terms
+  const uint32_t acc_cols = (uint32_t)p.tile_n * (two_acc ? 2u : 1u);
 
   if (warp == 0) {
     // ===================================================== TMA producer
@@ -72,22 +87,31 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       if (MODE == MODE_W4A8) tx_bytes += (uint32_t)p.tile_n * 64u;
       if (MODE == MODE_I8) tx_bytes += (uint32_t)p.tile_n * 128u;
       if (MODE == MODE_TF32) tx_bytes += (uint32_t)p.tile_n * 128u * (need_b_lo ? 2u : 1u);
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % S;
-        const uint32_t par = (uint32_t)(kb / S) & 1u;
-        mbar_wait(&empty[s], par ^ 1u);
-        uint8_t* st = smem + (size_t)s * p.stage_bytes;
-        const int tap = kb / kchunks, kc = kb - tap * kchunks;
-        const int ky = tap / p.ksize, kx = tap - ky * p.ksize;
-        mbar_expect_tx(&full_tma[s], tx_bytes);
-        tma_load_4d(st, &tmA, &full_tma[s], kc * p.kchunk, x0 * p.stride + kx + p.off, y0 * p.stride + ky + p.off,
-                    n0);
-        if (MODE == MODE_W4A8) {
-          // packed bytes: column = (tap*cin + kc*128)/2
-          tma_load_2d(st + p.offP, &tmB, &full_tma[s], (tap * p.cin + kc * p.kchunk) >> 1, c_out0);
-        } else {
-          tma_load_2d(st + p.offB, &tmB, &full_tma[s], tap * p.cin + kc * p.kchunk, c_out0);
-          if (need_b_lo) tma_load_2d(st + p.offB_lo, &tmB2, &full_tma[s], tap * p.cin + kc * p.kchunk, c_out0);
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int mt = tile % tiles_m;
+        const int c_out0 = (tile / tiles_m) * p.tile_n;
+        const int tx = mt % tiles_x;
+        mt /= tiles_x;
+        const int ty = mt % tiles_y;
+        const int n0 = (mt / tiles_y) * p.tn, y0 = ty * p.th, x0 = tx * p.tw;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % S;
+          const uint32_t par = (it / S) & 1u;
+          mbar_wait(&empty[s], par ^ 1u);
+          uint8_t* st = smem + (size_t)s * p.stage_bytes;
+          const int tap = kb / kchunks, kc = kb - tap * kchunks;
+          const int ky = tap / p.ksize, kx = tap - ky * p.ksize;
+          mbar_expect_tx(&full_tma[s], tx_bytes);
+          tma_load_4d(st, &tmA, &full_tma[s], kc * p.kchunk, x0 * p.stride + kx + p.off,
+                      y0 * p.stride + ky + p.off, n0);
+          if (MODE == MODE_W4A8) {
+            // packed bytes: column = (tap*cin + kc*128)/2
+            tma_load_2d(st + p.offP, &tmB, &full_tma[s], (tap * p.cin + kc * p.kchunk) >> 1, c_out0);
+          } else {
+            tma_load_2d(st + p.offB, &tmB, &full_tma[s], tap * p.cin + kc * p.kchunk, c_out0);
+            if (need_b_lo) tma_load_2d(st + p.offB_lo, &tmB2, &full_tma[s], tap * p.cin + kc * p.kchunk, c_out0);
+          }
         }
       }
     }
@@ -95,212 +119,284 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     // ===================================================== UMMA issuer
     const uint32_t idesc = (MODE == MODE_TF32) ? idesc_tf32(128, (uint32_t)p.tile_n)
                                                : idesc_i8_u8s8(128, (uint32_t)p.tile_n);
-    uint32_t accumulate = 0, accumulate_lo = 0;
-    // tf32: the two small cross terms accumulate in their own TMEM columns so the (truncating)
-    // tensor-core accumulator adds them to a small running sum, not to the large main one
-    const uint32_t tmem_lo = tmem_base + (uint32_t)p.tile_n;
-    for (int kb = 0; kb < nkb; ++kb) {
-      const int s = kb % S;
-      const uint32_t par = (uint32_t)(kb / S) & 1u;
-      mbar_wait(&full_tma[s], par);
-      mbar_wait(&full_xf[s], par);
+    uint32_t it = 0, tcount = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+      const uint32_t as = tcount % ACC;
+      mbar_wait(&acc_empty[as], ((tcount / ACC) & 1u) ^ 1u);   // epilogue has drained this stage
       tc_fence_after();
-      if (lane == 0) {
-        const uint32_t st = smem_u32(smem + (size_t)s * p.stage_bytes);
-        const int kc = kb % kchunks;
-        int rem = p.cin - kc * p.kchunk;
-        if (rem > p.kchunk) rem = p.kchunk;
-        const int nslice = rem / p.kslice;  // valid 32-byte K slices in this k-block
-        const uint64_t a_hi = smem_desc_sw128(st);
-        const uint64_t b_hi = smem_desc_sw128(st + p.offB);
-        if (MODE == MODE_TF32) {
-          const uint64_t a_lo = smem_desc_sw128(st + p.offA_lo);
-          const uint64_t b_lo = smem_desc_sw128(st + p.offB_lo);
-          // small terms first, then the main product
-          if (need_a_lo)
+      const uint32_t tmem_d = tmem_base + as * acc_cols;
+      // tf32: the two small cross terms accumulate in their own TMEM columns so the (truncating)
+      // tensor-core accumulator adds them to a small running sum, not to the large main one
+      const uint32_t tmem_lo = tmem_d + (uint32_t)p.tile_n;
+      uint32_t accumulate = 0, accumulate_lo = 0;
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const int s = it % S;
+        const uint32_t par = (it / S) & 1u;
+        mbar_wait(&full_tma[s], par);
+        mbar_wait(&full_xf[s], par);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t st = smem_u32(smem + (size_t)s * p.stage_bytes);
+          const int kc = kb % kchunks;
+          int rem = p.cin - kc * p.kchunk;
+          if (rem > p.kchunk) rem = p.kchunk;
+          const int nslice = rem / p.kslice;  // valid 32-byte K slices in this k-block
+          const uint64_t a_hi = smem_desc_sw128(st);
+          const uint64_t b_hi = smem_desc_sw128(st + p.offB);
+          if (MODE == MODE_TF32) {
+            const uint64_t a_lo = smem_desc_sw128(st + p.offA_lo);
+            const uint64_t b_lo = smem_desc_sw128(st + p.offB_lo);
+            if (need_a_lo)
+              for (int k = 0; k < nslice; ++k) {
+                umma_tf32(tmem_lo, a_lo + 2 * k, b_hi + 2 * k, idesc, accumulate_lo);
+                accumulate_lo = 1;
+              }
+            if (need_b_lo)
+              for (int k = 0; k < nslice; ++k) {
+                umma_tf32(tmem_lo, a_hi + 2 * k, b_lo + 2 * k, idesc, accumulate_lo);
+                accumulate_lo = 1;
+              }
             for (int k = 0; k < nslice; ++k) {
-              umma_tf32(tmem_lo, a_lo + 2 * k, b_hi + 2 * k, idesc, accumulate_lo);
-              accumulate_lo = 1;
+              umma_tf32(tmem_d, a_hi + 2 * k, b_hi + 2 * k, idesc, accumulate);
+              accumulate = 1;
             }
-          if (need_b_lo)
+          } else {
             for (int k = 0; k < nslice; ++k) {
-              umma_tf32(tmem_lo, a_hi + 2 * k, b_lo + 2 * k, idesc, accumulate_lo);
-              accumulate_lo = 1;
+              umma_i8(tmem_d, a_hi + 2 * k, b_hi + 2 * k, idesc, accumulate);
+              accumulate = 1;
             }
-          for (int k = 0; k < nslice; ++k) {
-            umma_tf32(tmem_base, a_hi + 2 * k, b_hi + 2 * k, idesc, accumulate);
-            accumulate = 1;
           }
-        } else {
-          for (int k = 0; k < nslice; ++k) {
-            umma_i8(tmem_base, a_hi + 2 * k, b_hi + 2 * k, idesc, accumulate);
-            accumulate = 1;
-          }
+          umma_commit(&empty[s]);
+          if (kb == nkb - 1) umma_commit(&acc_full[as]);
         }
-        umma_commit(&empty[s]);
-        if (kb == nkb - 1) umma_commit(acc_full);
+        __syncwarp();
       }
-      __syncwarp();
     }
-  } else {
+  } else if (warp < 6) {
     // ===================================================== transform warps (2..5)
     const int t = threadIdx.x - 64;  // 0..127
-    if (MODE == MODE_W4A8) {
-      // this thread always unpacks the same rows: row_i = (t + 128*i) >> 2, K slice = t & 3
-      const int sub = t & 3;
-      uint32_t zc[8];
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int c_out0 = (tile / tiles_m) * p.tile_n;
+      if (MODE == MODE_W4A8) {
+        // this thread always unpacks the same rows: row_i = (t + 128*i) >> 2, K slice = t & 3
+        const int sub = t & 3;
+        uint32_t zc[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int row = (t + 128 * i) >> 2;
-        uint32_t z = 0;
-        if (row < p.tile_n && c_out0 + row < p.cout) z = p.wzp[c_out0 + row];
-        zc[i] = 0x80808080u - z * 0x01010101u;
-      }
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % S;
-        const uint32_t par = (uint32_t)(kb / S) & 1u;
-        mbar_wait(&full_tma[s], par);
-        uint8_t* st = smem + (size_t)s * p.stage_bytes;
-        const int kc = kb % kchunks;
-        int rem = p.cin - kc * p.kchunk;
-        if (rem > p.kchunk) rem = p.kchunk;
-        const int nslice = rem >> 5;
-        if (sub < nslice) {
+        for (int i = 0; i < 8; ++i) {
+          const int row = (t + 128 * i) >> 2;
+          uint32_t z = 0;
+          if (row < p.tile_n && c_out0 + row < p.cout) z = p.wzp[c_out0 + row];
+          zc[i] = 0x80808080u - z * 0x01010101u;
+        }
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % S;
+          const uint32_t par = (it / S) & 1u;
+          mbar_wait(&full_tma[s], par);
+          uint8_t* st = smem + (size_t)s * p.stage_bytes;
+          const int kc = kb % kchunks;
+          int rem = p.cin - kc * p.kchunk;
+          if (rem > p.kchunk) rem = p.kchunk;
+          const int nslice = rem >> 5;
+          if (sub < nslice) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int row = (t + 128 * i) >> 2;
-            if (row < p.tile_n) {
-              const uint4 pk = *reinterpret_cast<const uint4*>(st + p.offP + row * 64 + sub * 16);
-              uint4 lo, hi;
-              lo.x = ((pk.x & 0x0F0F0F0Fu) + zc[i]) ^ 0x80808080u;
-              lo.y = ((pk.y & 0x0F0F0F0Fu) + zc[i]) ^ 0x80808080u;
-              lo.z = ((pk.z & 0x0F0F0F0Fu) + zc[i]) ^ 0x80808080u;
-              lo.w = ((pk.w & 0x0F0F0F0Fu) + zc[i]) ^ 0x80808080u;
-              hi.x = (((pk.x >> 4) & 0x0F0F0F0Fu) + zc[i]) ^ 0x80808080u;
-              hi.y = (((pk.y >> 4) & 0x0F0F0F0Fu) + zc[i]) ^ 0x80808080u;
-              hi.z = (((pk.z >> 4) & 0x0F0F0F0Fu) + zc[i]) ^ 0x80808080u;
-              hi.w = (((pk.w >> 4) & 0x0F0F0F0Fu) + zc[i]) ^ 0x80808080u;
-              uint8_t* brow = st + p.offB + row * 128;
-              const int sw = row & 7;
-              *reinterpret_cast<uint4*>(brow + (((2 * sub) ^ sw) << 4)) = lo;
-              *reinterpret_cast<uint4*>(brow + (((2 * sub + 1) ^ sw) << 4)) = hi;
+            for (int i = 0; i < 8; ++i) {
+              const int row = (t + 128 * i) >> 2;
+              if (row < p.tile_n) {
+                const uint4 pk = *reinterpret_cast<const uint4*>(st + p.offP + row * 64 + sub * 16);
+                uint4 lo, hi;
+                lo.x = ((pk.x & 0x0F0F0F0Fu) + zc[i]) ^ 0x80808080u;
+                lo.y = ((pk.y & 0x0F0F0F0Fu) + zc[i]) ^ 0x80808080u;
+                lo.z = ((pk.z & 0x0F0F0F0Fu) + zc[i]) ^ 0x80808080u;
+                lo.w = ((pk.w & 0x0F0F0F0Fu) + zc[i]) ^ 0x80808080u;
+                hi.x = (((pk.x >> 4) & 0x0F0F0F0Fu) + zc[i]) ^ 0x80808080u;
+                hi.y = (((pk.y >> 4) & 0x0F0F0F0Fu) + zc[i]) ^ 0x80808080u;
+                hi.z = (((pk.z >> 4) & 0x0F0F0F0Fu) + zc[i]) ^ 0x80808080u;
+                hi.w = (((pk.w >> 4) & 0x0F0F0F0Fu) + zc[i]) ^ 0x80808080u;
+                uint8_t* brow = st + p.offB + row * 128;
+                const int sw = row & 7;
+                *reinterpret_cast<uint4*>(brow + (((2 * sub) ^ sw) << 4)) = lo;
+                *reinterpret_cast<uint4*>(brow + (((2 * sub + 1) ^ sw) << 4)) = hi;
+              }
             }
           }
-        }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&full_xf[s]);
-      }
-    } else if (MODE == MODE_TF32) {
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % S;
-        const uint32_t par = (uint32_t)(kb / S) & 1u;
-        mbar_wait(&full_tma[s], par);
-        if (need_a_lo) {
-          uint8_t* st = smem + (size_t)s * p.stage_bytes;
-          uint4* a = reinterpret_cast<uint4*>(st);
-          uint4* al = reinterpret_cast<uint4*>(st + p.offA_lo);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int idx = t + 128 * i;
-            uint4 v = a[idx], h, l;
-            h.x = v.x & 0xFFFFE000u;
-            h.y = v.y & 0xFFFFE000u;
-            h.z = v.z & 0xFFFFE000u;
-            h.w = v.w & 0xFFFFE000u;
-            l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x));
-            l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y));
-            l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z));
-            l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w));
-            a[idx] = h;
-            al[idx] = l;
-          }
           fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&full_xf[s]);
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&full_xf[s]);
-      }
-    } else {
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % S;
-        const uint32_t par = (uint32_t)(kb / S) & 1u;
-        mbar_wait(&full_tma[s], par);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&full_xf[s]);
+      } else if (MODE == MODE_TF32) {
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % S;
+          const uint32_t par = (it / S) & 1u;
+          mbar_wait(&full_tma[s], par);
+          if (need_a_lo) {
+            uint8_t* st = smem + (size_t)s * p.stage_bytes;
+            uint4* a = reinterpret_cast<uint4*>(st);
+            uint4* al = reinterpret_cast<uint4*>(st + p.offA_lo);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int idx = t + 128 * i;
+              uint4 v = a[idx], h, l;
+              h.x = v.x & 0xFFFFE000u;
+              h.y = v.y & 0xFFFFE000u;
+              h.z = v.z & 0xFFFFE000u;
+              h.w = v.w & 0xFFFFE000u;
+              l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x));
+              l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y));
+              l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z));
+              l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w));
+              a[idx] = h;
+              al[idx] = l;
+            }
+            fence_proxy_async_smem();
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&full_xf[s]);
+        }
+      } else {
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % S;
+          const uint32_t par = (it / S) & 1u;
+          mbar_wait(&full_tma[s], par);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&full_xf[s]);
+        }
       }
     }
-
-    // ===================================================== epilogue (same 4 warps)
-    mbar_wait(acc_full, 0);
-    tc_fence_after();
-    const int q = warp & 3;             // TMEM lane quarter this warp may access
-    const int r = q * 32 + lane;        // accumulator row = pixel within the tile
+  } else {
+    // ===================================================== epilogue warps (6..9)
+    // All global I/O of the epilogue is TMA: the residual chunk is prefetched into a swizzled smem
+    // buffer, every thread folds its accumulator row into it (conflict-free float4 accesses), and the
+    // buffer is stored back with one bulk tensor store.  Two buffers alternate across chunks.
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int et = threadIdx.x - 192;       // 0..127 within the epilogue group
+    const int r = q * 32 + lane;            // accumulator row = pixel within the tile
+    const int CW = p.chunk_w;               // 32 (128B swizzle) or 16 (64B swizzle) channels per chunk
+    const int nchunks = p.tile_n / CW;
+    const uint32_t chunk_bytes = 128u * (uint32_t)CW * 4u;
+    // swizzled position of 16-byte piece k of this thread's row
+    const int sw = (CW == 32) ? (r & 7) : ((r >> 1) & 3);
     const int hw_t = p.th * p.tw;
-    const int n = n0 + r / hw_t;
-    const int y = y0 + (r / p.tw) % p.th;
-    const int x = x0 + r % p.tw;
-    const bool valid = n < p.n_img;
-    const long long pix = ((long long)n * p.H + y) * p.W + x;
-
     float a_scale = 1.f;
     int za = 0;
     if (MODE == MODE_W4A8) {
       a_scale = p.aq[0];
       za = (int)p.aq[1];
     }
-    for (int c0 = 0; c0 < p.tile_n; c0 += 16) {
-      uint32_t v[16];
-      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-      if (MODE == MODE_TF32 && (need_a_lo || need_b_lo)) {
-        uint32_t v2[16];
-        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(p.tile_n + c0), v2);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
-      }
-      tmem_ld_wait();
-      const int c = c_out0 + c0;
-      if (valid && c < p.cout) {
-        if (MODE == MODE_I8) {
-          int4* o = reinterpret_cast<int4*>(p.out_i32 + pix * p.cout + c);
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            o[j] = make_int4((int)v[4 * j], (int)v[4 * j + 1], (int)v[4 * j + 2], (int)v[4 * j + 3]);
-        } else {
-          float f[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            if (MODE == MODE_W4A8) {
-              const int acc = (int)v[j] - za * p.wsum[c + j];
-              f[j] = (float)acc * (a_scale * p.wscale[c + j]);
-            } else {
-              f[j] = __uint_as_float(v[j]);
-              if (p.wscale) f[j] *= p.wscale[c + j];
-            }
-            if (p.bias) f[j] += p.bias[c + j];
-          }
-          if (p.emb) {
-            const float* e = p.emb + (long long)n * p.emb_ld + c;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] += e[j];
-          }
-          if (p.res) {
-            const float4* rp = reinterpret_cast<const float4*>(p.res + pix * p.res_ld + c);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float4 rv = rp[j];
-              f[4 * j] += rv.x;
-              f[4 * j + 1] += rv.y;
-              f[4 * j + 2] += rv.z;
-              f[4 * j + 3] += rv.w;
-            }
-          }
-          float4* o = reinterpret_cast<float4*>(p.out + pix * p.out_ld + c);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) o[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+    uint32_t tcount = 0, g = 0;             // tiles / chunks processed by this CTA
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+      int mt = tile % tiles_m;
+      const int c_out0 = (tile / tiles_m) * p.tile_n;
+      const int tx = mt % tiles_x;
+      mt /= tiles_x;
+      const int ty = mt % tiles_y;
+      const int n0 = (mt / tiles_y) * p.tn, y0 = ty * p.th, x0 = tx * p.tw;
+      int n_l = n0 + r / hw_t;
+      if (n_l >= p.n_img) n_l = p.n_img - 1;   // rows past the batch are clipped by the TMA store
+
+      // residual prefetch for the first chunk overlaps the wait for the accumulator
+      if (et == 0) {
+        tma_store_wait_read<1>();             // the store that last used this buffer has read it
+        if (p.res) {
+          mbar_expect_tx(&res_full[g & 1], chunk_bytes);
+          tma_load_4d(ebuf + (g & 1) * chunk_bytes, &tmRes, &res_full[g & 1], c_out0, x0, y0, n0);
         }
       }
+      // per-channel constants of this N tile
+      named_bar_sync(1, 128);                 // previous tile is done with chp
+      for (int ch = et; ch < p.tile_n; ch += 128) {
+        const int c = c_out0 + ch;
+        float sc = 1.f, bi = 0.f;
+        int ws = 0;
+        if (MODE == MODE_W4A8) {
+          sc = a_scale * p.wscale[c];
+          ws = za * p.wsum[c];
+        } else if (p.wscale) {
+          sc = p.wscale[c];
+        }
+        if (p.bias) bi = p.bias[c];
+        chp[ch] = make_float4(sc, bi, __int_as_float(ws), 0.f);
+      }
+      const uint32_t as = tcount % ACC;
+      mbar_wait(&acc_full[as], (tcount / ACC) & 1u);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + as * acc_cols + ((uint32_t)(q * 32) << 16);
+      named_bar_sync(1, 128);                 // chp visible; first buffer known free
+
+      for (int ci = 0; ci < nchunks; ++ci, ++g) {
+        const int c0 = ci * CW;
+        uint8_t* buf = ebuf + (g & 1) * chunk_bytes;
+        uint32_t v[32];
+        tmem_ld16(tmem_d + (uint32_t)c0, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+        if (CW == 32) tmem_ld16(tmem_d + (uint32_t)(c0 + 16), *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
+        if (MODE == MODE_TF32 && two_acc) {
+          uint32_t v2[32];
+          tmem_ld16(tmem_d + (uint32_t)(p.tile_n + c0), *reinterpret_cast<uint32_t(*)[16]>(&v2[0]));
+          if (CW == 32)
+            tmem_ld16(tmem_d + (uint32_t)(p.tile_n + c0 + 16), *reinterpret_cast<uint32_t(*)[16]>(&v2[16]));
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
+        }
+        tmem_ld_wait();
+        if (ci == nchunks - 1) {
+          // last TMEM read of this tile: hand the accumulator stage back to the UMMA issuer
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[as]);
+        }
+        if (p.res) mbar_wait(&res_full[g & 1], (g >> 1) & 1u);
+        const float* embp = p.emb ? p.emb + (long long)n_l * p.emb_ld + c_out0 + c0 : nullptr;
+        const int npiece = CW / 4;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          if (k < npiece) {
+            float4* slot = reinterpret_cast<float4*>(buf + r * (CW * 4) + ((k ^ sw) << 4));
+            float4 o;
+            if (MODE == MODE_I8) {
+              o = make_float4(__uint_as_float(v[4 * k]), __uint_as_float(v[4 * k + 1]), __uint_as_float(v[4 * k + 2]),
+                              __uint_as_float(v[4 * k + 3]));
+            } else {
+              float f[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float4 cp = chp[c0 + 4 * k + j];
+                if (MODE == MODE_W4A8)
+                  f[j] = (float)((int)v[4 * k + j] - __float_as_int(cp.z)) * cp.x + cp.y;
+                else
+                  f[j] = __uint_as_float(v[4 * k + j]) * cp.x + cp.y;
+              }
+              if (embp) {
+                const float4 e4 = *reinterpret_cast<const float4*>(embp + 4 * k);
+                f[0] += e4.x, f[1] += e4.y, f[2] += e4.z, f[3] += e4.w;
+              }
+              if (p.res) {
+                const float4 r4 = *slot;
+                f[0] += r4.x, f[1] += r4.y, f[2] += r4.z, f[3] += r4.w;
+              }
+              o = make_float4(f[0], f[1], f[2], f[3]);
+            }
+            *slot = o;
+          }
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1, 128);               // all 128 rows of the chunk are in smem
+        if (et == 0) {
+          tma_store_4d(&tmOut, buf, c_out0 + c0, x0, y0, n0);
+          tma_store_commit();
+          if (ci + 1 < nchunks) {
+            tma_store_wait_read<1>();         // the other buffer's store has finished reading
+            if (p.res) {
+              mbar_expect_tx(&res_full[(g + 1) & 1], chunk_bytes);
+              tma_load_4d(ebuf + ((g + 1) & 1) * chunk_bytes, &tmRes, &res_full[(g + 1) & 1], c_out0 + c0 + CW, x0,
+                          y0, n0);
+            }
+          }
+        }
+        if (!p.res) named_bar_sync(1, 128);   // without a residual barrier, publish "next buffer is free"
+      }
     }
+    if (et == 0) tma_store_wait_all<0>();     // global writes complete before the CTA retires
   }
 
   tc_fence_before();
@@ -313,9 +409,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 // ---------------------------------------------------------------------------
 static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
-// largest multiple of 16 that divides cout and is <= 256 (prefer >= 64)
-static int pick_tile_n(int cout) {
-  for (int t = 256; t >= 16; t -= 16)
+// largest multiple of 16 that divides cout and is <= limit
+static int pick_tile_n(int cout, int limit = 256) {
+  for (int t = limit; t >= 16; t -= 16)
     if (cout % t == 0) return t;
   return 0;
 }
@@ -369,20 +465,20 @@ static int launch_igemm(tfmq_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap
     off += (uint32_t)p.tile_n * 64u;
   }
   p.stage_bytes = (off + 1023u) & ~1023u;
-  const uint32_t extra = 1024u /*alignment slack*/ + 256u /*barriers*/;
+  const uint32_t extra = 1024u /*alignment slack*/ + 2u * 128u * 32u * 4u /*epilogue chunks*/ + 256u * 16u /*chp*/ +
+                         256u /*barriers*/;
   const int kchunks = (p.cin + p.kchunk - 1) / p.kchunk;
   const int nkb = p.ksize * p.ksize * kchunks;
   int stages = (int)(((uint32_t)ctx->max_smem_optin - extra) / p.stage_bytes);
-  // two CTAs per SM (epilogue of one overlaps the main loop of the other) when >= 2 stages still fit
-  const int half = (int)(((uint32_t)ctx->max_smem_optin / 2 - 1024u - extra) / p.stage_bytes);
-  if (half >= 2) stages = half;
   if (stages > 6) stages = 6;
-  if (stages > nkb) stages = nkb;
   if (stages < 1) return tfmq_fail(ctx, TFMQ_ERR_SHAPE, "%s: tile does not fit shared memory", name);
+  (void)nkb;
   p.stages = stages;
   int acc_cols = p.tile_n;
   if (MODE == MODE_TF32 && (p.pass_flags & (PASS_LO_HI | PASS_HI_LO))) acc_cols *= 2;
-  p.tmem_cols = acc_cols <= 32 ? 32 : acc_cols <= 64 ? 64 : acc_cols <= 128 ? 128 : acc_cols <= 256 ? 256 : 512;
+  p.acc_stages = (2 * acc_cols <= 512) ? 2 : 1;
+  const int need = acc_cols * p.acc_stages;
+  p.tmem_cols = need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512;
   const size_t smem = (size_t)stages * p.stage_bytes + extra;
 
   auto kern = igemm_kernel<MODE>;
@@ -392,9 +488,33 @@ static int launch_igemm(tfmq_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap
     if (e != cudaSuccess) return tfmq_fail(ctx, TFMQ_ERR_CUDA, "%s: smem attr: %s", name, cudaGetErrorString(e));
     smem_set = smem;
   }
+  // epilogue tensor maps: output (and residual) as [cout][W][H][N] fp32 / s32 with pixel pitch ld
+  p.chunk_w = (p.tile_n % 32 == 0) ? 32 : 16;
+  CUtensorMap tmOut, tmRes;
+  {
+    const bool i32 = (MODE == MODE_I8);
+    const void* base = i32 ? (const void*)p.out_i32 : (const void*)p.out;
+    const cuuint64_t ld = i32 ? (cuuint64_t)p.cout : (cuuint64_t)p.out_ld;
+    cuuint64_t dims[4] = {(cuuint64_t)p.cout, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.n_img};
+    cuuint64_t str[3] = {ld * 4, (cuuint64_t)p.W * ld * 4, (cuuint64_t)p.H * p.W * ld * 4};
+    cuuint32_t box[4] = {(cuuint32_t)p.chunk_w, (cuuint32_t)p.tw, (cuuint32_t)p.th, (cuuint32_t)p.tn};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    const CUtensorMapSwizzle sw = p.chunk_w == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    int rc = encode(ctx, &tmOut, i32 ? CU_TENSOR_MAP_DATA_TYPE_INT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, dims,
+                    str, box, es, sw);
+    if (rc) return rc;
+    tmRes = tmOut;
+    if (p.res) {
+      cuuint64_t rstr[3] = {(cuuint64_t)p.res_ld * 4, (cuuint64_t)p.W * p.res_ld * 4,
+                            (cuuint64_t)p.H * p.W * p.res_ld * 4};
+      rc = encode(ctx, &tmRes, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, p.res, dims, rstr, box, es, sw);
+      if (rc) return rc;
+    }
+  }
   const int tiles_m = (p.W / p.tw) * (p.H / p.th) * ((p.n_img + p.tn - 1) / p.tn);
-  dim3 grid((unsigned)tiles_m, (unsigned)(p.cout / p.tile_n));
-  kern<<<grid, IGEMM_THREADS, smem, stream>>>(tmA, tmB, tmB2, p);
+  const int total = tiles_m * (p.cout / p.tile_n);
+  const int grid = total < ctx->sm_count ? total : ctx->sm_count;
+  kern<<<grid, IGEMM_THREADS, smem, stream>>>(tmA, tmB, tmB2, tmOut, tmRes, p);
   TFMQ_LAUNCH_CHECK(name);
   return TFMQ_OK;
 }
@@ -471,7 +591,7 @@ extern "C" int tfmq_conv_fp(tfmq_ctx* ctx, const tfmq_conv_fp_desc* d, void* str
   p.n_img = d->n, p.H = d->out_h, p.W = d->out_w, p.cin = d->cin, p.cout = d->cout;
   p.ksize = d->ksize, p.stride = d->stride, p.off = d->ksize == 3 ? -d->pad_lo : 0;
   p.th = g.th, p.tw = g.tw, p.tn = g.tn;
-  p.tile_n = pick_tile_n(d->cout);
+  p.tile_n = pick_tile_n(d->cout, d->passes == 3 ? 128 : 256);
   p.kchunk = 32, p.kslice = 8;
   p.pass_flags = PASS_HI_HI;
   if (d->passes == 3) p.pass_flags |= PASS_LO_HI | (d->w_lo ? PASS_HI_LO : 0);

@@ -25,7 +25,7 @@ struct IgemmParams {
   int cin, cout;
   int ksize, stride, off;  // input coord = out*stride + tap + off
   int th, tw, tn;          // tile = tn*th*tw = 128 output pixels
-  int tile_n, stages, tmem_cols;
+  int tile_n, stages, tmem_cols, acc_stages, chunk_w;
   int kchunk, kslice;  // channels per k-block / per UMMA
   uint32_t stage_bytes, offA_lo, offB, offB_lo, offP;
   int pass_flags;
@@ -44,11 +44,12 @@ struct IgemmParams {
   int32_t* out_i32;  // MODE_I8: raw accumulators [pixels][cout]
 };
 
-constexpr int IGEMM_THREADS = 192;
+constexpr int IGEMM_THREADS = 320;
 constexpr uint32_t IGEMM_A_BYTES = 128 * 128;
 
 template <int MODE>
 __global__ void igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                             const __grid_constant__ CUtensorMap tmB2, const IgemmParams p);
+                             const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmOut,
+                             const __grid_constant__ CUtensorMap tmRes, const IgemmParams p);
 
 }  // namespace tfmq
