@@ -23,8 +23,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
              const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmOut,
              const __grid_constant__ CUtensorMap tmRes, const IgemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // dynamic smem is only guaranteed 16-B aligned: round up to the 1024 B the 128B swizzle needs
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // dynamic smem is only guaranteed 16-B aligned: skip to the next 1024-B boundary (128B swizzle atoms).
+  // Pointer arithmetic on the __shared__ array (not an integer round trip) keeps the address space
+  // known to the compiler, so every access below is LDS/STS rather than a generic LD/ST.
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -87,7 +89,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       if (MODE == MODE_W4A8) tx_bytes += (uint32_t)p.tile_n * 64u;
       if (MODE == MODE_I8) tx_bytes += (uint32_t)p.tile_n * 128u;
       if (MODE == MODE_TF32) tx_bytes += (uint32_t)p.tile_n * 128u * (need_b_lo ? 2u : 1u);
-      uint32_t it = 0;
+      int s = 0;
+      uint32_t par = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         int mt = tile % tiles_m;
         const int c_out0 = (tile / tiles_m) * p.tile_n;
@@ -95,13 +98,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         mt /= tiles_x;
         const int ty = mt % tiles_y;
         const int n0 = (mt / tiles_y) * p.tn, y0 = ty * p.th, x0 = tx * p.tw;
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const int s = it % S;
-          const uint32_t par = (it / S) & 1u;
+        int kc = 0, kx = 0, ky = 0, tap = 0;
+        for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&empty[s], par ^ 1u);
           uint8_t* st = smem + (size_t)s * p.stage_bytes;
-          const int tap = kb / kchunks, kc = kb - tap * kchunks;
-          const int ky = tap / p.ksize, kx = tap - ky * p.ksize;
           mbar_expect_tx(&full_tma[s], tx_bytes);
           tma_load_4d(st, &tmA, &full_tma[s], kc * p.kchunk, x0 * p.stride + kx + p.off,
                       y0 * p.stride + ky + p.off, n0);
@@ -112,6 +112,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             tma_load_2d(st + p.offB, &tmB, &full_tma[s], tap * p.cin + kc * p.kchunk, c_out0);
             if (need_b_lo) tma_load_2d(st + p.offB_lo, &tmB2, &full_tma[s], tap * p.cin + kc * p.kchunk, c_out0);
           }
+          if (++kc == kchunks) {
+            kc = 0, ++tap;
+            if (++kx == p.ksize) kx = 0, ++ky;
+          }
+          if (++s == S) s = 0, par ^= 1u;
         }
       }
     }
@@ -119,7 +124,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     // ===================================================== UMMA issuer
     const uint32_t idesc = (MODE == MODE_TF32) ? idesc_tf32(128, (uint32_t)p.tile_n)
                                                : idesc_i8_u8s8(128, (uint32_t)p.tile_n);
-    uint32_t it = 0, tcount = 0;
+    uint32_t tcount = 0;
+    int s = 0;
+    uint32_t par = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
       const uint32_t as = tcount % ACC;
       mbar_wait(&acc_empty[as], ((tcount / ACC) & 1u) ^ 1u);   // epilogue has drained this stage
@@ -129,15 +136,13 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       // tensor-core accumulator adds them to a small running sum, not to the large main one
       const uint32_t tmem_lo = tmem_d + (uint32_t)p.tile_n;
       uint32_t accumulate = 0, accumulate_lo = 0;
-      for (int kb = 0; kb < nkb; ++kb, ++it) {
-        const int s = it % S;
-        const uint32_t par = (it / S) & 1u;
+      int kc = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait(&full_tma[s], par);
         mbar_wait(&full_xf[s], par);
         tc_fence_after();
         if (lane == 0) {
           const uint32_t st = smem_u32(smem + (size_t)s * p.stage_bytes);
-          const int kc = kb % kchunks;
           int rem = p.cin - kc * p.kchunk;
           if (rem > p.kchunk) rem = p.kchunk;
           const int nslice = rem / p.kslice;  // valid 32-byte K slices in this k-block
@@ -170,12 +175,15 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           if (kb == nkb - 1) umma_commit(&acc_full[as]);
         }
         __syncwarp();
+        if (++kc == kchunks) kc = 0;
+        if (++s == S) s = 0, par ^= 1u;
       }
     }
   } else if (warp < 6) {
     // ===================================================== transform warps (2..5)
     const int t = threadIdx.x - 64;  // 0..127
-    uint32_t it = 0;
+    int s = 0;
+    uint32_t par = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int c_out0 = (tile / tiles_m) * p.tile_n;
       if (MODE == MODE_W4A8) {
@@ -189,21 +197,24 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           if (row < p.tile_n && c_out0 + row < p.cout) z = p.wzp[c_out0 + row];
           zc[i] = 0x80808080u - z * 0x01010101u;
         }
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const int s = it % S;
-          const uint32_t par = (it / S) & 1u;
+        // row_i = (t >> 2) + 32 i: fixed per-thread offsets, +2048 B (packed) / +4096 B (s8 tile) per i
+        const uint32_t rd0 = p.offP + (uint32_t)(t >> 2) * 64u + (uint32_t)sub * 16u;
+        const uint32_t swz = (uint32_t)((t >> 2) & 7);
+        const uint32_t wr_lo = p.offB + (uint32_t)(t >> 2) * 128u + (((2u * sub) ^ swz) << 4);
+        const uint32_t wr_hi = p.offB + (uint32_t)(t >> 2) * 128u + (((2u * sub + 1u) ^ swz) << 4);
+        const int nrow_i = (p.tile_n - (t >> 2) + 31) >> 5;   // iterations with row < tile_n
+        int kc = 0;
+        for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&full_tma[s], par);
           uint8_t* st = smem + (size_t)s * p.stage_bytes;
-          const int kc = kb % kchunks;
           int rem = p.cin - kc * p.kchunk;
           if (rem > p.kchunk) rem = p.kchunk;
           const int nslice = rem >> 5;
           if (sub < nslice) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              const int row = (t + 128 * i) >> 2;
-              if (row < p.tile_n) {
-                const uint4 pk = *reinterpret_cast<const uint4*>(st + p.offP + row * 64 + sub * 16);
+              if (i < nrow_i) {
+                const uint4 pk = *reinterpret_cast<const uint4*>(st + rd0 + i * 2048);
                 uint4 lo, hi;
                 lo.x = ((pk.x & 0x0F0F0F0Fu) + zc[i]) ^ 0x80808080u;
                 lo.y = ((pk.y & 0x0F0F0F0Fu) + zc[i]) ^ 0x80808080u;
@@ -213,21 +224,19 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 hi.y = (((pk.y >> 4) & 0x0F0F0F0Fu) + zc[i]) ^ 0x80808080u;
                 hi.z = (((pk.z >> 4) & 0x0F0F0F0Fu) + zc[i]) ^ 0x80808080u;
                 hi.w = (((pk.w >> 4) & 0x0F0F0F0Fu) + zc[i]) ^ 0x80808080u;
-                uint8_t* brow = st + p.offB + row * 128;
-                const int sw = row & 7;
-                *reinterpret_cast<uint4*>(brow + (((2 * sub) ^ sw) << 4)) = lo;
-                *reinterpret_cast<uint4*>(brow + (((2 * sub + 1) ^ sw) << 4)) = hi;
+                *reinterpret_cast<uint4*>(st + wr_lo + i * 4096) = lo;
+                *reinterpret_cast<uint4*>(st + wr_hi + i * 4096) = hi;
               }
             }
           }
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) mbar_arrive(&full_xf[s]);
+          if (++kc == kchunks) kc = 0;
+          if (++s == S) s = 0, par ^= 1u;
         }
       } else if (MODE == MODE_TF32) {
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const int s = it % S;
-          const uint32_t par = (it / S) & 1u;
+        for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&full_tma[s], par);
           if (need_a_lo) {
             uint8_t* st = smem + (size_t)s * p.stage_bytes;
@@ -252,14 +261,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           }
           __syncwarp();
           if (lane == 0) mbar_arrive(&full_xf[s]);
+          if (++s == S) s = 0, par ^= 1u;
         }
       } else {
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const int s = it % S;
-          const uint32_t par = (it / S) & 1u;
+        for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&full_tma[s], par);
           __syncwarp();
           if (lane == 0) mbar_arrive(&full_xf[s]);
+          if (++s == S) s = 0, par ^= 1u;
         }
       }
     }
