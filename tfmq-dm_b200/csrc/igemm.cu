@@ -12,11 +12,13 @@ namespace tfmq {
 // ---------------------------------------------------------------------------
 // Persistent: grid = min(#tiles, #SMs); each CTA walks tiles t = blockIdx.x, +gridDim.x, ... with the
 // M index fastest, so CTAs running together share one weight tile in L2.
-//   warp 0      TMA producer
-//   warp 1      UMMA issuer (owns TMEM: 1 or 2 accumulator stages)
-//   warps 2-5   operand transform (int4 unpack / tf32 hi-lo split)
-//   warps 6-9   epilogue: TMEM -> registers -> per-warp smem transpose -> coalesced global I/O,
+//   warps 0-3   epilogue: TMEM -> registers -> swizzled smem chunk (+ TMA-prefetched residual) -> TMA store,
 //               overlapped with the next tile's main loop through the second accumulator stage
+//   warp 4      TMA producer
+//   warp 5      UMMA issuer (owns TMEM: 1 or 2 accumulator stages)
+//   warps 6-13  operand transform (int4 unpack / tf32 hi-lo split).  They are the critical path of the
+//               main loop, so they get the highest warp ids (the SM arbiter favours high ids) and the
+//               non-critical waits (producer, epilogue) back off with nanosleep instead of spinning.
 template <int MODE>
 __global__ void __launch_bounds__(IGEMM_THREADS, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -56,7 +58,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(&full_tma[s], 1);
-      mbar_init(&full_xf[s], 4);
+      mbar_init(&full_xf[s], IGEMM_XF_WARPS);
       mbar_init(&empty[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
@@ -71,7 +73,17 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     tma_prefetch_desc(&tmOut);
     if (p.res) tma_prefetch_desc(&tmRes);
   }
-  if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  if (warp == 5) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  if (MODE == MODE_W4A8) {
+    // rows [tile_n, tile_n+16) of every B stage: row tile_n = 0x01 bytes, the rest zero (swizzle-invariant)
+    for (int i = threadIdx.x; i < S * 16 * 8; i += IGEMM_THREADS) {
+      const int st_i = i / 128, rem = i - st_i * 128;
+      const uint32_t fill = (rem < 8) ? 0x01010101u : 0u;
+      *reinterpret_cast<uint4*>(smem + (size_t)st_i * p.stage_bytes + p.offB + (size_t)p.tile_n * 128 + rem * 16) =
+          make_uint4(fill, fill, fill, fill);
+    }
+    fence_proxy_async_smem();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -80,9 +92,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const bool need_a_lo = (MODE == MODE_TF32) && (p.pass_flags & PASS_LO_HI);
   const bool need_b_lo = (MODE == MODE_TF32) && (p.pass_flags & PASS_HI_LO);
   const bool two_acc = need_a_lo || need_b_lo;                 // tf32: separate accumulator for the small terms
-  const uint32_t acc_cols = (uint32_t)p.tile_n * (two_acc ? 2u : 1u);
+  const uint32_t acc_cols = (MODE == MODE_W4A8) ? (uint32_t)p.tile_n + 16u : (uint32_t)p.tile_n * (two_acc ? 2u : 1u);
 
-  if (warp == 0) {
+  if (warp == 4) {
     // ===================================================== TMA producer
     if (lane == 0) {
       uint32_t tx_bytes = IGEMM_A_BYTES;
@@ -100,7 +112,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const int n0 = (mt / tiles_y) * p.tn, y0 = ty * p.th, x0 = tx * p.tw;
         int kc = 0, kx = 0, ky = 0, tap = 0;
         for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait(&empty[s], par ^ 1u);
+          mbar_wait_relaxed(&empty[s], par ^ 1u);
           uint8_t* st = smem + (size_t)s * p.stage_bytes;
           mbar_expect_tx(&full_tma[s], tx_bytes);
           tma_load_4d(st, &tmA, &full_tma[s], kc * p.kchunk, x0 * p.stride + kx + p.off,
@@ -120,10 +132,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 5) {
     // ===================================================== UMMA issuer
-    const uint32_t idesc = (MODE == MODE_TF32) ? idesc_tf32(128, (uint32_t)p.tile_n)
-                                               : idesc_i8_u8s8(128, (uint32_t)p.tile_n);
+    // W4A8: the s8 B tile carries 16 extra rows; row tile_n is all ones, so accumulator column tile_n
+    // holds sum_k a[m][k] and the weight zero point can be applied in the epilogue instead of per code
+    const uint32_t umma_n = (uint32_t)p.tile_n + (MODE == MODE_W4A8 ? 16u : 0u);
+    const uint32_t idesc = (MODE == MODE_TF32) ? idesc_tf32(128, umma_n) : idesc_i8_u8s8(128, umma_n);
     uint32_t tcount = 0;
     int s = 0;
     uint32_t par = 0;
@@ -179,30 +193,23 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (++s == S) s = 0, par ^= 1u;
       }
     }
-  } else if (warp < 6) {
-    // ===================================================== transform warps (2..5)
-    const int t = threadIdx.x - 64;  // 0..127
+  } else if (warp >= 6) {
+    // ===================================================== transform warps (6..13)
+    const int t = threadIdx.x - 192;  // 0..255
     int s = 0;
     uint32_t par = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int c_out0 = (tile / tiles_m) * p.tile_n;
       if (MODE == MODE_W4A8) {
-        // this thread always unpacks the same rows: row_i = (t + 128*i) >> 2, K slice = t & 3
+        // 256 threads: piece (row, K slice) = ((t >> 2) + 64 i, t & 3); fixed per-thread offsets,
+        // +4096 B (packed) / +8192 B (s8 tile) per i.  Codes stay unsigned (0..15): two ANDs and a shift
+        // per packed word; the zero point is folded out through the ones row (see the UMMA issuer).
         const int sub = t & 3;
-        uint32_t zc[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int row = (t + 128 * i) >> 2;
-          uint32_t z = 0;
-          if (row < p.tile_n && c_out0 + row < p.cout) z = p.wzp[c_out0 + row];
-          zc[i] = 0x80808080u - z * 0x01010101u;
-        }
-        // row_i = (t >> 2) + 32 i: fixed per-thread offsets, +2048 B (packed) / +4096 B (s8 tile) per i
         const uint32_t rd0 = p.offP + (uint32_t)(t >> 2) * 64u + (uint32_t)sub * 16u;
         const uint32_t swz = (uint32_t)((t >> 2) & 7);
         const uint32_t wr_lo = p.offB + (uint32_t)(t >> 2) * 128u + (((2u * sub) ^ swz) << 4);
         const uint32_t wr_hi = p.offB + (uint32_t)(t >> 2) * 128u + (((2u * sub + 1u) ^ swz) << 4);
-        const int nrow_i = (p.tile_n - (t >> 2) + 31) >> 5;   // iterations with row < tile_n
+        const int nrow_i = (p.tile_n - (t >> 2) + 63) >> 6;   // iterations with row < tile_n
         int kc = 0;
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&full_tma[s], par);
@@ -211,21 +218,20 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           if (rem > p.kchunk) rem = p.kchunk;
           const int nslice = rem >> 5;
           if (sub < nslice) {
+            uint4 pkv[4];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
+            for (int i = 0; i < 4; ++i)
+              if (i < nrow_i) pkv[i] = *reinterpret_cast<const uint4*>(st + rd0 + i * 4096);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
               if (i < nrow_i) {
-                const uint4 pk = *reinterpret_cast<const uint4*>(st + rd0 + i * 2048);
+                const uint4 pk = pkv[i];
                 uint4 lo, hi;
-                lo.x = ((pk.x & 0x0F0F0F0Fu) + zc[i]) ^ 0x80808080u;
-                lo.y = ((pk.y & 0x0F0F0F0Fu) + zc[i]) ^ 0x80808080u;
-                lo.z = ((pk.z & 0x0F0F0F0Fu) + zc[i]) ^ 0x80808080u;
-                lo.w = ((pk.w & 0x0F0F0F0Fu) + zc[i]) ^ 0x80808080u;
-                hi.x = (((pk.x >> 4) & 0x0F0F0F0Fu) + zc[i]) ^ 0x80808080u;
-                hi.y = (((pk.y >> 4) & 0x0F0F0F0Fu) + zc[i]) ^ 0x80808080u;
-                hi.z = (((pk.z >> 4) & 0x0F0F0F0Fu) + zc[i]) ^ 0x80808080u;
-                hi.w = (((pk.w >> 4) & 0x0F0F0F0Fu) + zc[i]) ^ 0x80808080u;
-                *reinterpret_cast<uint4*>(st + wr_lo + i * 4096) = lo;
-                *reinterpret_cast<uint4*>(st + wr_hi + i * 4096) = hi;
+                lo.x = pk.x & 0x0F0F0F0Fu, lo.y = pk.y & 0x0F0F0F0Fu, lo.z = pk.z & 0x0F0F0F0Fu, lo.w = pk.w & 0x0F0F0F0Fu;
+                hi.x = (pk.x >> 4) & 0x0F0F0F0Fu, hi.y = (pk.y >> 4) & 0x0F0F0F0Fu;
+                hi.z = (pk.z >> 4) & 0x0F0F0F0Fu, hi.w = (pk.w >> 4) & 0x0F0F0F0Fu;
+                *reinterpret_cast<uint4*>(st + wr_lo + i * 8192) = lo;
+                *reinterpret_cast<uint4*>(st + wr_hi + i * 8192) = hi;
               }
             }
           }
@@ -243,8 +249,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             uint4* a = reinterpret_cast<uint4*>(st);
             uint4* al = reinterpret_cast<uint4*>(st + p.offA_lo);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int idx = t + 128 * i;
+            for (int i = 0; i < 4; ++i) {
+              const int idx = t + 256 * i;
               uint4 v = a[idx], h, l;
               h.x = v.x & 0xFFFFE000u;
               h.y = v.y & 0xFFFFE000u;
@@ -273,12 +279,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       }
     }
   } else {
-    // ===================================================== epilogue warps (6..9)
+    // ===================================================== epilogue warps (0..3)
     // All global I/O of the epilogue is TMA: the residual chunk is prefetched into a swizzled smem
     // buffer, every thread folds its accumulator row into it (conflict-free float4 accesses), and the
     // buffer is stored back with one bulk tensor store.  Two buffers alternate across chunks.
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
-    const int et = threadIdx.x - 192;       // 0..127 within the epilogue group
+    const int et = threadIdx.x;             // 0..127 within the epilogue group
     const int r = q * 32 + lane;            // accumulator row = pixel within the tile
     const int CW = p.chunk_w;               // 32 (128B swizzle) or 16 (64B swizzle) channels per chunk
     const int nchunks = p.tile_n / CW;
@@ -317,20 +323,29 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const int c = c_out0 + ch;
         float sc = 1.f, bi = 0.f;
         int ws = 0;
+        int zw = 0;
         if (MODE == MODE_W4A8) {
           sc = a_scale * p.wscale[c];
           ws = za * p.wsum[c];
+          zw = (int)p.wzp[c];
         } else if (p.wscale) {
           sc = p.wscale[c];
         }
         if (p.bias) bi = p.bias[c];
-        chp[ch] = make_float4(sc, bi, __int_as_float(ws), 0.f);
+        chp[ch] = make_float4(sc, bi, __int_as_float(ws), __int_as_float(zw));
       }
       const uint32_t as = tcount % ACC;
-      mbar_wait(&acc_full[as], (tcount / ACC) & 1u);
+      mbar_wait_relaxed(&acc_full[as], (tcount / ACC) & 1u);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + as * acc_cols + ((uint32_t)(q * 32) << 16);
       named_bar_sync(1, 128);                 // chp visible; first buffer known free
+      int a_sum = 0;                          // sum_k a[m][k] of this row (ones-row column)
+      if (MODE == MODE_W4A8) {
+        uint32_t sv[16];
+        tmem_ld16(tmem_d + (uint32_t)p.tile_n, sv);
+        tmem_ld_wait();
+        a_sum = (int)sv[0];
+      }
 
       for (int ci = 0; ci < nchunks; ++ci, ++g) {
         const int c0 = ci * CW;
@@ -371,7 +386,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               for (int j = 0; j < 4; ++j) {
                 const float4 cp = chp[c0 + 4 * k + j];
                 if (MODE == MODE_W4A8)
-                  f[j] = (float)((int)v[4 * k + j] - __float_as_int(cp.z)) * cp.x + cp.y;
+                  f[j] = (float)((int)v[4 * k + j] - __float_as_int(cp.w) * a_sum - __float_as_int(cp.z)) * cp.x + cp.y;
                 else
                   f[j] = __uint_as_float(v[4 * k + j]) * cp.x + cp.y;
               }
@@ -410,7 +425,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  if (warp == 5) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
 // ---------------------------------------------------------------------------
@@ -456,7 +471,7 @@ template <int MODE>
 static int launch_igemm(tfmq_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmB2,
                         IgemmParams& p, cudaStream_t stream, const char* name) {
   // shared-memory plan
-  const uint32_t bB = (uint32_t)p.tile_n * 128u;
+  const uint32_t bB = ((uint32_t)p.tile_n + (MODE == MODE_W4A8 ? 16u : 0u)) * 128u;
   uint32_t off = IGEMM_A_BYTES;
   p.offA_lo = p.offB_lo = p.offP = 0;
   if (MODE == MODE_TF32 && (p.pass_flags & PASS_LO_HI)) {
@@ -483,7 +498,7 @@ static int launch_igemm(tfmq_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap
   if (stages < 1) return tfmq_fail(ctx, TFMQ_ERR_SHAPE, "%s: tile does not fit shared memory", name);
   (void)nkb;
   p.stages = stages;
-  int acc_cols = p.tile_n;
+  int acc_cols = p.tile_n + (MODE == MODE_W4A8 ? 16 : 0);
   if (MODE == MODE_TF32 && (p.pass_flags & (PASS_LO_HI | PASS_HI_LO))) acc_cols *= 2;
   p.acc_stages = (2 * acc_cols <= 512) ? 2 : 1;
   const int need = acc_cols * p.acc_stages;
@@ -549,7 +564,7 @@ extern "C" int tfmq_conv_w4a8(tfmq_ctx* ctx, const tfmq_conv_w4a8_desc* d, void*
   p.n_img = d->n, p.H = d->h, p.W = d->w, p.cin = d->cin, p.cout = d->cout;
   p.ksize = d->ksize, p.stride = 1, p.off = 0;
   p.th = g.th, p.tw = g.tw, p.tn = g.tn;
-  p.tile_n = pick_tile_n(d->cout);
+  p.tile_n = pick_tile_n(d->cout, 240);   // + 16 rows for the activation-sum column, UMMA N <= 256
   p.kchunk = 128, p.kslice = 32;
   p.out = d->out, p.out_ld = d->out_ld, p.bias = d->bias, p.wscale = d->wdelta, p.wsum = d->wsum, p.wzp = d->wzp;
   p.aq = d->aq, p.emb = d->emb, p.emb_ld = d->emb_ld, p.res = d->res, p.res_ld = d->res_ld;

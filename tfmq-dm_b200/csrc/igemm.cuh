@@ -44,7 +44,8 @@ struct IgemmParams {
   int32_t* out_i32;  // MODE_I8: raw accumulators [pixels][cout]
 };
 
-constexpr int IGEMM_THREADS = 320;
+constexpr int IGEMM_XF_WARPS = 8;
+constexpr int IGEMM_THREADS = (6 + IGEMM_XF_WARPS) * 32;
 constexpr uint32_t IGEMM_A_BYTES = 128 * 128;
 
 template <int MODE>

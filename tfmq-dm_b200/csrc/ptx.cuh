@@ -41,6 +41,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// for waits that are not on the critical path: poll, then sleep, so the spinning warp does not take
+// issue slots from the warps it is waiting for
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(40);
+}
+
 // ------------------------------------------------------------ proxy fences
 // generic-proxy smem writes -> visible to the async proxy (TMA / UMMA reads)
 __device__ __forceinline__ void fence_proxy_async_smem() {
