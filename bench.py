@@ -240,12 +240,8 @@ def run_ours(args):
     qnn, eng, ts = build_quantised(dev, BATCH)
     if world > 1:
         # the one collective of the sampling path: rank 0's packed int4 weights / scales / FSC table -> all ranks
-        for q in eng.ql.values():
-            for name in ("packed", "wdelta", "wsum", "wzp_u8", "bias"):
-                t = getattr(q, name, None)
-                if t is not None:
-                    dist.broadcast(t, 0)
-        dist.broadcast(eng.table, 0)
+        from tfmq_b200.dist_utils import broadcast_tensors, engine_constants
+        broadcast_tensors(engine_constants(eng), 0)
     x_T = synth.latents((BATCH, 3, 64, 64), 100 + rank).to(dev)
     ctx = _lib.context(local)
 

@@ -1,0 +1,121 @@
+"""CPU: host-side logic of the drop-in surface (module surgery, state conventions, schedules,
+checkpoint plumbing) -- no kernel is launched."""
+import math
+
+import pytest
+import torch
+
+from helpers import fp_model, synth
+from oracle import quant_ref as Q
+from oracle import unet_ref as U
+
+
+def _qnn(kind, cali=True):
+    from tfmq_b200.quant.quant_layer import QMODE, Scaler
+    from tfmq_b200.quant.quant_model import QuantModel
+    wq = dict(bits=4, channel_wise=True, scaler=Scaler.MINMAX)
+    aq = dict(bits=8, channel_wise=False, scaler=Scaler.MINMAX, leaf_param=True)
+    return QuantModel(fp_model(kind), wq, aq, cali=cali, softmax_a_bit=8,
+                      aq_mode=[QMODE.NORMAL.value, QMODE.QDIFF.value])
+
+
+@pytest.mark.parametrize("kind,n_layers,n_emb", [("cifar", 97, 22), ("ldm", 73, 22)])
+def test_surgery_matches_reference_rules(kind, n_layers, n_emb):
+    from tfmq_b200.quant.quant_layer import QuantLayer
+    qnn = _qnn(kind)
+    names = [n for n, m in qnn.model.named_modules() if isinstance(m, QuantLayer)]
+    sd = fp_model(kind).state_dict()
+    assert names == U.wrapped_layer_names(sd)          # same leaves, same order as the oracle's restatement
+    assert len(names) == n_layers
+    emb = [n for n, m in qnn.model.named_modules() if isinstance(m, QuantLayer) and m.quant_emb]
+    assert len(emb) == n_emb
+    tib_layers = qnn.tib.temb_projs if kind == "cifar" else qnn.tib.emb_layers
+    assert len(tib_layers) == n_emb
+    # nothing named skip / op / shortcut / downsample.conv is wrapped; Conv1d stays a Conv1d
+    for n, m in qnn.model.named_modules():
+        leaf = n.split(".")[-1]
+        if isinstance(m, QuantLayer):
+            assert "skip" not in leaf and "op" not in leaf and "shortcut" not in leaf
+            assert not n.endswith("downsample.conv")
+    qnn.set_quant_state(True, True)
+    qnn.disable_out_quantization()
+    ql = qnn.quant_layers()
+    assert [l.ignore_recon for l in (ql[0], ql[1], ql[2], ql[3], ql[-1])] == [True, False, True, False, True]
+    assert ql[1].disable_aq and ql[3].disable_aq and not ql[4].disable_aq
+    qnn.set_quant_state(True, True)
+    assert not ql[0].use_wq and not ql[-1].use_wq and ql[1].use_wq       # ignore_recon overrides the toggle
+
+
+def test_state_dict_keys_follow_reference_checkpoint_format():
+    qnn = _qnn("cifar", cali=False)
+    keys = set(qnn.state_dict().keys())
+    assert "model.conv_in.w" in keys and "model.conv_in.b" in keys
+    assert "model.down.0.block.0.conv1.w" in keys and "model.down.1.attn.0.q.w" in keys
+    assert "model.down.0.downsample.conv.weight" in keys          # un-wrapped conv keeps torch's names
+    assert not any("original_w" in k for k in keys)                # plain tensor attribute, not a buffer
+
+
+def test_no_cpu_fallback():
+    qnn = _qnn("cifar", cali=False)
+    qnn.set_quant_state(True, True)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        qnn(torch.zeros(1, 3, 32, 32), torch.zeros(1))
+    from tfmq_b200.engine import StepEngine
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        StepEngine(qnn, batch=1)
+
+
+def test_ddim_coefficients_match_oracle():
+    from tfmq_b200 import samplers
+    betas = synth.ddim_betas()
+    seq = list(range(0, 1000, 20))
+    assert samplers.ddim_coefficients(seq, betas) == U.ddim_coef_table(seq, betas)
+
+
+def test_ldm_ddim_schedule_matches_reference_formulas():
+    import numpy as np
+    from tfmq_b200.samplers import DDIMSampler, make_beta_schedule, make_ddim_timesteps
+    s = DDIMSampler(None)
+    s.make_schedule(200)
+    assert list(s.ddim_timesteps[:3]) == [1, 6, 11] and s.ddim_timesteps[-1] == 996
+    betas = make_beta_schedule("linear", 1000, 0.0015, 0.0195)
+    ac = np.cumprod(1 - betas)
+    assert abs(float(s.ddim_alphas[0]) - ac[1]) < 1e-7 and abs(float(s.ddim_alphas_prev[0]) - ac[0]) < 1e-7
+    rows = s.coefficient_rows()
+    assert len(rows) == 200
+    sa, s1, sp, c2, c1 = rows[0]                       # first sampling step = largest t
+    assert abs(sa - math.sqrt(ac[996])) < 1e-6 and abs(s1 - math.sqrt(1 - ac[996])) < 1e-6
+    assert abs(sp - math.sqrt(ac[991])) < 1e-6 and abs(c2 - math.sqrt(1 - ac[991])) < 1e-6 and c1 == 0.0
+    assert list(make_ddim_timesteps(50)) == [i + 1 for i in range(0, 1000, 20)]
+
+
+def test_temp_decay_and_round_loss_match_oracle():
+    from tfmq_b200.quant.reconstruction_util import LinearTempDecay
+    d = LinearTempDecay(20000, 0.2, 20, 2)
+    for t in (1, 3999, 4000, 4001, 12000, 20000):
+        assert d(t) == Q.temp_decay(t, 20000, 0.2, 20, 2)
+    from tfmq_b200.quant.quant_layer import lp_loss, REDUCTION
+    a, b = synth.latents((4, 3, 8, 8), 1), synth.latents((4, 3, 8, 8), 2)
+    assert torch.equal(lp_loss(a, b), Q.lp_loss(a, b))
+    assert torch.equal(lp_loss(a, b, 2.4, REDUCTION.ALL), Q.lp_loss(a, b, 2.4, True))
+
+
+def test_act_tables_from_ckpt_and_fsc_index():
+    from tfmq_b200.quant.calibration import act_tables_from_ckpt
+    ckpt = {"weight": {}, "act_0": {"a": 0}, "act_1": {"a": 1}, "act_2": {"a": 2}}
+    assert [t["a"] for t in act_tables_from_ckpt(ckpt)] == [0, 1, 2]
+
+
+def test_adaround_quantizer_matches_oracle_on_cpu_math():
+    """AdaRoundQuantizer's pure-torch forward (hard / soft / init) is device-agnostic arithmetic."""
+    from tfmq_b200.quant.adaptive_rounding import RMODE, AdaRoundQuantizer
+    from tfmq_b200.quant.quant_layer import UniformAffineQuantizer
+    w = synth.latents((8, 4, 3, 3), 5) * 0.1
+    d, z = Q.channel_wise(Q.minmax_scale, w, 16)
+    u = UniformAffineQuantizer(bits=4, channel_wise=True)
+    u.delta, u.zero_point, u.init = d, z, True
+    a = AdaRoundQuantizer(u, w, RMODE.LEARNED_HARD_SIGMOID)
+    assert torch.equal(a.alpha.detach(), Q.adaround_init_alpha(w, d))
+    assert torch.equal(a(w), Q.adaround_fake_quant(w, d, z, a.alpha.detach(), 16))
+    a.soft_tgt = True
+    assert torch.equal(a(w).detach(), Q.adaround_fake_quant(w, d, z, a.alpha.detach(), 16, soft=True))

@@ -72,7 +72,9 @@ struct ActParams {
   int pix_per_cta;      // destination pixels (incl. halo) per CTA
 };
 
-__device__ __forceinline__ float silu_f(float v) { return v * (1.f / (1.f + expf(-v))); }
+// x*sigmoid(x); __expf / __frcp_rn keep the result within ~2 ulp of the accurate form, far below the
+// activation quantisation step, at a fraction of the instruction count
+__device__ __forceinline__ float silu_f(float v) { return v * __frcp_rn(1.f + __expf(-v)); }
 
 __global__ void __launch_bounds__(ACT_THREADS) act_prepare_kernel(const ActParams P) {
   extern __shared__ float sp[];  // [c] a = rstd*gamma, [c] b = beta - a*mean

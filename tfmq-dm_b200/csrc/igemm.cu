@@ -315,6 +315,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (p.res) {
           mbar_expect_tx(&res_full[g & 1], chunk_bytes);
           tma_load_4d(ebuf + (g & 1) * chunk_bytes, &tmRes, &res_full[g & 1], c_out0, x0, y0, n0);
+          // pull the rest of the residual tile into L2 while the main loop of this tile runs
+          for (int ci = 1; ci < nchunks; ++ci) tma_prefetch_l2_4d(&tmRes, c_out0 + ci * CW, x0, y0, n0);
         }
       }
       // per-channel constants of this N tile
@@ -615,7 +617,10 @@ extern "C" int tfmq_conv_fp(tfmq_ctx* ctx, const tfmq_conv_fp_desc* d, void* str
   p.n_img = d->n, p.H = d->out_h, p.W = d->out_w, p.cin = d->cin, p.cout = d->cout;
   p.ksize = d->ksize, p.stride = d->stride, p.off = d->ksize == 3 ? -d->pad_lo : 0;
   p.th = g.th, p.tw = g.tw, p.tn = g.tn;
-  p.tile_n = pick_tile_n(d->cout, d->passes == 3 ? 128 : 256);
+  // two accumulator stages (each hi + lo) need tile_n <= 128; long main loops (3x3 convs) amortise an
+  // un-overlapped epilogue better than they tolerate re-reading and re-splitting A once per N tile
+  const int nkb_est = d->ksize * d->ksize * ((d->cin + 31) / 32);
+  p.tile_n = pick_tile_n(d->cout, (d->passes == 3 && nkb_est < 48) ? 128 : 256);
   p.kchunk = 32, p.kslice = 8;
   p.pass_flags = PASS_HI_HI;
   if (d->passes == 3) p.pass_flags |= PASS_LO_HI | (d->w_lo ? PASS_HI_LO : 0);

@@ -17,74 +17,143 @@ __device__ __forceinline__ int warp_sum_i(int v) {
   return v;
 }
 
-// one warp per output element (m, o)
-__global__ void __launch_bounds__(256) linear_small_kernel(const tfmq_linear_desc d) {
-  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (wid >= d.m * d.out_f) return;
-  const int m = wid / d.out_f, o = wid - m * d.out_f;
+// grid (out chunks of 64, m); phase 1: the row's inputs are transformed ONCE (SiLU, act fake-quant) into
+// shared memory; phase 2: every warp produces 8 outputs, lanes striding over the input features.
+constexpr int LIN_THREADS = 256;
+constexpr int LIN_OUT_PER_CTA = 64;
+
+__global__ void __launch_bounds__(LIN_THREADS) linear_small_kernel(const tfmq_linear_desc d) {
+  extern __shared__ float xs[];                 // [in_f] transformed inputs (fp32, or integer codes - zp as fp32)
+  const int m = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float* x = d.x + (long long)m * d.x_ld;
-  float r;
-  if (d.w_f32) {
-    const float* w = d.w_f32 + (long long)o * d.in_f;
-    float acc = 0.f;
-    for (int i = lane; i < d.in_f; i += 32) {
-      float v = x[i];
-      if (d.silu_in) v = silu1(v);
-      if (d.aq) {
-        const float dl = d.aq[0], z = d.aq[1];
-        const float q = fminf(fmaxf(rintf(__fdiv_rn(v, dl)) + z, 0.f), 255.f);
-        v = dl * (q - z);
-      }
-      acc = fmaf(v, w[i], acc);
-    }
-    r = warp_sum(acc);
-  } else {
-    const uint8_t* cw = d.codes + (long long)o * d.in_f;
-    const int zw = (int)d.wzp_f[o];
+  float dl = 1.f, z = 0.f;
+  if (d.aq) dl = d.aq[0], z = d.aq[1];
+  for (int i = threadIdx.x; i < d.in_f; i += LIN_THREADS) {
+    float v = x[i];
+    if (d.silu_in) v = silu1(v);
     if (d.aq) {
-      const float dl = d.aq[0], z = d.aq[1];
-      const int za = (int)z;
-      int acc = 0;
-      for (int i = lane; i < d.in_f; i += 32) {
-        float v = x[i];
-        if (d.silu_in) v = silu1(v);
-        const int qa = (int)fminf(fmaxf(rintf(__fdiv_rn(v, dl)) + z, 0.f), 255.f);
-        acc += (qa - za) * ((int)cw[i] - zw);
+      const float q = fminf(fmaxf(rintf(__fdiv_rn(v, dl)) + z, 0.f), 255.f);
+      v = d.w_f32 ? dl * (q - z) : (q - z);     // integer path keeps the exact (code - zp)
+    }
+    xs[i] = v;
+  }
+  __syncthreads();
+  // 8 outputs per warp, all in flight at once: the feature loop is outermost so every iteration issues 8
+  // independent weight loads (the per-output loops were latency-bound)
+  constexpr int OPW = LIN_OUT_PER_CTA / 8;
+  const int o0 = blockIdx.x * LIN_OUT_PER_CTA + warp * OPW;
+  float facc[OPW];
+  int iacc[OPW];
+#pragma unroll
+  for (int oo = 0; oo < OPW; ++oo) facc[oo] = 0.f, iacc[oo] = 0;
+  const bool int_path = !d.w_f32 && d.aq;
+  for (int i = lane; i < d.in_f; i += 32) {
+    const float xv = xs[i];
+#pragma unroll
+    for (int oo = 0; oo < OPW; ++oo) {
+      const int o = min(o0 + oo, d.out_f - 1);
+      if (d.w_f32) {
+        facc[oo] = fmaf(xv, d.w_f32[(long long)o * d.in_f + i], facc[oo]);
+      } else {
+        const int wv = (int)d.codes[(long long)o * d.in_f + i] - (int)d.wzp_f[o];
+        if (int_path)
+          iacc[oo] += (int)xv * wv;
+        else
+          facc[oo] = fmaf(xv, (float)wv, facc[oo]);
       }
-      r = (float)warp_sum_i(acc) * (dl * d.wdelta[o]);
-    } else {
-      float acc = 0.f;
-      for (int i = lane; i < d.in_f; i += 32) {
-        float v = x[i];
-        if (d.silu_in) v = silu1(v);
-        acc = fmaf(v, (float)((int)cw[i] - zw), acc);
-      }
-      r = warp_sum(acc) * d.wdelta[o];
     }
   }
-  if (lane == 0) {
-    if (d.bias) r += d.bias[o];
-    d.out[(long long)m * d.out_ld + o] = r;
+#pragma unroll
+  for (int oo = 0; oo < OPW; ++oo) {
+    const int o = o0 + oo;
+    float r = int_path ? (float)warp_sum_i(iacc[oo]) : warp_sum(facc[oo]);
+    if (o < d.out_f && lane == 0) {
+      if (!d.w_f32) r *= int_path ? (dl * d.wdelta[o]) : d.wdelta[o];
+      if (d.bias) r += d.bias[o];
+      d.out[(long long)m * d.out_ld + o] = r;
+    }
   }
 }
 
-// conv_in: NCHW (cin<=4) -> NHWC, 3x3 pad 1.  thread per (pixel, cout)
+// conv_in: NCHW (cin<=4) -> NHWC, 3x3 pad 1.  CTA = 16 pixels x 16 channel groups; weights transposed in
+// smem as ws[tap*cin][cout] so each thread reads float4 of 4 consecutive output channels.
+constexpr int CIN_PIX = 16;
 __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                       const float* __restrict__ bias, int n, int h, int wd, int cin,
                                                       int cout, float* __restrict__ out, long long out_ld) {
-  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  const long long total = (long long)n * h * wd * cout;
-  if (idx >= total) return;
-  const int co = (int)(idx % cout);
-  long long pix = idx / cout;
+  extern __shared__ float ws[];                 // [cin*9][cout]
+  const int K = cin * 9;
+  for (int i = threadIdx.x; i < K * cout; i += 256) {
+    const int co = i / K, k = i - co * K;       // w is [co][ci][ky][kx] = [co][k]
+    ws[k * cout + co] = w[i];
+  }
+  __syncthreads();
+  const long long total = (long long)n * h * wd;
+  const long long pix = blockIdx.x * (long long)CIN_PIX + (threadIdx.x >> 4);
+  if (pix >= total) return;
+  const int cg = threadIdx.x & 15;
   const int xx = (int)(pix % wd);
   const int yy = (int)((pix / wd) % h);
   const int nn = (int)(pix / ((long long)wd * h));
-  float acc = bias ? bias[co] : 0.f;
-  for (int ci = 0; ci < cin; ++ci) {
-    const float* xp = x + ((long long)nn * cin + ci) * h * wd;
-    const float* wp = w + ((long long)co * cin + ci) * 9;
+  float in[36];
+#pragma unroll
+  for (int k = 0; k < 36; ++k) in[k] = 0.f;
+#pragma unroll
+  for (int ci = 0; ci < 4; ++ci) {
+    if (ci < cin) {
+      const float* xp = x + ((long long)nn * cin + ci) * h * wd;
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int y = yy + ky - 1;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int xq = xx + kx - 1;
+          if (y >= 0 && y < h && xq >= 0 && xq < wd) in[ci * 9 + ky * 3 + kx] = xp[(long long)y * wd + xq];
+        }
+      }
+    }
+  }
+  for (int co = cg * 4; co < cout; co += 64) {
+    float4 acc = bias ? *reinterpret_cast<const float4*>(bias + co) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < 36; ++k) {
+      if (k < K) {
+        const float4 w4 = *reinterpret_cast<const float4*>(ws + k * cout + co);
+        const float v = in[k];
+        acc.x = fmaf(v, w4.x, acc.x), acc.y = fmaf(v, w4.y, acc.y);
+        acc.z = fmaf(v, w4.z, acc.z), acc.w = fmaf(v, w4.w, acc.w);
+      }
+    }
+    *reinterpret_cast<float4*>(out + pix * out_ld + co) = acc;
+  }
+}
+
+// conv_out: NHWC -> NCHW (cout<=4), 3x3 pad 1.  CTA = 8 warps x 8 pixels each; weights in smem as
+// float4 per (tap, ci) over the (<=4) output channels; lanes stride over ci (coalesced input rows).
+constexpr int COUT_PIX_PER_WARP = 8;
+__global__ void __launch_bounds__(256) conv_out_kernel(const float* __restrict__ x, long long x_ld,
+                                                       const float* __restrict__ w, const float* __restrict__ bias,
+                                                       int n, int h, int wd, int cin, int cout,
+                                                       float* __restrict__ out) {
+  extern __shared__ float4 w4s[];               // [9][cin]
+  for (int i = threadIdx.x; i < 9 * cin; i += 256) {
+    const int tap = i / cin, ci = i - tap * cin;
+    float t[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int co = 0; co < cout; ++co) t[co] = w[((long long)co * cin + ci) * 9 + tap];
+    w4s[i] = make_float4(t[0], t[1], t[2], t[3]);
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long total = (long long)n * h * wd;
+  const long long p0 = (blockIdx.x * 8LL + warp) * COUT_PIX_PER_WARP;
+  for (int pp = 0; pp < COUT_PIX_PER_WARP; ++pp) {
+    const long long pix = p0 + pp;
+    if (pix >= total) break;
+    const int xx = (int)(pix % wd);
+    const int yy = (int)((pix / wd) % h);
+    const int nn = (int)(pix / ((long long)wd * h));
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
       const int y = yy + ky - 1;
@@ -93,45 +162,19 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ 
       for (int kx = 0; kx < 3; ++kx) {
         const int xq = xx + kx - 1;
         if (xq < 0 || xq >= wd) continue;
-        acc = fmaf(xp[(long long)y * wd + xq], wp[ky * 3 + kx], acc);
+        const float* xp = x + (((long long)nn * h + y) * wd + xq) * x_ld;
+        const float4* wp = w4s + (ky * 3 + kx) * cin;
+        for (int ci = lane; ci < cin; ci += 32) {
+          const float v = xp[ci];
+          const float4 w4 = wp[ci];
+          acc.x = fmaf(v, w4.x, acc.x), acc.y = fmaf(v, w4.y, acc.y);
+          acc.z = fmaf(v, w4.z, acc.z), acc.w = fmaf(v, w4.w, acc.w);
+        }
       }
     }
-  }
-  out[pix * out_ld + co] = acc;
-}
-
-// conv_out: NHWC -> NCHW (cout<=4), 3x3 pad 1.  warp per output pixel, lanes over cin
-__global__ void __launch_bounds__(256) conv_out_kernel(const float* __restrict__ x, long long x_ld,
-                                                       const float* __restrict__ w, const float* __restrict__ bias,
-                                                       int n, int h, int wd, int cin, int cout,
-                                                       float* __restrict__ out) {
-  const long long wid = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  const long long total = (long long)n * h * wd;
-  if (wid >= total) return;
-  const int xx = (int)(wid % wd);
-  const int yy = (int)((wid / wd) % h);
-  const int nn = (int)(wid / ((long long)wd * h));
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int ky = 0; ky < 3; ++ky) {
-    const int y = yy + ky - 1;
-    if (y < 0 || y >= h) continue;
-    for (int kx = 0; kx < 3; ++kx) {
-      const int xq = xx + kx - 1;
-      if (xq < 0 || xq >= wd) continue;
-      const float* xp = x + (((long long)nn * h + y) * wd + xq) * x_ld;
-      for (int ci = lane; ci < cin; ci += 32) {
-        const float v = xp[ci];
-#pragma unroll
-        for (int co = 0; co < 4; ++co)
-          if (co < cout) acc[co] = fmaf(v, w[(((long long)co * cin + ci) * 3 + ky) * 3 + kx], acc[co]);
-      }
-    }
-  }
-#pragma unroll
-  for (int co = 0; co < 4; ++co) {
-    const float r = warp_sum(acc[co]);
-    if (lane == 0 && co < cout) out[(((long long)nn * cout + co) * h + yy) * wd + xx] = r + (bias ? bias[co] : 0.f);
+    const float r0 = warp_sum(acc.x), r1 = warp_sum(acc.y), r2 = warp_sum(acc.z), r3 = warp_sum(acc.w);
+    const float rl = lane == 0 ? r0 : lane == 1 ? r1 : lane == 2 ? r2 : r3;
+    if (lane < cout) out[(((long long)nn * cout + lane) * h + yy) * wd + xx] = rl + (bias ? bias[lane] : 0.f);
   }
 }
 
@@ -145,9 +188,9 @@ extern "C" int tfmq_linear_small(tfmq_ctx* ctx, const tfmq_linear_desc* d, void*
   TFMQ_REQUIRE(d->w_f32 || (d->codes && d->wzp_f && d->wdelta), TFMQ_ERR_ARG, "linear_small: weights missing");
   TFMQ_REQUIRE(d->m >= 0 && d->m <= 4096 && d->in_f > 0 && d->out_f > 0, TFMQ_ERR_SHAPE, "linear_small: m=%d", d->m);
   if (d->m == 0) return TFMQ_OK;
-  const long long warps = (long long)d->m * d->out_f;
-  const int blocks = (int)((warps * 32 + 255) / 256);
-  linear_small_kernel<<<blocks, 256, 0, tfmq_stream(stream)>>>(*d);
+  TFMQ_REQUIRE(d->in_f <= 8192, TFMQ_ERR_SHAPE, "linear_small: in_f %d > 8192", d->in_f);
+  dim3 grid((d->out_f + LIN_OUT_PER_CTA - 1) / LIN_OUT_PER_CTA, d->m);
+  linear_small_kernel<<<grid, LIN_THREADS, (size_t)d->in_f * sizeof(float), tfmq_stream(stream)>>>(*d);
   TFMQ_LAUNCH_CHECK("linear_small");
   return TFMQ_OK;
 }
@@ -157,10 +200,14 @@ extern "C" int tfmq_conv_in(tfmq_ctx* ctx, const float* x_nchw, const float* w, 
   if (!ctx) return TFMQ_ERR_ARG;
   TFMQ_REQUIRE(x_nchw && w && out, TFMQ_ERR_ARG, "conv_in: null pointer");
   TFMQ_REQUIRE(cin >= 1 && cin <= 4, TFMQ_ERR_SHAPE, "conv_in: cin %d > 4", cin);
-  const long long total = (long long)n * h * wd * cout;
+  TFMQ_REQUIRE(cout % 4 == 0 && out_ld % 4 == 0 && cout * cin * 9 * 4 <= 48 * 1024, TFMQ_ERR_SHAPE,
+               "conv_in: cout %d", cout);
+  TFMQ_REQUIRE(((uintptr_t)out & 15) == 0 && (!bias || ((uintptr_t)bias & 15) == 0), TFMQ_ERR_ARG,
+               "conv_in: out / bias must be 16-byte aligned");
+  const long long total = (long long)n * h * wd;
   if (total == 0) return TFMQ_OK;
-  conv_in_kernel<<<(unsigned)((total + 255) / 256), 256, 0, tfmq_stream(stream)>>>(x_nchw, w, bias, n, h, wd, cin,
-                                                                                  cout, out, out_ld);
+  conv_in_kernel<<<(unsigned)((total + CIN_PIX - 1) / CIN_PIX), 256, (size_t)cout * cin * 9 * sizeof(float),
+                   tfmq_stream(stream)>>>(x_nchw, w, bias, n, h, wd, cin, cout, out, out_ld);
   TFMQ_LAUNCH_CHECK("conv_in");
   return TFMQ_OK;
 }
@@ -170,10 +217,12 @@ extern "C" int tfmq_conv_out(tfmq_ctx* ctx, const float* x, int64_t x_ld, const 
   if (!ctx) return TFMQ_ERR_ARG;
   TFMQ_REQUIRE(x && w && out_nchw, TFMQ_ERR_ARG, "conv_out: null pointer");
   TFMQ_REQUIRE(cout >= 1 && cout <= 4, TFMQ_ERR_SHAPE, "conv_out: cout %d > 4", cout);
+  TFMQ_REQUIRE(9 * cin * 16 <= 48 * 1024, TFMQ_ERR_SHAPE, "conv_out: cin %d too large", cin);
   const long long total = (long long)n * h * wd;
   if (total == 0) return TFMQ_OK;
-  conv_out_kernel<<<(unsigned)((total * 32 + 255) / 256), 256, 0, tfmq_stream(stream)>>>(x, x_ld, w, bias, n, h, wd,
-                                                                                        cin, cout, out_nchw);
+  const long long per_cta = 8LL * COUT_PIX_PER_WARP;
+  conv_out_kernel<<<(unsigned)((total + per_cta - 1) / per_cta), 256, (size_t)9 * cin * sizeof(float4),
+                    tfmq_stream(stream)>>>(x, x_ld, w, bias, n, h, wd, cin, cout, out_nchw);
   TFMQ_LAUNCH_CHECK("conv_out");
   return TFMQ_OK;
 }

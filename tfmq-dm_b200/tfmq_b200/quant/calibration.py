@@ -226,10 +226,8 @@ def cali_model_multi(gpu: int, dist_backend: str, world_size: int, dist_url: str
     qnn.eval()
 
     def shard(data, per):
-        """rank-th 1/world slice inside every consecutive block of `per` samples (reference :269-282)."""
-        n = data[0].shape[0]
-        per_rank = per // world_size
-        idx = torch.cat([torch.arange(b + rank * per_rank, b + (rank + 1) * per_rank) for b in range(0, n, per)])
+        from ..dist_utils import shard_interval_indices
+        idx = shard_interval_indices(data[0].shape[0], per, rank, world_size)
         return tuple(x[idx] for x in data)
 
     w_shard = shard(w_cali_data, interval) if w_cali_data[0].shape[0] >= interval else w_cali_data

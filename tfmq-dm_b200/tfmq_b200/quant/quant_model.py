@@ -108,14 +108,9 @@ class QuantModel(nn.Module):
     def synchorize_activation_statistics(self) -> None:
         """Average every initialised activation delta over the ranks: one all-reduce of a
         [n_layers] vector instead of the reference's one call per layer (reference :127-132)."""
-        import torch.distributed as dist
-        deltas = [m.aqtizer.delta for m in self.modules() if isinstance(m, QuantLayer) and m.aqtizer.delta is not None]
-        if not deltas or not dist.is_initialized():
-            return
-        flat = torch.stack([d.detach().reshape(()) for d in deltas]) / dist.get_world_size()
-        dist.all_reduce(flat)
-        for d, v in zip(deltas, flat):
-            d.data.copy_(v)
+        from ..dist_utils import allaverage_
+        allaverage_([m.aqtizer.delta for m in self.modules()
+                     if isinstance(m, QuantLayer) and m.aqtizer.delta is not None])
 
     def set_running_stat(self, running_stat: bool = False) -> None:
         for m in self.model.modules():

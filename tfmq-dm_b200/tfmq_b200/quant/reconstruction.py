@@ -90,13 +90,8 @@ def _adaround_loop(forward, layers: List[QuantLayer], cached_inputs, cached_outp
         grads = torch.autograd.grad(rec, leaves, allow_unused=True)
         grads = [g if g is not None else torch.zeros_like(l_) for g, l_ in zip(grads, leaves)]
         if world > 1:
-            import torch.distributed as dist
-            flat = torch.cat([g.reshape(-1) for g in grads])
-            dist.all_reduce(flat)
-            off = 0
-            for i, g in enumerate(grads):
-                grads[i] = flat[off:off + g.numel()].view_as(g)
-                off += g.numel()
+            from ..dist_utils import allreduce_flat_
+            grads = allreduce_flat_(grads)
         b = decay(it) if it >= loss_start else 0.0
         log = it % print_freq == 0
         if log:
