@@ -329,6 +329,32 @@ def ldm_golden():
     print("ldm4_w4a8.pt written")
 
 
+def cali_schema():
+    """G9: run the reference's cali_model on a tiny synthetic set and record the checkpoint's key set and
+    shapes (the on-disk format the drop-in must read and write)."""
+    from ddim.models.diffusion import Model
+    from quant.calibration import cali_model
+    from quant.reconstruction_util import RLOSS
+    from tfmq_b200.host.ddim_unet import cifar10_config
+    t0 = time.time()
+    fp = Model(cifar10_config())
+    fp.eval()
+    synth.fill_state_dict(fp, SEED)
+    wq, aq = wq_aq()
+    qnn = QuantModel(fp, wq, aq, cali=True, softmax_a_bit=8, aq_mode=[QMODE.NORMAL.value, QMODE.QDIFF.value])
+    qnn.eval()
+    w_cali = (synth.latents((8, 3, 32, 32), 31), torch.randint(0, 1000, (8,), generator=torch.Generator().manual_seed(1)).float())
+    a_cali = (synth.latents((32, 3, 32, 32), 32), torch.cat([torch.full((16,), 980.0), torch.full((16,), 960.0)]))
+    kwargs = dict(iters=2, batch_size=4, w=0.01, asym=True, warmup=0.2, opt_mode=RLOSS.MSE, multi_gpu=False)
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "c.pth")
+        cali_model(qnn, w_cali, a_cali, use_aq=True, path=path, running_stat=True, interval=16, **kwargs)
+        ckpt = torch.load(path, map_location="cpu", weights_only=False)
+    schema = {k: {kk: tuple(v.shape) for kk, v in d.items()} for k, d in ckpt.items()}
+    torch.save(schema, os.path.join(HERE, "cali_schema.pt"))
+    print("cali_schema.pt written", {k: len(v) for k, v in schema.items()}, time.time() - t0)
+
+
 if __name__ == "__main__":
     what = sys.argv[1:] or ["kats", "cifar", "ldm"]
     if "kats" in what:
@@ -337,3 +363,5 @@ if __name__ == "__main__":
         cifar_golden()
     if "ldm" in what:
         ldm_golden()
+    if "schema" in what:
+        cali_schema()

@@ -1,0 +1,98 @@
+"""GPU: the PTQ calibration passes through the drop-in API (cali_model -> checkpoint -> load_cali_model ->
+step engine), against the reference's checkpoint schema (tests/golden/cali_schema.pt, produced by the
+reference's own cali_model on the same tiny synthetic set)."""
+import os
+import tempfile
+
+import pytest
+import torch
+
+from helpers import fp_model, load_golden, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _data():
+    w_cali = (synth.latents((8, 3, 32, 32), 31),
+              torch.randint(0, 1000, (8,), generator=torch.Generator().manual_seed(1)).float())
+    a_cali = (synth.latents((32, 3, 32, 32), 32), torch.cat([torch.full((16,), 980.0), torch.full((16,), 960.0)]))
+    return w_cali, a_cali
+
+
+def _qnn(dev, cali):
+    from tfmq_b200.quant.quant_layer import QMODE, Scaler
+    from tfmq_b200.quant.quant_model import QuantModel
+    wq = dict(bits=4, channel_wise=True, scaler=Scaler.MINMAX)
+    aq = dict(bits=8, channel_wise=False, scaler=Scaler.MINMAX, leaf_param=True)
+    q = QuantModel(fp_model("cifar").to(dev), wq, aq, cali=cali, softmax_a_bit=8,
+                   aq_mode=[QMODE.NORMAL.value, QMODE.QDIFF.value])
+    q.eval()
+    return q
+
+
+def test_cali_model_checkpoint_schema_and_reload(dev):
+    from tfmq_b200.quant.calibration import act_tables_from_ckpt, cali_model, load_cali_model
+    from tfmq_b200.quant.reconstruction_util import RLOSS
+    from tfmq_b200.samplers import generalized_steps
+    schema = load_golden("cali_schema.pt")
+    w_cali, a_cali = _data()
+    qnn = _qnn(dev, cali=True)
+    torch.manual_seed(0)
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "c.pth")
+        ckpt = cali_model(qnn, w_cali, a_cali, use_aq=True, path=path, running_stat=True, interval=16, iters=2,
+                          batch_size=4, w=0.01, asym=True, warmup=0.2, opt_mode=RLOSS.MSE, multi_gpu=False)
+        on_disk = torch.load(path, map_location="cpu", weights_only=False)
+    mine = {k: {kk: tuple(v.shape) for kk, v in d.items()} for k, d in on_disk.items()}
+    assert set(mine) == set(schema)
+    for part in schema:
+        missing = set(schema[part]) - set(mine[part])
+        extra = set(mine[part]) - set(schema[part])
+        assert not missing and not extra, (part, sorted(missing)[:5], sorted(extra)[:5])
+        for k, shp in schema[part].items():
+            assert mine[part][k] == shp, (part, k, mine[part][k], shp)
+    # the checkpoint drives sampling through a freshly built model: AdaRound detected by 'alpha' keys
+    q2 = _qnn(dev, cali=False)
+    x = synth.latents((2, 3, 32, 32), 40)
+    load_cali_model(q2, (x, torch.full((2,), 980.0)), use_aq=True, ckpt=ckpt)
+    from tfmq_b200.quant.adaptive_rounding import AdaRoundQuantizer
+    assert isinstance(q2.model.down[0].block[0].conv2.wqtizer, AdaRoundQuantizer)
+    assert torch.equal(q2.model.down[0].block[0].conv2.wqtizer.alpha.detach().cpu(),
+                       ckpt["weight"]["model.down.0.block.0.conv2.wqtizer.alpha"])
+    assert len(act_tables_from_ckpt(ckpt)) == 2
+    seq = [960, 980]
+    xs, x0, _, _ = generalized_steps(x.to(dev), seq, q2, synth.ddim_betas().to(dev), eta=0.0, tot=20, cali_ckpt=ckpt,
+                                     t_max=1)
+    assert torch.isfinite(xs[-1]).all() and xs[-1].shape == x.shape
+
+
+def test_block_reconstruction_reduces_the_loss(dev):
+    """AdaRound on one QuantResnetBlock with the fused kernels: the reconstruction error of the hard-rounded
+    block after optimisation is lower than with round-to-nearest."""
+    from tfmq_b200.quant.data_utill import save_inout
+    from tfmq_b200.quant.quant_layer import lp_loss
+    from tfmq_b200.quant.reconstruction import block_reconstruction
+    from tfmq_b200.quant.reconstruction_util import RLOSS
+    qnn = _qnn(dev, cali=True)
+    w_cali = (synth.latents((64, 3, 32, 32), 51),
+              torch.randint(0, 1000, (64,), generator=torch.Generator().manual_seed(2)).float())
+    qnn.set_quant_state(True, False)
+    with torch.no_grad():
+        qnn(*(d[:8].to(dev) for d in w_cali))
+    qnn.disable_out_quantization()
+    blk = qnn.model.down[1].block[0]
+    ins, outs = save_inout(qnn, blk, w_cali, asym=False, use_act=False, batch_size=32)
+
+    def err():
+        qnn.set_quant_state(False, False)
+        blk.set_quant_state(True, False)
+        blk.eval()
+        with torch.no_grad():
+            return lp_loss(blk(*ins), outs).item()
+    before = err()
+    torch.manual_seed(0)
+    block_reconstruction(qnn, blk, w_cali, batch_size=32, iters=300, w=0.01, opt_mode=RLOSS.MSE, asym=False,
+                         b_range=(20, 2), warmup=0.2, multi_gpu=False)
+    after = err()
+    print(f"block reconstruction: lp_loss nearest {before:.5f} -> AdaRound {after:.5f}")
+    assert after < before

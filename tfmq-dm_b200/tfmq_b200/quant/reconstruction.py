@@ -153,7 +153,13 @@ def tib_reconstruction(block: BaseQuantBlock, cali_data, batch_size: int = 32, i
                        p: float = 2.0, multi_gpu: bool = True, keep_gpu=True) -> None:
     """TIAR: all time-embedding projections reconstructed jointly against the tuple of their FP outputs."""
     block.set_quant_state(use_wq=True, use_aq=use_aq)
-    layers = [m for m in dict.fromkeys(unit_layers_all(block)) if not m.ignore_recon]
+    every = list(dict.fromkeys(unit_layers_all(block)))
+    layers = [m for m in every if not m.ignore_recon]
+    for m in every:
+        # the reference swaps EVERY TIB layer to AdaRound (:233-253), including the fp first layer whose alpha
+        # never receives a gradient; keep the same checkpoint schema without optimising it
+        if m.ignore_recon and not isinstance(m.wqtizer, AdaRoundQuantizer) and m.wqtizer.delta is not None:
+            m.wqtizer = AdaRoundQuantizer(uaqtizer=m.wqtizer, rmode=RMODE.LEARNED_HARD_SIGMOID, w=m.original_w.data)
     _common(block, block, cali_data, batch_size, iters, w, opt_mode, asym, include_act_func, b_range, warmup, use_aq,
             p, multi_gpu, keep_gpu, layers, block, block)
 
