@@ -222,6 +222,27 @@ def int8_cublas_tops(dev):
         return None
 
 
+def int8_pipeline_tops(dev):
+    """The conv kernel's own TMA -> UMMA pipeline on a dense u8 x s8 GEMM (8192^3, no int4 unpack, no halo):
+    what the tcgen05 structure reaches when nothing but the main loop is in the way."""
+    try:
+        from tfmq_b200 import ops
+        a = torch.randint(0, 255, (8192, 8192), dtype=torch.uint8, device=dev)
+        b = torch.randint(-8, 8, (8192, 8192), dtype=torch.int8, device=dev)
+        out = torch.empty((8192, 8192), dtype=torch.int32, device=dev)
+        best = 1e9
+        for _ in range(6):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            ops.gemm_i8_peak(a, b, out)
+            e.record()
+            torch.cuda.synchronize()
+            best = min(best, s.elapsed_time(e))
+        return 2 * 8192 ** 3 / (best * 1e-3) / 1e12
+    except Exception as exc:      # noqa: BLE001
+        return f"failed: {exc}"
+
+
 def run_ours(args):
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -307,6 +328,7 @@ def run_ours(args):
         achieved = int8_ops / conv_s / 1e12
         int8_peak = 2.0 * pk["bf16_sustained"]
         cub = int8_cublas_tops(dev)
+        own = int8_pipeline_tops(dev)
         images_s = BATCH * world / (DDIM_STEPS * ms_per_step * 1e-3)
         e2e_images_s = BATCH * world / (DDIM_STEPS * ms_e2e * 1e-3)
         cpu_line = None
@@ -334,7 +356,8 @@ def run_ours(args):
                          "kernel": "igemm_kernel<MODE_W4A8> (tcgen05 kind::i8)", "launches_per_step": conv_n,
                          "kernel_ms_per_step": conv_s * 1e3,
                          "peak_note": f"int8 dense = 2 x measured bf16 sustained ({pk['source']}); "
-                                      f"cuBLASLt int8 8192^3 measured here: {cub}",
+                                      f"cuBLASLt int8 8192^3 measured here: {cub}; this kernel's pipeline on a "
+                                      f"dense u8 x s8 8192^3 GEMM (MODE_I8): {own}",
                          "step_frac": GFLOP_PER_SAMPLE * BATCH / ms_per_step / int8_peak},
             "clocks": sampler.summary() if sampler else None,
         }

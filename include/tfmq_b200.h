@@ -74,6 +74,21 @@ int tfmq_gn_stats(tfmq_ctx* ctx, const float* x, int64_t ld, int n, int hw, int 
                   void* stream);
 int tfmq_fill_zero(tfmq_ctx* ctx, void* p, size_t bytes, void* stream);
 
+/* GroupNorm statistics of a convolution's OUTPUT, accumulated by the convolution's own epilogue
+ * (fused when an output tile lies inside one image, otherwise by a follow-up tfmq_gn_stats_part launch).
+ * The output's channel ch belongs to group (ch_off + ch) / cpg of the tensor that will be normalised
+ * (ch_off != 0 when the output is the second part of a skip concatenation). */
+typedef struct {
+  double* stats;        /* [n][groups][2], accumulated */
+  int cpg;              /* channels per group of the normalised tensor */
+  int ch_off;           /* offset of this tensor's channel 0 inside the normalised tensor */
+  int groups;
+  int reserved;
+} tfmq_gn_target;
+/* partial statistics of x (c channels) into the group geometry above */
+int tfmq_gn_stats_part(tfmq_ctx* ctx, const float* x, int64_t ld, int n, int hw, int c, const tfmq_gn_target* target,
+                       void* stream);
+
 /* ------------------------------------------------------------------------- *
  * Activation producer: [GroupNorm-apply] -> [SiLU] -> [act fake-quant codes].
  * Replaces GN + nonlinearity + UniformAffineQuantizer.forward on the input of
@@ -130,6 +145,8 @@ typedef struct {
   int64_t res_ld;
   float* out;            /* fp32 NHWC */
   int64_t out_ld;
+  int n_stat;            /* 0..2 GroupNorm statistics targets fed by this output */
+  tfmq_gn_target stat[2];
 } tfmq_conv_w4a8_desc;
 int tfmq_conv_w4a8(tfmq_ctx* ctx, const tfmq_conv_w4a8_desc* d, void* stream);
 
@@ -161,6 +178,8 @@ typedef struct {
   int passes;           /* 1 or 3 */
   const float* emb;     /* [n][cout] per-image add (time embedding) or NULL */
   int64_t emb_ld;
+  int n_stat;
+  tfmq_gn_target stat[2];
 } tfmq_conv_fp_desc;
 int tfmq_conv_fp(tfmq_ctx* ctx, const tfmq_conv_fp_desc* d, void* stream);
 

@@ -458,3 +458,49 @@ def test_adaround_kernels_vs_autograd(dev):
     ops.rec_loss(pred.to(dev), tg.to(dev), denom, loss, grad)
     assert abs(loss.item() - q.lp_loss(pred, tg, 2.0).item()) < 1e-4
     assert (grad.cpu() - 2 * (pred - tg) / denom).abs().max().item() < 1e-6
+
+
+# ------------------------------------------------------------------ GN statistics fused into the conv epilogue
+@pytest.mark.parametrize("n,h,w,cin,cout,cpg,ch_off,groups", [
+    (2, 32, 32, 64, 224, 7, 0, 32),        # plain: 32 groups of 7 channels
+    (2, 16, 16, 64, 448, 35, 672, 32),     # second part of a 672+448 concat: groups of 35 straddle the boundary
+    (3, 8, 8, 64, 64, 2, 0, 32),           # tile spans two images: the launcher falls back to a separate pass
+])
+def test_conv_epilogue_gn_stats(dev, n, h, w, cin, cout, cpg, ch_off, groups):
+    ops, q = _ops(), _qref()
+    g = torch.Generator().manual_seed(cout + ch_off)
+    wt = torch.randn(cout, cin, 3, 3, generator=g) * 0.05
+    bias = torch.randn(cout, generator=g) * 0.1
+    delta_w, zp_w = q.channel_wise(q.minmax_scale, wt, 16)
+    x = torch.randn(n, cin, h, w, generator=g)
+    delta_a, zp_a = q.minmax_scale(x, 256)
+    codes_a = q.uaq_codes(x, delta_a, zp_a, 256)
+    act = torch.full((n, h + 2, w + 2, cin), int(zp_a.item()), dtype=torch.uint8)
+    act[:, 1:-1, 1:-1, :] = nhwc(codes_a).to(torch.uint8)
+    _, packed, wsum = ops.pack_w4(to_ohwi(wt).to(dev), delta_w.to(dev), zp_w.to(dev))
+    out = torch.zeros((n, h, w, cout), device=dev)
+    aq = torch.tensor([delta_a.item(), zp_a.item()], device=dev)
+    stats = torch.zeros((n, groups, 2), dtype=torch.float64, device=dev)
+    ops.conv_w4a8(act.to(dev), 3, packed, zp_w.reshape(-1).to(torch.uint8).to(dev),
+                  delta_w.reshape(-1).contiguous().to(dev), wsum, bias.to(dev), aq, out, stats=[(stats, cpg, ch_off)])
+    torch.cuda.synchronize()
+    o = out.cpu().double()                                   # [n,h,w,cout]
+    ref = torch.zeros(n, groups, 2, dtype=torch.float64)
+    for ch in range(cout):
+        gi = (ch_off + ch) // cpg
+        ref[:, gi, 0] += o[..., ch].sum((1, 2))
+        ref[:, gi, 1] += (o[..., ch] ** 2).sum((1, 2))
+    assert torch.allclose(stats.cpu(), ref, rtol=1e-5, atol=1e-3)
+    # same through the fp (tf32) conv
+    hi, lo = ops.split_tf32(to_ohwi(wt).to(dev))
+    out2 = torch.zeros_like(out)
+    stats2 = torch.zeros_like(stats)
+    ops.conv_fp(nhwc(x).to(dev), 3, 1, 1, hi, lo, out2, bias=bias.to(dev), stats=[(stats2, cpg, ch_off)])
+    torch.cuda.synchronize()
+    o2 = out2.cpu().double()
+    ref2 = torch.zeros_like(ref)
+    for ch in range(cout):
+        gi = (ch_off + ch) // cpg
+        ref2[:, gi, 0] += o2[..., ch].sum((1, 2))
+        ref2[:, gi, 1] += (o2[..., ch] ** 2).sum((1, 2))
+    assert torch.allclose(stats2.cpu(), ref2, rtol=1e-5, atol=1e-3)

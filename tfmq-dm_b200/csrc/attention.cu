@@ -1,11 +1,14 @@
 // Fused QK^T - softmax - PV attention in fp32 (flash-style: no T x T matrix in HBM).
 //
-// Two kernels:
-//  * attn_mma_kernel<D>  : head dim D in {32,40,64,80}: warp-level tensor-core MMAs
-//    (m16n8k8 tf32) with 3-pass hi/lo error compensation so the result is fp32-accurate.
-//    The tcgen05/TMEM version of this kernel is the next step.
+// Three kernels:
+//  * attn_h16_kernel<D>  : head dim D in {32,64,80}: warp-level tensor-core MMAs (m16n8k16 fp16) on
+//    two-term fp16 splits of the fp32 operands, 3 products per term pair: fp32-accurate.
+//  * attn_mma_kernel<D>  : head dim 40 (not a multiple of 16) or unaligned q: the same with m16n8k8 tf32.
+//    The tcgen05/TMEM version of these kernels is the next step.
 //  * attn_generic_kernel<G> : any head dim (CIFAR d=256, cin d=384..960): G lanes share one
 //    query, FFMA only.
+#include <cuda_fp16.h>
+
 #include "ctx.h"
 
 namespace tfmq {
@@ -261,6 +264,201 @@ __global__ void __launch_bounds__(128) attn_mma_kernel(const AttnP P) {
   }
 }
 
+// ------------------------------------------------------------------ tensor-core kernel, fp16 split
+// Same algorithm with m16n8k16 fp16 MMAs: every fp32 operand is split into two fp16 terms
+// (hi = half(x), lo = half(x - hi): 22 significand bits, the same as the tf32 hi/lo split) and each product
+// is hi*hi + lo*hi + hi*lo with fp32 accumulation.  One k16 instruction covers twice the depth of a k8 tf32
+// instruction, so the tensor-pipe work halves.  K is staged [key][D+8] and V transposed [dim][64+8] (fp16) so
+// every B fragment is one conflict-free 32-bit load; the S accumulator fragment is directly the A fragment of
+// the PV product (no permutation needed for k16).
+__device__ __forceinline__ void mma_f16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void split2_h(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(x0, x1);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+__device__ __forceinline__ void split1_h(float x, __half& hi, __half& lo) {
+  hi = __float2half_rn(x);
+  lo = __float2half_rn(x - __half2float(hi));
+}
+
+template <int D>
+__global__ void __launch_bounds__(128) attn_h16_kernel(const AttnP P) {
+  constexpr int KP = D + 8;          // K row pitch (halves)
+  constexpr int VP = ATT_TK + 8;     // V^T row pitch (halves)
+  constexpr int KS = D / 16;         // k-steps of Q K^T
+  constexpr int NT = D / 8;          // n-tiles of P V
+  extern __shared__ __half smh[];
+  __half* Khi = smh;
+  __half* Klo = Khi + ATT_TK * KP;
+  __half* Vhi = Klo + ATT_TK * KP;   // transposed: [D][VP]
+  __half* Vlo = Vhi + D * VP;
+  const tfmq_attn_desc& a = P.a;
+  const int bh = blockIdx.y, b = bh / a.heads, h = bh % a.heads;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int q0 = blockIdx.x * 64 + warp * 16;
+  const float* qb = a.q + (long long)b * a.q_sb + (long long)h * a.q_sh;
+  const float* kb = a.k + (long long)b * a.k_sb + (long long)h * a.k_sh;
+  const float* vb = a.v + (long long)b * a.v_sb + (long long)h * a.v_sh;
+
+  uint32_t qh[KS][4], ql[KS][4];
+  {
+    const int r0 = min(q0 + g, a.tq - 1), r1 = min(q0 + g + 8, a.tq - 1);
+    const float* p0 = qb + (long long)r0 * a.q_st;
+    const float* p1 = qb + (long long)r1 * a.q_st;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      const float2 x0 = *reinterpret_cast<const float2*>(p0 + ks * 16 + 2 * t);
+      const float2 x1 = *reinterpret_cast<const float2*>(p1 + ks * 16 + 2 * t);
+      const float2 x2 = *reinterpret_cast<const float2*>(p0 + ks * 16 + 2 * t + 8);
+      const float2 x3 = *reinterpret_cast<const float2*>(p1 + ks * 16 + 2 * t + 8);
+      split2_h(x0.x * a.scale, x0.y * a.scale, qh[ks][0], ql[ks][0]);
+      split2_h(x1.x * a.scale, x1.y * a.scale, qh[ks][1], ql[ks][1]);
+      split2_h(x2.x * a.scale, x2.y * a.scale, qh[ks][2], ql[ks][2]);
+      split2_h(x3.x * a.scale, x3.y * a.scale, qh[ks][3], ql[ks][3]);
+    }
+  }
+  float o[NT][4];
+#pragma unroll
+  for (int i = 0; i < NT; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+
+  for (int k0 = 0; k0 < a.tk; k0 += ATT_TK) {
+    __syncthreads();
+    const int kn = min(ATT_TK, a.tk - k0);
+    for (int i = threadIdx.x; i < ATT_TK * (D / 4); i += 128) {
+      const int j = i / (D / 4), c4 = (i - j * (D / 4)) * 4;
+      float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
+      if (j < kn) {
+        kv = *reinterpret_cast<const float4*>(kb + (long long)(k0 + j) * a.k_st + c4);
+        vv = *reinterpret_cast<const float4*>(vb + (long long)(k0 + j) * a.v_st + c4);
+      }
+      uint32_t h01, l01, h23, l23;
+      split2_h(kv.x, kv.y, h01, l01);
+      split2_h(kv.z, kv.w, h23, l23);
+      *reinterpret_cast<uint2*>(Khi + j * KP + c4) = make_uint2(h01, h23);
+      *reinterpret_cast<uint2*>(Klo + j * KP + c4) = make_uint2(l01, l23);
+      const float ve[4] = {vv.x, vv.y, vv.z, vv.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        __half vh, vl;
+        split1_h(ve[e], vh, vl);
+        Vhi[(c4 + e) * VP + j] = vh;
+        Vlo[(c4 + e) * VP + j] = vl;
+      }
+    }
+    __syncthreads();
+
+    // ---- S = Q K^T
+    float s[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+      const uint32_t* kh = reinterpret_cast<const uint32_t*>(Khi + (nt * 8 + g) * KP) + t;
+      const uint32_t* kl = reinterpret_cast<const uint32_t*>(Klo + (nt * 8 + g) * KP) + t;
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        const uint32_t bh0 = kh[ks * 8], bh1 = kh[ks * 8 + 4];
+        const uint32_t bl0 = kl[ks * 8], bl1 = kl[ks * 8 + 4];
+        mma_f16(s[nt], ql[ks], bh0, bh1);
+        mma_f16(s[nt], qh[ks], bl0, bl1);
+        mma_f16(s[nt], qh[ks], bh0, bh1);
+      }
+    }
+    float mx0 = m0, mx1 = m1;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const int c = nt * 8 + 2 * t;
+      if (c >= kn) s[nt][0] = -INFINITY, s[nt][2] = -INFINITY;
+      if (c + 1 >= kn) s[nt][1] = -INFINITY, s[nt][3] = -INFINITY;
+      mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+      mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float c0 = expf(m0 - mx0), c1 = expf(m1 - mx1);
+    m0 = mx0, m1 = mx1;
+    float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      s[nt][0] = expf(s[nt][0] - mx0);
+      s[nt][1] = expf(s[nt][1] - mx0);
+      s[nt][2] = expf(s[nt][2] - mx1);
+      s[nt][3] = expf(s[nt][3] - mx1);
+      rs0 += s[nt][0] + s[nt][1];
+      rs1 += s[nt][2] + s[nt][3];
+    }
+    l0 = l0 * c0 + rs0;
+    l1 = l1 * c1 + rs1;
+#pragma unroll
+    for (int i = 0; i < NT; ++i) {
+      o[i][0] *= c0, o[i][1] *= c0;
+      o[i][2] *= c1, o[i][3] *= c1;
+    }
+    // ---- O += P V : k-step = 16 keys = two n-tiles of S
+#pragma unroll
+    for (int kt = 0; kt < 4; ++kt) {
+      uint32_t ph[4], pl[4];
+      split2_h(s[2 * kt][0], s[2 * kt][1], ph[0], pl[0]);
+      split2_h(s[2 * kt][2], s[2 * kt][3], ph[1], pl[1]);
+      split2_h(s[2 * kt + 1][0], s[2 * kt + 1][1], ph[2], pl[2]);
+      split2_h(s[2 * kt + 1][2], s[2 * kt + 1][3], ph[3], pl[3]);
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        const uint32_t* vh = reinterpret_cast<const uint32_t*>(Vhi + (nt * 8 + g) * VP) + kt * 8 + t;
+        const uint32_t* vl = reinterpret_cast<const uint32_t*>(Vlo + (nt * 8 + g) * VP) + kt * 8 + t;
+        const uint32_t bh0 = vh[0], bh1 = vh[4];
+        const uint32_t bl0 = vl[0], bl1 = vl[4];
+        mma_f16(o[nt], pl, bh0, bh1);
+        mma_f16(o[nt], ph, bl0, bl1);
+        mma_f16(o[nt], ph, bh0, bh1);
+      }
+    }
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float i0 = 1.f / l0, i1 = 1.f / l1;
+  float* ob = a.o + (long long)b * a.o_sb + (long long)h * a.o_sh;
+  const int r0 = q0 + g, r1 = q0 + g + 8;
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+    if (r0 < a.tq)
+      *reinterpret_cast<float2*>(ob + (long long)r0 * a.o_st + nt * 8 + 2 * t) =
+          make_float2(o[nt][0] * i0, o[nt][1] * i0);
+    if (r1 < a.tq)
+      *reinterpret_cast<float2*>(ob + (long long)r1 * a.o_st + nt * 8 + 2 * t) =
+          make_float2(o[nt][2] * i1, o[nt][3] * i1);
+  }
+}
+
+template <int D>
+static int launch_h16(tfmq_ctx* ctx, const AttnP& P, cudaStream_t st) {
+  const size_t smem = (size_t)(2 * ATT_TK * (D + 8) + 2 * D * (ATT_TK + 8)) * sizeof(__half);
+  auto kern = attn_h16_kernel<D>;
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return tfmq_fail(ctx, TFMQ_ERR_CUDA, "attention: smem attr: %s", cudaGetErrorString(e));
+    smem_set = smem;
+  }
+  dim3 grid((P.a.tq + 63) / 64, P.a.b * P.a.heads);
+  kern<<<grid, 128, smem, st>>>(P);
+  TFMQ_LAUNCH_CHECK("attention_h16");
+  return TFMQ_OK;
+}
+
 template <int D>
 static int launch_mma(tfmq_ctx* ctx, const AttnP& P, cudaStream_t st) {
   const size_t smem = (size_t)4 * ATT_TK * (D + 4) * sizeof(float);
@@ -319,12 +517,13 @@ extern "C" int tfmq_attention(tfmq_ctx* ctx, const tfmq_attn_desc* d, void* stre
   };
   const bool vec_ok = al16(d->k, d->k_sb, d->k_sh, d->k_st) && al16(d->v, d->v_sb, d->v_sh, d->v_st) &&
                       (((uintptr_t)d->o & 7) == 0) && d->o_sb % 2 == 0 && d->o_sh % 2 == 0 && d->o_st % 2 == 0;
+  const bool q_ok = (((uintptr_t)d->q & 7) == 0) && d->q_sb % 2 == 0 && d->q_sh % 2 == 0 && d->q_st % 2 == 0;
   if (vec_ok) {
     switch (d->d) {
-      case 32: return launch_mma<32>(ctx, P, st);
+      case 32: return q_ok ? launch_h16<32>(ctx, P, st) : launch_mma<32>(ctx, P, st);
       case 40: return launch_mma<40>(ctx, P, st);
-      case 64: return launch_mma<64>(ctx, P, st);
-      case 80: return launch_mma<80>(ctx, P, st);
+      case 64: return q_ok ? launch_h16<64>(ctx, P, st) : launch_mma<64>(ctx, P, st);
+      case 80: return q_ok ? launch_h16<80>(ctx, P, st) : launch_mma<80>(ctx, P, st);
       default: break;
     }
   }

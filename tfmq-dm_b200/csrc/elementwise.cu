@@ -14,7 +14,7 @@ constexpr int GN_MAXVEC = 2;  // c <= 2048
 
 __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const float* __restrict__ x, long long ld, int hw, int c,
                                                               int groups, int pix_per_cta,
-                                                              double* __restrict__ stats) {
+                                                              double* __restrict__ stats, int cpg, int ch_off) {
   extern __shared__ double sm[];  // [c] sum, [c] sumsq
   const int n = blockIdx.y;
   const int p0 = blockIdx.x * pix_per_cta;
@@ -51,12 +51,14 @@ __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const float* __res
     }
   }
   __syncthreads();
-  const int cpg = c / groups;
-  for (int g = threadIdx.x; g < groups; g += GN_THREADS) {
+  // channel ch of this tensor lies in group (ch_off + ch) / cpg of the normalised tensor
+  const int g_lo = ch_off / cpg, g_hi = (ch_off + c - 1) / cpg;
+  for (int g = g_lo + threadIdx.x; g <= g_hi; g += GN_THREADS) {
+    const int lo = max(g * cpg - ch_off, 0), hi = min((g + 1) * cpg - ch_off, c);
     double a = 0, b = 0;
-    for (int j = 0; j < cpg; ++j) {
-      a += sm[g * cpg + j];
-      b += sm[c + g * cpg + j];
+    for (int j = lo; j < hi; ++j) {
+      a += sm[j];
+      b += sm[c + j];
     }
     atomicAdd(&stats[((long long)n * groups + g) * 2], a);
     atomicAdd(&stats[((long long)n * groups + g) * 2 + 1], b);
@@ -76,6 +78,23 @@ struct ActParams {
 // activation quantisation step, at a fraction of the instruction count
 __device__ __forceinline__ float silu_f(float v) { return v * __frcp_rn(1.f + __expf(-v)); }
 
+// code = clamp(rint(RN(t / delta)) + zp, 0, 255), bit-identical to the reference's fp32 divide + round,
+// without paying for an IEEE division on every element: rint(t * (1/delta)) can differ from rint(RN(t/delta))
+// only when t/delta lies within a few ulps of a rounding boundary; the exact remainder (one FMA) detects that
+// case and only then the correctly rounded division is evaluated.
+__device__ __forceinline__ uint32_t quant1(float t, float delta, float inv, float zp) {
+  float nq = rintf(t * inv);
+  const float rem = fmaf(-nq, delta, t);
+  if (fabsf(fabsf(rem) * inv - 0.5f) < 1e-6f * fmaxf(fabsf(nq), 1.f)) nq = rintf(__fdiv_rn(t, delta));
+  return (uint32_t)fminf(fmaxf(nq + zp, 0.f), 255.f);
+}
+__device__ __forceinline__ uint32_t quant4(const float (&t)[4], float delta, float inv, float zp) {
+  return quant1(t[0], delta, inv, zp) | (quant1(t[1], delta, inv, zp) << 8) | (quant1(t[2], delta, inv, zp) << 16) |
+         (quant1(t[3], delta, inv, zp) << 24);
+}
+
+// One warp per destination pixel (lanes = float4 channel vectors): the pixel decode / border test is per
+// warp, not per element, and every global access is a full row.
 __global__ void __launch_bounds__(ACT_THREADS) act_prepare_kernel(const ActParams P) {
   extern __shared__ float sp[];  // [c] a = rstd*gamma, [c] b = beta - a*mean
   const tfmq_act_desc& d = P.d;
@@ -103,51 +122,57 @@ __global__ void __launch_bounds__(ACT_THREADS) act_prepare_kernel(const ActParam
     delta = d.aq[0];
     zp = d.aq[1];
   }
+  const float inv = __frcp_rn(delta);
   const int halo = d.dst_u8 ? d.halo : 0;
   const int Wp = P.out_w + 2 * halo, Hp = P.out_h + 2 * halo;
   const int npix = Wp * Hp;
   const int nvec = c >> 2;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int NW = ACT_THREADS / 32;
   const int p0 = blockIdx.x * P.pix_per_cta;
-  int p1 = p0 + P.pix_per_cta;
-  if (p1 > npix) p1 = npix;
-  const int total = (p1 - p0) * nvec;
-  for (int i = threadIdx.x; i < total; i += ACT_THREADS) {
-    const int pp = p0 + i / nvec;
-    const int v = i - (i / nvec) * nvec;
+  const int p1 = min(p0 + P.pix_per_cta, npix);
+  const uint32_t zfill = (uint32_t)zp * 0x01010101u;
+  const bool gn = d.gn_stats != nullptr;
+  for (int pp = p0 + warp; pp < p1; pp += NW) {
     const int yy = pp / Wp, xx = pp - yy * Wp;
     const int y = yy - halo, x = xx - halo;
     const bool border = (y < 0) | (x < 0) | (y >= P.out_h) | (x >= P.out_w);
+    uint32_t* o8 = d.dst_u8 ? reinterpret_cast<uint32_t*>(d.dst_u8 + ((long long)n * npix + pp) * d.dst_c + d.dst_c_off)
+                            : nullptr;
     if (border) {
-      const uint32_t z = (uint32_t)zp;
-      uint32_t* o = reinterpret_cast<uint32_t*>(d.dst_u8 + ((long long)n * npix + pp) * d.dst_c + d.dst_c_off);
-      o[v] = z * 0x01010101u;
+      for (int v = lane; v < nvec; v += 32) o8[v] = zfill;
       continue;
     }
     const int sy = d.upsample ? (y >> 1) : y, sx = d.upsample ? (x >> 1) : x;
-    const float4 f =
-        reinterpret_cast<const float4*>(d.src + (((long long)n * d.h + sy) * d.w + sx) * d.src_ld)[v];
-    float t[4] = {f.x, f.y, f.z, f.w};
-    if (d.gn_stats) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) t[j] = fmaf(t[j], sp[v * 4 + j], sp[c + v * 4 + j]);
-    }
-    if (d.silu) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) t[j] = silu_f(t[j]);
-    }
-    if (d.dst_u8) {
-      uint32_t pk = 0;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float q = rintf(__fdiv_rn(t[j], delta)) + zp;
-        q = fminf(fmaxf(q, 0.f), 255.f);
-        pk |= ((uint32_t)q) << (8 * j);
+    const float4* src = reinterpret_cast<const float4*>(d.src + (((long long)n * d.h + sy) * d.w + sx) * d.src_ld);
+    float4* o32 = d.dst_f32 ? reinterpret_cast<float4*>(d.dst_f32 + ((long long)n * npix + pp) * d.dst_ld) : nullptr;
+    for (int v0 = lane; v0 < nvec; v0 += 64) {
+      const int v1 = v0 + 32;
+      const bool has1 = v1 < nvec;
+      const float4 f0 = src[v0];
+      const float4 f1 = has1 ? src[v1] : make_float4(0.f, 0.f, 0.f, 0.f);
+      float t0[4] = {f0.x, f0.y, f0.z, f0.w}, t1[4] = {f1.x, f1.y, f1.z, f1.w};
+      if (gn) {
+        const float4 a0 = *reinterpret_cast<const float4*>(sp + v0 * 4), b0 = *reinterpret_cast<const float4*>(sp + c + v0 * 4);
+        t0[0] = fmaf(t0[0], a0.x, b0.x), t0[1] = fmaf(t0[1], a0.y, b0.y);
+        t0[2] = fmaf(t0[2], a0.z, b0.z), t0[3] = fmaf(t0[3], a0.w, b0.w);
+        if (has1) {
+          const float4 a1 = *reinterpret_cast<const float4*>(sp + v1 * 4), b1 = *reinterpret_cast<const float4*>(sp + c + v1 * 4);
+          t1[0] = fmaf(t1[0], a1.x, b1.x), t1[1] = fmaf(t1[1], a1.y, b1.y);
+          t1[2] = fmaf(t1[2], a1.z, b1.z), t1[3] = fmaf(t1[3], a1.w, b1.w);
+        }
       }
-      uint32_t* o = reinterpret_cast<uint32_t*>(d.dst_u8 + ((long long)n * npix + pp) * d.dst_c + d.dst_c_off);
-      o[v] = pk;
-    } else {
-      float4* o = reinterpret_cast<float4*>(d.dst_f32 + ((long long)n * npix + pp) * d.dst_ld);
-      o[v] = make_float4(t[0], t[1], t[2], t[3]);
+      if (d.silu) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) t0[j] = silu_f(t0[j]), t1[j] = silu_f(t1[j]);
+      }
+      if (o8) {
+        o8[v0] = quant4(t0, delta, inv, zp);
+        if (has1) o8[v1] = quant4(t1, delta, inv, zp);
+      } else {
+        o32[v0] = make_float4(t0[0], t0[1], t0[2], t0[3]);
+        if (has1) o32[v1] = make_float4(t1[0], t1[1], t1[2], t1[3]);
+      }
     }
   }
 }
@@ -217,9 +242,22 @@ extern "C" int tfmq_fill_zero(tfmq_ctx* ctx, void* p, size_t bytes, void* stream
 extern "C" int tfmq_gn_stats(tfmq_ctx* ctx, const float* x, int64_t ld, int n, int hw, int c, int groups,
                              double* stats, void* stream) {
   if (!ctx) return TFMQ_ERR_ARG;
-  TFMQ_REQUIRE(x && stats, TFMQ_ERR_ARG, "gn_stats: null pointer");
-  TFMQ_REQUIRE(c % 4 == 0 && ld % 4 == 0 && c <= 4 * GN_THREADS * GN_MAXVEC && c % groups == 0, TFMQ_ERR_SHAPE,
-               "gn_stats: c=%d groups=%d ld=%lld", c, groups, (long long)ld);
+  TFMQ_REQUIRE(groups > 0 && c % groups == 0, TFMQ_ERR_SHAPE, "gn_stats: c=%d groups=%d", c, groups);
+  tfmq_gn_target t;
+  t.stats = stats, t.cpg = c / groups, t.ch_off = 0, t.groups = groups, t.reserved = 0;
+  return tfmq_gn_stats_part(ctx, x, ld, n, hw, c, &t, stream);
+}
+
+extern "C" int tfmq_gn_stats_part(tfmq_ctx* ctx, const float* x, int64_t ld, int n, int hw, int c,
+                                  const tfmq_gn_target* target, void* stream) {
+  if (!ctx) return TFMQ_ERR_ARG;
+  TFMQ_REQUIRE(x && target && target->stats, TFMQ_ERR_ARG, "gn_stats: null pointer");
+  double* stats = target->stats;
+  const int groups = target->groups;
+  TFMQ_REQUIRE(c % 4 == 0 && ld % 4 == 0 && c <= 4 * GN_THREADS * GN_MAXVEC && target->cpg > 0 &&
+                   target->ch_off >= 0 && (target->ch_off + c + target->cpg - 1) / target->cpg <= groups,
+               TFMQ_ERR_SHAPE, "gn_stats: c=%d cpg=%d ch_off=%d groups=%d ld=%lld", c, target->cpg, target->ch_off, groups,
+               (long long)ld);
   TFMQ_REQUIRE(((uintptr_t)x & 15) == 0, TFMQ_ERR_ARG, "gn_stats: x must be 16-byte aligned");
   if (n == 0 || hw == 0) return TFMQ_OK;
   int chunks = (ctx->sm_count * 4 + n - 1) / n;
@@ -227,8 +265,8 @@ extern "C" int tfmq_gn_stats(tfmq_ctx* ctx, const float* x, int64_t ld, int n, i
   if (chunks < 1) chunks = 1;
   const int ppc = (hw + chunks - 1) / chunks;
   chunks = (hw + ppc - 1) / ppc;
-  gn_stats_kernel<<<dim3(chunks, n), GN_THREADS, 2 * c * sizeof(double), tfmq_stream(stream)>>>(x, ld, hw, c, groups,
-                                                                                                ppc, stats);
+  gn_stats_kernel<<<dim3(chunks, n), GN_THREADS, 2 * c * sizeof(double), tfmq_stream(stream)>>>(
+      x, ld, hw, c, groups, ppc, stats, target->cpg, target->ch_off);
   TFMQ_LAUNCH_CHECK("gn_stats");
   return TFMQ_OK;
 }

@@ -1,5 +1,9 @@
 // tcgen05 implicit-GEMM convolution kernels + their C-ABI launchers.
 // See igemm.cuh for the pipeline description and DESIGN.md for the roofline.
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
 #include "igemm.cuh"
 
 #include "ctx.h"
@@ -19,6 +23,32 @@ namespace tfmq {
 //   warps 6-13  operand transform (int4 unpack / tf32 hi-lo split).  They are the critical path of the
 //               main loop, so they get the highest warp ids (the SM arbiter favours high ids) and the
 //               non-critical waits (producer, epilogue) back off with nanosleep instead of spinning.
+// GroupNorm partial sums of one epilogue chunk: thread = (column, block of rows); loads batched by full unrolling
+template <int CW>
+__device__ __forceinline__ float2 chunk_col_partial(const uint8_t* buf, int et) {
+  constexpr int PARTS = IGEMM_EPI_WARPS * 32 / CW, ROWS = 128 / PARTS;
+  const int col = et & (CW - 1), part = et / CW;
+  const uint32_t piece = (uint32_t)(col >> 2), within = (uint32_t)(col & 3) * 4u;
+  float v[ROWS];
+#pragma unroll
+  for (int rr = 0; rr < ROWS; ++rr) {
+    const int row = part * ROWS + rr;
+    const uint32_t rsw = (uint32_t)((CW == 32) ? (row & 7) : ((row >> 1) & 3));
+    v[rr] = *reinterpret_cast<const float*>(buf + row * (CW * 4) + ((piece ^ rsw) << 4) + within);
+  }
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int rr = 0; rr < ROWS; ++rr) s1 += v[rr], s2 = fmaf(v[rr], v[rr], s2);
+  return make_float2(s1, s2);
+}
+
+#define PROF_T(idx)                                         \
+  if (prof_on) {                                            \
+    const long long now_ = clock64();                       \
+    prof_acc[idx] += now_ - prof_t;                         \
+    prof_t = now_;                                          \
+  }
+
 template <int MODE>
 __global__ void __launch_bounds__(IGEMM_THREADS, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -37,7 +67,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 
   uint8_t* ebuf = smem + (size_t)S * p.stage_bytes;                       // 2 epilogue chunks [128][chunk_w] f32
   float4* chp = reinterpret_cast<float4*>(ebuf + 2 * 128 * 32 * 4);        // [tile_n] per-channel constants
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ebuf + 2 * 128 * 32 * 4 + 256 * 16);
+  float2* cstat = reinterpret_cast<float2*>(ebuf + 2 * 128 * 32 * 4 + 256 * 16);  // [256] per-channel (sum, sumsq)
+  float2* cpart = cstat + 256;          // [2][parts][chunk_w] row-block partials of the last two chunks
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ebuf + 2 * 128 * 32 * 4 + 256 * 16 + 3 * 256 * 8);
   uint64_t* full_tma = bars;            // [S] TMA bytes landed
   uint64_t* full_xf = bars + S;         // [S] transform warps done
   uint64_t* empty = bars + 2 * S;       // [S] UMMAs that read the stage retired
@@ -63,7 +95,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], 4);
+      mbar_init(&acc_empty[s], IGEMM_EPI_WARPS);
       mbar_init(&res_full[s], 1);
     }
     mbar_fence_init();
@@ -73,7 +105,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     tma_prefetch_desc(&tmOut);
     if (p.res) tma_prefetch_desc(&tmRes);
   }
-  if (warp == 5) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  if (warp == IGEMM_WARP_MMA) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
   if (MODE == MODE_W4A8) {
     // rows [tile_n, tile_n+16) of every B stage: row tile_n = 0x01 bytes, the rest zero (swizzle-invariant)
     for (int i = threadIdx.x; i < S * 16 * 8; i += IGEMM_THREADS) {
@@ -94,57 +126,79 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const bool two_acc = need_a_lo || need_b_lo;                 // tf32: separate accumulator for the small terms
   const uint32_t acc_cols = (MODE == MODE_W4A8) ? (uint32_t)p.tile_n + 16u : (uint32_t)p.tile_n * (two_acc ? 2u : 1u);
 
-  if (warp == 4) {
+  if (warp == IGEMM_WARP_TMA) {
     // ===================================================== TMA producer
-    if (lane == 0) {
-      uint32_t tx_bytes = IGEMM_A_BYTES;
-      if (MODE == MODE_W4A8) tx_bytes += (uint32_t)p.tile_n * 64u;
-      if (MODE == MODE_I8) tx_bytes += (uint32_t)p.tile_n * 128u;
-      if (MODE == MODE_TF32) tx_bytes += (uint32_t)p.tile_n * 128u * (need_b_lo ? 2u : 1u);
-      int s = 0;
-      uint32_t par = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        int mt = tile % tiles_m;
-        const int c_out0 = (tile / tiles_m) * p.tile_n;
-        const int tx = mt % tiles_x;
-        mt /= tiles_x;
-        const int ty = mt % tiles_y;
-        const int n0 = (mt / tiles_y) * p.tn, y0 = ty * p.th, x0 = tx * p.tw;
-        int kc = 0, kx = 0, ky = 0, tap = 0;
-        for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait_relaxed(&empty[s], par ^ 1u);
-          uint8_t* st = smem + (size_t)s * p.stage_bytes;
-          mbar_expect_tx(&full_tma[s], tx_bytes);
-          tma_load_4d(st, &tmA, &full_tma[s], kc * p.kchunk, x0 * p.stride + kx + p.off,
-                      y0 * p.stride + ky + p.off, n0);
-          if (MODE == MODE_W4A8) {
-            // packed bytes: column = (tap*cin + kc*128)/2
-            tma_load_2d(st + p.offP, &tmB, &full_tma[s], (tap * p.cin + kc * p.kchunk) >> 1, c_out0);
+    // (whole warp convergent, one elected lane issues: coordinates and addresses stay warp-uniform)
+    uint32_t tx_bytes = IGEMM_A_BYTES;
+    if (MODE == MODE_W4A8) tx_bytes += (uint32_t)p.tile_n * 64u;
+    if (MODE == MODE_I8) tx_bytes += (uint32_t)p.tile_n * 128u;
+    if (MODE == MODE_TF32) tx_bytes += (uint32_t)p.tile_n * 128u * (need_b_lo ? 2u : 1u);
+    int s = 0;
+    uint32_t par = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int mt = tile % tiles_m;
+      const int c_out0 = (tile / tiles_m) * p.tile_n;
+      const int tx = mt % tiles_x;
+      mt /= tiles_x;
+      const int ty = mt % tiles_y;
+      const int n0 = (mt / tiles_y) * p.tn, y0 = ty * p.th, x0 = tx * p.tw;
+      int kc = 0, kx = 0, ky = 0, tap = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait_relaxed(&empty[s], par ^ 1u);
+        uint8_t* st = smem + (size_t)s * p.stage_bytes;
+        if (elect_one_sync()) {
+          if (p.dbg & 1) {
+            mbar_arrive(&full_tma[s]);
           } else {
-            tma_load_2d(st + p.offB, &tmB, &full_tma[s], tap * p.cin + kc * p.kchunk, c_out0);
-            if (need_b_lo) tma_load_2d(st + p.offB_lo, &tmB2, &full_tma[s], tap * p.cin + kc * p.kchunk, c_out0);
+            mbar_expect_tx(&full_tma[s], tx_bytes);
+            tma_load_4d(st, &tmA, &full_tma[s], kc * p.kchunk, x0 * p.stride + kx + p.off, y0 * p.stride + ky + p.off,
+                        n0);
+            if (MODE == MODE_W4A8) {
+              // packed bytes: column = (tap*cin + kc*128)/2
+              tma_load_2d(st + p.offP, &tmB, &full_tma[s], (tap * p.cin + kc * p.kchunk) >> 1, c_out0);
+            } else {
+              tma_load_2d(st + p.offB, &tmB, &full_tma[s], tap * p.cin + kc * p.kchunk, c_out0);
+              if (need_b_lo) tma_load_2d(st + p.offB_lo, &tmB2, &full_tma[s], tap * p.cin + kc * p.kchunk, c_out0);
+            }
           }
-          if (++kc == kchunks) {
-            kc = 0, ++tap;
-            if (++kx == p.ksize) kx = 0, ++ky;
-          }
-          if (++s == S) s = 0, par ^= 1u;
         }
+        __syncwarp();
+        if (++kc == kchunks) {
+          kc = 0, ++tap;
+          if (++kx == p.ksize) kx = 0, ++ky;
+        }
+        if (++s == S) s = 0, par ^= 1u;
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == IGEMM_WARP_MMA) {
     // ===================================================== UMMA issuer
+    // The whole warp runs this loop convergently and every operand of the tcgen05 instructions is computed
+    // outside the elected-thread region, so descriptors live in uniform registers and each UTC*MMA issues
+    // without a per-instruction register shuffle; the tensor pipe starves on anything slower.
     // W4A8: the s8 B tile carries 16 extra rows; row tile_n is all ones, so accumulator column tile_n
     // holds sum_k a[m][k] and the weight zero point can be applied in the epilogue instead of per code
     const uint32_t umma_n = (uint32_t)p.tile_n + (MODE == MODE_W4A8 ? 16u : 0u);
     const uint32_t idesc = (MODE == MODE_TF32) ? idesc_tf32(128, umma_n) : idesc_i8_u8s8(128, umma_n);
+    const uint32_t smem_base = smem_u32(smem);
+    const uint64_t d_a = smem_desc_sw128(smem_base);
+    const uint64_t d_b = smem_desc_sw128(smem_base + p.offB);
+    const uint64_t d_alo = smem_desc_sw128(smem_base + p.offA_lo);
+    const uint64_t d_blo = smem_desc_sw128(smem_base + p.offB_lo);
+    const uint32_t stage_units = p.stage_bytes >> 4;       // descriptor start-address units per stage
+    const int nslice_last = (p.cin - (kchunks - 1) * p.kchunk) / p.kslice;   // valid 32-byte K slices of the last chunk
+    const bool wait_xf = (MODE == MODE_W4A8) || need_a_lo;  // otherwise the TMA barrier alone gates the stage
     uint32_t tcount = 0;
     int s = 0;
-    uint32_t par = 0;
+    uint32_t par = 0, s_units = 0;
+    const bool prof_on = p.prof != nullptr && lane == 0;
+    long long prof_acc[6] = {0, 0, 0, 0, 0, 0};
+    long long prof_t = prof_on ? clock64() : 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
       const uint32_t as = tcount % ACC;
+      PROF_T(2)
       mbar_wait(&acc_empty[as], ((tcount / ACC) & 1u) ^ 1u);   // epilogue has drained this stage
       tc_fence_after();
+      PROF_T(0)
       const uint32_t tmem_d = tmem_base + as * acc_cols;
       // tf32: the two small cross terms accumulate in their own TMEM columns so the (truncating)
       // tensor-core accumulator adds them to a small running sum, not to the large main one
@@ -152,64 +206,68 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       uint32_t accumulate = 0, accumulate_lo = 0;
       int kc = 0;
       for (int kb = 0; kb < nkb; ++kb) {
+        PROF_T(2)
         mbar_wait(&full_tma[s], par);
-        mbar_wait(&full_xf[s], par);
+        if (wait_xf) mbar_wait(&full_xf[s], par);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t st = smem_u32(smem + (size_t)s * p.stage_bytes);
-          int rem = p.cin - kc * p.kchunk;
-          if (rem > p.kchunk) rem = p.kchunk;
-          const int nslice = rem / p.kslice;  // valid 32-byte K slices in this k-block
-          const uint64_t a_hi = smem_desc_sw128(st);
-          const uint64_t b_hi = smem_desc_sw128(st + p.offB);
+        PROF_T(1)
+        const int nslice = (kc == kchunks - 1) ? nslice_last : 4;
+        const uint64_t a_hi = d_a + s_units, b_hi = d_b + s_units;
+        const uint64_t a_lo = d_alo + s_units, b_lo = d_blo + s_units;
+        const bool last = kb == nkb - 1;
+        if (elect_one_sync()) {
           if (MODE == MODE_TF32) {
-            const uint64_t a_lo = smem_desc_sw128(st + p.offA_lo);
-            const uint64_t b_lo = smem_desc_sw128(st + p.offB_lo);
-            if (need_a_lo)
-              for (int k = 0; k < nslice; ++k) {
-                umma_tf32(tmem_lo, a_lo + 2 * k, b_hi + 2 * k, idesc, accumulate_lo);
-                accumulate_lo = 1;
-              }
-            if (need_b_lo)
-              for (int k = 0; k < nslice; ++k) {
-                umma_tf32(tmem_lo, a_hi + 2 * k, b_lo + 2 * k, idesc, accumulate_lo);
-                accumulate_lo = 1;
-              }
-            for (int k = 0; k < nslice; ++k) {
-              umma_tf32(tmem_d, a_hi + 2 * k, b_hi + 2 * k, idesc, accumulate);
-              accumulate = 1;
+            if (need_a_lo) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                if (k < nslice) umma_tf32(tmem_lo, a_lo + 2 * k, b_hi + 2 * k, idesc, (k > 0) | accumulate_lo);
             }
+            if (need_b_lo) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                if (k < nslice)
+                  umma_tf32(tmem_lo, a_hi + 2 * k, b_lo + 2 * k, idesc, (k > 0) | accumulate_lo | (need_a_lo ? 1u : 0u));
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (k < nslice) umma_tf32(tmem_d, a_hi + 2 * k, b_hi + 2 * k, idesc, (k > 0) | accumulate);
           } else {
-            for (int k = 0; k < nslice; ++k) {
-              umma_i8(tmem_d, a_hi + 2 * k, b_hi + 2 * k, idesc, accumulate);
-              accumulate = 1;
-            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (k < nslice) umma_i8(tmem_d, a_hi + 2 * k, b_hi + 2 * k, idesc, (k > 0) | accumulate);
           }
           umma_commit(&empty[s]);
-          if (kb == nkb - 1) umma_commit(&acc_full[as]);
+          if (last) umma_commit(&acc_full[as]);
         }
         __syncwarp();
+        accumulate = 1, accumulate_lo = 1;
         if (++kc == kchunks) kc = 0;
-        if (++s == S) s = 0, par ^= 1u;
+        s_units += stage_units;
+        if (++s == S) s = 0, s_units = 0, par ^= 1u;
       }
     }
-  } else if (warp >= 6) {
-    // ===================================================== transform warps (6..13)
-    const int t = threadIdx.x - 192;  // 0..255
+    if (prof_on)
+      for (int i = 0; i < 6; ++i) p.prof[blockIdx.x * 16 + 10 + i] = prof_acc[i];
+  } else if (warp >= IGEMM_WARP_XF0) {
+    // ===================================================== transform warps
+    const int t = threadIdx.x - IGEMM_WARP_XF0 * 32;  // 0..XF_T-1
+    constexpr int XF_T = IGEMM_XF_WARPS * 32;          // transform threads
+    constexpr int XF_ROWS = XF_T / 4;                   // B rows unpacked per pass
+    constexpr int XF_IT = 256 / XF_ROWS;                // passes to cover up to 256 rows
     int s = 0;
     uint32_t par = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int c_out0 = (tile / tiles_m) * p.tile_n;
       if (MODE == MODE_W4A8) {
-        // 256 threads: piece (row, K slice) = ((t >> 2) + 64 i, t & 3); fixed per-thread offsets,
-        // +4096 B (packed) / +8192 B (s8 tile) per i.  Codes stay unsigned (0..15): two ANDs and a shift
+        // piece (row, K slice) = ((t >> 2) + XF_ROWS i, t & 3); fixed per-thread offsets,
+        // + XF_ROWS*64 B (packed) / + XF_ROWS*128 B (s8 tile) per i.  Codes stay unsigned (0..15): two ANDs and a shift
         // per packed word; the zero point is folded out through the ones row (see the UMMA issuer).
         const int sub = t & 3;
         const uint32_t rd0 = p.offP + (uint32_t)(t >> 2) * 64u + (uint32_t)sub * 16u;
         const uint32_t swz = (uint32_t)((t >> 2) & 7);
         const uint32_t wr_lo = p.offB + (uint32_t)(t >> 2) * 128u + (((2u * sub) ^ swz) << 4);
         const uint32_t wr_hi = p.offB + (uint32_t)(t >> 2) * 128u + (((2u * sub + 1u) ^ swz) << 4);
-        const int nrow_i = (p.tile_n - (t >> 2) + 63) >> 6;   // iterations with row < tile_n
+        const int nrow_i = (p.tile_n - (t >> 2) + XF_ROWS - 1) / XF_ROWS;   // iterations with row < tile_n
         int kc = 0;
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&full_tma[s], par);
@@ -218,20 +276,20 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           if (rem > p.kchunk) rem = p.kchunk;
           const int nslice = rem >> 5;
           if (sub < nslice) {
-            uint4 pkv[4];
+            uint4 pkv[XF_IT];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-              if (i < nrow_i) pkv[i] = *reinterpret_cast<const uint4*>(st + rd0 + i * 4096);
+            for (int i = 0; i < XF_IT; ++i)
+              if (i < nrow_i) pkv[i] = *reinterpret_cast<const uint4*>(st + rd0 + i * (XF_ROWS * 64));
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < XF_IT; ++i) {
               if (i < nrow_i) {
                 const uint4 pk = pkv[i];
                 uint4 lo, hi;
                 lo.x = pk.x & 0x0F0F0F0Fu, lo.y = pk.y & 0x0F0F0F0Fu, lo.z = pk.z & 0x0F0F0F0Fu, lo.w = pk.w & 0x0F0F0F0Fu;
                 hi.x = (pk.x >> 4) & 0x0F0F0F0Fu, hi.y = (pk.y >> 4) & 0x0F0F0F0Fu;
                 hi.z = (pk.z >> 4) & 0x0F0F0F0Fu, hi.w = (pk.w >> 4) & 0x0F0F0F0Fu;
-                *reinterpret_cast<uint4*>(st + wr_lo + i * 8192) = lo;
-                *reinterpret_cast<uint4*>(st + wr_hi + i * 8192) = hi;
+                *reinterpret_cast<uint4*>(st + wr_lo + i * (XF_ROWS * 128)) = lo;
+                *reinterpret_cast<uint4*>(st + wr_hi + i * (XF_ROWS * 128)) = hi;
               }
             }
           }
@@ -241,16 +299,16 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           if (++kc == kchunks) kc = 0;
           if (++s == S) s = 0, par ^= 1u;
         }
-      } else if (MODE == MODE_TF32) {
+      } else if (MODE == MODE_TF32 && need_a_lo) {
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&full_tma[s], par);
-          if (need_a_lo) {
+          {
             uint8_t* st = smem + (size_t)s * p.stage_bytes;
             uint4* a = reinterpret_cast<uint4*>(st);
             uint4* al = reinterpret_cast<uint4*>(st + p.offA_lo);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int idx = t + 256 * i;
+            for (int i = 0; i < 1024 / XF_T; ++i) {
+              const int idx = t + XF_T * i;
               uint4 v = a[idx], h, l;
               h.x = v.x & 0xFFFFE000u;
               h.y = v.y & 0xFFFFE000u;
@@ -269,29 +327,29 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           if (lane == 0) mbar_arrive(&full_xf[s]);
           if (++s == S) s = 0, par ^= 1u;
         }
-      } else {
-        for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait(&full_tma[s], par);
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&full_xf[s]);
-          if (++s == S) s = 0, par ^= 1u;
-        }
       }
+      // other modes: nothing to transform; the UMMA issuer waits on the TMA barrier alone
     }
   } else {
-    // ===================================================== epilogue warps (0..3)
+    // ===================================================== epilogue warps (0..7)
     // All global I/O of the epilogue is TMA: the residual chunk is prefetched into a swizzled smem
-    // buffer, every thread folds its accumulator row into it (conflict-free float4 accesses), and the
-    // buffer is stored back with one bulk tensor store.  Two buffers alternate across chunks.
+    // buffer, every thread folds its part of an accumulator row into it (conflict-free float4 accesses), and
+    // the buffer is stored back with one bulk tensor store.  Two buffers alternate across chunks.
+    // Two warps share a TMEM lane quarter: warp w handles columns [half*CW/2, (half+1)*CW/2) of every chunk.
+    constexpr int ET = IGEMM_EPI_WARPS * 32;
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
-    const int et = threadIdx.x;             // 0..127 within the epilogue group
+    const int half = warp >> 2;             // which half of a chunk's columns
+    const int et = threadIdx.x;             // 0..ET-1 within the epilogue group
     const int r = q * 32 + lane;            // accumulator row = pixel within the tile
     const int CW = p.chunk_w;               // 32 (128B swizzle) or 16 (64B swizzle) channels per chunk
+    const int HC = CW >> 1;                 // columns per thread per chunk
     const int nchunks = p.tile_n / CW;
     const uint32_t chunk_bytes = 128u * (uint32_t)CW * 4u;
-    // swizzled position of 16-byte piece k of this thread's row
-    const int sw = (CW == 32) ? (r & 7) : ((r >> 1) & 3);
+    // byte offset (within the row) of 16-byte piece k: (k*16) ^ sw16
+    const uint32_t sw16 = (uint32_t)((CW == 32) ? (r & 7) : ((r >> 1) & 3)) << 4;
+    const uint32_t row_off = (uint32_t)r * (uint32_t)(CW * 4);
     const int hw_t = p.th * p.tw;
+    const bool emb_folded = p.emb && p.tn == 1;   // one image per tile: the embedding row joins the bias
     float a_scale = 1.f;
     int za = 0;
     if (MODE == MODE_W4A8) {
@@ -299,6 +357,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       za = (int)p.aq[1];
     }
     uint32_t tcount = 0, g = 0;             // tiles / chunks processed by this CTA
+    const bool prof_on = p.prof != nullptr && et == 0;
+    long long prof_acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long prof_t = prof_on ? clock64() : 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
       int mt = tile % tiles_m;
       const int c_out0 = (tile / tiles_m) * p.tile_n;
@@ -320,12 +381,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         }
       }
       // per-channel constants of this N tile
-      named_bar_sync(1, 128);                 // previous tile is done with chp
-      for (int ch = et; ch < p.tile_n; ch += 128) {
+      named_bar_sync(1, ET);                  // previous tile is done with chp / cstat
+      for (int ch = et; ch < p.tile_n; ch += ET) {
         const int c = c_out0 + ch;
         float sc = 1.f, bi = 0.f;
-        int ws = 0;
-        int zw = 0;
+        int ws = 0, zw = 0;
         if (MODE == MODE_W4A8) {
           sc = a_scale * p.wscale[c];
           ws = za * p.wsum[c];
@@ -334,35 +394,43 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           sc = p.wscale[c];
         }
         if (p.bias) bi = p.bias[c];
+        if (emb_folded) bi += p.emb[(long long)n0 * p.emb_ld + c];
         chp[ch] = make_float4(sc, bi, __int_as_float(ws), __int_as_float(zw));
       }
       const uint32_t as = tcount % ACC;
+      PROF_T(0)
       mbar_wait_relaxed(&acc_full[as], (tcount / ACC) & 1u);
       tc_fence_after();
+      PROF_T(1)
       const uint32_t tmem_d = tmem_base + as * acc_cols + ((uint32_t)(q * 32) << 16);
-      named_bar_sync(1, 128);                 // chp visible; first buffer known free
+      named_bar_sync(1, ET);                  // chp visible; first buffer known free
       int a_sum = 0;                          // sum_k a[m][k] of this row (ones-row column)
       if (MODE == MODE_W4A8) {
-        uint32_t sv[16];
-        tmem_ld16(tmem_d + (uint32_t)p.tile_n, sv);
+        uint32_t sv[8];
+        tmem_ld8(tmem_d + (uint32_t)p.tile_n, sv);
         tmem_ld_wait();
         a_sum = (int)sv[0];
       }
 
       for (int ci = 0; ci < nchunks; ++ci, ++g) {
-        const int c0 = ci * CW;
+        const int c0 = ci * CW + half * HC;   // first column (within the tile) this thread handles
         uint8_t* buf = ebuf + (g & 1) * chunk_bytes;
-        uint32_t v[32];
-        tmem_ld16(tmem_d + (uint32_t)c0, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
-        if (CW == 32) tmem_ld16(tmem_d + (uint32_t)(c0 + 16), *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
+        uint32_t v[16];
+        if (CW == 32) {
+          tmem_ld16(tmem_d + (uint32_t)c0, v);
+        } else {
+          tmem_ld8(tmem_d + (uint32_t)c0, *reinterpret_cast<uint32_t(*)[8]>(&v[0]));
+        }
         if (MODE == MODE_TF32 && two_acc) {
-          uint32_t v2[32];
-          tmem_ld16(tmem_d + (uint32_t)(p.tile_n + c0), *reinterpret_cast<uint32_t(*)[16]>(&v2[0]));
-          if (CW == 32)
-            tmem_ld16(tmem_d + (uint32_t)(p.tile_n + c0 + 16), *reinterpret_cast<uint32_t(*)[16]>(&v2[16]));
+          uint32_t v2[16];
+          if (CW == 32) {
+            tmem_ld16(tmem_d + (uint32_t)(p.tile_n + c0), v2);
+          } else {
+            tmem_ld8(tmem_d + (uint32_t)(p.tile_n + c0), *reinterpret_cast<uint32_t(*)[8]>(&v2[0]));
+          }
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
+          for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
         }
         tmem_ld_wait();
         if (ci == nchunks - 1) {
@@ -371,13 +439,16 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           __syncwarp();
           if (lane == 0) mbar_arrive(&acc_empty[as]);
         }
+        PROF_T(2)
         if (p.res) mbar_wait(&res_full[g & 1], (g >> 1) & 1u);
-        const float* embp = p.emb ? p.emb + (long long)n_l * p.emb_ld + c_out0 + c0 : nullptr;
-        const int npiece = CW / 4;
+        PROF_T(3)
+        const float* embp = (p.emb && !emb_folded) ? p.emb + (long long)n_l * p.emb_ld + c_out0 + c0 : nullptr;
+        const int npiece = HC >> 2;           // 16-byte pieces per thread: 4 (CW 32) or 2 (CW 16)
+        const int k0 = half * npiece;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
+        for (int k = 0; k < 4; ++k) {
           if (k < npiece) {
-            float4* slot = reinterpret_cast<float4*>(buf + r * (CW * 4) + ((k ^ sw) << 4));
+            float4* slot = reinterpret_cast<float4*>(buf + row_off + ((uint32_t)((k0 + k) << 4) ^ sw16));
             float4 o;
             if (MODE == MODE_I8) {
               o = make_float4(__uint_as_float(v[4 * k]), __uint_as_float(v[4 * k + 1]), __uint_as_float(v[4 * k + 2]),
@@ -405,29 +476,76 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             *slot = o;
           }
         }
+        PROF_T(4)
         fence_proxy_async_smem();
-        named_bar_sync(1, 128);               // all 128 rows of the chunk are in smem
+        named_bar_sync(1, ET);                // all 128 rows of the chunk are in smem
+        PROF_T(5)
+        if (p.n_stat > 0) {
+          // GroupNorm statistics of the finished output values: thread = (column, block of rows) sums its rows;
+          // the partials of the previous chunk are combined here too, in a fixed order (bit-reproducible)
+          if (ci > 0 && et < CW) {
+            const float2* pp = cpart + ((g - 1) & 1) * ET + et;
+            float a1 = 0.f, a2 = 0.f;
+            for (int k = 0; k < ET / CW; ++k) a1 += pp[k * CW].x, a2 += pp[k * CW].y;
+            cstat[(ci - 1) * CW + et] = make_float2(a1, a2);
+          }
+          cpart[(g & 1) * ET + et] = (CW == 32) ? chunk_col_partial<32>(buf, et) : chunk_col_partial<16>(buf, et);   // [part][col]
+        }
+        PROF_T(6)
         if (et == 0) {
-          tma_store_4d(&tmOut, buf, c_out0 + c0, x0, y0, n0);
+          tma_store_4d(&tmOut, buf, c_out0 + ci * CW, x0, y0, n0);
           tma_store_commit();
           if (ci + 1 < nchunks) {
             tma_store_wait_read<1>();         // the other buffer's store has finished reading
             if (p.res) {
               mbar_expect_tx(&res_full[(g + 1) & 1], chunk_bytes);
-              tma_load_4d(ebuf + ((g + 1) & 1) * chunk_bytes, &tmRes, &res_full[(g + 1) & 1], c_out0 + c0 + CW, x0,
-                          y0, n0);
+              tma_load_4d(ebuf + ((g + 1) & 1) * chunk_bytes, &tmRes, &res_full[(g + 1) & 1], c_out0 + (ci + 1) * CW,
+                          x0, y0, n0);
             }
           }
         }
-        if (!p.res) named_bar_sync(1, 128);   // without a residual barrier, publish "next buffer is free"
+        PROF_T(7)
+        if (!p.res) named_bar_sync(1, ET);    // without a residual barrier, publish "next buffer is free"
+        PROF_T(8)
+      }
+      if (p.n_stat > 0) {
+        named_bar_sync(1, ET);                // the last chunk's partials are written
+        if (et < CW) {
+          const float2* pp = cpart + ((g - 1) & 1) * ET + et;
+          float a1 = 0.f, a2 = 0.f;
+          for (int k = 0; k < ET / CW; ++k) a1 += pp[k * CW].x, a2 += pp[k * CW].y;
+          cstat[(nchunks - 1) * CW + et] = make_float2(a1, a2);
+        }
+        named_bar_sync(1, ET);                // every chunk's sums are in cstat
+        for (int k = 0; k < p.n_stat; ++k) {
+          const tfmq_gn_target tg = p.stat[k];
+          const int g_lo = (tg.ch_off + c_out0) / tg.cpg;
+          const int g_hi = (tg.ch_off + c_out0 + p.tile_n - 1) / tg.cpg;
+          for (int gi = g_lo + et; gi <= g_hi; gi += ET) {
+            const int ch_lo = max(gi * tg.cpg - tg.ch_off, c_out0) - c_out0;
+            const int ch_hi = min((gi + 1) * tg.cpg - tg.ch_off, c_out0 + p.tile_n) - c_out0;
+            double a1 = 0.0, a2 = 0.0;
+            for (int ch = ch_lo; ch < ch_hi; ++ch) {
+              const float2 v2 = cstat[ch];
+              a1 += (double)v2.x;
+              a2 += (double)v2.y;
+            }
+            double* dst = tg.stats + ((long long)n0 * tg.groups + gi) * 2;
+            atomicAdd(dst, a1);
+            atomicAdd(dst + 1, a2);
+          }
+        }
       }
     }
     if (et == 0) tma_store_wait_all<0>();     // global writes complete before the CTA retires
+    PROF_T(9)
+    if (prof_on)
+      for (int i = 0; i < 10; ++i) p.prof[blockIdx.x * 16 + i] = prof_acc[i];
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  if (warp == IGEMM_WARP_MMA) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
 // ---------------------------------------------------------------------------
@@ -440,6 +558,22 @@ static int pick_tile_n(int cout, int limit = 256) {
   for (int t = limit; t >= 16; t -= 16)
     if (cout % t == 0) return t;
   return 0;
+}
+
+// N tile for a persistent grid: the widest tile has the best operand reuse, but small feature maps then
+// leave most SMs idle (8x8x16 images = 8 M tiles).  Pick the divisor of cout that minimises
+//   waves(tiles) x (k-blocks x (k_fix + k_col * tile_n) + epilogue(tile_n))   [cycles, fitted to the phase counters]
+static int pick_tile_n_balanced(int cout, int limit, int tiles_m, int nkb, int sm_count, double k_fix, double k_col) {
+  int best = 0;
+  double best_cost = 0.0;
+  for (int t = limit; t >= 16; t -= 16) {
+    if (cout % t) continue;
+    const long long tiles = (long long)tiles_m * (cout / t);
+    const double waves = (double)((tiles + sm_count - 1) / sm_count);
+    const double cost = waves * (nkb * (k_fix + k_col * t) + 3000.0 + 30.0 * t);
+    if (!best || cost < best_cost * 0.97) best = t, best_cost = cost;   // prefer the wider tile on near-ties
+  }
+  return best;
 }
 
 struct TileGeom {
@@ -492,7 +626,7 @@ static int launch_igemm(tfmq_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap
   }
   p.stage_bytes = (off + 1023u) & ~1023u;
   const uint32_t extra = 1024u /*alignment slack*/ + 2u * 128u * 32u * 4u /*epilogue chunks*/ + 256u * 16u /*chp*/ +
-                         256u /*barriers*/;
+                         3u * 256u * 8u /*GN channel sums + partials*/ + 256u /*barriers*/;
   const int kchunks = (p.cin + p.kchunk - 1) / p.kchunk;
   const int nkb = p.ksize * p.ksize * kchunks;
   int stages = (int)(((uint32_t)ctx->max_smem_optin - extra) / p.stage_bytes);
@@ -540,8 +674,49 @@ static int launch_igemm(tfmq_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap
   const int tiles_m = (p.W / p.tw) * (p.H / p.th) * ((p.n_img + p.tn - 1) / p.tn);
   const int total = tiles_m * (p.cout / p.tile_n);
   const int grid = total < ctx->sm_count ? total : ctx->sm_count;
+  static const bool time_env = getenv("TFMQ_IGEMM_TIME") != nullptr;   // debug aid: per-launch time, synchronous
+  static const bool prof_env = getenv("TFMQ_IGEMM_PROF") != nullptr;   // debug aid: + in-kernel phase counters
+  static const int dbg_env = getenv("TFMQ_IGEMM_DBG") ? atoi(getenv("TFMQ_IGEMM_DBG")) : 0;
+  p.dbg = dbg_env;
+  p.prof = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  if (prof_env) {
+    cudaMalloc(&p.prof, (size_t)grid * 16 * sizeof(long long));
+    cudaMemsetAsync(p.prof, 0, (size_t)grid * 16 * sizeof(long long), stream);
+  }
+  if (prof_env || time_env) {
+    cudaEventCreate(&ev0);
+    cudaEventCreate(&ev1);
+    cudaEventRecord(ev0, stream);
+  }
   kern<<<grid, IGEMM_THREADS, smem, stream>>>(tmA, tmB, tmB2, tmOut, tmRes, p);
   TFMQ_LAUNCH_CHECK(name);
+  if (prof_env || time_env) {
+    cudaEventRecord(ev1, stream);
+    cudaStreamSynchronize(stream);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ev0, ev1);
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
+    fprintf(stderr, "[igemm layer %s] n %d %dx%d cin %d cout %d k%d s%d passes 0x%x res %d emb %d stat %d : %.1f us\n", name,
+            p.n_img, p.H, p.W, p.cin, p.cout, p.ksize, p.stride, p.pass_flags, p.res != nullptr, p.emb != nullptr,
+            p.n_stat, ms * 1e3f);
+  }
+  if (prof_env) {
+    std::vector<long long> hbuf((size_t)grid * 16);
+    cudaMemcpy(hbuf.data(), p.prof, hbuf.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+    cudaFree(p.prof);
+    double avg[16] = {0};
+    for (int b = 0; b < grid; ++b)
+      for (int i = 0; i < 16; ++i) avg[i] += (double)hbuf[(size_t)b * 16 + i] / grid;
+    const double tpc = (double)total / grid;
+    fprintf(stderr,
+            "[igemm prof %s] tiles/cta %.2f nkb %d tile_n %d | epi per tile: prologue %.0f wait_acc %.0f tmem_ld %.0f "
+            "wait_res %.0f fold %.0f fence+bar %.0f stats %.0f store %.0f bar2 %.0f | tail %.0f | mma per tile: "
+            "wait_acc_empty %.0f wait_full %.0f issue %.0f\n",
+            name, tpc, nkb, p.tile_n, avg[0] / tpc, avg[1] / tpc, avg[2] / tpc, avg[3] / tpc, avg[4] / tpc, avg[5] / tpc,
+            avg[6] / tpc, avg[7] / tpc, avg[8] / tpc, avg[9], avg[10] / tpc, avg[11] / tpc, avg[12] / tpc);
+  }
   return TFMQ_OK;
 }
 
@@ -566,10 +741,21 @@ extern "C" int tfmq_conv_w4a8(tfmq_ctx* ctx, const tfmq_conv_w4a8_desc* d, void*
   p.n_img = d->n, p.H = d->h, p.W = d->w, p.cin = d->cin, p.cout = d->cout;
   p.ksize = d->ksize, p.stride = 1, p.off = 0;
   p.th = g.th, p.tw = g.tw, p.tn = g.tn;
-  p.tile_n = pick_tile_n(d->cout, 240);   // + 16 rows for the activation-sum column, UMMA N <= 256
+  {
+    // + 16 rows for the activation-sum column, UMMA N <= 256
+    const int tiles_m = (d->w / g.tw) * (d->h / g.th) * ((d->n + g.tn - 1) / g.tn);
+    const int nkb = d->ksize * d->ksize * ((d->cin + 127) / 128);
+    p.tile_n = pick_tile_n_balanced(d->cout, 240, tiles_m, nkb, ctx->sm_count, 400.0, 2.6);
+  }
   p.kchunk = 128, p.kslice = 32;
   p.out = d->out, p.out_ld = d->out_ld, p.bias = d->bias, p.wscale = d->wdelta, p.wsum = d->wsum, p.wzp = d->wzp;
   p.aq = d->aq, p.emb = d->emb, p.emb_ld = d->emb_ld, p.res = d->res, p.res_ld = d->res_ld;
+  TFMQ_REQUIRE(d->n_stat >= 0 && d->n_stat <= 2, TFMQ_ERR_ARG, "conv_w4a8: n_stat");
+  const bool fuse_stats = d->n_stat > 0 && g.tn == 1;
+  if (fuse_stats) {
+    p.n_stat = d->n_stat;
+    for (int i = 0; i < d->n_stat; ++i) p.stat[i] = d->stat[i];
+  }
 
   const int halo = d->ksize == 3 ? 1 : 0;
   const cuuint64_t Hp = d->h + 2 * halo, Wp = d->w + 2 * halo;
@@ -593,7 +779,10 @@ extern "C" int tfmq_conv_w4a8(tfmq_ctx* ctx, const tfmq_conv_w4a8_desc* d, void*
                     CU_TENSOR_MAP_SWIZZLE_NONE);
     if (rc) return rc;
   }
-  return launch_igemm<MODE_W4A8>(ctx, tmA, tmB, tmB, p, tfmq_stream(stream), "conv_w4a8");
+  int rc = launch_igemm<MODE_W4A8>(ctx, tmA, tmB, tmB, p, tfmq_stream(stream), "conv_w4a8");
+  for (int i = 0; rc == TFMQ_OK && !fuse_stats && i < d->n_stat; ++i)
+    rc = tfmq_gn_stats_part(ctx, d->out, d->out_ld, d->n, d->h * d->w, d->cout, &d->stat[i], stream);
+  return rc;
 }
 
 extern "C" int tfmq_conv_fp(tfmq_ctx* ctx, const tfmq_conv_fp_desc* d, void* stream) {
@@ -620,13 +809,23 @@ extern "C" int tfmq_conv_fp(tfmq_ctx* ctx, const tfmq_conv_fp_desc* d, void* str
   // two accumulator stages (each hi + lo) need tile_n <= 128; long main loops (3x3 convs) amortise an
   // un-overlapped epilogue better than they tolerate re-reading and re-splitting A once per N tile
   const int nkb_est = d->ksize * d->ksize * ((d->cin + 31) / 32);
-  p.tile_n = pick_tile_n(d->cout, (d->passes == 3 && nkb_est < 48) ? 128 : 256);
+  {
+    const int tiles_m = (d->out_w / g.tw) * (d->out_h / g.th) * ((d->n + g.tn - 1) / g.tn);
+    const int limit = (d->passes == 3 && nkb_est < 48) ? 128 : 256;
+    p.tile_n = pick_tile_n_balanced(d->cout, limit, tiles_m, nkb_est, ctx->sm_count, 300.0, 2.0 * d->passes);
+  }
   p.kchunk = 32, p.kslice = 8;
   p.pass_flags = PASS_HI_HI;
   if (d->passes == 3) p.pass_flags |= PASS_LO_HI | (d->w_lo ? PASS_HI_LO : 0);
   p.out = d->out, p.out_ld = d->out_ld, p.bias = d->bias, p.wscale = d->wscale;
   p.res = d->res, p.res_ld = d->res_ld;
   p.emb = d->emb, p.emb_ld = d->emb_ld;
+  TFMQ_REQUIRE(d->n_stat >= 0 && d->n_stat <= 2, TFMQ_ERR_ARG, "conv_fp: n_stat");
+  const bool fuse_stats = d->n_stat > 0 && g.tn == 1;
+  if (fuse_stats) {
+    p.n_stat = d->n_stat;
+    for (int i = 0; i < d->n_stat; ++i) p.stat[i] = d->stat[i];
+  }
 
   CUtensorMap tmA, tmB, tmB2;
   {
@@ -657,7 +856,10 @@ extern "C" int tfmq_conv_fp(tfmq_ctx* ctx, const tfmq_conv_fp_desc* d, void* str
                     CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
-  return launch_igemm<MODE_TF32>(ctx, tmA, tmB, tmB2, p, tfmq_stream(stream), "conv_fp");
+  int rc = launch_igemm<MODE_TF32>(ctx, tmA, tmB, tmB2, p, tfmq_stream(stream), "conv_fp");
+  for (int i = 0; rc == TFMQ_OK && !fuse_stats && i < d->n_stat; ++i)
+    rc = tfmq_gn_stats_part(ctx, d->out, d->out_ld, d->n, d->out_h * d->out_w, d->cout, &d->stat[i], stream);
+  return rc;
 }
 
 extern "C" int tfmq_gemm_i8_peak(tfmq_ctx* ctx, const uint8_t* a, const int8_t* b, int m, int n, int k, int32_t* out,

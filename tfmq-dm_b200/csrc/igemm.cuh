@@ -15,6 +15,8 @@
 #include <cstdint>
 #include <cuda.h>
 
+#include "../../include/tfmq_b200.h"
+
 namespace tfmq {
 
 enum { MODE_W4A8 = 0, MODE_I8 = 1, MODE_TF32 = 2 };
@@ -42,10 +44,16 @@ struct IgemmParams {
   const float* res;
   long long res_ld;
   int32_t* out_i32;  // MODE_I8: raw accumulators [pixels][cout]
+  int n_stat;        // fused GroupNorm statistics of the output (only when tn == 1)
+  tfmq_gn_target stat[2];
+  int dbg;           // debug: bit0 = producer skips the TMA loads (timing experiments only, TFMQ_IGEMM_DBG)
+  long long* prof;   // debug: per-CTA phase cycle counters [grid][16] (TFMQ_IGEMM_PROF=1), else null
 };
 
-constexpr int IGEMM_XF_WARPS = 8;
-constexpr int IGEMM_THREADS = (6 + IGEMM_XF_WARPS) * 32;
+constexpr int IGEMM_EPI_WARPS = 8;   // warps 0..7: two per TMEM lane quarter (each takes half of a chunk's columns)
+constexpr int IGEMM_XF_WARPS = 4;    // last warps: operand transform
+constexpr int IGEMM_WARP_TMA = IGEMM_EPI_WARPS, IGEMM_WARP_MMA = IGEMM_EPI_WARPS + 1, IGEMM_WARP_XF0 = IGEMM_EPI_WARPS + 2;
+constexpr int IGEMM_THREADS = (IGEMM_EPI_WARPS + 2 + IGEMM_XF_WARPS) * 32;
 constexpr uint32_t IGEMM_A_BYTES = 128 * 128;
 
 template <int MODE>

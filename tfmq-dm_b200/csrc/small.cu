@@ -17,61 +17,83 @@ __device__ __forceinline__ int warp_sum_i(int v) {
   return v;
 }
 
-// grid (out chunks of 64, m); phase 1: the row's inputs are transformed ONCE (SiLU, act fake-quant) into
-// shared memory; phase 2: every warp produces 8 outputs, lanes striding over the input features.
+// Time-embedding MLP layer.  grid (out chunks of 64, row chunks of 8).  Phase 1: the 8 rows' inputs are
+// transformed ONCE (SiLU, act fake-quant) into shared memory.  Phase 2: every warp produces 8 outputs; each
+// weight is read once (4 consecutive features per lane, all loads of an output issued before use) and applied
+// to the 8 rows.
 constexpr int LIN_THREADS = 256;
-constexpr int LIN_OUT_PER_CTA = 64;
+constexpr int LIN_OUT_PER_CTA = 8;   // one output per warp: many small CTAs, short dependent-load chains
+constexpr int LIN_ROWS = 8;
 
 __global__ void __launch_bounds__(LIN_THREADS) linear_small_kernel(const tfmq_linear_desc d) {
-  extern __shared__ float xs[];                 // [in_f] transformed inputs (fp32, or integer codes - zp as fp32)
-  const int m = blockIdx.y;
+  extern __shared__ float xs[];                 // [LIN_ROWS][in_f]: fp32 inputs, or (code - zp) as fp32
+  const int m0 = blockIdx.y * LIN_ROWS;
+  const int rows = min(LIN_ROWS, d.m - m0);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const float* x = d.x + (long long)m * d.x_ld;
   float dl = 1.f, z = 0.f;
   if (d.aq) dl = d.aq[0], z = d.aq[1];
-  for (int i = threadIdx.x; i < d.in_f; i += LIN_THREADS) {
-    float v = x[i];
-    if (d.silu_in) v = silu1(v);
-    if (d.aq) {
-      const float q = fminf(fmaxf(rintf(__fdiv_rn(v, dl)) + z, 0.f), 255.f);
-      v = d.w_f32 ? dl * (q - z) : (q - z);     // integer path keeps the exact (code - zp)
+  for (int i = threadIdx.x; i < LIN_ROWS * d.in_f; i += LIN_THREADS) {
+    const int r = i / d.in_f, f = i - r * d.in_f;
+    float v = 0.f;
+    if (r < rows) {
+      v = d.x[(long long)(m0 + r) * d.x_ld + f];
+      if (d.silu_in) v = silu1(v);
+      if (d.aq) {
+        const float q = fminf(fmaxf(rintf(__fdiv_rn(v, dl)) + z, 0.f), 255.f);
+        v = d.w_f32 ? dl * (q - z) : (q - z);   // integer path keeps the exact (code - zp)
+      }
     }
     xs[i] = v;
   }
   __syncthreads();
-  // 8 outputs per warp, all in flight at once: the feature loop is outermost so every iteration issues 8
-  // independent weight loads (the per-output loops were latency-bound)
-  constexpr int OPW = LIN_OUT_PER_CTA / 8;
-  const int o0 = blockIdx.x * LIN_OUT_PER_CTA + warp * OPW;
-  float facc[OPW];
-  int iacc[OPW];
-#pragma unroll
-  for (int oo = 0; oo < OPW; ++oo) facc[oo] = 0.f, iacc[oo] = 0;
   const bool int_path = !d.w_f32 && d.aq;
-  for (int i = lane; i < d.in_f; i += 32) {
-    const float xv = xs[i];
+  const int nv = d.in_f >> 2;                   // in_f is a multiple of 4
+  for (int oo = 0; oo < LIN_OUT_PER_CTA / 8; ++oo) {
+    const int o = blockIdx.x * LIN_OUT_PER_CTA + warp * (LIN_OUT_PER_CTA / 8) + oo;
+    if (o >= d.out_f) break;
+    float acc[LIN_ROWS];
 #pragma unroll
-    for (int oo = 0; oo < OPW; ++oo) {
-      const int o = min(o0 + oo, d.out_f - 1);
-      if (d.w_f32) {
-        facc[oo] = fmaf(xv, d.w_f32[(long long)o * d.in_f + i], facc[oo]);
-      } else {
-        const int wv = (int)d.codes[(long long)o * d.in_f + i] - (int)d.wzp_f[o];
-        if (int_path)
-          iacc[oo] += (int)xv * wv;
-        else
-          facc[oo] = fmaf(xv, (float)wv, facc[oo]);
+    for (int r = 0; r < LIN_ROWS; ++r) acc[r] = 0.f;
+    const float zw = d.w_f32 ? 0.f : d.wzp_f[o];
+    for (int v0 = lane; v0 < nv; v0 += 32 * 4) {
+      float4 wv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int v = v0 + 32 * u;
+        wv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (v < nv) {
+          if (d.w_f32) {
+            wv[u] = *reinterpret_cast<const float4*>(d.w_f32 + (long long)o * d.in_f + 4 * v);
+          } else {
+            const uint32_t c4 = *reinterpret_cast<const uint32_t*>(d.codes + (long long)o * d.in_f + 4 * v);
+            wv[u] = make_float4((float)(c4 & 255u) - zw, (float)((c4 >> 8) & 255u) - zw,
+                                (float)((c4 >> 16) & 255u) - zw, (float)(c4 >> 24) - zw);
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int v = v0 + 32 * u;
+        if (v < nv) {
+#pragma unroll
+          for (int r = 0; r < LIN_ROWS; ++r) {
+            const float4 xv = *reinterpret_cast<const float4*>(xs + r * d.in_f + 4 * v);
+            acc[r] = fmaf(xv.x, wv[u].x, fmaf(xv.y, wv[u].y, fmaf(xv.z, wv[u].z, fmaf(xv.w, wv[u].w, acc[r]))));
+          }
+        }
       }
     }
-  }
+    // integer path: every product and partial sum is an exact integer below 2^24 in magnitude per lane
+    // (|code - zp| <= 255, |w| <= 15, in_f / 32 terms), so fp32 accumulation is exact
 #pragma unroll
-  for (int oo = 0; oo < OPW; ++oo) {
-    const int o = o0 + oo;
-    float r = int_path ? (float)warp_sum_i(iacc[oo]) : warp_sum(facc[oo]);
-    if (o < d.out_f && lane == 0) {
-      if (!d.w_f32) r *= int_path ? (dl * d.wdelta[o]) : d.wdelta[o];
-      if (d.bias) r += d.bias[o];
-      d.out[(long long)m * d.out_ld + o] = r;
+    for (int r = 0; r < LIN_ROWS; ++r) {
+      const float t = warp_sum(acc[r]);
+      if (lane == 0 && r < rows) {
+        float res = t;
+        if (!d.w_f32) res *= int_path ? (dl * d.wdelta[o]) : d.wdelta[o];
+        if (d.bias) res += d.bias[o];
+        d.out[(long long)(m0 + r) * d.out_ld + o] = res;
+      }
     }
   }
 }
@@ -188,9 +210,12 @@ extern "C" int tfmq_linear_small(tfmq_ctx* ctx, const tfmq_linear_desc* d, void*
   TFMQ_REQUIRE(d->w_f32 || (d->codes && d->wzp_f && d->wdelta), TFMQ_ERR_ARG, "linear_small: weights missing");
   TFMQ_REQUIRE(d->m >= 0 && d->m <= 4096 && d->in_f > 0 && d->out_f > 0, TFMQ_ERR_SHAPE, "linear_small: m=%d", d->m);
   if (d->m == 0) return TFMQ_OK;
-  TFMQ_REQUIRE(d->in_f <= 8192, TFMQ_ERR_SHAPE, "linear_small: in_f %d > 8192", d->in_f);
-  dim3 grid((d->out_f + LIN_OUT_PER_CTA - 1) / LIN_OUT_PER_CTA, d->m);
-  linear_small_kernel<<<grid, LIN_THREADS, (size_t)d->in_f * sizeof(float), tfmq_stream(stream)>>>(*d);
+  TFMQ_REQUIRE(d->in_f <= 1536 && d->in_f % 4 == 0, TFMQ_ERR_SHAPE, "linear_small: in_f %d (multiple of 4, <= 1536)",
+               d->in_f);
+  TFMQ_REQUIRE(d->w_f32 ? ((uintptr_t)d->w_f32 & 15) == 0 : ((uintptr_t)d->codes & 3) == 0, TFMQ_ERR_ARG,
+               "linear_small: weights must be 16-byte (fp32) / 4-byte (codes) aligned");
+  dim3 grid((d->out_f + LIN_OUT_PER_CTA - 1) / LIN_OUT_PER_CTA, (d->m + LIN_ROWS - 1) / LIN_ROWS);
+  linear_small_kernel<<<grid, LIN_THREADS, (size_t)LIN_ROWS * d->in_f * sizeof(float), tfmq_stream(stream)>>>(*d);
   TFMQ_LAUNCH_CHECK("linear_small");
   return TFMQ_OK;
 }

@@ -15,6 +15,11 @@ c_f32p = C.c_void_p  # device pointers travel as integers
 i64 = C.c_int64
 
 
+class GnTarget(C.Structure):
+    _fields_ = [("stats", C.c_void_p), ("cpg", C.c_int), ("ch_off", C.c_int), ("groups", C.c_int),
+                ("reserved", C.c_int)]
+
+
 class ActDesc(C.Structure):
     _fields_ = [
         ("src", C.c_void_p), ("src_ld", i64),
@@ -38,6 +43,7 @@ class ConvW4A8Desc(C.Structure):
         ("emb", C.c_void_p), ("emb_ld", i64),
         ("res", C.c_void_p), ("res_ld", i64),
         ("out", C.c_void_p), ("out_ld", i64),
+        ("n_stat", C.c_int), ("stat", GnTarget * 2),
     ]
 
 
@@ -52,6 +58,7 @@ class ConvFpDesc(C.Structure):
         ("out", C.c_void_p), ("out_ld", i64),
         ("passes", C.c_int),
         ("emb", C.c_void_p), ("emb_ld", i64),
+        ("n_stat", C.c_int), ("stat", GnTarget * 2),
     ]
 
 
@@ -87,6 +94,7 @@ _SIGS = {
     "tfmq_launch_count": (i64, [P]),
     "tfmq_pack_w4": (C.c_int, [P, P, P, P, P, C.c_int, C.c_int, P, P, P, P]),
     "tfmq_gn_stats": (C.c_int, [P, P, i64, C.c_int, C.c_int, C.c_int, C.c_int, P, P]),
+    "tfmq_gn_stats_part": (C.c_int, [P, P, i64, C.c_int, C.c_int, C.c_int, C.POINTER(GnTarget), P]),
     "tfmq_fill_zero": (C.c_int, [P, P, C.c_size_t, P]),
     "tfmq_act_prepare": (C.c_int, [P, C.POINTER(ActDesc), P]),
     "tfmq_conv_w4a8": (C.c_int, [P, C.POINTER(ConvW4A8Desc), P]),

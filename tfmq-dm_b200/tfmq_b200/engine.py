@@ -40,6 +40,8 @@ class T:
         self.c_off = 0
         self.buf: Optional[torch.Tensor] = None
         self._view = None
+        self.producer: Optional[dict] = None   # record of the LAST conv writing this tensor (fused GN statistics)
+        self.children: List["T"] = []
 
     def root(self):
         t, off = self, 0
@@ -61,6 +63,7 @@ def _cat(a: T, b: T) -> T:
     p = T(a.n, a.h, a.w, a.c + b.c)
     a.parent, a.c_off = p, 0
     b.parent, b.c_off = p, a.c
+    p.children = [a, b]
     return p
 
 
@@ -107,12 +110,14 @@ class _QL:
 
 class StepEngine:
     def __init__(self, qnn, batch: int, act_tables: Optional[Sequence[Dict[str, torch.Tensor]]] = None,
-                 timesteps: Optional[Sequence[int]] = None, fp_passes: int = 3, device=None, use_graph: bool = True):
+                 timesteps: Optional[Sequence[int]] = None, fp_passes: int = 3, device=None, use_graph: bool = True,
+                 fuse_gn: bool = True):
         model = qnn.model
         self.dev = torch.device(device) if device is not None else next(model.parameters()).device
         if self.dev.type != "cuda":
             raise RuntimeError("StepEngine needs the model on an sm_100a GPU (no CPU path)")
         self.batch, self.fp_passes, self.use_graph = batch, fp_passes, use_graph
+        self.fuse_gn = fuse_gn   # GroupNorm statistics accumulated by the producing conv's epilogue
         self.kind = "ddim" if hasattr(model, "temb") else "ldm"
         self.model = model
         self.ops: List = []
@@ -219,11 +224,25 @@ class StepEngine:
         return t
 
     def _gn(self, x: T, norm: nn.GroupNorm):
+        """GroupNorm statistics of x.  Every leaf of x (x itself, or the two parts of a skip concat) whose last
+        writer is one of the tensor-core convs gets the statistics accumulated by that conv's epilogue;
+        other leaves (conv_in output) get a stand-alone partial-statistics launch here."""
         slot = self._gn_slots
         self._gn_slots += 1
         g = norm.num_groups
-        self.ops.append(lambda: ops.gn_stats(x.view, g, self.gn_ws[slot]))
+        cpg = x.c // g
+        leaves = x.children if x.children else [x]
+        off = 0
+        for leaf in leaves:
+            if self.fuse_gn and leaf.producer is not None and len(leaf.producer["stats"]) < 2:
+                leaf.producer["stats"].append((slot, cpg, off))
+            else:
+                self.ops.append(lambda leaf=leaf, off=off: ops.gn_stats_part(leaf.view, self.gn_ws[slot], cpg, off))
+            off += leaf.c
         return (norm, slot)
+
+    def _stats_of(self, rec):
+        return [(self.gn_ws[slot], cpg, off) for slot, cpg, off in rec["stats"]] or None
 
     def _gn_args(self, gn):
         if gn is None:
@@ -253,6 +272,8 @@ class StepEngine:
             self._u8_bufs.append(u8)
             self.u8_by_name[q.name] = (u8, halo)
             aq = self._aq_ptr(q)
+            rec = {"stats": []}
+            out.producer = rec
 
             def run():
                 ops.act_prepare(x.view, aq=aq, dst_u8=u8, halo=halo, silu=silu, upsample=upsample, **self._gn_args(gn))
@@ -260,7 +281,7 @@ class StepEngine:
                     forced = self.teacher[q.name].to(self.dev).permute(0, 2, 3, 1)
                     (u8[:, 1:-1, 1:-1] if halo else u8).copy_(forced)
                 ops.conv_w4a8(u8, q.ksize, q.packed, q.wzp_u8, q.wdelta, q.wsum, q.bias, aq, out.view, emb=emb,
-                              res=res.view if res is not None else None)
+                              res=res.view if res is not None else None, stats=self._stats_of(rec))
             self.ops.append(run)
         else:
             assert not upsample
@@ -274,10 +295,12 @@ class StepEngine:
     def _fp_conv(self, q: _QL, src: T, out: T, res: Optional[T], pad_lo: int, stride: int = 1, emb=None):
         wscale = q.wdelta if q.quant_w else None
         passes = self.fp_passes
+        rec = {"stats": []}
+        out.producer = rec
 
         def run():
             ops.conv_fp(src.view, q.ksize, stride, pad_lo, q.w_hi, q.w_lo, out.view, bias=q.bias, wscale=wscale,
-                        res=res.view if res is not None else None, passes=passes, emb=emb)
+                        res=res.view if res is not None else None, passes=passes, emb=emb, stats=self._stats_of(rec))
         self.ops.append(run)
 
     def _plain_conv(self, conv: nn.Module, src: T, out: T, res: Optional[T], pad_lo: int, stride: int):
@@ -294,8 +317,11 @@ class StepEngine:
             self._plain[key] = (hi, lo, b, k)
         hi, lo, b, k = self._plain[key]
         passes = self.fp_passes
+        rec = {"stats": []}
+        out.producer = rec
         self.ops.append(lambda: ops.conv_fp(src.view, k, stride, pad_lo, hi, lo, out.view, bias=b,
-                                            res=res.view if res is not None else None, passes=passes))
+                                            res=res.view if res is not None else None, passes=passes,
+                                            stats=self._stats_of(rec)))
 
     def _linear(self, layer: QuantLayer, x: torch.Tensor, x_ld_zero: bool, silu_in: bool) -> torch.Tensor:
         """Time-embedding MLP layer on [batch, in] rows (row pitch 0 = the same row for every sample)."""

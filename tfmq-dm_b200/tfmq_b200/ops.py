@@ -11,7 +11,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import ActDesc, AttnDesc, ConvFpDesc, ConvW4A8Desc, LinearDesc
+from ._lib import ActDesc, AttnDesc, ConvFpDesc, ConvW4A8Desc, GnTarget, LinearDesc
 
 
 def _ctx(t: torch.Tensor) -> _lib.Context:
@@ -65,6 +65,24 @@ def gn_stats(x: torch.Tensor, groups: int, stats: torch.Tensor | None = None) ->
     return stats
 
 
+def _set_stats(d, stats):
+    """stats: list of (stats tensor [n, groups, 2] f64, cpg, ch_off) -- GroupNorm targets fed by a conv output."""
+    if not stats:
+        return
+    assert len(stats) <= 2
+    d.n_stat = len(stats)
+    for i, (t, cpg, ch_off) in enumerate(stats):
+        d.stat[i].stats, d.stat[i].cpg, d.stat[i].ch_off, d.stat[i].groups = t.data_ptr(), cpg, ch_off, t.shape[-2]
+
+
+def gn_stats_part(x: torch.Tensor, stats: torch.Tensor, cpg: int, ch_off: int):
+    ctx = _ctx(x)
+    n, h, w, c, ld = _nhwc(x)
+    t = GnTarget()
+    t.stats, t.cpg, t.ch_off, t.groups = stats.data_ptr(), cpg, ch_off, stats.shape[-2]
+    ctx.call("tfmq_gn_stats_part", _p(x), ld, n, h * w, c, C.byref(t), _stream())
+
+
 def fill_zero(t: torch.Tensor):
     _ctx(t).call("tfmq_fill_zero", _p(t), t.numel() * t.element_size(), _stream())
 
@@ -100,7 +118,7 @@ def act_prepare(src: torch.Tensor, *, aq: torch.Tensor | None = None, dst_u8: to
 
 # --------------------------------------------------------------------------- tensor-core convs
 def conv_w4a8(act: torch.Tensor, ksize: int, packed, wzp_u8, wdelta, wsum, bias, aq, out: torch.Tensor,
-              emb: torch.Tensor | None = None, res: torch.Tensor | None = None):
+              emb: torch.Tensor | None = None, res: torch.Tensor | None = None, stats=None):
     """act: u8 [N, H+2h, W+2h, Cin] (h = 1 for 3x3, 0 for 1x1); out: fp32 NHWC view [N,H,W,Cout]."""
     ctx = _ctx(out)
     n, h, w, cout, out_ld = _nhwc(out)
@@ -121,11 +139,12 @@ def conv_w4a8(act: torch.Tensor, ksize: int, packed, wzp_u8, wdelta, wsum, bias,
         assert (rn, rh, rw, rc) == (n, h, w, cout)
         d.res, d.res_ld = res.data_ptr(), rld
     d.out, d.out_ld = out.data_ptr(), out_ld
+    _set_stats(d, stats)
     ctx.call("tfmq_conv_w4a8", C.byref(d), _stream())
 
 
 def conv_fp(x: torch.Tensor, ksize: int, stride: int, pad_lo: int, w_hi, w_lo, out: torch.Tensor, bias=None,
-            wscale=None, res=None, passes: int = 3, emb=None):
+            wscale=None, res=None, passes: int = 3, emb=None, stats=None):
     ctx = _ctx(out)
     n, h, w, cin, x_ld = _nhwc(x)
     on, oh, ow, cout, out_ld = _nhwc(out)
@@ -147,6 +166,7 @@ def conv_fp(x: torch.Tensor, ksize: int, stride: int, pad_lo: int, w_hi, w_lo, o
     if emb is not None:
         assert emb.stride(-1) == 1
         d.emb, d.emb_ld = emb.data_ptr(), (emb.stride(0) if emb.dim() == 2 and emb.shape[0] > 1 else 0)
+    _set_stats(d, stats)
     ctx.call("tfmq_conv_fp", C.byref(d), _stream())
 
 
