@@ -76,17 +76,26 @@ struct ActParams {
 
 // x*sigmoid(x); __expf / __frcp_rn keep the result within ~2 ulp of the accurate form, far below the
 // activation quantisation step, at a fraction of the instruction count
-__device__ __forceinline__ float silu_f(float v) { return v * __frcp_rn(1.f + __expf(-v)); }
+__device__ __forceinline__ float rcp_approx(float v) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+  return r;
+}
+__device__ __forceinline__ float silu_f(float v) { return v * rcp_approx(1.f + __expf(-v)); }
 
 // code = clamp(rint(RN(t / delta)) + zp, 0, 255), bit-identical to the reference's fp32 divide + round,
 // without paying for an IEEE division on every element: rint(t * (1/delta)) can differ from rint(RN(t/delta))
 // only when t/delta lies within a few ulps of a rounding boundary; the exact remainder (one FMA) detects that
 // case and only then the correctly rounded division is evaluated.
+// Rounding and the float -> integer move use the 1.5*2^23 / 2^23 add tricks (full-rate FADD, round-half-even
+// like rintf) instead of FRND / F2I, which share the quarter-rate pipe with the SiLU's EX2 / RCP.
 __device__ __forceinline__ uint32_t quant1(float t, float delta, float inv, float zp) {
-  float nq = rintf(t * inv);
+  const float q = fminf(fmaxf(t * inv, -1024.f), 1024.f);   // beyond +-1024 steps the code saturates either way
+  float nq = __fsub_rn(__fadd_rn(q, 12582912.f), 12582912.f);
   const float rem = fmaf(-nq, delta, t);
   if (fabsf(fabsf(rem) * inv - 0.5f) < 1e-6f * fmaxf(fabsf(nq), 1.f)) nq = rintf(__fdiv_rn(t, delta));
-  return (uint32_t)fminf(fmaxf(nq + zp, 0.f), 255.f);
+  const float code = fminf(fmaxf(nq + zp, 0.f), 255.f);
+  return __float_as_uint(__fadd_rn(code, 8388608.f)) & 0xFFu;
 }
 __device__ __forceinline__ uint32_t quant4(const float (&t)[4], float delta, float inv, float zp) {
   return quant1(t[0], delta, inv, zp) | (quant1(t[1], delta, inv, zp) << 8) | (quant1(t[2], delta, inv, zp) << 16) |
@@ -101,19 +110,25 @@ __global__ void __launch_bounds__(ACT_THREADS) act_prepare_kernel(const ActParam
   const int n = blockIdx.y;
   const int c = d.c;
   if (d.gn_stats) {
+    // the double-precision part (mean, 1/sqrt(var+eps)) once per group, not per channel
+    __shared__ float sg[2 * 64];
     const int cpg = c / d.groups;
     const double cnt = (double)cpg * d.h * d.w;
-    for (int ch = threadIdx.x; ch < c; ch += ACT_THREADS) {
-      const int g = ch / cpg;
+    for (int g = threadIdx.x; g < d.groups; g += ACT_THREADS) {
       const double su = d.gn_stats[((long long)n * d.groups + g) * 2];
       const double sq = d.gn_stats[((long long)n * d.groups + g) * 2 + 1];
       const double mean = su / cnt;
       double var = sq / cnt - mean * mean;
       if (var < 0) var = 0;
-      const float rstd = (float)(1.0 / sqrt(var + (double)d.eps));
-      const float a = rstd * d.gamma[ch];
+      sg[2 * g] = (float)(1.0 / sqrt(var + (double)d.eps));
+      sg[2 * g + 1] = (float)mean;
+    }
+    __syncthreads();
+    for (int ch = threadIdx.x; ch < c; ch += ACT_THREADS) {
+      const int g = ch / cpg;
+      const float a = sg[2 * g] * d.gamma[ch];
       sp[ch] = a;
-      sp[c + ch] = -a * (float)mean + d.beta[ch];
+      sp[c + ch] = -a * sg[2 * g + 1] + d.beta[ch];
     }
     __syncthreads();
   }
@@ -288,8 +303,8 @@ extern "C" int tfmq_act_prepare(tfmq_ctx* ctx, const tfmq_act_desc* d, void* str
     TFMQ_REQUIRE(d->dst_ld % 4 == 0 && ((uintptr_t)d->dst_f32 & 15) == 0, TFMQ_ERR_SHAPE, "act_prepare: dst_ld/align");
   }
   if (d->gn_stats) {
-    TFMQ_REQUIRE(d->gamma && d->beta && d->groups > 0 && d->c % d->groups == 0, TFMQ_ERR_ARG,
-                 "act_prepare: GroupNorm parameters");
+    TFMQ_REQUIRE(d->gamma && d->beta && d->groups > 0 && d->groups <= 64 && d->c % d->groups == 0, TFMQ_ERR_ARG,
+                 "act_prepare: GroupNorm parameters (groups <= 64)");
     TFMQ_REQUIRE(!d->upsample, TFMQ_ERR_ARG, "act_prepare: GN with upsample unsupported");
   }
   if (d->n == 0) return TFMQ_OK;
