@@ -215,6 +215,15 @@ typedef struct {
 } tfmq_linear_desc;
 int tfmq_linear_small(tfmq_ctx* ctx, const tfmq_linear_desc* d, void* stream);
 
+/* Several small-M linears in ONE launch: the per-block embedding projections of a Temporal Information Block
+ * (quant/quant_block.py:58-63,108-114 -- a Python loop over `emb_layers`, one SiLU + quantise + F.linear per block) all
+ * read the same embedding.  `tfmq_linear_grouped_plan` validates n HOST descriptors (same m) and fills
+ * cta_start_host[0..n] (prefix sums of ceil(out_f / 8)); the caller uploads the descriptors and the prefix array
+ * once and replays `tfmq_linear_grouped` (descs_dev / cta_start_dev are DEVICE pointers; total_ctas = cta_start[n]). */
+int tfmq_linear_grouped_plan(tfmq_ctx* ctx, const tfmq_linear_desc* descs_host, int n, int* cta_start_host);
+int tfmq_linear_grouped(tfmq_ctx* ctx, const tfmq_linear_desc* descs_dev, const int* cta_start_dev, int n,
+                        int total_ctas, int m, int max_in_f, void* stream);
+
 /* sinusoidal timestep embedding.  style 0: DDIM [sin|cos], freq = exp(-ln(1e4) i/(half-1))
  * (ddim/models/diffusion.py:6-24); style 1: LDM [cos|sin], freq = exp(-ln(1e4) i/half)
  * (ldm/modules/diffusionmodules/util.py:151-171). t is fp32 [m]. */

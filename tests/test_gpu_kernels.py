@@ -259,6 +259,39 @@ def test_linear_small_variants(dev):
     assert (out.cpu() - ref).abs().max().item() < 2e-2 * da.item() * 16 + 1e-5
 
 
+def test_linear_grouped_equals_separate_launches(dev):
+    """The Temporal Information Block's per-block projections as one launch: bit-identical to one launch each."""
+    ops, q = _ops(), _qref()
+    g = torch.Generator().manual_seed(12)
+    m, i = 11, 896
+    x = torch.randn(m, i, generator=g).to(dev)
+    layers, sep = [], []
+    for o in (896, 224, 448, 672, 8, 100):
+        w = torch.randn(o, i, generator=g) / math.sqrt(i)
+        b = (torch.randn(o, generator=g) * 0.1).to(dev)
+        dw, zw = q.channel_wise(q.minmax_scale, w, 16)
+        codes = q.uaq_codes(w, dw, zw, 16).to(torch.uint8).to(dev)
+        da, za = q.minmax_scale(q.silu(x.cpu()), 256)
+        aq = torch.tensor([da.item() * (1 + 0.01 * o), za.item()], device=dev)
+        kw = dict(x=x, codes=codes, wzp_f=zw.reshape(-1).to(dev), wdelta=dw.reshape(-1).contiguous().to(dev), bias=b,
+                  aq=aq, silu_in=True)
+        layers.append(dict(kw, out=torch.zeros((m, o), device=dev)))
+        sep.append(dict(kw, out=torch.zeros((m, o), device=dev)))
+    wf = (torch.randn(64, i, generator=g) / math.sqrt(i)).to(dev)    # an fp member
+    layers.append(dict(x=x, w_f32=wf, out=torch.zeros((m, 64), device=dev)))
+    sep.append(dict(x=x, w_f32=wf, out=torch.zeros((m, 64), device=dev)))
+    grp = ops.LinearGroup(layers)
+    grp.run()
+    for kw in sep:
+        kw = dict(kw)
+        xx, out = kw.pop("x"), kw.pop("out")
+        ops.linear_small(xx, out, **kw)
+    torch.cuda.synchronize()
+    for a, b_ in zip(layers, sep):
+        assert torch.equal(a["out"], b_["out"])
+        assert a["out"].abs().max().item() > 0
+
+
 def test_conv_in_out(dev):
     ops = _ops()
     g = torch.Generator().manual_seed(2)

@@ -16,13 +16,14 @@ namespace tfmq {
 // ---------------------------------------------------------------------------
 // Persistent: grid = min(#tiles, #SMs); each CTA walks tiles t = blockIdx.x, +gridDim.x, ... with the
 // M index fastest, so CTAs running together share one weight tile in L2.
-//   warps 0-3   epilogue: TMEM -> registers -> swizzled smem chunk (+ TMA-prefetched residual) -> TMA store,
+//   warps 0-7   epilogue: TMEM -> registers -> swizzled smem chunk (+ TMA-prefetched residual) -> TMA store,
 //               overlapped with the next tile's main loop through the second accumulator stage
-//   warp 4      TMA producer
-//   warp 5      UMMA issuer (owns TMEM: 1 or 2 accumulator stages)
-//   warps 6-13  operand transform (int4 unpack / tf32 hi-lo split).  They are the critical path of the
-//               main loop, so they get the highest warp ids (the SM arbiter favours high ids) and the
-//               non-critical waits (producer, epilogue) back off with nanosleep instead of spinning.
+//   warp 8      TMA producer
+//   warp 9      UMMA issuer (owns TMEM: 1 or 2 accumulator stages)
+//   warps 10-13 operand transform (int4 -> s8 expansion / tf32 hi-lo split); highest warp ids because the SM
+//               arbiter favours them and they sit on the critical path of the main loop
+// w4a8 pipeline: A ring (TMA -> UMMA), s8 B ring (transform warps -> UMMA); the packed int4 weights never sit in
+// shared memory, they are prefetched from L2 into registers.  See the transform warps.
 // GroupNorm partial sums of one epilogue chunk: thread = (column, block of rows); loads batched by full unrolling
 template <int CW>
 __device__ __forceinline__ float2 chunk_col_partial(const uint8_t* buf, int et) {
@@ -49,7 +50,7 @@ __device__ __forceinline__ float2 chunk_col_partial(const uint8_t* buf, int et) 
     prof_t = now_;                                          \
   }
 
-template <int MODE>
+template <int MODE, int CG>
 __global__ void __launch_bounds__(IGEMM_THREADS, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmOut,
@@ -62,82 +63,120 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int S = p.stages;
+  const int S = p.stages;        // pipeline stages (w4a8: depth of the A ring)
+  const int SU = p.u_stages;     // w4a8: depth of the unpacked-B ring
   const int ACC = p.acc_stages;
+  constexpr bool W4 = (MODE == MODE_W4A8);
 
-  uint8_t* ebuf = smem + (size_t)S * p.stage_bytes;                       // 2 epilogue chunks [128][chunk_w] f32
+  // w4a8:   [A ring: S x 16 KB][s8 B ring: SU x u_bytes][packed int4 ring: SP x p_bytes] | other modes: [S x stage_bytes]
+  const int SP = p.p_stages;
+  uint8_t* u_ring = smem + (size_t)S * IGEMM_A_BYTES;
+  uint8_t* p_ring = u_ring + (size_t)SU * p.u_bytes;
+  uint8_t* ebuf = W4 ? p_ring + (size_t)SP * p.p_bytes : smem + (size_t)S * p.stage_bytes;   // 2 epilogue chunks
   float4* chp = reinterpret_cast<float4*>(ebuf + 2 * 128 * 32 * 4);        // [tile_n] per-channel constants
-  float2* cstat = reinterpret_cast<float2*>(ebuf + 2 * 128 * 32 * 4 + 256 * 16);  // [256] per-channel (sum, sumsq)
-  float2* cpart = cstat + 256;          // [2][parts][chunk_w] row-block partials of the last two chunks
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ebuf + 2 * 128 * 32 * 4 + 256 * 16 + 3 * 256 * 8);
-  uint64_t* full_tma = bars;            // [S] TMA bytes landed
-  uint64_t* full_xf = bars + S;         // [S] transform warps done
-  uint64_t* empty = bars + 2 * S;       // [S] UMMAs that read the stage retired
-  uint64_t* acc_full = bars + 3 * S;    // [2] accumulator stage complete
-  uint64_t* acc_empty = bars + 3 * S + 2;  // [2] accumulator stage drained by the epilogue
-  uint64_t* res_full = bars + 3 * S + 4;   // [2] residual chunk landed in the epilogue buffer
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * S + 6);
+  float2* cstat = reinterpret_cast<float2*>(ebuf + 2 * 128 * 32 * 4 + p.tile_n * 16);  // [tile_n] per-channel (sum, sumsq)
+  float2* cpart = cstat + p.tile_n;     // [2][parts][chunk_w] row-block partials of the last two chunks
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ebuf + 2 * 128 * 32 * 4 + p.tile_n * 24 + 2 * 256 * 8);
+  // barrier slots (8 bytes each, 32 slots): the two pipelines use the first 24 differently
+  uint64_t* full_tma = bars;            // [<=8] TMA bytes landed (w4a8: the A tile; CTA pair: of both CTAs, at the leader)
+  uint64_t* empty = bars + 8;           // [<=8] UMMAs that read the stage (w4a8: the A slot) retired
+  uint64_t* full_xf = bars + 16;        // [<=8] transform warps done (w4a8: s8 B slot written, [<=4])
+  uint64_t* empty_u = bars + 20;        // w4a8 [<=4]: UMMAs that read the s8 B slot retired
+  uint64_t* acc_full = bars + 24;       // [2] accumulator stage complete
+  uint64_t* acc_empty = bars + 26;      // [2] accumulator stage drained by the epilogue
+  uint64_t* res_full = bars + 28;       // [2] residual chunk landed in the epilogue buffer
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 30);
+  uint64_t* full_p = bars + 32;         // w4a8 [<=4]: packed int4 tile landed
+  uint64_t* empty_p = bars + 36;        // w4a8 [<=4]: the transform warps hold the packed tile in registers
 
   const int tiles_x = p.W / p.tw;
   const int tiles_y = p.H / p.th;
   const int tiles_m = tiles_x * tiles_y * ((p.n_img + p.tn - 1) / p.tn);
   const int tiles_n = p.cout / p.tile_n;
-  const int total_tiles = tiles_m * tiles_n;
+  // CG == 2: a cluster of two CTAs (one TPC) works on two M-adjacent tiles of the same N tile with
+  // tcgen05.mma.cta_group::2 (M = 256): every CTA stages its own 128 pixels of A but only HALF of the N rows of B.
+  static_assert(CG == 1 || MODE == MODE_W4A8, "the CTA-pair path exists for the w4a8 mode");
+  const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const int unit0 = (CG == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;     // cluster (or CTA) index
+  const int nunits = (CG == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int tiles_mu = tiles_m / CG;
+  const int total_units = tiles_mu * tiles_n;
+  const int b_rows = p.b_rows[rank];       // weight rows of the N tile this CTA stages
   const int kchunks = (p.cin + p.kchunk - 1) / p.kchunk;
   const int taps = p.ksize * p.ksize;
   const int nkb = taps * kchunks;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < S; ++s) {
-      mbar_init(&full_tma[s], 1);
-      mbar_init(&full_xf[s], IGEMM_XF_WARPS);
-      mbar_init(&empty[s], 1);
+    if (W4) {
+      for (int s = 0; s < S; ++s) {
+        mbar_init(&full_tma[s], (CG == 2 && rank == 0) ? 2 : 1);   // own TMA (+ the peer's "my A landed" arrive)
+        mbar_init(&empty[s], 1);
+      }
+      for (int s = 0; s < SU; ++s) {
+        mbar_init(&full_xf[s], IGEMM_XF_GROUP_WARPS * CG);         // one transform group, of both CTAs of a pair
+        mbar_init(&empty_u[s], 1);
+      }
+      for (int s = 0; s < SP; ++s) {
+        mbar_init(&full_p[s], 1);
+        mbar_init(&empty_p[s], IGEMM_XF_GROUP_WARPS);
+      }
+    } else {
+      for (int s = 0; s < S; ++s) {
+        mbar_init(&full_tma[s], 1);
+        mbar_init(&full_xf[s], IGEMM_XF_WARPS);
+        mbar_init(&empty[s], 1);
+      }
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], IGEMM_EPI_WARPS);
+      mbar_init(&acc_empty[s], IGEMM_EPI_WARPS * CG);
       mbar_init(&res_full[s], 1);
     }
     mbar_fence_init();
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    if (MODE == MODE_TF32) tma_prefetch_desc(&tmB2);
+    if (MODE == MODE_TF32 || CG == 2) tma_prefetch_desc(&tmB2);
     tma_prefetch_desc(&tmOut);
     if (p.res) tma_prefetch_desc(&tmRes);
   }
-  if (warp == IGEMM_WARP_MMA) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
-  if (MODE == MODE_W4A8) {
-    // rows [tile_n, tile_n+16) of every B stage: row tile_n = 0x01 bytes, the rest zero (swizzle-invariant)
-    for (int i = threadIdx.x; i < S * 16 * 8; i += IGEMM_THREADS) {
+  if (warp == IGEMM_WARP_MMA) {
+    if (CG == 2) tmem_alloc2(tmem_slot, (uint32_t)p.tmem_cols);
+    else tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  }
+  if (W4 && rank == CG - 1) {
+    // the 16 B rows after the weight rows of every s8 B slot: first row = 0x01 bytes, the rest zero (swizzle-
+    // invariant); in a CTA pair they are the last rows of the second CTA's half.  Accumulator column tile_n then
+    // holds sum_k a[m][k], and the weight zero point is applied in the epilogue instead of per code.
+    for (int i = threadIdx.x; i < SU * 16 * 8; i += IGEMM_THREADS) {
       const int st_i = i / 128, rem = i - st_i * 128;
       const uint32_t fill = (rem < 8) ? 0x01010101u : 0u;
-      *reinterpret_cast<uint4*>(smem + (size_t)st_i * p.stage_bytes + p.offB + (size_t)p.tile_n * 128 + rem * 16) =
+      *reinterpret_cast<uint4*>(u_ring + (size_t)st_i * p.u_bytes + (size_t)b_rows * 128 + rem * 16) =
           make_uint4(fill, fill, fill, fill);
     }
     fence_proxy_async_smem();
   }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all();    // the peer's barriers are initialised before anything arrives on them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   const bool need_a_lo = (MODE == MODE_TF32) && (p.pass_flags & PASS_LO_HI);
   const bool need_b_lo = (MODE == MODE_TF32) && (p.pass_flags & PASS_HI_LO);
   const bool two_acc = need_a_lo || need_b_lo;                 // tf32: separate accumulator for the small terms
-  const uint32_t acc_cols = (MODE == MODE_W4A8) ? (uint32_t)p.tile_n + 16u : (uint32_t)p.tile_n * (two_acc ? 2u : 1u);
+  const uint32_t acc_cols = W4 ? (uint32_t)p.tile_n + 16u : (uint32_t)p.tile_n * (two_acc ? 2u : 1u);
 
   if (warp == IGEMM_WARP_TMA) {
     // ===================================================== TMA producer
     // (whole warp convergent, one elected lane issues: coordinates and addresses stay warp-uniform)
-    uint32_t tx_bytes = IGEMM_A_BYTES;
-    if (MODE == MODE_W4A8) tx_bytes += (uint32_t)p.tile_n * 64u;
+    uint32_t tx_bytes = IGEMM_A_BYTES;          // w4a8: the A tile only (B comes through the transform warps)
     if (MODE == MODE_I8) tx_bytes += (uint32_t)p.tile_n * 128u;
     if (MODE == MODE_TF32) tx_bytes += (uint32_t)p.tile_n * 128u * (need_b_lo ? 2u : 1u);
     int s = 0;
     uint32_t par = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      int mt = tile % tiles_m;
-      const int c_out0 = (tile / tiles_m) * p.tile_n;
+    for (int ut = unit0; ut < total_units; ut += nunits) {
+      int mt = (ut % tiles_mu) * CG + (int)rank;
+      const int c_out0 = (ut / tiles_mu) * p.tile_n;
       const int tx = mt % tiles_x;
       mt /= tiles_x;
       const int ty = mt % tiles_y;
@@ -145,7 +184,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       int kc = 0, kx = 0, ky = 0, tap = 0;
       for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait_relaxed(&empty[s], par ^ 1u);
-        uint8_t* st = smem + (size_t)s * p.stage_bytes;
+        uint8_t* st = W4 ? smem + (size_t)s * IGEMM_A_BYTES : smem + (size_t)s * p.stage_bytes;
         if (elect_one_sync()) {
           if (p.dbg & 1) {
             mbar_arrive(&full_tma[s]);
@@ -153,10 +192,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             mbar_expect_tx(&full_tma[s], tx_bytes);
             tma_load_4d(st, &tmA, &full_tma[s], kc * p.kchunk, x0 * p.stride + kx + p.off, y0 * p.stride + ky + p.off,
                         n0);
-            if (MODE == MODE_W4A8) {
-              // packed bytes: column = (tap*cin + kc*128)/2
-              tma_load_2d(st + p.offP, &tmB, &full_tma[s], (tap * p.cin + kc * p.kchunk) >> 1, c_out0);
-            } else {
+            if (!W4) {
               tma_load_2d(st + p.offB, &tmB, &full_tma[s], tap * p.cin + kc * p.kchunk, c_out0);
               if (need_b_lo) tma_load_2d(st + p.offB_lo, &tmB2, &full_tma[s], tap * p.cin + kc * p.kchunk, c_out0);
             }
@@ -170,33 +206,73 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (++s == S) s = 0, par ^= 1u;
       }
     }
+  } else if (warp == IGEMM_WARP_TMB) {
+    // ===================================================== TMA producer of the packed int4 weight tiles (w4a8)
+    if (W4) {
+      const CUtensorMap* tmBr = (CG == 2 && rank == 1) ? &tmB2 : &tmB;     // the two halves differ in box height
+      const int b_row0 = p.b_row0[rank];
+      const uint32_t tx_bytes = (uint32_t)b_rows * 64u;
+      int s = 0;
+      uint32_t par = 0;
+      for (int ut = unit0; ut < total_units; ut += nunits) {
+        const int c_out0 = (ut / tiles_mu) * p.tile_n;
+        int kc = 0, tap = 0;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait_relaxed(&empty_p[s], par ^ 1u);
+          if (elect_one_sync()) {
+            mbar_expect_tx(&full_p[s], tx_bytes);
+            // packed bytes: column = (tap*cin + kc*128)/2
+            tma_load_2d(p_ring + (size_t)s * p.p_bytes, tmBr, &full_p[s], (tap * p.cin + kc * p.kchunk) >> 1,
+                        c_out0 + b_row0);
+          }
+          __syncwarp();
+          if (++kc == kchunks) kc = 0, ++tap;
+          if (++s == SP) s = 0, par ^= 1u;
+        }
+      }
+    }
   } else if (warp == IGEMM_WARP_MMA) {
-    // ===================================================== UMMA issuer
+   if (CG == 2 && rank != 0) {
+    // ===================================================== CTA pair, second CTA: its UMMA warp only reports
+    // "my A tile of slot s has landed" to the leader's barrier (the leader issues the UMMAs for both)
+    const uint32_t remote = mapa_u32(smem_u32(full_tma), 0);
+    int s = 0;
+    uint32_t par = 0;
+    for (int ut = unit0; ut < total_units; ut += nunits) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&full_tma[s], par);
+        if (lane == 0) mbar_arrive_remote(remote + 8u * (uint32_t)s);
+        __syncwarp();
+        if (++s == S) s = 0, par ^= 1u;
+      }
+    }
+   } else {
+    // ===================================================== UMMA issuer (CTA pair: the leader CTA only)
     // The whole warp runs this loop convergently and every operand of the tcgen05 instructions is computed
     // outside the elected-thread region, so descriptors live in uniform registers and each UTC*MMA issues
     // without a per-instruction register shuffle; the tensor pipe starves on anything slower.
-    // W4A8: the s8 B tile carries 16 extra rows; row tile_n is all ones, so accumulator column tile_n
-    // holds sum_k a[m][k] and the weight zero point can be applied in the epilogue instead of per code
-    const uint32_t umma_n = (uint32_t)p.tile_n + (MODE == MODE_W4A8 ? 16u : 0u);
-    const uint32_t idesc = (MODE == MODE_TF32) ? idesc_tf32(128, umma_n) : idesc_i8_u8s8(128, umma_n);
+    const uint32_t umma_n = (uint32_t)p.tile_n + (W4 ? 16u : 0u);
+    const uint32_t idesc = (MODE == MODE_TF32) ? idesc_tf32(128, umma_n) : idesc_i8_u8s8(128 * CG, umma_n);
     const uint32_t smem_base = smem_u32(smem);
     const uint64_t d_a = smem_desc_sw128(smem_base);
-    const uint64_t d_b = smem_desc_sw128(smem_base + p.offB);
+    const uint64_t d_b = W4 ? smem_desc_sw128(smem_u32(u_ring)) : smem_desc_sw128(smem_base + p.offB);
     const uint64_t d_alo = smem_desc_sw128(smem_base + p.offA_lo);
     const uint64_t d_blo = smem_desc_sw128(smem_base + p.offB_lo);
-    const uint32_t stage_units = p.stage_bytes >> 4;       // descriptor start-address units per stage
+    const uint32_t stage_units = W4 ? (IGEMM_A_BYTES >> 4) : (p.stage_bytes >> 4);   // descriptor address units per A slot
+    const uint32_t u_units = p.u_bytes >> 4;
     const int nslice_last = (p.cin - (kchunks - 1) * p.kchunk) / p.kslice;   // valid 32-byte K slices of the last chunk
-    const bool wait_xf = (MODE == MODE_W4A8) || need_a_lo;  // otherwise the TMA barrier alone gates the stage
+    const bool wait_xf = need_a_lo;             // tf32 with a split A: the transform warp's barrier gates the stage
     uint32_t tcount = 0;
-    int s = 0;
-    uint32_t par = 0, s_units = 0;
+    int s = 0, su = 0;
+    uint32_t par = 0, s_units = 0, pu = 0, su_units = 0;
     const bool prof_on = p.prof != nullptr && lane == 0;
     long long prof_acc[6] = {0, 0, 0, 0, 0, 0};
     long long prof_t = prof_on ? clock64() : 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+    for (int ut = unit0; ut < total_units; ut += nunits, ++tcount) {
       const uint32_t as = tcount % ACC;
       PROF_T(2)
-      mbar_wait(&acc_empty[as], ((tcount / ACC) & 1u) ^ 1u);   // epilogue has drained this stage
+      // the epilogue (of both CTAs of a pair) has drained this accumulator stage
+      mbar_wait(&acc_empty[as], ((tcount / ACC) & 1u) ^ 1u);
       tc_fence_after();
       PROF_T(0)
       const uint32_t tmem_d = tmem_base + as * acc_cols;
@@ -207,12 +283,18 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       int kc = 0;
       for (int kb = 0; kb < nkb; ++kb) {
         PROF_T(2)
-        mbar_wait(&full_tma[s], par);
-        if (wait_xf) mbar_wait(&full_xf[s], par);
+        if (W4) {
+          mbar_wait(&full_tma[s], par);
+          mbar_wait(&full_xf[su], pu);
+        } else {
+          // a transform warp arrives only after the stage's TMA barrier completed, so its barrier alone gates the stage
+          if (wait_xf) mbar_wait(&full_xf[s], par);
+          else mbar_wait(&full_tma[s], par);
+        }
         tc_fence_after();
         PROF_T(1)
         const int nslice = (kc == kchunks - 1) ? nslice_last : 4;
-        const uint64_t a_hi = d_a + s_units, b_hi = d_b + s_units;
+        const uint64_t a_hi = d_a + s_units, b_hi = d_b + (W4 ? su_units : s_units);
         const uint64_t a_lo = d_alo + s_units, b_lo = d_blo + s_units;
         const bool last = kb == nkb - 1;
         if (elect_one_sync()) {
@@ -234,102 +316,138 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           } else {
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              if (k < nslice) umma_i8(tmem_d, a_hi + 2 * k, b_hi + 2 * k, idesc, (k > 0) | accumulate);
+              if (k < nslice) {
+                if (CG == 2) umma_i8_2cta(tmem_d, a_hi + 2 * k, b_hi + 2 * k, idesc, (k > 0) | accumulate);
+                else umma_i8(tmem_d, a_hi + 2 * k, b_hi + 2 * k, idesc, (k > 0) | accumulate);
+              }
           }
-          umma_commit(&empty[s]);
-          if (last) umma_commit(&acc_full[as]);
+          if (CG == 2) {          // slot / accumulator hand-over goes to the same barrier of both CTAs
+            umma_commit_2cta(&empty[s], 3);
+            umma_commit_2cta(&empty_u[su], 3);
+            if (last) umma_commit_2cta(&acc_full[as], 3);
+          } else {
+            umma_commit(&empty[s]);
+            if (W4) umma_commit(&empty_u[su]);
+            if (last) umma_commit(&acc_full[as]);
+          }
         }
         __syncwarp();
         accumulate = 1, accumulate_lo = 1;
         if (++kc == kchunks) kc = 0;
         s_units += stage_units;
         if (++s == S) s = 0, s_units = 0, par ^= 1u;
+        if (W4) {
+          su_units += u_units;
+          if (++su == SU) su = 0, su_units = 0, pu ^= 1u;
+        }
       }
     }
     if (prof_on)
       for (int i = 0; i < 6; ++i) p.prof[blockIdx.x * 16 + 10 + i] = prof_acc[i];
+   }
   } else if (warp >= IGEMM_WARP_XF0) {
     // ===================================================== transform warps
-    const int t = threadIdx.x - IGEMM_WARP_XF0 * 32;  // 0..XF_T-1
-    constexpr int XF_T = IGEMM_XF_WARPS * 32;          // transform threads
-    constexpr int XF_ROWS = XF_T / 4;                   // B rows unpacked per pass
-    constexpr int XF_IT = 256 / XF_ROWS;                // passes to cover up to 256 rows
-    int s = 0;
-    uint32_t par = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int c_out0 = (tile / tiles_m) * p.tile_n;
-      if (MODE == MODE_W4A8) {
-        // piece (row, K slice) = ((t >> 2) + XF_ROWS i, t & 3); fixed per-thread offsets,
-        // + XF_ROWS*64 B (packed) / + XF_ROWS*128 B (s8 tile) per i.  Codes stay unsigned (0..15): two ANDs and a shift
-        // per packed word; the zero point is folded out through the ones row (see the UMMA issuer).
-        const int sub = t & 3;
-        const uint32_t rd0 = p.offP + (uint32_t)(t >> 2) * 64u + (uint32_t)sub * 16u;
-        const uint32_t swz = (uint32_t)((t >> 2) & 7);
-        const uint32_t wr_lo = p.offB + (uint32_t)(t >> 2) * 128u + (((2u * sub) ^ swz) << 4);
-        const uint32_t wr_hi = p.offB + (uint32_t)(t >> 2) * 128u + (((2u * sub + 1u) ^ swz) << 4);
-        const int nrow_i = (p.tile_n - (t >> 2) + XF_ROWS - 1) / XF_ROWS;   // iterations with row < tile_n
+    if (W4) {
+      // int4 -> s8 expansion of the weight operand.  The packed tile of a k-block arrives by TMA in a small ring of
+      // its own (dense [b_rows][64 B]); a transform group reads it into registers, gives the slot straight back, and
+      // writes the 128B-swizzled K-major s8 tile into the next free slot of the B ring.  The three rings (A, packed B,
+      // s8 B) have independent depths, so a slot is only held for as long as ITS data is in flight.  Two groups of two
+      // warps work on alternate k-blocks (ring depths are even, so a group sees consecutive phases of every barrier
+      // it waits on).  Codes stay unsigned (0..15): two ANDs and a shift per word; the zero point is folded out
+      // through the ones row.  Thread tg of a group owns pieces (row (tg >> 2) + 16 i, K slice tg & 3).
+      constexpr int NP = (CG == 2) ? 8 : 15;            // pieces per thread: ceil(max rows / 16)
+      const int grp = (warp - IGEMM_WARP_XF0) / IGEMM_XF_GROUP_WARPS;
+      const int tg = threadIdx.x - (IGEMM_WARP_XF0 + grp * IGEMM_XF_GROUP_WARPS) * 32;
+      const int sub = tg & 3, row0 = tg >> 2;
+      const uint32_t swz = (uint32_t)(row0 & 7);
+      const uint32_t rd0 = (uint32_t)row0 * 64u + (uint32_t)sub * 16u;
+      const uint32_t wr_lo = (uint32_t)row0 * 128u + (((2u * sub) ^ swz) << 4);
+      const uint32_t wr_hi = (uint32_t)row0 * 128u + (((2u * sub + 1u) ^ swz) << 4);
+      const uint32_t xf_remote = (CG == 2 && rank != 0) ? mapa_u32(smem_u32(full_xf), 0) : 0u;
+      constexpr int NG = IGEMM_XF_WARPS / IGEMM_XF_GROUP_WARPS;
+      uint32_t it = 0;                                   // k-blocks of this CTA so far (all units)
+      int su = 0, sp = 0;
+      uint32_t pu = 0, pp = 0;
+      for (int ut = unit0; ut < total_units; ut += nunits) {
         int kc = 0;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          if ((int)(it % NG) == grp) {
+            int rem = p.cin - kc * p.kchunk;
+            if (rem > p.kchunk) rem = p.kchunk;
+            const bool active = sub < (rem >> 5) && !(p.dbg & 8);
+            mbar_wait(&full_p[sp], pp);
+            const uint8_t* src = p_ring + (size_t)sp * p.p_bytes + rd0;
+            uint4 pk[NP];
+            if (active) {
+#pragma unroll
+              for (int i = 0; i < NP; ++i)
+                if (row0 + 16 * i < b_rows) pk[i] = *reinterpret_cast<const uint4*>(src + i * 1024);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_p[sp]);    // release: the reads above are ordered before it
+            mbar_wait(&empty_u[su], pu ^ 1u);
+            uint8_t* dst = u_ring + (size_t)su * p.u_bytes;
+            if (active) {
+#pragma unroll
+              for (int i = 0; i < NP; ++i) {
+                if (row0 + 16 * i < b_rows) {
+                  const uint4 k4 = pk[i];
+                  uint4 lo, hi;
+                  lo.x = k4.x & 0x0F0F0F0Fu, lo.y = k4.y & 0x0F0F0F0Fu, lo.z = k4.z & 0x0F0F0F0Fu, lo.w = k4.w & 0x0F0F0F0Fu;
+                  hi.x = (k4.x >> 4) & 0x0F0F0F0Fu, hi.y = (k4.y >> 4) & 0x0F0F0F0Fu;
+                  hi.z = (k4.z >> 4) & 0x0F0F0F0Fu, hi.w = (k4.w >> 4) & 0x0F0F0F0Fu;
+                  *reinterpret_cast<uint4*>(dst + wr_lo + i * 2048) = lo;
+                  *reinterpret_cast<uint4*>(dst + wr_hi + i * 2048) = hi;
+                }
+              }
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              if (CG == 2 && rank != 0) mbar_arrive_remote(xf_remote + 8u * (uint32_t)su);
+              else mbar_arrive(&full_xf[su]);
+            }
+          }
+          if (++kc == kchunks) kc = 0;
+          if (++su == SU) su = 0, pu ^= 1u;
+          if (++sp == SP) sp = 0, pp ^= 1u;
+        }
+      }
+    } else if (MODE == MODE_TF32 && need_a_lo) {
+      // split the fp32 A tile into hi = a & 0xFFFFE000 (exactly a tf32) and lo = a - hi; the four warps share a stage
+      const int t = threadIdx.x - IGEMM_WARP_XF0 * 32;
+      constexpr int XF_T = IGEMM_XF_WARPS * 32;
+      int s = 0;
+      uint32_t par = 0;
+      for (int ut = unit0; ut < total_units; ut += nunits) {
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&full_tma[s], par);
           uint8_t* st = smem + (size_t)s * p.stage_bytes;
-          int rem = p.cin - kc * p.kchunk;
-          if (rem > p.kchunk) rem = p.kchunk;
-          const int nslice = rem >> 5;
-          if (sub < nslice) {
-            uint4 pkv[XF_IT];
+          uint4* a = reinterpret_cast<uint4*>(st);
+          uint4* al = reinterpret_cast<uint4*>(st + p.offA_lo);
 #pragma unroll
-            for (int i = 0; i < XF_IT; ++i)
-              if (i < nrow_i) pkv[i] = *reinterpret_cast<const uint4*>(st + rd0 + i * (XF_ROWS * 64));
-#pragma unroll
-            for (int i = 0; i < XF_IT; ++i) {
-              if (i < nrow_i) {
-                const uint4 pk = pkv[i];
-                uint4 lo, hi;
-                lo.x = pk.x & 0x0F0F0F0Fu, lo.y = pk.y & 0x0F0F0F0Fu, lo.z = pk.z & 0x0F0F0F0Fu, lo.w = pk.w & 0x0F0F0F0Fu;
-                hi.x = (pk.x >> 4) & 0x0F0F0F0Fu, hi.y = (pk.y >> 4) & 0x0F0F0F0Fu;
-                hi.z = (pk.z >> 4) & 0x0F0F0F0Fu, hi.w = (pk.w >> 4) & 0x0F0F0F0Fu;
-                *reinterpret_cast<uint4*>(st + wr_lo + i * (XF_ROWS * 128)) = lo;
-                *reinterpret_cast<uint4*>(st + wr_hi + i * (XF_ROWS * 128)) = hi;
-              }
-            }
+          for (int i = 0; i < 1024 / XF_T; ++i) {
+            const int idx = t + XF_T * i;
+            uint4 v = a[idx], h, l;
+            h.x = v.x & 0xFFFFE000u;
+            h.y = v.y & 0xFFFFE000u;
+            h.z = v.z & 0xFFFFE000u;
+            h.w = v.w & 0xFFFFE000u;
+            l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x));
+            l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y));
+            l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z));
+            l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w));
+            a[idx] = h;
+            al[idx] = l;
           }
           fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&full_xf[s]);
-          if (++kc == kchunks) kc = 0;
-          if (++s == S) s = 0, par ^= 1u;
-        }
-      } else if (MODE == MODE_TF32 && need_a_lo) {
-        for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait(&full_tma[s], par);
-          {
-            uint8_t* st = smem + (size_t)s * p.stage_bytes;
-            uint4* a = reinterpret_cast<uint4*>(st);
-            uint4* al = reinterpret_cast<uint4*>(st + p.offA_lo);
-#pragma unroll
-            for (int i = 0; i < 1024 / XF_T; ++i) {
-              const int idx = t + XF_T * i;
-              uint4 v = a[idx], h, l;
-              h.x = v.x & 0xFFFFE000u;
-              h.y = v.y & 0xFFFFE000u;
-              h.z = v.z & 0xFFFFE000u;
-              h.w = v.w & 0xFFFFE000u;
-              l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x));
-              l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y));
-              l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z));
-              l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w));
-              a[idx] = h;
-              al[idx] = l;
-            }
-            fence_proxy_async_smem();
-          }
           __syncwarp();
           if (lane == 0) mbar_arrive(&full_xf[s]);
           if (++s == S) s = 0, par ^= 1u;
         }
       }
-      // other modes: nothing to transform; the UMMA issuer waits on the TMA barrier alone
     }
+    // other modes: nothing to transform; the UMMA issuer waits on the TMA barrier alone
   } else {
     // ===================================================== epilogue warps (0..7)
     // All global I/O of the epilogue is TMA: the residual chunk is prefetched into a swizzled smem
@@ -360,9 +478,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const bool prof_on = p.prof != nullptr && et == 0;
     long long prof_acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     long long prof_t = prof_on ? clock64() : 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
-      int mt = tile % tiles_m;
-      const int c_out0 = (tile / tiles_m) * p.tile_n;
+    const uint32_t acc_empty_remote = (CG == 2 && rank != 0) ? mapa_u32(smem_u32(acc_empty), 0) : 0u;
+    for (int ut = unit0; ut < total_units; ut += nunits, ++tcount) {
+      int mt = (ut % tiles_mu) * CG + (int)rank;
+      const int c_out0 = (ut / tiles_mu) * p.tile_n;
       const int tx = mt % tiles_x;
       mt /= tiles_x;
       const int ty = mt % tiles_y;
@@ -437,7 +556,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           // last TMEM read of this tile: hand the accumulator stage back to the UMMA issuer
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&acc_empty[as]);
+          if (lane == 0) {
+            if (CG == 2 && rank != 0) mbar_arrive_remote(acc_empty_remote + 8u * as);
+            else mbar_arrive(&acc_empty[as]);
+          }
         }
         PROF_T(2)
         if (p.res) mbar_wait(&res_full[g & 1], (g >> 1) & 1u);
@@ -544,8 +666,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   }
 
   tc_fence_before();
-  __syncthreads();
-  if (warp == IGEMM_WARP_MMA) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  if (CG == 2) cluster_sync_all();    // neither CTA leaves while its peer may still signal its barriers / read its TMEM
+  else __syncthreads();
+  if (warp == IGEMM_WARP_MMA) {
+    if (CG == 2) tmem_dealloc2(tmem_base, (uint32_t)p.tmem_cols);
+    else tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -603,45 +729,65 @@ static int encode(tfmq_ctx* ctx, CUtensorMap* m, CUtensorMapDataType dt, int ran
   return TFMQ_OK;
 }
 
-template <int MODE>
+template <int MODE, int CG>
 static int launch_igemm(tfmq_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmB2,
                         IgemmParams& p, cudaStream_t stream, const char* name) {
   // shared-memory plan
-  const uint32_t bB = ((uint32_t)p.tile_n + (MODE == MODE_W4A8 ? 16u : 0u)) * 128u;
-  uint32_t off = IGEMM_A_BYTES;
-  p.offA_lo = p.offB_lo = p.offP = 0;
-  if (MODE == MODE_TF32 && (p.pass_flags & PASS_LO_HI)) {
-    p.offA_lo = off;
-    off += IGEMM_A_BYTES;
-  }
-  p.offB = off;
-  off += bB;
-  if (MODE == MODE_TF32 && (p.pass_flags & PASS_HI_LO)) {
-    p.offB_lo = off;
-    off += bB;
-  }
+  if (CG == 1) p.b_rows[0] = p.tile_n, p.b_row0[0] = 0, p.b_rows[1] = 0, p.b_row0[1] = 0;
+  const uint32_t extra = 1024u /*alignment slack*/ + 2u * 128u * 32u * 4u /*epilogue chunks*/ +
+                         (uint32_t)p.tile_n * 24u /*chp + GN channel sums*/ + 2u * 256u * 8u /*GN partials*/ +
+                         512u /*barriers*/;
+  static const int stages_env = getenv("TFMQ_IGEMM_STAGES") ? atoi(getenv("TFMQ_IGEMM_STAGES")) : 0;   // experiments
+  int stages;
+  size_t smem;
+  p.offA_lo = p.offB_lo = p.offP = p.offB = 0;
+  p.u_stages = 0, p.u_bytes = 0, p.p_stages = 0, p.p_bytes = 0;
   if (MODE == MODE_W4A8) {
-    p.offP = off;
-    off += (uint32_t)p.tile_n * 64u;
+    // A ring + s8 B ring (CTA pair: each CTA holds half of the N rows of B, incl. the 16 ones / zero rows)
+    p.u_bytes = ((uint32_t)(p.tile_n + 16) * 128u / (uint32_t)CG + 1023u) & ~1023u;
+    static const int su_env = getenv("TFMQ_IGEMM_USTAGES") ? atoi(getenv("TFMQ_IGEMM_USTAGES")) : 0;
+    p.u_stages = su_env > 0 ? su_env : (p.u_bytes * 4u <= 64u * 1024u ? 4 : 2);     // even: two transform groups
+    // packed int4 ring: this CTA's weight rows x 64 B per k-block
+    p.p_bytes = ((uint32_t)(CG == 2 ? p.b_rows[0] : p.tile_n) * 64u + 1023u) & ~1023u;
+    static const int sp_env = getenv("TFMQ_IGEMM_PSTAGES") ? atoi(getenv("TFMQ_IGEMM_PSTAGES")) : 0;
+    p.p_stages = sp_env > 0 ? sp_env : 4;
+    const long long left = (long long)ctx->max_smem_optin - extra - (long long)p.u_stages * p.u_bytes -
+                           (long long)p.p_stages * p.p_bytes;
+    stages = (int)(left / (long long)IGEMM_A_BYTES);
+    if (stages > 8) stages = 8;
+    if (stages_env > 0 && stages_env < stages) stages = stages_env;
+    if (stages < 2) return tfmq_fail(ctx, TFMQ_ERR_SHAPE, "%s: tile does not fit shared memory", name);
+    p.stage_bytes = IGEMM_A_BYTES;
+    smem = (size_t)stages * IGEMM_A_BYTES + (size_t)p.u_stages * p.u_bytes + (size_t)p.p_stages * p.p_bytes + extra;
+  } else {
+    const uint32_t bB = (uint32_t)p.tile_n * 128u;
+    uint32_t off = IGEMM_A_BYTES;
+    if (MODE == MODE_TF32 && (p.pass_flags & PASS_LO_HI)) {
+      p.offA_lo = off;
+      off += IGEMM_A_BYTES;
+    }
+    p.offB = off;
+    off += bB;
+    if (MODE == MODE_TF32 && (p.pass_flags & PASS_HI_LO)) {
+      p.offB_lo = off;
+      off += bB;
+    }
+    p.stage_bytes = (off + 1023u) & ~1023u;
+    stages = (int)(((uint32_t)ctx->max_smem_optin - extra) / p.stage_bytes);
+    if (stages > 8) stages = 8;
+    if (stages_env > 0 && stages_env < stages) stages = stages_env;
+    if (stages < 1) return tfmq_fail(ctx, TFMQ_ERR_SHAPE, "%s: tile does not fit shared memory", name);
+    smem = (size_t)stages * p.stage_bytes + extra;
   }
-  p.stage_bytes = (off + 1023u) & ~1023u;
-  const uint32_t extra = 1024u /*alignment slack*/ + 2u * 128u * 32u * 4u /*epilogue chunks*/ + 256u * 16u /*chp*/ +
-                         3u * 256u * 8u /*GN channel sums + partials*/ + 256u /*barriers*/;
-  const int kchunks = (p.cin + p.kchunk - 1) / p.kchunk;
-  const int nkb = p.ksize * p.ksize * kchunks;
-  int stages = (int)(((uint32_t)ctx->max_smem_optin - extra) / p.stage_bytes);
-  if (stages > 6) stages = 6;
-  if (stages < 1) return tfmq_fail(ctx, TFMQ_ERR_SHAPE, "%s: tile does not fit shared memory", name);
-  (void)nkb;
   p.stages = stages;
+  const int nkb = p.ksize * p.ksize * ((p.cin + p.kchunk - 1) / p.kchunk);
   int acc_cols = p.tile_n + (MODE == MODE_W4A8 ? 16 : 0);
   if (MODE == MODE_TF32 && (p.pass_flags & (PASS_LO_HI | PASS_HI_LO))) acc_cols *= 2;
   p.acc_stages = (2 * acc_cols <= 512) ? 2 : 1;
   const int need = acc_cols * p.acc_stages;
   p.tmem_cols = need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512;
-  const size_t smem = (size_t)stages * p.stage_bytes + extra;
 
-  auto kern = igemm_kernel<MODE>;
+  auto kern = igemm_kernel<MODE, CG>;
   static size_t smem_set = 0;  // per template instance; one device per process
   if (smem > smem_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -672,8 +818,9 @@ static int launch_igemm(tfmq_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap
     }
   }
   const int tiles_m = (p.W / p.tw) * (p.H / p.th) * ((p.n_img + p.tn - 1) / p.tn);
-  const int total = tiles_m * (p.cout / p.tile_n);
-  const int grid = total < ctx->sm_count ? total : ctx->sm_count;
+  const int total = tiles_m / CG * (p.cout / p.tile_n);           // tiles, or pairs of M-adjacent tiles
+  const int units = ctx->sm_count / CG;
+  const int grid = (total < units ? total : units) * CG;
   static const bool time_env = getenv("TFMQ_IGEMM_TIME") != nullptr;   // debug aid: per-launch time, synchronous
   static const bool prof_env = getenv("TFMQ_IGEMM_PROF") != nullptr;   // debug aid: + in-kernel phase counters
   static const int dbg_env = getenv("TFMQ_IGEMM_DBG") ? atoi(getenv("TFMQ_IGEMM_DBG")) : 0;
@@ -689,7 +836,18 @@ static int launch_igemm(tfmq_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap
     cudaEventCreate(&ev1);
     cudaEventRecord(ev0, stream);
   }
-  kern<<<grid, IGEMM_THREADS, smem, stream>>>(tmA, tmB, tmB2, tmOut, tmRes, p);
+  if (CG == 1) {
+    kern<<<grid, IGEMM_THREADS, smem, stream>>>(tmA, tmB, tmB2, tmOut, tmRes, p);
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid), cfg.blockDim = dim3(IGEMM_THREADS), cfg.dynamicSmemBytes = smem, cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr, cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmB2, tmOut, tmRes, p);
+    if (e != cudaSuccess) return tfmq_fail(ctx, TFMQ_ERR_CUDA, "%s: cluster launch: %s", name, cudaGetErrorString(e));
+  }
   TFMQ_LAUNCH_CHECK(name);
   if (prof_env || time_env) {
     cudaEventRecord(ev1, stream);
@@ -741,11 +899,23 @@ extern "C" int tfmq_conv_w4a8(tfmq_ctx* ctx, const tfmq_conv_w4a8_desc* d, void*
   p.n_img = d->n, p.H = d->h, p.W = d->w, p.cin = d->cin, p.cout = d->cout;
   p.ksize = d->ksize, p.stride = 1, p.off = 0;
   p.th = g.th, p.tw = g.tw, p.tn = g.tn;
+  // CTA pairs (cta_group::2) whenever the M tiles pair up; TFMQ_IGEMM_CG=1 forces single CTAs (debug / comparison)
+  static const int cg_env = getenv("TFMQ_IGEMM_CG") ? atoi(getenv("TFMQ_IGEMM_CG")) : 2;
+  const int tiles_m_all = (d->w / g.tw) * (d->h / g.th) * ((d->n + g.tn - 1) / g.tn);
+  int cg = (cg_env == 2 && tiles_m_all % 2 == 0 && ctx->sm_count % 2 == 0) ? 2 : 1;
   {
     // + 16 rows for the activation-sum column, UMMA N <= 256
-    const int tiles_m = (d->w / g.tw) * (d->h / g.th) * ((d->n + g.tn - 1) / g.tn);
     const int nkb = d->ksize * d->ksize * ((d->cin + 127) / 128);
-    p.tile_n = pick_tile_n_balanced(d->cout, 240, tiles_m, nkb, ctx->sm_count, 400.0, 2.6);
+    p.tile_n = pick_tile_n_balanced(d->cout, 240, tiles_m_all / cg, nkb, ctx->sm_count / cg, 400.0, 2.6);
+    if (cg == 2 && p.tile_n < 32) {       // the second CTA's half would hold no weight rows
+      cg = 1;
+      p.tile_n = pick_tile_n_balanced(d->cout, 240, tiles_m_all, nkb, ctx->sm_count, 400.0, 2.6);
+    }
+  }
+  if (cg == 2) {
+    const int half = (p.tile_n + 16) / 2;                   // B rows per CTA, a multiple of 8
+    p.b_rows[0] = half, p.b_row0[0] = 0;
+    p.b_rows[1] = p.tile_n - half, p.b_row0[1] = half;     // + the 16 ones / zero rows
   }
   p.kchunk = 128, p.kslice = 32;
   p.out = d->out, p.out_ld = d->out_ld, p.bias = d->bias, p.wscale = d->wdelta, p.wsum = d->wsum, p.wzp = d->wzp;
@@ -759,7 +929,7 @@ extern "C" int tfmq_conv_w4a8(tfmq_ctx* ctx, const tfmq_conv_w4a8_desc* d, void*
 
   const int halo = d->ksize == 3 ? 1 : 0;
   const cuuint64_t Hp = d->h + 2 * halo, Wp = d->w + 2 * halo;
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA;
   {
     cuuint64_t dims[4] = {(cuuint64_t)d->cin, Wp, Hp, (cuuint64_t)d->n};
     cuuint64_t str[3] = {(cuuint64_t)d->cin, Wp * d->cin, Hp * Wp * d->cin};
@@ -769,17 +939,23 @@ extern "C" int tfmq_conv_w4a8(tfmq_ctx* ctx, const tfmq_conv_w4a8_desc* d, void*
                     CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
+  CUtensorMap tmB, tmB2;
   {
+    // packed int4 weights [cout][ksize^2 * cin / 2 bytes]; box = this CTA's weight rows x 64 B (one 128-channel k-block)
     const cuuint64_t kbytes = (cuuint64_t)d->ksize * d->ksize * d->cin / 2;
     cuuint64_t dims[2] = {kbytes, (cuuint64_t)d->cout};
     cuuint64_t str[1] = {kbytes};
-    cuuint32_t box[2] = {64, (cuuint32_t)p.tile_n};
     cuuint32_t es[2] = {1, 1};
-    int rc = encode(ctx, &tmB, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, d->packed, dims, str, box, es,
-                    CU_TENSOR_MAP_SWIZZLE_NONE);
-    if (rc) return rc;
+    for (int r = 0; r < cg; ++r) {
+      cuuint32_t box[2] = {64, (cuuint32_t)(cg == 2 ? p.b_rows[r] : p.tile_n)};
+      int rc = encode(ctx, r ? &tmB2 : &tmB, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, d->packed, dims, str, box, es,
+                      CU_TENSOR_MAP_SWIZZLE_NONE);
+      if (rc) return rc;
+    }
+    if (cg == 1) tmB2 = tmB;
   }
-  int rc = launch_igemm<MODE_W4A8>(ctx, tmA, tmB, tmB, p, tfmq_stream(stream), "conv_w4a8");
+  int rc = cg == 2 ? launch_igemm<MODE_W4A8, 2>(ctx, tmA, tmB, tmB2, p, tfmq_stream(stream), "conv_w4a8")
+                   : launch_igemm<MODE_W4A8, 1>(ctx, tmA, tmB, tmB2, p, tfmq_stream(stream), "conv_w4a8");
   for (int i = 0; rc == TFMQ_OK && !fuse_stats && i < d->n_stat; ++i)
     rc = tfmq_gn_stats_part(ctx, d->out, d->out_ld, d->n, d->h * d->w, d->cout, &d->stat[i], stream);
   return rc;
@@ -856,7 +1032,7 @@ extern "C" int tfmq_conv_fp(tfmq_ctx* ctx, const tfmq_conv_fp_desc* d, void* str
                     CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
-  int rc = launch_igemm<MODE_TF32>(ctx, tmA, tmB, tmB2, p, tfmq_stream(stream), "conv_fp");
+  int rc = launch_igemm<MODE_TF32, 1>(ctx, tmA, tmB, tmB2, p, tfmq_stream(stream), "conv_fp");
   for (int i = 0; rc == TFMQ_OK && !fuse_stats && i < d->n_stat; ++i)
     rc = tfmq_gn_stats_part(ctx, d->out, d->out_ld, d->n, d->out_h * d->out_w, d->cout, &d->stat[i], stream);
   return rc;
@@ -890,5 +1066,5 @@ extern "C" int tfmq_gemm_i8_peak(tfmq_ctx* ctx, const uint8_t* a, const int8_t* 
     int rc = encode(ctx, &tmB, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, b, dims, str, box, es, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
-  return launch_igemm<MODE_I8>(ctx, tmA, tmB, tmB, p, tfmq_stream(stream), "gemm_i8_peak");
+  return launch_igemm<MODE_I8, 1>(ctx, tmA, tmB, tmB, p, tfmq_stream(stream), "gemm_i8_peak");
 }

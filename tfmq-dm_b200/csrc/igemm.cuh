@@ -5,12 +5,15 @@
 // A tiles (activations, NHWC) arrive by 4-D TMA boxes [tn][th][tw][kchunk] so that one
 // box is one 128-row, 128-byte-wide, 128B-swizzled K-major UMMA operand.  B tiles
 // (weights, [cout][tap*cin]) arrive by 2-D TMA.  A warp-specialised pipeline:
-//   warp 0    TMA producer
-//   warp 1    UMMA issuer, owns TMEM
-//   warps 2-5 operand transform between TMA and UMMA, then the epilogue
+//   warps 0-7   epilogue (TMEM -> registers -> smem -> TMA store), overlapped with the next tile's main loop
+//   warp 8      TMA producer
+//   warp 9      UMMA issuer, owns TMEM
+//   warps 10-13 operand transform between TMA and UMMA (each owns whole pipeline stages)
 //     MODE_W4A8 : unpack packed int4 codes -> (q - zp) s8 into the swizzled B tile
 //     MODE_TF32 : split fp32 A into tf32 hi + lo planes (3-pass error compensation)
 //     MODE_I8   : nothing (dense s8 weights; used for the measured int8 peak)
+// CG = 2 (w4a8 only): a cluster of two CTAs runs tcgen05.mma.cta_group::2 on two M-adjacent tiles (M = 256); each
+// CTA stages its own A tile and half of the weight rows.
 #pragma once
 #include <cstdint>
 #include <cuda.h>
@@ -29,6 +32,11 @@ struct IgemmParams {
   int th, tw, tn;          // tile = tn*th*tw = 128 output pixels
   int tile_n, stages, tmem_cols, acc_stages, chunk_w;
   int kchunk, kslice;  // channels per k-block / per UMMA
+  int u_stages;              // w4a8: slots of the s8 B ring
+  uint32_t u_bytes;          // w4a8: bytes per s8 B slot
+  int p_stages;              // w4a8: slots of the packed int4 ring
+  uint32_t p_bytes;          // w4a8: bytes per packed slot
+  int b_rows[2], b_row0[2];  // weight rows of the N tile staged by CTA rank 0 / 1 of a pair (rank 0 only when CG == 1)
   uint32_t stage_bytes, offA_lo, offB, offB_lo, offP;
   int pass_flags;
   // epilogue
@@ -51,12 +59,14 @@ struct IgemmParams {
 };
 
 constexpr int IGEMM_EPI_WARPS = 8;   // warps 0..7: two per TMEM lane quarter (each takes half of a chunk's columns)
-constexpr int IGEMM_XF_WARPS = 4;    // last warps: operand transform
+constexpr int IGEMM_XF_WARPS = 4;    // operand transform
+constexpr int IGEMM_XF_GROUP_WARPS = 2;   // w4a8: transform groups of 2 warps take alternate k-blocks
 constexpr int IGEMM_WARP_TMA = IGEMM_EPI_WARPS, IGEMM_WARP_MMA = IGEMM_EPI_WARPS + 1, IGEMM_WARP_XF0 = IGEMM_EPI_WARPS + 2;
-constexpr int IGEMM_THREADS = (IGEMM_EPI_WARPS + 2 + IGEMM_XF_WARPS) * 32;
+constexpr int IGEMM_WARP_TMB = IGEMM_WARP_XF0 + IGEMM_XF_WARPS;   // w4a8: TMA producer of the packed weight tiles
+constexpr int IGEMM_THREADS = (IGEMM_EPI_WARPS + 3 + IGEMM_XF_WARPS) * 32;
 constexpr uint32_t IGEMM_A_BYTES = 128 * 128;
 
-template <int MODE>
+template <int MODE, int CG>
 __global__ void igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                              const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmOut,
                              const __grid_constant__ CUtensorMap tmRes, const IgemmParams p);

@@ -25,31 +25,41 @@ constexpr int LIN_THREADS = 256;
 constexpr int LIN_OUT_PER_CTA = 8;   // one output per warp: many small CTAs, short dependent-load chains
 constexpr int LIN_ROWS = 8;
 
-__global__ void __launch_bounds__(LIN_THREADS) linear_small_kernel(const tfmq_linear_desc d) {
-  extern __shared__ float xs[];                 // [LIN_ROWS][in_f]: fp32 inputs, or (code - zp) as fp32
-  const int m0 = blockIdx.y * LIN_ROWS;
+__device__ __forceinline__ void linear_small_body(const tfmq_linear_desc& d, const int bx, const int by, float* xs) {
+  const int m0 = by * LIN_ROWS;
   const int rows = min(LIN_ROWS, d.m - m0);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float dl = 1.f, z = 0.f;
   if (d.aq) dl = d.aq[0], z = d.aq[1];
-  for (int i = threadIdx.x; i < LIN_ROWS * d.in_f; i += LIN_THREADS) {
-    const int r = i / d.in_f, f = i - r * d.in_f;
-    float v = 0.f;
+  // phase 1: float4 loads, four in flight per thread (in_f % 4 == 0; x rows 16-byte aligned when x_ld % 4 == 0)
+  const int nv4 = d.in_f >> 2;
+  const bool vec = (d.x_ld & 3) == 0 && ((uintptr_t)d.x & 15) == 0;
+#pragma unroll 4
+  for (int i = threadIdx.x; i < LIN_ROWS * nv4; i += LIN_THREADS) {
+    const int r = i / nv4, f4 = i - r * nv4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (r < rows) {
-      v = d.x[(long long)(m0 + r) * d.x_ld + f];
-      if (d.silu_in) v = silu1(v);
-      if (d.aq) {
-        const float q = fminf(fmaxf(rintf(__fdiv_rn(v, dl)) + z, 0.f), 255.f);
-        v = d.w_f32 ? dl * (q - z) : (q - z);   // integer path keeps the exact (code - zp)
+      const float* src = d.x + (long long)(m0 + r) * d.x_ld + 4 * f4;
+      if (vec) v = *reinterpret_cast<const float4*>(src);
+      else v = make_float4(src[0], src[1], src[2], src[3]);
+      float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (d.silu_in) e[j] = silu1(e[j]);
+        if (d.aq) {
+          const float q = fminf(fmaxf(rintf(__fdiv_rn(e[j], dl)) + z, 0.f), 255.f);
+          e[j] = d.w_f32 ? dl * (q - z) : (q - z);   // integer path keeps the exact (code - zp)
+        }
       }
+      v = make_float4(e[0], e[1], e[2], e[3]);
     }
-    xs[i] = v;
+    *reinterpret_cast<float4*>(xs + 4 * i) = v;
   }
   __syncthreads();
   const bool int_path = !d.w_f32 && d.aq;
   const int nv = d.in_f >> 2;                   // in_f is a multiple of 4
   for (int oo = 0; oo < LIN_OUT_PER_CTA / 8; ++oo) {
-    const int o = blockIdx.x * LIN_OUT_PER_CTA + warp * (LIN_OUT_PER_CTA / 8) + oo;
+    const int o = bx * LIN_OUT_PER_CTA + warp * (LIN_OUT_PER_CTA / 8) + oo;
     if (o >= d.out_f) break;
     float acc[LIN_ROWS];
 #pragma unroll
@@ -96,6 +106,22 @@ __global__ void __launch_bounds__(LIN_THREADS) linear_small_kernel(const tfmq_li
       }
     }
   }
+}
+
+__global__ void __launch_bounds__(LIN_THREADS) linear_small_kernel(const tfmq_linear_desc d) {
+  extern __shared__ __align__(16) float xs[];   // [LIN_ROWS][in_f]: fp32 inputs, or (code - zp) as fp32
+  linear_small_body(d, blockIdx.x, blockIdx.y, xs);
+}
+
+// Several layers in one launch (the 22 per-block embedding projections of a Temporal Information Block all read the
+// same input): CTA x-range [cta_start[l], cta_start[l+1]) belongs to layer l.
+__global__ void __launch_bounds__(LIN_THREADS) linear_grouped_kernel(const tfmq_linear_desc* __restrict__ descs,
+                                                                     const int* __restrict__ cta_start, int n) {
+  extern __shared__ __align__(16) float xs[];
+  int l = 0;
+  while (l + 1 < n && (int)blockIdx.x >= cta_start[l + 1]) ++l;
+  const tfmq_linear_desc d = descs[l];
+  linear_small_body(d, blockIdx.x - cta_start[l], blockIdx.y, xs);
 }
 
 // conv_in: NCHW (cin<=4) -> NHWC, 3x3 pad 1.  CTA = 16 pixels x 16 channel groups; weights transposed in
@@ -204,19 +230,52 @@ __global__ void __launch_bounds__(256) conv_out_kernel(const float* __restrict__
 
 using namespace tfmq;
 
-extern "C" int tfmq_linear_small(tfmq_ctx* ctx, const tfmq_linear_desc* d, void* stream) {
-  if (!ctx) return TFMQ_ERR_ARG;
+static int check_linear(tfmq_ctx* ctx, const tfmq_linear_desc* d) {
   TFMQ_REQUIRE(d && d->x && d->out, TFMQ_ERR_ARG, "linear_small: null pointer");
   TFMQ_REQUIRE(d->w_f32 || (d->codes && d->wzp_f && d->wdelta), TFMQ_ERR_ARG, "linear_small: weights missing");
   TFMQ_REQUIRE(d->m >= 0 && d->m <= 4096 && d->in_f > 0 && d->out_f > 0, TFMQ_ERR_SHAPE, "linear_small: m=%d", d->m);
-  if (d->m == 0) return TFMQ_OK;
   TFMQ_REQUIRE(d->in_f <= 1536 && d->in_f % 4 == 0, TFMQ_ERR_SHAPE, "linear_small: in_f %d (multiple of 4, <= 1536)",
                d->in_f);
   TFMQ_REQUIRE(d->w_f32 ? ((uintptr_t)d->w_f32 & 15) == 0 : ((uintptr_t)d->codes & 3) == 0, TFMQ_ERR_ARG,
                "linear_small: weights must be 16-byte (fp32) / 4-byte (codes) aligned");
+  return TFMQ_OK;
+}
+
+extern "C" int tfmq_linear_small(tfmq_ctx* ctx, const tfmq_linear_desc* d, void* stream) {
+  if (!ctx) return TFMQ_ERR_ARG;
+  if (int rc = check_linear(ctx, d)) return rc;
+  if (d->m == 0) return TFMQ_OK;
   dim3 grid((d->out_f + LIN_OUT_PER_CTA - 1) / LIN_OUT_PER_CTA, (d->m + LIN_ROWS - 1) / LIN_ROWS);
   linear_small_kernel<<<grid, LIN_THREADS, (size_t)LIN_ROWS * d->in_f * sizeof(float), tfmq_stream(stream)>>>(*d);
   TFMQ_LAUNCH_CHECK("linear_small");
+  return TFMQ_OK;
+}
+
+extern "C" int tfmq_linear_grouped_plan(tfmq_ctx* ctx, const tfmq_linear_desc* descs_host, int n, int* cta_start_host) {
+  if (!ctx) return TFMQ_ERR_ARG;
+  TFMQ_REQUIRE(descs_host && cta_start_host && n >= 1 && n <= 256, TFMQ_ERR_ARG, "linear_grouped_plan: n=%d", n);
+  int acc = 0;
+  for (int l = 0; l < n; ++l) {
+    if (int rc = check_linear(ctx, &descs_host[l])) return rc;
+    TFMQ_REQUIRE(descs_host[l].m == descs_host[0].m, TFMQ_ERR_SHAPE, "linear_grouped_plan: layers differ in m");
+    cta_start_host[l] = acc;
+    acc += (descs_host[l].out_f + LIN_OUT_PER_CTA - 1) / LIN_OUT_PER_CTA;
+  }
+  cta_start_host[n] = acc;
+  return TFMQ_OK;
+}
+
+extern "C" int tfmq_linear_grouped(tfmq_ctx* ctx, const tfmq_linear_desc* descs_dev, const int* cta_start_dev, int n,
+                                   int total_ctas, int m, int max_in_f, void* stream) {
+  if (!ctx) return TFMQ_ERR_ARG;
+  TFMQ_REQUIRE(descs_dev && cta_start_dev && n >= 1 && n <= 256 && total_ctas >= 1, TFMQ_ERR_ARG, "linear_grouped: args");
+  TFMQ_REQUIRE(m >= 0 && m <= 4096 && max_in_f > 0 && max_in_f <= 1536 && max_in_f % 4 == 0, TFMQ_ERR_SHAPE,
+               "linear_grouped: m=%d max_in_f=%d", m, max_in_f);
+  if (m == 0) return TFMQ_OK;
+  dim3 grid(total_ctas, (m + LIN_ROWS - 1) / LIN_ROWS);
+  linear_grouped_kernel<<<grid, LIN_THREADS, (size_t)LIN_ROWS * max_in_f * sizeof(float), tfmq_stream(stream)>>>(
+      descs_dev, cta_start_dev, n);
+  TFMQ_LAUNCH_CHECK("linear_grouped");
   return TFMQ_OK;
 }
 

@@ -102,6 +102,8 @@ _SIGS = {
     "tfmq_conv_in": (C.c_int, [P, P, P, P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, P, i64, P]),
     "tfmq_conv_out": (C.c_int, [P, P, i64, P, P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, P, P]),
     "tfmq_linear_small": (C.c_int, [P, C.POINTER(LinearDesc), P]),
+    "tfmq_linear_grouped_plan": (C.c_int, [P, C.POINTER(LinearDesc), C.c_int, C.POINTER(C.c_int)]),
+    "tfmq_linear_grouped": (C.c_int, [P, P, P, C.c_int, C.c_int, C.c_int, C.c_int, P]),
     "tfmq_timestep_embedding": (C.c_int, [P, P, C.c_int, C.c_int, C.c_int, P, P]),
     "tfmq_attention": (C.c_int, [P, C.POINTER(AttnDesc), P]),
     "tfmq_ddim_update": (C.c_int, [P, P, P, P, P, i64, P, P, P]),

@@ -323,23 +323,52 @@ class StepEngine:
                                             res=res.view if res is not None else None, passes=passes,
                                             stats=self._stats_of(rec)))
 
-    def _linear(self, layer: QuantLayer, x: torch.Tensor, x_ld_zero: bool, silu_in: bool) -> torch.Tensor:
-        """Time-embedding MLP layer on [batch, in] rows (row pitch 0 = the same row for every sample)."""
+    def _linear_kw(self, q: _QL, xin: torch.Tensor, out: torch.Tensor, silu_in: bool) -> dict:
+        aq = self._aq_ptr(q) if (q.quant_w and q.aq_index is not None) else None
+        if q.quant_w:
+            return dict(x=xin, out=out, codes=q.codes, wzp_f=q.wzp_f, wdelta=q.wdelta, bias=q.bias, aq=aq, silu_in=silu_in)
+        return dict(x=xin, out=out, w_f32=q.w_f32, bias=q.bias, silu_in=silu_in)
+
+    def _linear(self, layer: QuantLayer, x: torch.Tensor, x_ld_zero: bool, silu_in: bool, group: bool = False) -> torch.Tensor:
+        """Time-embedding MLP layer on [batch, in] rows (row pitch 0 = the same row for every sample).
+        group=True: the layer joins the grouped launch opened by `_open_linear_group` (all per-block embedding
+        projections of the Temporal Information Block read the same input and run as ONE kernel)."""
         q = self.ql[id(layer)]
         out = torch.empty((self.batch, q.cout), dtype=torch.float32, device=self.dev)
         self._emb_bufs.append(out)
         xin = x if not x_ld_zero else x.reshape(1, -1).expand(self.batch, -1)
-        aq = self._aq_ptr(q) if (q.quant_w and q.aq_index is not None) else None
+        kw = self._linear_kw(q, xin, out, silu_in)
+        if group:
+            self._lin_group.append((q, kw))
+            return out
+
         def run():
-            if q.quant_w:
-                ops.linear_small(xin, out, codes=q.codes, wzp_f=q.wzp_f, wdelta=q.wdelta, bias=q.bias, aq=aq,
-                                 silu_in=silu_in)
-            else:
-                ops.linear_small(xin, out, w_f32=q.w_f32, bias=q.bias, silu_in=silu_in)
+            ops.linear_small(**kw)
             if self.teacher is not None and ("out:" + q.name) in self.teacher:
                 out.copy_(self.teacher["out:" + q.name].to(self.dev))
         self.ops.append(run)
         return out
+
+    def _open_linear_group(self):
+        self._lin_group: List = []
+        self._lin_group_slot = len(self.ops)
+        self.ops.append(None)
+
+    def _close_linear_group(self):
+        members = self._lin_group
+        if not members:
+            self.ops[self._lin_group_slot] = lambda: None
+            return
+        grp = ops.LinearGroup([kw for _, kw in members])
+        self._lin_group_obj = grp
+
+        def run():
+            grp.run()
+            if self.teacher is not None:
+                for q, kw in members:
+                    if ("out:" + q.name) in self.teacher:
+                        kw["out"].copy_(self.teacher["out:" + q.name].to(self.dev))
+        self.ops[self._lin_group_slot] = run
 
     def _attention(self, q_t, k_t, v_t, o: T, heads: int, d: int, scale: float, strides):
         b, tq = o.n, o.h * o.w
@@ -352,9 +381,10 @@ class StepEngine:
         self.emb_rows = torch.zeros((N, self.emb_dim), dtype=torch.float32, device=self.dev)
         t1 = self._linear(m.temb.dense[0], self.emb_rows, False, silu_in=False)
         temb = self._linear(m.temb.dense[1], t1, False, silu_in=True)
+        self._open_linear_group()
 
         def resblock(blk: QuantResnetBlock, x: T) -> T:
-            e = self._linear(blk.temb_proj, temb, False, silu_in=True)
+            e = self._linear(blk.temb_proj, temb, False, silu_in=True, group=True)
             h = self._qconv(blk.conv1, x, gn=self._gn(x, blk.norm1), silu=True, emb=e)
             out = self._new(x.n, x.h, x.w, blk.out_channels)
             r = x
@@ -419,6 +449,7 @@ class StepEngine:
                 h = self._qconv(st.upsample.conv, h, upsample=True)
                 self.block_out[self._names[id(st.upsample)]] = h
         self._final(m.norm_out, m.conv_out, h)
+        self._close_linear_group()
 
     def _final(self, norm, conv_out_layer, h: T):
         gn = self._gn(h, norm)
@@ -435,9 +466,10 @@ class StepEngine:
         self.emb_rows = torch.zeros((N, self.emb_dim), dtype=torch.float32, device=self.dev)
         t1 = self._linear(m.time_embed[0], self.emb_rows, False, silu_in=False)
         emb = self._linear(m.time_embed[2], t1, False, silu_in=True)
+        self._open_linear_group()
 
         def resblock(blk: QuantResBlock, x: T) -> T:
-            e = self._linear(blk.emb_layers[1], emb, False, silu_in=True)
+            e = self._linear(blk.emb_layers[1], emb, False, silu_in=True, group=True)
             n1, c1 = blk.in_layers[0], blk.in_layers[2]
             n2, c2 = blk.out_layers[0], blk.out_layers[3]
             h = self._qconv(c1, x, gn=self._gn(x, n1), silu=True, emb=e)
@@ -510,6 +542,7 @@ class StepEngine:
         for blk in m.output_blocks:
             h = run_seq(blk, _cat(h, hs.pop()))
         self._final(m.out[0], m.out[2], h)
+        self._close_linear_group()
 
     # ================================================================ allocation / execution
     def _allocate(self):

@@ -202,9 +202,7 @@ def conv_out(x: torch.Tensor, w, bias, out_nchw: torch.Tensor):
     ctx.call("tfmq_conv_out", _p(x), ld, _p(w), _p(bias), n, h, wd, cin, cout, _p(out_nchw), _stream())
 
 
-def linear_small(x: torch.Tensor, out: torch.Tensor, *, w_f32=None, codes=None, wzp_f=None, wdelta=None, bias=None,
-                 aq=None, silu_in: bool = False):
-    ctx = _ctx(out)
+def _linear_desc(x, out, w_f32, codes, wzp_f, wdelta, bias, aq, silu_in) -> LinearDesc:
     m, in_f = x.shape
     d = LinearDesc()
     d.x, d.x_ld = x.data_ptr(), x.stride(0)
@@ -217,7 +215,42 @@ def linear_small(x: torch.Tensor, out: torch.Tensor, *, w_f32=None, codes=None, 
     d.wdelta = wdelta.data_ptr() if wdelta is not None else None
     d.bias = bias.data_ptr() if bias is not None else None
     d.out, d.out_ld = out.data_ptr(), out.stride(0)
+    return d
+
+
+def linear_small(x: torch.Tensor, out: torch.Tensor, *, w_f32=None, codes=None, wzp_f=None, wdelta=None, bias=None,
+                 aq=None, silu_in: bool = False):
+    ctx = _ctx(out)
+    d = _linear_desc(x, out, w_f32, codes, wzp_f, wdelta, bias, aq, silu_in)
     ctx.call("tfmq_linear_small", C.byref(d), _stream())
+
+
+class LinearGroup:
+    """Several small-M linears replayed as one launch (tfmq_linear_grouped).  `layers` is a list of keyword
+    dicts with the arguments of `linear_small` (x, out, ...); every tensor must stay alive with this object."""
+
+    def __init__(self, layers):
+        assert len(layers) >= 1
+        self.layers = layers
+        out0 = layers[0]["out"]
+        self.ctx = _ctx(out0)
+        n = len(layers)
+        descs = (LinearDesc * n)()
+        for i, kw in enumerate(layers):
+            descs[i] = _linear_desc(kw["x"], kw["out"], kw.get("w_f32"), kw.get("codes"), kw.get("wzp_f"),
+                                    kw.get("wdelta"), kw.get("bias"), kw.get("aq"), kw.get("silu_in", False))
+        starts = (C.c_int * (n + 1))()
+        self.ctx.call("tfmq_linear_grouped_plan", descs, n, starts)
+        raw = bytes(descs)
+        self.descs_dev = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(out0.device)
+        self.starts_dev = torch.tensor(list(starts), dtype=torch.int32, device=out0.device)
+        self.n, self.total = n, int(starts[n])
+        self.m = layers[0]["x"].shape[0]
+        self.max_in = max(kw["x"].shape[1] for kw in layers)
+
+    def run(self):
+        self.ctx.call("tfmq_linear_grouped", _p(self.descs_dev), _p(self.starts_dev), self.n, self.total, self.m,
+                      self.max_in, _stream())
 
 
 def timestep_embedding(t: torch.Tensor, dim: int, style: int, out: torch.Tensor):

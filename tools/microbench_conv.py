@@ -47,7 +47,7 @@ def w4a8(n, h, w, cin, cout, ks, res, emb, stats):
     us = timeit(fn)
     gop = 2 * n * h * w * cout * ks * ks * cin / 1e9
     print(f"w4a8 n={n} {h}x{w} {cin}->{cout} k{ks} res={int(res)} emb={int(emb)} stats={int(stats)}: {us:7.1f} us  "
-          f"{gop / us * 1e-6:7.3f} POP/s", flush=True)
+          f"{gop / us * 1e-3:7.3f} POP/s", flush=True)
 
 
 def fp(n, h, w, cin, cout, ks, res, passes=3, wlo=True):
@@ -60,7 +60,7 @@ def fp(n, h, w, cin, cout, ks, res, passes=3, wlo=True):
     us = timeit(fn)
     gf = 2 * n * h * w * cout * ks * ks * cin / 1e9
     print(f"tf32 n={n} {h}x{w} {cin}->{cout} k{ks} res={int(res)} passes={passes} wlo={int(wlo)}: {us:7.1f} us  "
-          f"{gf / us * 1e-6:7.3f} PFLOP/s (algorithmic)", flush=True)
+          f"{gf / us * 1e-3:7.3f} PFLOP/s (algorithmic)", flush=True)
 
 
 def i8gemm(mm, nn, kk):
@@ -71,22 +71,23 @@ def i8gemm(mm, nn, kk):
     print(f"i8 gemm {mm}x{nn}x{kk}: {us:7.1f} us  {2 * mm * nn * kk / us * 1e-9:7.3f} POP/s", flush=True)
 
 
-i8gemm(8192, 8192, 8192)
-i8gemm(148 * 128, 256, 4096)
-i8gemm(8192, 8576, 8192)
-if os.environ.get('TFMQ_ONLY_GEMM'):
-    sys.exit(0)
-w4a8(16, 64, 64, 224, 224, 3, True, True, True)
-w4a8(16, 64, 64, 224, 224, 3, True, False, False)
-w4a8(16, 64, 64, 224, 224, 3, False, False, False)
-w4a8(16, 64, 64, 224, 224, 1, False, False, False)
-w4a8(16, 64, 64, 224, 224, 1, True, False, False)
-w4a8(16, 32, 32, 448, 448, 3, True, True, True)
-w4a8(16, 16, 16, 672, 672, 3, True, True, True)
-w4a8(16, 8, 8, 896, 896, 3, True, True, True)
-w4a8(64, 64, 64, 256, 256, 3, False, False, False)
-fp(16, 64, 64, 224, 224, 3, False, 3, False)
-fp(16, 32, 32, 448, 1344, 1, False, 3, True)
-fp(16, 32, 32, 448, 1344, 1, False, 1, True)
-fp(16, 32, 32, 448, 448, 1, True, 3, True)
-fp(16, 64, 64, 448, 224, 1, False, 3, True)
+if __name__ == "__main__":
+  i8gemm(8192, 8192, 8192)
+  i8gemm(148 * 128, 256, 4096)
+  i8gemm(8192, 8576, 8192)
+  if os.environ.get('TFMQ_ONLY_GEMM'):
+      sys.exit(0)
+  w4a8(16, 64, 64, 224, 224, 3, True, True, True)
+  w4a8(16, 64, 64, 224, 224, 3, True, False, False)
+  w4a8(16, 64, 64, 224, 224, 3, False, False, False)
+  w4a8(16, 64, 64, 224, 224, 1, False, False, False)
+  w4a8(16, 64, 64, 224, 224, 1, True, False, False)
+  w4a8(16, 32, 32, 448, 448, 3, True, True, True)
+  w4a8(16, 16, 16, 672, 672, 3, True, True, True)
+  w4a8(16, 8, 8, 896, 896, 3, True, True, True)
+  w4a8(64, 64, 64, 256, 256, 3, False, False, False)
+  fp(16, 64, 64, 224, 224, 3, False, 3, False)
+  fp(16, 32, 32, 448, 1344, 1, False, 3, True)
+  fp(16, 32, 32, 448, 1344, 1, False, 1, True)
+  fp(16, 32, 32, 448, 448, 1, True, 3, True)
+  fp(16, 64, 64, 448, 224, 1, False, 3, True)
