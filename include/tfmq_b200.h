@@ -109,7 +109,7 @@ typedef struct {
   int groups;
   float eps;
   int silu;              /* apply x*sigmoid(x) after GN */
-  /* output: exactly one of dst_u8 / dst_f32 */
+  /* output: exactly one of dst_u8 / dst_f32 / (dst_hi, dst_lo) */
   const float* aq;       /* device (delta, zp) for dst_u8 */
   uint8_t* dst_u8;       /* [n][H+2*halo][W+2*halo][dst_c] codes, border = zp */
   int halo;              /* 0 or 1 */
@@ -117,6 +117,10 @@ typedef struct {
   int dst_c_off;         /* first destination channel written */
   float* dst_f32;        /* fp32 NHWC (no halo) */
   int64_t dst_ld;
+  /* third kind of output: fp16 hi / lo planes (hi = half(v), lo = half(v - hi)) for tfmq_conv_h16 */
+  void* dst_hi;
+  void* dst_lo;
+  int64_t dst_h_ld;      /* in halves, multiple of 4 */
 } tfmq_act_desc;
 int tfmq_act_prepare(tfmq_ctx* ctx, const tfmq_act_desc* d, void* stream);
 
@@ -183,6 +187,36 @@ typedef struct {
 } tfmq_conv_fp_desc;
 int tfmq_conv_fp(tfmq_ctx* ctx, const tfmq_conv_fp_desc* d, void* stream);
 
+/* The same layers on kind::f16 (twice the tensor rate and half the operand bytes of kind::tf32): every fp32 operand
+ * is split into two fp16 terms, hi = half(v) and lo = half(v - hi) (22 significand bits, like the tf32 hi/lo split),
+ * and the product is hi*hi + lo*hi + hi*lo with fp32 accumulation.  Both operands arrive pre-split: the activation
+ * planes are written by tfmq_act_prepare (dst_hi / dst_lo), the weight planes once at load time, scaled per output
+ * channel by a power of two so that w_lo stays a normal fp16 (the inverse goes into wscale).
+ * Range: |x| must stay below 65504 (the split saturates instead of overflowing).
+ *   out = wscale[c] * conv(x_hi + x_lo, w_hi + w_lo) + bias[c] [+ emb[n][c]] [+ res] */
+typedef struct {
+  const void* x_hi;     /* fp16 NHWC, no halo (zero padding via TMA OOB fill) */
+  const void* x_lo;
+  int64_t x_ld;         /* in halves, multiple of 8 */
+  int n, h, w, cin, cout; /* INPUT spatial extent; cin % 16 == 0 */
+  int ksize, stride;    /* (1|3), (1|2) */
+  int pad_lo;
+  int out_h, out_w;
+  const void* w_hi;     /* fp16 [cout][ksize*ksize*cin], (tap, cin) order */
+  const void* w_lo;     /* or NULL (weights exact in fp16, e.g. integer codes) */
+  const float* wscale;  /* [cout] or NULL */
+  const float* bias;
+  const float* res;
+  int64_t res_ld;
+  float* out;
+  int64_t out_ld;
+  const float* emb;
+  int64_t emb_ld;
+  int n_stat;
+  tfmq_gn_target stat[2];
+} tfmq_conv_h16_desc;
+int tfmq_conv_h16(tfmq_ctx* ctx, const tfmq_conv_h16_desc* d, void* stream);
+
 /* first / last convolution with <= 4 input or output channels, fp32 FFMA.
  * in : NCHW [n][cin<=4][h][w]  -> NHWC fp32 (ld)        (conv_in)
  * out: NHWC fp32 (ld)          -> NCHW [n][cout<=4][h][w] (conv_out)
@@ -218,7 +252,7 @@ int tfmq_linear_small(tfmq_ctx* ctx, const tfmq_linear_desc* d, void* stream);
 /* Several small-M linears in ONE launch: the per-block embedding projections of a Temporal Information Block
  * (quant/quant_block.py:58-63,108-114 -- a Python loop over `emb_layers`, one SiLU + quantise + F.linear per block) all
  * read the same embedding.  `tfmq_linear_grouped_plan` validates n HOST descriptors (same m) and fills
- * cta_start_host[0..n] (prefix sums of ceil(out_f / 8)); the caller uploads the descriptors and the prefix array
+ * cta_start_host[0..n] (prefix sums of the CTAs each layer gets); the caller uploads the descriptors and the prefix array
  * once and replays `tfmq_linear_grouped` (descs_dev / cta_start_dev are DEVICE pointers; total_ctas = cta_start[n]). */
 int tfmq_linear_grouped_plan(tfmq_ctx* ctx, const tfmq_linear_desc* descs_host, int n, int* cta_start_host);
 int tfmq_linear_grouped(tfmq_ctx* ctx, const tfmq_linear_desc* descs_dev, const int* cta_start_dev, int n,

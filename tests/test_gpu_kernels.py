@@ -173,6 +173,81 @@ def test_conv_fp_tf32x3(dev, n, h, w, cin, cout, ks, stride, pad_lo):
     assert err1 <= 2e-2, f"tf32 single-pass err {err1}"
 
 
+# ------------------------------------------------------------------ fp (fp16 hi/lo split x3) conv
+@pytest.mark.parametrize("n,h,w,cin,cout,ks,stride,pad_lo", [
+    (2, 32, 32, 224, 448, 1, 1, 0),     # skip_connection 1x1 (K tail: 224 = 3 * 64 + 32)
+    (1, 64, 64, 224, 224, 3, 1, 1),     # weight-only-quantised first conv
+    (2, 32, 32, 224, 224, 3, 2, 1),     # LDM Downsample.op
+    (2, 32, 32, 128, 128, 3, 2, 0),     # DDIM Downsample (pad right/bottom only)
+    (4, 8, 8, 896, 2688, 1, 1, 0),      # LDM qkv Conv1d
+    (16, 16, 16, 1568, 672, 1, 1, 0),   # skip over a concat, many tiles per CTA
+])
+def test_conv_h16x3(dev, n, h, w, cin, cout, ks, stride, pad_lo):
+    """kind::f16 on fp16 hi/lo planes: the activation planes come from act_prepare's split output, the weight planes
+    from split_h16; the result must be as accurate as the tf32x3 path (accumulation-order level)."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(h * 31 + cin + cout + stride)
+    wt = torch.randn(cout, cin, ks, ks, generator=g) / math.sqrt(cin * ks * ks)
+    wt[0] *= 300.0        # per-channel weight scales far apart
+    wt[1] *= 1e-4
+    bias = torch.randn(cout, generator=g) * 0.1
+    x = torch.randn(n, cin, h, w, generator=g) * 3.0
+    x[0, 0, 0, 0] = 1234.5
+    x[0, 1, 0, 0] = 3e-6
+    if ks == 3 and pad_lo == 0:
+        xin = F.pad(x, (0, 1, 0, 1))
+        ref = F.conv2d(xin.double(), wt.double(), bias.double(), stride=stride)
+    else:
+        ref = F.conv2d(x.double(), wt.double(), bias.double(), stride=stride, padding=ks // 2)
+    oh, ow = ref.shape[2], ref.shape[3]
+    res = torch.randn(n, cout, oh, ow, generator=g)
+    ref = ref + res.double()
+    w_hi, w_lo, wscale = ops.split_h16(to_ohwi(wt).to(dev))
+    assert w_lo is not None
+    xd = nhwc(x).to(dev)
+    x_hi = torch.empty(xd.shape, dtype=torch.float16, device=dev)
+    x_lo = torch.empty_like(x_hi)
+    ops.act_prepare(xd, dst_h16=(x_hi, x_lo))
+    torch.cuda.synchronize()
+    # the split itself: hi + lo reproduces x to 2^-21 relative (22 significand bits), or 2^-25 absolute for tiny values
+    back = x_hi.double() + x_lo.double()
+    assert ((back - xd.double()).abs() <= 2.0 ** -21 * xd.double().abs() + 2.0 ** -24).all()
+    out = nhwc(res).to(dev)
+    ops.conv_h16(x_hi, x_lo, ks, stride, pad_lo, w_hi, w_lo, out, bias=bias.to(dev), wscale=wscale, res=out)
+    torch.cuda.synchronize()
+    got = out.cpu().permute(0, 3, 1, 2).double()
+    # same bound as the tf32x3 path (the tensor-core fp32 accumulator truncates: error grows with the number of
+    # accumulation steps, K/16 here), per output channel because the channels' weight scales are far apart
+    steps = cin * ks * ks / 16
+    tol = max(3e-6, 8 * 2.0 ** -26 * steps)     # 2x the tf32 test's factor: the planted 1234.5 sits early in the sum
+    allowed = tol * ref.abs().amax(dim=(0, 2, 3)).clamp_min(1.0)
+    err = ((got - ref).abs().amax(dim=(0, 2, 3)) / allowed).max().item()
+    assert err <= 1.0, f"h16x3 err / allowed = {err}"
+
+
+def test_conv_h16_integer_weights_exact(dev):
+    """Weight-only-quantised layer: integer weights (code - zp) are exact in fp16, no lo plane, per-channel delta in wscale."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(3)
+    n, h, w, cin, cout = 2, 16, 16, 64, 64
+    wi = torch.randint(-8, 8, (cout, 3 * 3 * cin), generator=g).float()
+    delta = torch.rand(cout, generator=g) * 0.01 + 0.001
+    x = torch.randn(n, h, w, cin, generator=g)
+    w_hi, w_lo, wscale = ops.split_h16(wi.to(dev), delta.to(dev))
+    assert w_lo is None
+    xd = x.to(dev)
+    x_hi = torch.empty(xd.shape, dtype=torch.float16, device=dev)
+    x_lo = torch.empty_like(x_hi)
+    ops.act_prepare(xd, dst_h16=(x_hi, x_lo))
+    out = torch.zeros((n, h, w, cout), device=dev)
+    ops.conv_h16(x_hi, x_lo, 3, 1, 1, w_hi, None, out, wscale=wscale)
+    torch.cuda.synchronize()
+    wt = (wi * delta[:, None]).reshape(cout, 3, 3, cin).permute(0, 3, 1, 2)
+    ref = F.conv2d(x.permute(0, 3, 1, 2).double(), wt.double(), padding=1)
+    err = (out.cpu().permute(0, 3, 1, 2).double() - ref).abs().max().item()
+    assert err <= 2e-6 * max(1.0, ref.abs().max().item()), err
+
+
 # ------------------------------------------------------------------ GroupNorm + producer
 @pytest.mark.parametrize("n,h,w,c,eps", [(2, 16, 16, 128, 1e-6), (3, 32, 32, 224, 1e-5), (1, 8, 8, 1792, 1e-5)])
 def test_gn_silu_quant(dev, n, h, w, c, eps):

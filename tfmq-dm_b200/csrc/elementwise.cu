@@ -1,6 +1,8 @@
 // HBM-bound producer / consumer kernels around the tcgen05 GEMMs:
 // GroupNorm statistics, the fused GN-apply + SiLU + activation-quantise producer,
 // DDIM update, classifier-free-guidance combine, timestep embedding.
+#include <cuda_fp16.h>
+
 #include "ctx.h"
 
 namespace tfmq {
@@ -102,6 +104,23 @@ __device__ __forceinline__ uint32_t quant4(const float (&t)[4], float delta, flo
          (quant1(t[3], delta, inv, zp) << 24);
 }
 
+// v = hi + lo (+ O(2^-22 |v|)): hi = half(v), lo = half(v - hi); saturating, so an out-of-range value cannot become inf
+__device__ __forceinline__ uint32_t half_sat_bits(float v) {
+  uint16_t h;
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h) : "f"(v));
+  return h;
+}
+__device__ __forceinline__ void split_h16x4(const float (&t)[4], uint2& hi, uint2& lo) {
+  uint32_t hb[4], lb[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    hb[j] = half_sat_bits(t[j]);
+    lb[j] = half_sat_bits(t[j] - __half2float(__ushort_as_half((unsigned short)hb[j])));
+  }
+  hi = make_uint2(hb[0] | (hb[1] << 16), hb[2] | (hb[3] << 16));
+  lo = make_uint2(lb[0] | (lb[1] << 16), lb[2] | (lb[3] << 16));
+}
+
 // One warp per destination pixel (lanes = float4 channel vectors): the pixel decode / border test is per
 // warp, not per element, and every global access is a full row.
 __global__ void __launch_bounds__(ACT_THREADS) act_prepare_kernel(const ActParams P) {
@@ -161,6 +180,10 @@ __global__ void __launch_bounds__(ACT_THREADS) act_prepare_kernel(const ActParam
     const int sy = d.upsample ? (y >> 1) : y, sx = d.upsample ? (x >> 1) : x;
     const float4* src = reinterpret_cast<const float4*>(d.src + (((long long)n * d.h + sy) * d.w + sx) * d.src_ld);
     float4* o32 = d.dst_f32 ? reinterpret_cast<float4*>(d.dst_f32 + ((long long)n * npix + pp) * d.dst_ld) : nullptr;
+    uint2* ohi = d.dst_hi ? reinterpret_cast<uint2*>(static_cast<__half*>(d.dst_hi) + ((long long)n * npix + pp) * d.dst_h_ld)
+                          : nullptr;
+    uint2* olo = d.dst_hi ? reinterpret_cast<uint2*>(static_cast<__half*>(d.dst_lo) + ((long long)n * npix + pp) * d.dst_h_ld)
+                          : nullptr;
     for (int v0 = lane; v0 < nvec; v0 += 64) {
       const int v1 = v0 + 32;
       const bool has1 = v1 < nvec;
@@ -184,6 +207,14 @@ __global__ void __launch_bounds__(ACT_THREADS) act_prepare_kernel(const ActParam
       if (o8) {
         o8[v0] = quant4(t0, delta, inv, zp);
         if (has1) o8[v1] = quant4(t1, delta, inv, zp);
+      } else if (ohi) {
+        uint2 h, l;
+        split_h16x4(t0, h, l);
+        ohi[v0] = h, olo[v0] = l;
+        if (has1) {
+          split_h16x4(t1, h, l);
+          ohi[v1] = h, olo[v1] = l;
+        }
       } else {
         o32[v0] = make_float4(t0[0], t0[1], t0[2], t0[3]);
         if (has1) o32[v1] = make_float4(t1[0], t1[1], t1[2], t1[3]);
@@ -289,8 +320,11 @@ extern "C" int tfmq_gn_stats_part(tfmq_ctx* ctx, const float* x, int64_t ld, int
 extern "C" int tfmq_act_prepare(tfmq_ctx* ctx, const tfmq_act_desc* d, void* stream) {
   if (!ctx) return TFMQ_ERR_ARG;
   TFMQ_REQUIRE(d && d->src, TFMQ_ERR_ARG, "act_prepare: null pointer");
-  TFMQ_REQUIRE((d->dst_u8 != nullptr) != (d->dst_f32 != nullptr), TFMQ_ERR_ARG,
-               "act_prepare: exactly one of dst_u8 / dst_f32");
+  TFMQ_REQUIRE((d->dst_u8 != nullptr) + (d->dst_f32 != nullptr) + (d->dst_hi != nullptr) == 1, TFMQ_ERR_ARG,
+               "act_prepare: exactly one of dst_u8 / dst_f32 / dst_hi");
+  TFMQ_REQUIRE(!d->dst_hi || (d->dst_lo && d->dst_h_ld % 4 == 0 && ((uintptr_t)d->dst_hi & 7) == 0 &&
+                              ((uintptr_t)d->dst_lo & 7) == 0),
+               TFMQ_ERR_ARG, "act_prepare: dst_lo missing or dst_h_ld / alignment");
   TFMQ_REQUIRE(d->c % 4 == 0 && d->src_ld % 4 == 0, TFMQ_ERR_SHAPE, "act_prepare: c/ld not multiple of 4");
   TFMQ_REQUIRE(((uintptr_t)d->src & 15) == 0, TFMQ_ERR_ARG, "act_prepare: src must be 16-byte aligned");
   if (d->dst_u8) {
@@ -299,7 +333,7 @@ extern "C" int tfmq_act_prepare(tfmq_ctx* ctx, const tfmq_act_desc* d, void* str
                  "act_prepare: bad dst channel window");
     TFMQ_REQUIRE(d->halo == 0 || d->halo == 1, TFMQ_ERR_ARG, "act_prepare: halo");
     TFMQ_REQUIRE(((uintptr_t)d->dst_u8 & 3) == 0, TFMQ_ERR_ARG, "act_prepare: dst must be 4-byte aligned");
-  } else {
+  } else if (d->dst_f32) {
     TFMQ_REQUIRE(d->dst_ld % 4 == 0 && ((uintptr_t)d->dst_f32 & 15) == 0, TFMQ_ERR_SHAPE, "act_prepare: dst_ld/align");
   }
   if (d->gn_stats) {

@@ -43,6 +43,12 @@ __device__ __forceinline__ float2 chunk_col_partial(const uint8_t* buf, int et) 
   return make_float2(s1, s2);
 }
 
+template <int MODE>
+__device__ __forceinline__ void umma_fp(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  if (MODE == MODE_F16) umma_f16(tmem_d, adesc, bdesc, idesc, acc);
+  else umma_tf32(tmem_d, adesc, bdesc, idesc, acc);
+}
+
 #define PROF_T(idx)                                         \
   if (prof_on) {                                            \
     const long long now_ = clock64();                       \
@@ -52,8 +58,8 @@ __device__ __forceinline__ float2 chunk_col_partial(const uint8_t* buf, int et) 
 
 template <int MODE, int CG>
 __global__ void __launch_bounds__(IGEMM_THREADS, 1)
-igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-             const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmOut,
+igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+             const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmOut,
              const __grid_constant__ CUtensorMap tmRes, const IgemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // dynamic smem is only guaranteed 16-B aligned: skip to the next 1024-B boundary (128B swizzle atoms).
@@ -67,6 +73,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const int SU = p.u_stages;     // w4a8: depth of the unpacked-B ring
   const int ACC = p.acc_stages;
   constexpr bool W4 = (MODE == MODE_W4A8);
+  constexpr bool FP = (MODE == MODE_TF32 || MODE == MODE_F16);   // fp32-accurate modes: 3 error-compensated products
 
   // w4a8:   [A ring: S x 16 KB][s8 B ring: SU x u_bytes][packed int4 ring: SP x p_bytes] | other modes: [S x stage_bytes]
   const int SP = p.p_stages;
@@ -135,7 +142,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     mbar_fence_init();
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    if (MODE == MODE_TF32 || CG == 2) tma_prefetch_desc(&tmB2);
+    if (FP || CG == 2) tma_prefetch_desc(&tmB2);
+    if (MODE == MODE_F16) tma_prefetch_desc(&tmA2);
     tma_prefetch_desc(&tmOut);
     if (p.res) tma_prefetch_desc(&tmRes);
   }
@@ -161,8 +169,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const bool need_a_lo = (MODE == MODE_TF32) && (p.pass_flags & PASS_LO_HI);
-  const bool need_b_lo = (MODE == MODE_TF32) && (p.pass_flags & PASS_HI_LO);
+  const bool need_a_lo = FP && (p.pass_flags & PASS_LO_HI);
+  const bool need_b_lo = FP && (p.pass_flags & PASS_HI_LO);
+  const bool xf_split = (MODE == MODE_TF32) && need_a_lo;      // tf32: A lo is made in the kernel; f16: it arrives by TMA
   const bool two_acc = need_a_lo || need_b_lo;                 // tf32: separate accumulator for the small terms
   const uint32_t acc_cols = W4 ? (uint32_t)p.tile_n + 16u : (uint32_t)p.tile_n * (two_acc ? 2u : 1u);
 
@@ -171,7 +180,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     // (whole warp convergent, one elected lane issues: coordinates and addresses stay warp-uniform)
     uint32_t tx_bytes = IGEMM_A_BYTES;          // w4a8: the A tile only (B comes through the transform warps)
     if (MODE == MODE_I8) tx_bytes += (uint32_t)p.tile_n * 128u;
-    if (MODE == MODE_TF32) tx_bytes += (uint32_t)p.tile_n * 128u * (need_b_lo ? 2u : 1u);
+    if (FP) tx_bytes += (uint32_t)p.tile_n * 128u * (need_b_lo ? 2u : 1u);
+    if (MODE == MODE_F16 && need_a_lo) tx_bytes += IGEMM_A_BYTES;
     int s = 0;
     uint32_t par = 0;
     for (int ut = unit0; ut < total_units; ut += nunits) {
@@ -192,6 +202,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             mbar_expect_tx(&full_tma[s], tx_bytes);
             tma_load_4d(st, &tmA, &full_tma[s], kc * p.kchunk, x0 * p.stride + kx + p.off, y0 * p.stride + ky + p.off,
                         n0);
+            if (MODE == MODE_F16 && need_a_lo)
+              tma_load_4d(st + p.offA_lo, &tmA2, &full_tma[s], kc * p.kchunk, x0 * p.stride + kx + p.off,
+                          y0 * p.stride + ky + p.off, n0);
             if (!W4) {
               tma_load_2d(st + p.offB, &tmB, &full_tma[s], tap * p.cin + kc * p.kchunk, c_out0);
               if (need_b_lo) tma_load_2d(st + p.offB_lo, &tmB2, &full_tma[s], tap * p.cin + kc * p.kchunk, c_out0);
@@ -252,7 +265,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     // outside the elected-thread region, so descriptors live in uniform registers and each UTC*MMA issues
     // without a per-instruction register shuffle; the tensor pipe starves on anything slower.
     const uint32_t umma_n = (uint32_t)p.tile_n + (W4 ? 16u : 0u);
-    const uint32_t idesc = (MODE == MODE_TF32) ? idesc_tf32(128, umma_n) : idesc_i8_u8s8(128 * CG, umma_n);
+    const uint32_t idesc = (MODE == MODE_TF32)  ? idesc_tf32(128, umma_n)
+                           : (MODE == MODE_F16) ? idesc_f16(128, umma_n)
+                                                : idesc_i8_u8s8(128 * CG, umma_n);
     const uint32_t smem_base = smem_u32(smem);
     const uint64_t d_a = smem_desc_sw128(smem_base);
     const uint64_t d_b = W4 ? smem_desc_sw128(smem_u32(u_ring)) : smem_desc_sw128(smem_base + p.offB);
@@ -261,7 +276,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const uint32_t stage_units = W4 ? (IGEMM_A_BYTES >> 4) : (p.stage_bytes >> 4);   // descriptor address units per A slot
     const uint32_t u_units = p.u_bytes >> 4;
     const int nslice_last = (p.cin - (kchunks - 1) * p.kchunk) / p.kslice;   // valid 32-byte K slices of the last chunk
-    const bool wait_xf = need_a_lo;             // tf32 with a split A: the transform warp's barrier gates the stage
+    const bool wait_xf = xf_split;              // tf32 with a split A: the transform warps' barrier gates the stage
     uint32_t tcount = 0;
     int s = 0, su = 0;
     uint32_t par = 0, s_units = 0, pu = 0, su_units = 0;
@@ -298,21 +313,21 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const uint64_t a_lo = d_alo + s_units, b_lo = d_blo + s_units;
         const bool last = kb == nkb - 1;
         if (elect_one_sync()) {
-          if (MODE == MODE_TF32) {
+          if (FP) {
             if (need_a_lo) {
 #pragma unroll
               for (int k = 0; k < 4; ++k)
-                if (k < nslice) umma_tf32(tmem_lo, a_lo + 2 * k, b_hi + 2 * k, idesc, (k > 0) | accumulate_lo);
+                if (k < nslice) umma_fp<MODE>(tmem_lo, a_lo + 2 * k, b_hi + 2 * k, idesc, (k > 0) | accumulate_lo);
             }
             if (need_b_lo) {
 #pragma unroll
               for (int k = 0; k < 4; ++k)
                 if (k < nslice)
-                  umma_tf32(tmem_lo, a_hi + 2 * k, b_lo + 2 * k, idesc, (k > 0) | accumulate_lo | (need_a_lo ? 1u : 0u));
+                  umma_fp<MODE>(tmem_lo, a_hi + 2 * k, b_lo + 2 * k, idesc, (k > 0) | accumulate_lo | (need_a_lo ? 1u : 0u));
             }
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              if (k < nslice) umma_tf32(tmem_d, a_hi + 2 * k, b_hi + 2 * k, idesc, (k > 0) | accumulate);
+              if (k < nslice) umma_fp<MODE>(tmem_d, a_hi + 2 * k, b_hi + 2 * k, idesc, (k > 0) | accumulate);
           } else {
 #pragma unroll
             for (int k = 0; k < 4; ++k)
@@ -413,7 +428,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           if (++sp == SP) sp = 0, pp ^= 1u;
         }
       }
-    } else if (MODE == MODE_TF32 && need_a_lo) {
+    } else if (xf_split) {
       // split the fp32 A tile into hi = a & 0xFFFFE000 (exactly a tf32) and lo = a - hi; the four warps share a stage
       const int t = threadIdx.x - IGEMM_WARP_XF0 * 32;
       constexpr int XF_T = IGEMM_XF_WARPS * 32;
@@ -540,7 +555,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         } else {
           tmem_ld8(tmem_d + (uint32_t)c0, *reinterpret_cast<uint32_t(*)[8]>(&v[0]));
         }
-        if (MODE == MODE_TF32 && two_acc) {
+        if (FP && two_acc) {
           uint32_t v2[16];
           if (CW == 32) {
             tmem_ld16(tmem_d + (uint32_t)(p.tile_n + c0), v2);
@@ -730,8 +745,8 @@ static int encode(tfmq_ctx* ctx, CUtensorMap* m, CUtensorMapDataType dt, int ran
 }
 
 template <int MODE, int CG>
-static int launch_igemm(tfmq_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmB2,
-                        IgemmParams& p, cudaStream_t stream, const char* name) {
+static int launch_igemm(tfmq_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmB,
+                        const CUtensorMap& tmB2, IgemmParams& p, cudaStream_t stream, const char* name) {
   // shared-memory plan
   if (CG == 1) p.b_rows[0] = p.tile_n, p.b_row0[0] = 0, p.b_rows[1] = 0, p.b_row0[1] = 0;
   const uint32_t extra = 1024u /*alignment slack*/ + 2u * 128u * 32u * 4u /*epilogue chunks*/ +
@@ -762,13 +777,14 @@ static int launch_igemm(tfmq_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap
   } else {
     const uint32_t bB = (uint32_t)p.tile_n * 128u;
     uint32_t off = IGEMM_A_BYTES;
-    if (MODE == MODE_TF32 && (p.pass_flags & PASS_LO_HI)) {
+    constexpr bool FPM = (MODE == MODE_TF32 || MODE == MODE_F16);
+    if (FPM && (p.pass_flags & PASS_LO_HI)) {
       p.offA_lo = off;
       off += IGEMM_A_BYTES;
     }
     p.offB = off;
     off += bB;
-    if (MODE == MODE_TF32 && (p.pass_flags & PASS_HI_LO)) {
+    if (FPM && (p.pass_flags & PASS_HI_LO)) {
       p.offB_lo = off;
       off += bB;
     }
@@ -782,7 +798,7 @@ static int launch_igemm(tfmq_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap
   p.stages = stages;
   const int nkb = p.ksize * p.ksize * ((p.cin + p.kchunk - 1) / p.kchunk);
   int acc_cols = p.tile_n + (MODE == MODE_W4A8 ? 16 : 0);
-  if (MODE == MODE_TF32 && (p.pass_flags & (PASS_LO_HI | PASS_HI_LO))) acc_cols *= 2;
+  if ((MODE == MODE_TF32 || MODE == MODE_F16) && (p.pass_flags & (PASS_LO_HI | PASS_HI_LO))) acc_cols *= 2;
   p.acc_stages = (2 * acc_cols <= 512) ? 2 : 1;
   const int need = acc_cols * p.acc_stages;
   p.tmem_cols = need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512;
@@ -837,7 +853,7 @@ static int launch_igemm(tfmq_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap
     cudaEventRecord(ev0, stream);
   }
   if (CG == 1) {
-    kern<<<grid, IGEMM_THREADS, smem, stream>>>(tmA, tmB, tmB2, tmOut, tmRes, p);
+    kern<<<grid, IGEMM_THREADS, smem, stream>>>(tmA, tmA2, tmB, tmB2, tmOut, tmRes, p);
   } else {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid), cfg.blockDim = dim3(IGEMM_THREADS), cfg.dynamicSmemBytes = smem, cfg.stream = stream;
@@ -845,7 +861,7 @@ static int launch_igemm(tfmq_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr, cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmB2, tmOut, tmRes, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmA2, tmB, tmB2, tmOut, tmRes, p);
     if (e != cudaSuccess) return tfmq_fail(ctx, TFMQ_ERR_CUDA, "%s: cluster launch: %s", name, cudaGetErrorString(e));
   }
   TFMQ_LAUNCH_CHECK(name);
@@ -954,8 +970,8 @@ extern "C" int tfmq_conv_w4a8(tfmq_ctx* ctx, const tfmq_conv_w4a8_desc* d, void*
     }
     if (cg == 1) tmB2 = tmB;
   }
-  int rc = cg == 2 ? launch_igemm<MODE_W4A8, 2>(ctx, tmA, tmB, tmB2, p, tfmq_stream(stream), "conv_w4a8")
-                   : launch_igemm<MODE_W4A8, 1>(ctx, tmA, tmB, tmB2, p, tfmq_stream(stream), "conv_w4a8");
+  int rc = cg == 2 ? launch_igemm<MODE_W4A8, 2>(ctx, tmA, tmA, tmB, tmB2, p, tfmq_stream(stream), "conv_w4a8")
+                   : launch_igemm<MODE_W4A8, 1>(ctx, tmA, tmA, tmB, tmB2, p, tfmq_stream(stream), "conv_w4a8");
   for (int i = 0; rc == TFMQ_OK && !fuse_stats && i < d->n_stat; ++i)
     rc = tfmq_gn_stats_part(ctx, d->out, d->out_ld, d->n, d->h * d->w, d->cout, &d->stat[i], stream);
   return rc;
@@ -1032,7 +1048,82 @@ extern "C" int tfmq_conv_fp(tfmq_ctx* ctx, const tfmq_conv_fp_desc* d, void* str
                     CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
-  int rc = launch_igemm<MODE_TF32, 1>(ctx, tmA, tmB, tmB2, p, tfmq_stream(stream), "conv_fp");
+  int rc = launch_igemm<MODE_TF32, 1>(ctx, tmA, tmA, tmB, tmB2, p, tfmq_stream(stream), "conv_fp");
+  for (int i = 0; rc == TFMQ_OK && !fuse_stats && i < d->n_stat; ++i)
+    rc = tfmq_gn_stats_part(ctx, d->out, d->out_ld, d->n, d->out_h * d->out_w, d->cout, &d->stat[i], stream);
+  return rc;
+}
+
+extern "C" int tfmq_conv_h16(tfmq_ctx* ctx, const tfmq_conv_h16_desc* d, void* stream) {
+  if (!ctx) return TFMQ_ERR_ARG;
+  TFMQ_REQUIRE(d && d->x_hi && d->x_lo && d->w_hi && d->out, TFMQ_ERR_ARG, "conv_h16: null pointer");
+  TFMQ_REQUIRE(d->ksize == 1 || d->ksize == 3, TFMQ_ERR_SHAPE, "conv_h16: ksize %d", d->ksize);
+  TFMQ_REQUIRE(d->stride == 1 || d->stride == 2, TFMQ_ERR_SHAPE, "conv_h16: stride %d", d->stride);
+  TFMQ_REQUIRE(d->cin % 16 == 0 && d->cin >= 16, TFMQ_ERR_SHAPE, "conv_h16: cin %d not a multiple of 16", d->cin);
+  TFMQ_REQUIRE(d->cout % 16 == 0, TFMQ_ERR_SHAPE, "conv_h16: cout %d not a multiple of 16", d->cout);
+  TFMQ_REQUIRE(d->x_ld % 8 == 0 && d->out_ld % 4 == 0 && (!d->res || d->res_ld % 4 == 0), TFMQ_ERR_SHAPE,
+               "conv_h16: x_ld must be a multiple of 8 halves, out_ld / res_ld of 4 floats");
+  TFMQ_REQUIRE(((uintptr_t)d->out & 15) == 0 && ((uintptr_t)d->x_hi & 15) == 0 && ((uintptr_t)d->x_lo & 15) == 0 &&
+                   ((uintptr_t)d->w_hi & 15) == 0 && (!d->w_lo || ((uintptr_t)d->w_lo & 15) == 0) &&
+                   (!d->res || ((uintptr_t)d->res & 15) == 0),
+               TFMQ_ERR_ARG, "conv_h16: pointers must be 16-byte aligned");
+  TileGeom g;
+  TFMQ_REQUIRE(pick_geom(d->out_h, d->out_w, &g), TFMQ_ERR_SHAPE, "conv_h16: unsupported spatial %dx%d", d->out_h,
+               d->out_w);
+  TFMQ_REQUIRE(g.tw * d->stride <= 256 && g.th * d->stride <= 256, TFMQ_ERR_SHAPE, "conv_h16: box too large");
+  IgemmParams p{};
+  p.n_img = d->n, p.H = d->out_h, p.W = d->out_w, p.cin = d->cin, p.cout = d->cout;
+  p.ksize = d->ksize, p.stride = d->stride, p.off = d->ksize == 3 ? -d->pad_lo : 0;
+  p.th = g.th, p.tw = g.tw, p.tn = g.tn;
+  const int nkb_est = d->ksize * d->ksize * ((d->cin + 63) / 64);
+  {
+    // two accumulator stages (each main + small-terms) need tile_n <= 128
+    const int tiles_m = (d->out_w / g.tw) * (d->out_h / g.th) * ((d->n + g.tn - 1) / g.tn);
+    const int limit = nkb_est < 24 ? 128 : 256;
+    p.tile_n = pick_tile_n_balanced(d->cout, limit, tiles_m, nkb_est, ctx->sm_count, 300.0, 6.0);
+  }
+  p.kchunk = 64, p.kslice = 16;
+  p.pass_flags = PASS_HI_HI | PASS_LO_HI | (d->w_lo ? PASS_HI_LO : 0);
+  p.out = d->out, p.out_ld = d->out_ld, p.bias = d->bias, p.wscale = d->wscale;
+  p.res = d->res, p.res_ld = d->res_ld;
+  p.emb = d->emb, p.emb_ld = d->emb_ld;
+  TFMQ_REQUIRE(d->n_stat >= 0 && d->n_stat <= 2, TFMQ_ERR_ARG, "conv_h16: n_stat");
+  const bool fuse_stats = d->n_stat > 0 && g.tn == 1;
+  if (fuse_stats) {
+    p.n_stat = d->n_stat;
+    for (int i = 0; i < d->n_stat; ++i) p.stat[i] = d->stat[i];
+  }
+
+  CUtensorMap tmA, tmA2, tmB, tmB2;
+  for (int i = 0; i < 2; ++i) {
+    cuuint64_t dims[4] = {(cuuint64_t)d->cin, (cuuint64_t)d->w, (cuuint64_t)d->h, (cuuint64_t)d->n};
+    cuuint64_t str[3] = {(cuuint64_t)d->x_ld * 2, (cuuint64_t)d->w * d->x_ld * 2,
+                         (cuuint64_t)d->h * d->w * d->x_ld * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)(g.tw * d->stride), (cuuint32_t)(g.th * d->stride), (cuuint32_t)g.tn};
+    cuuint32_t es[4] = {1, (cuuint32_t)d->stride, (cuuint32_t)d->stride, 1};
+    // a box dimension of extent 1 must not carry a traversal stride
+    if (g.tw == 1) box[1] = 1, es[1] = 1;
+    if (g.th == 1) box[2] = 1, es[2] = 1;
+    int rc = encode(ctx, i ? &tmA2 : &tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, i ? d->x_lo : d->x_hi, dims, str, box, es,
+                    CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  const cuuint64_t kk = (cuuint64_t)d->ksize * d->ksize * d->cin;
+  for (int i = 0; i < 2; ++i) {
+    const void* w = i ? d->w_lo : d->w_hi;
+    if (!w) {
+      tmB2 = tmB;
+      continue;
+    }
+    cuuint64_t dims[2] = {kk, (cuuint64_t)d->cout};
+    cuuint64_t str[1] = {kk * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)p.tile_n};
+    cuuint32_t es[2] = {1, 1};
+    int rc = encode(ctx, i ? &tmB2 : &tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, w, dims, str, box, es,
+                    CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  int rc = launch_igemm<MODE_F16, 1>(ctx, tmA, tmA2, tmB, tmB2, p, tfmq_stream(stream), "conv_h16");
   for (int i = 0; rc == TFMQ_OK && !fuse_stats && i < d->n_stat; ++i)
     rc = tfmq_gn_stats_part(ctx, d->out, d->out_ld, d->n, d->out_h * d->out_w, d->cout, &d->stat[i], stream);
   return rc;
@@ -1066,5 +1157,5 @@ extern "C" int tfmq_gemm_i8_peak(tfmq_ctx* ctx, const uint8_t* a, const int8_t* 
     int rc = encode(ctx, &tmB, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, b, dims, str, box, es, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
-  return launch_igemm<MODE_I8, 1>(ctx, tmA, tmB, tmB, p, tfmq_stream(stream), "gemm_i8_peak");
+  return launch_igemm<MODE_I8, 1>(ctx, tmA, tmA, tmB, tmB, p, tfmq_stream(stream), "gemm_i8_peak");
 }

@@ -12,6 +12,7 @@
 //     MODE_W4A8 : unpack packed int4 codes -> (q - zp) s8 into the swizzled B tile
 //     MODE_TF32 : split fp32 A into tf32 hi + lo planes (3-pass error compensation)
 //     MODE_I8   : nothing (dense s8 weights; used for the measured int8 peak)
+//     MODE_F16  : nothing: both operands arrive pre-split as fp16 hi + lo planes (kind::f16, 3 products)
 // CG = 2 (w4a8 only): a cluster of two CTAs runs tcgen05.mma.cta_group::2 on two M-adjacent tiles (M = 256); each
 // CTA stages its own A tile and half of the weight rows.
 #pragma once
@@ -22,7 +23,7 @@
 
 namespace tfmq {
 
-enum { MODE_W4A8 = 0, MODE_I8 = 1, MODE_TF32 = 2 };
+enum { MODE_W4A8 = 0, MODE_I8 = 1, MODE_TF32 = 2, MODE_F16 = 3 };
 enum { PASS_HI_HI = 1, PASS_LO_HI = 2, PASS_HI_LO = 4 };
 
 struct IgemmParams {
@@ -67,8 +68,8 @@ constexpr int IGEMM_THREADS = (IGEMM_EPI_WARPS + 3 + IGEMM_XF_WARPS) * 32;
 constexpr uint32_t IGEMM_A_BYTES = 128 * 128;
 
 template <int MODE, int CG>
-__global__ void igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                             const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmOut,
+__global__ void igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+                             const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmOut,
                              const __grid_constant__ CUtensorMap tmRes, const IgemmParams p);
 
 }  // namespace tfmq

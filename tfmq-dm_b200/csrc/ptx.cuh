@@ -206,6 +206,9 @@ __device__ __forceinline__ uint32_t idesc_i8_u8s8(uint32_t M, uint32_t N) {
 __device__ __forceinline__ uint32_t idesc_tf32(uint32_t M, uint32_t N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
+__device__ __forceinline__ uint32_t idesc_f16(uint32_t M, uint32_t N) {   // A, B fp16; D f32
+  return (1u << 4) | (0u << 7) | (0u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
 __device__ __forceinline__ uint32_t idesc_bf16(uint32_t M, uint32_t N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }

@@ -24,7 +24,9 @@ __device__ __forceinline__ int warp_sum_i(int v) {
 constexpr int LIN_THREADS = 256;
 constexpr int LIN_OUT_PER_CTA = 8;   // one output per warp: many small CTAs, short dependent-load chains
 constexpr int LIN_ROWS = 8;
+constexpr int LIN_GROUP_OUT_PER_CTA = 32;   // grouped launch: the input transform of a CTA is shared by 32 outputs
 
+template <int OPC>
 __device__ __forceinline__ void linear_small_body(const tfmq_linear_desc& d, const int bx, const int by, float* xs) {
   const int m0 = by * LIN_ROWS;
   const int rows = min(LIN_ROWS, d.m - m0);
@@ -58,8 +60,8 @@ __device__ __forceinline__ void linear_small_body(const tfmq_linear_desc& d, con
   __syncthreads();
   const bool int_path = !d.w_f32 && d.aq;
   const int nv = d.in_f >> 2;                   // in_f is a multiple of 4
-  for (int oo = 0; oo < LIN_OUT_PER_CTA / 8; ++oo) {
-    const int o = bx * LIN_OUT_PER_CTA + warp * (LIN_OUT_PER_CTA / 8) + oo;
+  for (int oo = 0; oo < OPC / 8; ++oo) {
+    const int o = bx * OPC + warp * (OPC / 8) + oo;
     if (o >= d.out_f) break;
     float acc[LIN_ROWS];
 #pragma unroll
@@ -110,7 +112,7 @@ __device__ __forceinline__ void linear_small_body(const tfmq_linear_desc& d, con
 
 __global__ void __launch_bounds__(LIN_THREADS) linear_small_kernel(const tfmq_linear_desc d) {
   extern __shared__ __align__(16) float xs[];   // [LIN_ROWS][in_f]: fp32 inputs, or (code - zp) as fp32
-  linear_small_body(d, blockIdx.x, blockIdx.y, xs);
+  linear_small_body<LIN_OUT_PER_CTA>(d, blockIdx.x, blockIdx.y, xs);
 }
 
 // Several layers in one launch (the 22 per-block embedding projections of a Temporal Information Block all read the
@@ -121,7 +123,7 @@ __global__ void __launch_bounds__(LIN_THREADS) linear_grouped_kernel(const tfmq_
   int l = 0;
   while (l + 1 < n && (int)blockIdx.x >= cta_start[l + 1]) ++l;
   const tfmq_linear_desc d = descs[l];
-  linear_small_body(d, blockIdx.x - cta_start[l], blockIdx.y, xs);
+  linear_small_body<LIN_GROUP_OUT_PER_CTA>(d, blockIdx.x - cta_start[l], blockIdx.y, xs);
 }
 
 // conv_in: NCHW (cin<=4) -> NHWC, 3x3 pad 1.  CTA = 16 pixels x 16 channel groups; weights transposed in
@@ -259,7 +261,7 @@ extern "C" int tfmq_linear_grouped_plan(tfmq_ctx* ctx, const tfmq_linear_desc* d
     if (int rc = check_linear(ctx, &descs_host[l])) return rc;
     TFMQ_REQUIRE(descs_host[l].m == descs_host[0].m, TFMQ_ERR_SHAPE, "linear_grouped_plan: layers differ in m");
     cta_start_host[l] = acc;
-    acc += (descs_host[l].out_f + LIN_OUT_PER_CTA - 1) / LIN_OUT_PER_CTA;
+    acc += (descs_host[l].out_f + LIN_GROUP_OUT_PER_CTA - 1) / LIN_GROUP_OUT_PER_CTA;
   }
   cta_start_host[n] = acc;
   return TFMQ_OK;

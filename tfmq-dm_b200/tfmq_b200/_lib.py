@@ -30,6 +30,7 @@ class ActDesc(C.Structure):
         ("aq", C.c_void_p), ("dst_u8", C.c_void_p),
         ("halo", C.c_int), ("dst_c", C.c_int), ("dst_c_off", C.c_int),
         ("dst_f32", C.c_void_p), ("dst_ld", i64),
+        ("dst_hi", C.c_void_p), ("dst_lo", C.c_void_p), ("dst_h_ld", i64),
     ]
 
 
@@ -57,6 +58,20 @@ class ConvFpDesc(C.Structure):
         ("res", C.c_void_p), ("res_ld", i64),
         ("out", C.c_void_p), ("out_ld", i64),
         ("passes", C.c_int),
+        ("emb", C.c_void_p), ("emb_ld", i64),
+        ("n_stat", C.c_int), ("stat", GnTarget * 2),
+    ]
+
+
+class ConvH16Desc(C.Structure):
+    _fields_ = [
+        ("x_hi", C.c_void_p), ("x_lo", C.c_void_p), ("x_ld", i64),
+        ("n", C.c_int), ("h", C.c_int), ("w", C.c_int), ("cin", C.c_int), ("cout", C.c_int),
+        ("ksize", C.c_int), ("stride", C.c_int), ("pad_lo", C.c_int),
+        ("out_h", C.c_int), ("out_w", C.c_int),
+        ("w_hi", C.c_void_p), ("w_lo", C.c_void_p), ("wscale", C.c_void_p), ("bias", C.c_void_p),
+        ("res", C.c_void_p), ("res_ld", i64),
+        ("out", C.c_void_p), ("out_ld", i64),
         ("emb", C.c_void_p), ("emb_ld", i64),
         ("n_stat", C.c_int), ("stat", GnTarget * 2),
     ]
@@ -99,6 +114,7 @@ _SIGS = {
     "tfmq_act_prepare": (C.c_int, [P, C.POINTER(ActDesc), P]),
     "tfmq_conv_w4a8": (C.c_int, [P, C.POINTER(ConvW4A8Desc), P]),
     "tfmq_conv_fp": (C.c_int, [P, C.POINTER(ConvFpDesc), P]),
+    "tfmq_conv_h16": (C.c_int, [P, C.POINTER(ConvH16Desc), P]),
     "tfmq_conv_in": (C.c_int, [P, P, P, P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, P, i64, P]),
     "tfmq_conv_out": (C.c_int, [P, P, i64, P, P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, P, P]),
     "tfmq_linear_small": (C.c_int, [P, C.POINTER(LinearDesc), P]),

@@ -99,25 +99,32 @@ class _QL:
             self.wdelta, self.wzp_f = delta.contiguous(), zp.contiguous()
             self.wzp_u8 = zp.to(torch.uint8).contiguous()
             if aq_index is None and self.is_conv:
-                # weight-only quantised conv with fp activations: exact integer weights on the tf32 path
+                # weight-only quantised conv with fp activations: exact integer weights on the fp paths
                 self.w_hi = (self.codes.float() - zp[:, None]).contiguous()
                 self.w_lo = None
+                self.h_hi, self.h_lo, self.h_scale = ops.split_h16(self.w_hi, self.wdelta)
         else:
             self.w_f32 = w2d
             if self.is_conv and self.cin > 4 and self.cout > 4:
                 self.w_hi, self.w_lo = ops.split_tf32(w2d)
+                self.h_hi, self.h_lo, self.h_scale = ops.split_h16(w2d)
 
 
 class StepEngine:
     def __init__(self, qnn, batch: int, act_tables: Optional[Sequence[Dict[str, torch.Tensor]]] = None,
                  timesteps: Optional[Sequence[int]] = None, fp_passes: int = 3, device=None, use_graph: bool = True,
-                 fuse_gn: bool = True):
+                 fuse_gn: bool = True, fp_mode: str = "h16"):
         model = qnn.model
         self.dev = torch.device(device) if device is not None else next(model.parameters()).device
         if self.dev.type != "cuda":
             raise RuntimeError("StepEngine needs the model on an sm_100a GPU (no CPU path)")
         self.batch, self.fp_passes, self.use_graph = batch, fp_passes, use_graph
         self.fuse_gn = fuse_gn   # GroupNorm statistics accumulated by the producing conv's epilogue
+        # layers the reference keeps in floating point: "h16" = kind::f16 on fp16 hi/lo planes (3 products),
+        # "tf32" = kind::tf32 (fp_passes = 3: error-compensated, 1: plain tf32)
+        assert fp_mode in ("h16", "tf32")
+        self.fp_mode = fp_mode if fp_passes == 3 else "tf32"
+        self._h16: Dict[int, tuple] = {}
         self.kind = "ddim" if hasattr(model, "temb") else "ldm"
         self.model = model
         self.ops: List = []
@@ -285,26 +292,50 @@ class StepEngine:
             self.ops.append(run)
         else:
             assert not upsample
-            src = x
-            if gn is not None or silu:
-                src = self._new(x.n, x.h, x.w, x.c)
-                self.ops.append(lambda: ops.act_prepare(x.view, dst_f32=src.view, silu=silu, **self._gn_args(gn)))
+            src = self._fp_input(x, gn, silu)
             self._fp_conv(q, src, out, res, pad_lo=q.ksize // 2, emb=emb)
         return out
 
-    def _fp_conv(self, q: _QL, src: T, out: T, res: Optional[T], pad_lo: int, stride: int = 1, emb=None):
+    def _fp_input(self, x: T, gn=None, silu: bool = False):
+        """Input of a floating-point conv: x itself, or [GN][SiLU](x).  h16 mode: the fp16 hi / lo planes of it (one
+        act_prepare launch, which is also where GN / SiLU are applied); tf32 mode: an fp32 tensor."""
+        if self.fp_mode == "h16":
+            key = (id(x), id(gn[0]) if gn is not None else None, silu)
+            if key not in self._h16:
+                hi = torch.empty((x.n, x.h, x.w, x.c), dtype=torch.float16, device=self.dev)
+                lo = torch.empty_like(hi)
+                self._h16[key] = (hi, lo)
+                self.ops.append(lambda: ops.act_prepare(x.view, dst_h16=(hi, lo), silu=silu, **self._gn_args(gn)))
+            return self._h16[key]
+        if gn is None and not silu:
+            return x
+        src = self._new(x.n, x.h, x.w, x.c)
+        self.ops.append(lambda: ops.act_prepare(x.view, dst_f32=src.view, silu=silu, **self._gn_args(gn)))
+        return src
+
+    def _fp_launch(self, src, ksize, stride, pad_lo, w_tf32, w_h16, out: T, res: Optional[T], bias, wscale, emb, rec):
+        """src: what `_fp_input` returned; w_tf32 = (hi, lo) fp32 planes, w_h16 = (hi, lo, scale) fp16 planes."""
+        if self.fp_mode == "h16":
+            hi, lo = src
+            ops.conv_h16(hi, lo, ksize, stride, pad_lo, w_h16[0], w_h16[1], out.view, bias=bias, wscale=w_h16[2],
+                         res=res.view if res is not None else None, emb=emb, stats=self._stats_of(rec))
+        else:
+            ops.conv_fp(src.view, ksize, stride, pad_lo, w_tf32[0], w_tf32[1], out.view, bias=bias, wscale=wscale,
+                        res=res.view if res is not None else None, passes=self.fp_passes, emb=emb,
+                        stats=self._stats_of(rec))
+
+    def _fp_conv(self, q: _QL, src, out: T, res: Optional[T], pad_lo: int, stride: int = 1, emb=None):
         wscale = q.wdelta if q.quant_w else None
-        passes = self.fp_passes
         rec = {"stats": []}
         out.producer = rec
+        self.ops.append(lambda: self._fp_launch(src, q.ksize, stride, pad_lo, (q.w_hi, q.w_lo),
+                                                (q.h_hi, q.h_lo, q.h_scale), out, res, q.bias, wscale, emb, rec))
 
-        def run():
-            ops.conv_fp(src.view, q.ksize, stride, pad_lo, q.w_hi, q.w_lo, out.view, bias=q.bias, wscale=wscale,
-                        res=res.view if res is not None else None, passes=passes, emb=emb, stats=self._stats_of(rec))
-        self.ops.append(run)
-
-    def _plain_conv(self, conv: nn.Module, src: T, out: T, res: Optional[T], pad_lo: int, stride: int):
-        """An nn.Conv2d / nn.Conv1d the reference never wraps (skip / op / shortcut / qkv / proj_out)."""
+    def _plain_conv(self, conv: nn.Module, src, out: T, res: Optional[T], pad_lo: int, stride: int):
+        """An nn.Conv2d / nn.Conv1d the reference never wraps (skip / op / shortcut / qkv / proj_out).
+        src: a T (split here if needed) or what `_fp_input` returned."""
+        if isinstance(src, T):
+            src = self._fp_input(src)
         key = id(conv)
         if key not in self._plain:
             w = conv.weight.detach().float()
@@ -312,16 +343,12 @@ class StepEngine:
                 w = w[..., None]
             cout, k = w.shape[0], w.shape[2]
             w2d = w.permute(0, 2, 3, 1).reshape(cout, -1).contiguous().to(self.dev)
-            hi, lo = ops.split_tf32(w2d)
             b = conv.bias.detach().float().contiguous().to(self.dev) if conv.bias is not None else None
-            self._plain[key] = (hi, lo, b, k)
-        hi, lo, b, k = self._plain[key]
-        passes = self.fp_passes
+            self._plain[key] = (ops.split_tf32(w2d), ops.split_h16(w2d), b, k)
+        w_tf32, w_h16, b, k = self._plain[key]
         rec = {"stats": []}
         out.producer = rec
-        self.ops.append(lambda: ops.conv_fp(src.view, k, stride, pad_lo, hi, lo, out.view, bias=b,
-                                            res=res.view if res is not None else None, passes=passes,
-                                            stats=self._stats_of(rec)))
+        self.ops.append(lambda: self._fp_launch(src, k, stride, pad_lo, w_tf32, w_h16, out, res, b, None, None, rec))
 
     def _linear_kw(self, q: _QL, xin: torch.Tensor, out: torch.Tensor, silu_in: bool) -> dict:
         aq = self._aq_ptr(q) if (q.quant_w and q.aq_index is not None) else None
@@ -484,8 +511,7 @@ class StepEngine:
 
         def attnblock(blk: QuantAttentionBlock, x: T) -> T:
             gn = self._gn(x, blk.norm)
-            xn = self._new(x.n, x.h, x.w, x.c)
-            self.ops.append(lambda: ops.act_prepare(x.view, dst_f32=xn.view, silu=False, **self._gn_args(gn)))
+            xn = self._fp_input(x, gn)
             qkv = self._new(x.n, x.h, x.w, 3 * x.c)
             self._plain_conv(blk.qkv, xn, qkv, None, pad_lo=0, stride=1)
             heads = blk.num_heads

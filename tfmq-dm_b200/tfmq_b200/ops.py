@@ -11,7 +11,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import ActDesc, AttnDesc, ConvFpDesc, ConvW4A8Desc, GnTarget, LinearDesc
+from ._lib import ActDesc, AttnDesc, ConvFpDesc, ConvH16Desc, ConvW4A8Desc, GnTarget, LinearDesc
 
 
 def _ctx(t: torch.Tensor) -> _lib.Context:
@@ -90,8 +90,9 @@ def fill_zero(t: torch.Tensor):
 def act_prepare(src: torch.Tensor, *, aq: torch.Tensor | None = None, dst_u8: torch.Tensor | None = None,
                 halo: int = 0, dst_c_off: int = 0, dst_f32: torch.Tensor | None = None,
                 gn_stats_t: torch.Tensor | None = None, gamma=None, beta=None, groups: int = 32,
-                eps: float = 1e-5, silu: bool = False, upsample: bool = False):
-    """[GN] -> [SiLU] -> u8 codes into a halo-padded NHWC buffer, or fp32 NHWC."""
+                eps: float = 1e-5, silu: bool = False, upsample: bool = False, dst_h16=None):
+    """[GN] -> [SiLU] -> u8 codes into a halo-padded NHWC buffer, or fp32 NHWC, or (dst_h16 = (hi, lo)) the fp16
+    hi / lo planes `conv_h16` reads."""
     ctx = _ctx(src)
     n, h, w, c, ld = _nhwc(src)
     d = ActDesc()
@@ -109,6 +110,12 @@ def act_prepare(src: torch.Tensor, *, aq: torch.Tensor | None = None, dst_u8: to
         d.aq = aq.data_ptr()
         d.dst_u8 = dst_u8.data_ptr()
         d.halo, d.dst_c, d.dst_c_off = halo, dst_u8.shape[3], dst_c_off
+    elif dst_h16 is not None:
+        hi, lo = dst_h16
+        assert hi.dtype == torch.float16 and lo.dtype == torch.float16 and hi.shape == lo.shape
+        dn, dh, dw, dc, dld = _nhwc(hi)
+        assert (dn, dh, dw, dc) == (n, oh, ow, c) and _nhwc(lo)[4] == dld
+        d.dst_hi, d.dst_lo, d.dst_h_ld = hi.data_ptr(), lo.data_ptr(), dld
     else:
         dn, dh, dw, dc, dld = _nhwc(dst_f32)
         assert (dn, dh, dw, dc) == (n, oh, ow, c)
@@ -168,6 +175,53 @@ def conv_fp(x: torch.Tensor, ksize: int, stride: int, pad_lo: int, w_hi, w_lo, o
         d.emb, d.emb_ld = emb.data_ptr(), (emb.stride(0) if emb.dim() == 2 and emb.shape[0] > 1 else 0)
     _set_stats(d, stats)
     ctx.call("tfmq_conv_fp", C.byref(d), _stream())
+
+
+def conv_h16(x_hi: torch.Tensor, x_lo: torch.Tensor, ksize: int, stride: int, pad_lo: int, w_hi, w_lo, out: torch.Tensor,
+             bias=None, wscale=None, res=None, emb=None, stats=None):
+    """fp32-accurate conv on kind::f16 from pre-split fp16 hi / lo planes (see include/tfmq_b200.h)."""
+    ctx = _ctx(out)
+    assert x_hi.dtype == torch.float16 and x_lo.dtype == torch.float16 and w_hi.dtype == torch.float16
+    n, h, w, cin, x_ld = _nhwc(x_hi)
+    assert _nhwc(x_lo) == (n, h, w, cin, x_ld)
+    on, oh, ow, cout, out_ld = _nhwc(out)
+    assert on == n
+    d = ConvH16Desc()
+    d.x_hi, d.x_lo, d.x_ld = x_hi.data_ptr(), x_lo.data_ptr(), x_ld
+    d.n, d.h, d.w, d.cin, d.cout = n, h, w, cin, cout
+    d.ksize, d.stride, d.pad_lo, d.out_h, d.out_w = ksize, stride, pad_lo, oh, ow
+    d.w_hi = w_hi.data_ptr()
+    d.w_lo = w_lo.data_ptr() if w_lo is not None else None
+    d.wscale = wscale.data_ptr() if wscale is not None else None
+    d.bias = bias.data_ptr() if bias is not None else None
+    if res is not None:
+        rn, rh, rw, rc, rld = _nhwc(res)
+        assert (rn, rh, rw, rc) == (n, oh, ow, cout)
+        d.res, d.res_ld = res.data_ptr(), rld
+    d.out, d.out_ld = out.data_ptr(), out_ld
+    if emb is not None:
+        assert emb.stride(-1) == 1
+        d.emb, d.emb_ld = emb.data_ptr(), (emb.stride(0) if emb.dim() == 2 and emb.shape[0] > 1 else 0)
+    _set_stats(d, stats)
+    ctx.call("tfmq_conv_h16", C.byref(d), _stream())
+
+
+def split_h16(w2d: torch.Tensor, wscale: torch.Tensor | None = None):
+    """Load-time split of fp32 weights [cout][k] into fp16 planes: w * 2^e = hi + lo per output channel, with e chosen so
+    that max|w| lands in [2^12, 2^13) (lo stays a normal fp16).  Returns (hi, lo or None, scale) where scale[c] = 2^-e
+    (times `wscale` if given) is what the conv epilogue multiplies by; lo is None when every weight is exact in fp16."""
+    w2d = w2d.contiguous().float()
+    amax = w2d.abs().amax(dim=1).clamp_min(1e-30)
+    e = 12 - torch.floor(torch.log2(amax))
+    e = torch.where(amax * torch.exp2(e) >= 8192.0, e - 1, e)      # guard the log2 rounding at powers of two
+    sc = torch.exp2(e)
+    ws = w2d * sc[:, None]
+    hi = ws.half()
+    lo = (ws - hi.float()).half()
+    inv = torch.exp2(-e)
+    if wscale is not None:
+        inv = inv * wscale.float()
+    return hi.contiguous(), (lo.contiguous() if bool((lo != 0).any()) else None), inv.contiguous()
 
 
 def split_tf32(w2d: torch.Tensor):
