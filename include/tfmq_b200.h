@@ -121,6 +121,14 @@ typedef struct {
   void* dst_hi;
   void* dst_lo;
   int64_t dst_h_ld;      /* in halves, multiple of 4 */
+  /* token producers of the transformer blocks (quant/quant_block.py:248-299; ldm/modules/attention.py:37-44,205-216),
+   * one NHWC "pixel" = one token:
+   *   ln_gamma != NULL: LayerNorm over the c channels (eps ln_eps) instead of GroupNorm;
+   *   geglu != 0: src rows hold 2c channels [value | gate], the output is value * gelu(gate) (c channels). */
+  const float* ln_gamma;
+  const float* ln_beta;
+  float ln_eps;
+  int geglu;
 } tfmq_act_desc;
 int tfmq_act_prepare(tfmq_ctx* ctx, const tfmq_act_desc* d, void* stream);
 

@@ -94,7 +94,8 @@ class _Net:
         aq = self.act.get(name, x) if (s["aq"] and self.act is not None) else None
         if s["aq"] and self.act is not None and aq is None:
             raise KeyError(f"no activation quant parameters for {name}")
-        if self.record is not None and aq is not None and x.dim() == 4:
+        if self.record is not None and aq is not None and x.dim() in (3, 4):
+            # conv inputs [b, c, h, w] and token / context inputs [b, n, c] of the transformer linears
             self.record[name] = Q.uaq_codes(x, aq[0], aq[1], 256).to(torch.uint8)
         y = Q.quant_layer_forward(x, w, b, wq=s["wq"], aq=aq, conv=conv)
         if self.record is not None and x.dim() == 2:
@@ -184,10 +185,12 @@ def ldm_timestep_embedding(t, dim):
     return torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
 
 
-def ldm_unet_forward(sd, cfg, x, t, spec, act: Optional[ActParams] = None, record=None):
+def ldm_unet_forward(sd, cfg, x, t, spec, act: Optional[ActParams] = None, record=None, context=None):
     """openaimodel.py:744-780 with quant/quant_block.py:178-209 (QuantResBlock) and the fp
-    AttentionBlock / QKVAttentionLegacy (:320-326, :383-405).  Block structure is read off the
-    state_dict keys."""
+    AttentionBlock / QKVAttentionLegacy (:320-326, :383-405); for SpatialTransformer UNets (SD v1.4, cin256) the
+    transformer path of ldm/modules/attention.py:250-261 with quant/quant_block.py:212-299
+    (QuantBasicTransformerBlock / cross_attn_forward: quantised projections, fp32 attention core -- the block's
+    own q/k/v/softmax quantisers are inert).  Block structure is read off the state_dict keys."""
     net = _Net(sd, spec, act, record)
     mc = cfg["model_channels"]
     has = lambda k: (k + ".weight") in sd  # noqa: E731
@@ -213,12 +216,54 @@ def ldm_unet_forward(sd, cfg, x, t, spec, act: Optional[ActParams] = None, recor
         a = torch.einsum("bts,bcs->bct", w, v).reshape(bs, -1, length)
         return net.mark(p, (xf + net.layer(p + ".proj_out", a)).reshape(b, c, hh, ww))
 
+    def cross_attn(p, xq, ctx, heads):
+        """quant_block.py:212-245 with use_aq False on the block."""
+        q = net.layer(p + ".to_q", xq)
+        ctx = xq if ctx is None else ctx
+        k, v = net.layer(p + ".to_k", ctx), net.layer(p + ".to_v", ctx)
+        b, n, inner = q.shape
+        dh = inner // heads
+
+        def split(t_):
+            return t_.reshape(b, t_.shape[1], heads, dh).permute(0, 2, 1, 3).reshape(b * heads, t_.shape[1], dh)
+
+        q, k, v = split(q), split(k), split(v)
+        attn = (torch.einsum("bid,bjd->bij", q, k) * (dh ** -0.5)).softmax(dim=-1)
+        out = torch.einsum("bij,bjd->bid", attn, v)
+        out = out.reshape(b, heads, n, dh).permute(0, 2, 1, 3).reshape(b, n, inner)
+        return net.layer(p + ".to_out.0", out)
+
+    def ln(p, t_):
+        return F.layer_norm(t_, (t_.shape[-1],), sd[p + ".weight"], sd[p + ".bias"], 1e-5)
+
+    def spatial_transformer(p, x):
+        """attention.py:250-261; GroupNorm eps 1e-6 (attention.py:76-77)."""
+        b, c, hh, ww = x.shape
+        h = net.layer(p + ".proj_in", net.gn(p + ".norm", x, 1e-6), P0)
+        inner = h.shape[1]
+        heads = cfg["num_heads"] if cfg.get("num_head_channels", -1) == -1 else c // cfg["num_head_channels"]
+        tok = h.reshape(b, inner, hh * ww).permute(0, 2, 1)
+        d = 0
+        while has(f"{p}.transformer_blocks.{d}.attn1.to_q"):
+            bp = f"{p}.transformer_blocks.{d}"
+            tok = cross_attn(bp + ".attn1", ln(bp + ".norm1", tok), None, heads) + tok
+            tok = cross_attn(bp + ".attn2", ln(bp + ".norm2", tok), context, heads) + tok
+            y = net.layer(bp + ".ff.net.0.proj", ln(bp + ".norm3", tok))
+            a, gate = y.chunk(2, dim=-1)
+            tok = net.layer(bp + ".ff.net.2", a * F.gelu(gate)) + tok
+            net.mark(bp, tok)
+            d += 1
+        h = tok.permute(0, 2, 1).reshape(b, inner, hh, ww)
+        return net.mark(p, net.layer(p + ".proj_out", h, P0) + x)
+
     def run_block(p, h, emb):
         j = 0
         while True:
             q = f"{p}.{j}"
             if has(q + ".in_layers.2"):
                 h = resblock(q, h, emb)
+            elif has(q + ".transformer_blocks.0.attn1.to_q"):
+                h = spatial_transformer(q, h)
             elif has(q + ".qkv"):
                 h = attn(q, h, cfg["num_head_channels"])
             elif has(q + ".op"):

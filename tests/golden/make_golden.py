@@ -25,6 +25,10 @@ plud = types.ModuleType("pytorch_lightning.utilities.distributed")
 plud.rank_zero_only = lambda f: f
 sys.modules.update({"pytorch_lightning": pl, "pytorch_lightning.utilities": plu,
                     "pytorch_lightning.utilities.distributed": plud})
+oc = types.ModuleType("omegaconf")          # openaimodel.py:509 imports ListConfig only to test `type(context_dim)`
+ocl = types.ModuleType("omegaconf.listconfig")
+ocl.ListConfig = type("ListConfig", (list,), {})
+sys.modules.update({"omegaconf": oc, "omegaconf.listconfig": ocl})
 ddpm_stub = types.ModuleType("ldm.models.diffusion.ddpm")
 ddpm_stub.LatentDiffusion = torch.nn.Module
 sys.modules["ldm.models.diffusion.ddpm"] = ddpm_stub
@@ -126,6 +130,11 @@ def build_ref_qnn(kind):
         from tfmq_b200.host.ddim_unet import cifar10_config
         fp = Model(cifar10_config())
         x = synth.latents((1, 3, 32, 32), 11)
+    elif kind == "sdmini":
+        from ldm.modules.diffusionmodules.openaimodel import UNetModel
+        from tfmq_b200.host.ldm_unet import sd_mini_config
+        fp = UNetModel(**sd_mini_config())
+        x = synth.latents((2, 4, 16, 16), 13)
     else:
         from ldm.modules.diffusionmodules.openaimodel import UNetModel
         sys.path.insert(0, os.path.join(HERE, "..", "..", "tfmq-dm_b200"))
@@ -329,6 +338,29 @@ def ldm_golden():
     print("ldm4_w4a8.pt written")
 
 
+def sdmini_golden():
+    """SpatialTransformer UNet (structure of SD v1.4 at a size the CPU oracle runs in seconds): the reference's
+    QuantModel with QuantBasicTransformerBlock / cross_attn_forward, batch 2, a 7-token context per sample."""
+    t0 = time.time()
+    qnn, x = build_ref_qnn("sdmini")
+    t = torch.tensor([801.0, 801.0])
+    ctx = synth.latents((2, 7, 96), 14)
+    attach_alpha(qnn, (x, t, ctx))
+    with torch.no_grad():
+        reset_aq(qnn)
+        e = qnn(x, t, ctx)
+        act = collect_aq(qnn)
+        e2 = qnn(x, t, ctx)
+    # the block-level attention quantisers must be inert (SURVEY F3): record the evidence with the fixture
+    inert = all(not getattr(m, "use_aq", False) for m in qnn.model.modules()
+                if m.__class__.__name__ == "QuantBasicTransformerBlock")
+    names, tab = pack_act([act])
+    torch.save(dict(seed=SEED, x=x, t=t, context=ctx, act_names=names, act_table=tab, eps=e2, eps_init=e,
+                    block_attention_quantisers_inert=inert),
+               os.path.join(HERE, "sdmini_w4a8.pt"))
+    print("sdmini_w4a8.pt written", len(names), "act-quantised layers; inert:", inert, time.time() - t0)
+
+
 def cali_schema():
     """G9: run the reference's cali_model on a tiny synthetic set and record the checkpoint's key set and
     shapes (the on-disk format the drop-in must read and write)."""
@@ -365,3 +397,5 @@ if __name__ == "__main__":
         ldm_golden()
     if "schema" in what:
         cali_schema()
+    if "sdmini" in what:
+        sdmini_golden()

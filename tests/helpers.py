@@ -12,6 +12,7 @@ import synth  # noqa: E402
 
 CIFAR_CFG = dict(ch=128, ch_mult=[1, 2, 2, 2], num_res_blocks=2)
 LDM4_CFG = dict(model_channels=224, num_head_channels=32)
+SDMINI_CFG = dict(model_channels=64, num_heads=2)
 
 
 def load_golden(name):
@@ -22,6 +23,9 @@ def fp_model(kind: str, seed: int = 1234):
     if kind == "cifar":
         from tfmq_b200.host.ddim_unet import Model, cifar10_config
         m = Model(cifar10_config())
+    elif kind == "sdmini":
+        from tfmq_b200.host.ldm_unet import UNetModel, sd_mini_config
+        m = UNetModel(**sd_mini_config())
     else:
         from tfmq_b200.host.ldm_unet import UNetModel, celebahq_ldm4_config
         m = UNetModel(**celebahq_ldm4_config())

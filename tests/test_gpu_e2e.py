@@ -3,7 +3,7 @@ fixtures produced by the reference itself (tests/golden/*.pt) and against the CP
 import pytest
 import torch
 
-from helpers import CIFAR_CFG, LDM4_CFG, fp_model, load_golden, oracle_spec, synth
+from helpers import CIFAR_CFG, LDM4_CFG, SDMINI_CFG, fp_model, load_golden, oracle_spec, synth
 
 pytestmark = pytest.mark.gpu
 
@@ -17,7 +17,7 @@ TOL_EPS = 1e-3      # stated fp tolerance on the UNet output / denoised latent (
 FREE = 3.0
 
 
-def _quantised(kind, dev, g, x, t):
+def _quantised(kind, dev, g, x, t, context=None):
     """Product path: FP host model -> QuantModel -> load_cali_model(synthetic AdaRound ckpt)."""
     from oracle import quant_ref as Q
     from oracle import unet_ref as U
@@ -36,7 +36,8 @@ def _quantised(kind, dev, g, x, t):
     aq = dict(bits=8, channel_wise=False, scaler=Scaler.MINMAX, leaf_param=True)
     qnn = QuantModel(fp, wq, aq, cali=False, softmax_a_bit=8, aq_mode=[QMODE.NORMAL.value, QMODE.QDIFF.value])
     qnn.eval()
-    load_cali_model(qnn, (x.to(dev), t.to(dev)), use_aq=True, ckpt={"weight": weight})
+    init = (x.to(dev), t.to(dev)) + ((context.to(dev),) if context is not None else ())
+    load_cali_model(qnn, init, use_aq=True, ckpt={"weight": weight})
     return qnn, sd
 
 
@@ -62,6 +63,8 @@ def _flip_report(eng, record, tag, verbose=False):
         ref = codes.permute(0, 2, 3, 1) if codes.dim() == 4 else codes
         if ref.dim() == 2:
             continue
+        if ref.dim() == 3:                        # token / context inputs [b, tokens, c]
+            got = got.reshape(ref.shape)
         if got.shape[1] == 2 * ref.shape[1]:      # engine quantises after the nearest-x2 upsample
             ref = ref.repeat_interleave(2, 1).repeat_interleave(2, 2)
         d = (got != ref).float().mean().item()
@@ -82,7 +85,7 @@ def _block_report(eng, record, tag):
         if ref is None:
             print(f"    {name:36s} (no oracle record)")
             continue
-        got = t.view.cpu().permute(0, 3, 1, 2)
+        got = t.view.cpu().permute(0, 3, 1, 2) if ref.dim() == 4 else t.view.cpu().reshape(ref.shape)
         print(f"    {name:36s} {(got - ref).abs().max().item():.3e}   |ref| max {ref.abs().max().item():.2f}")
 
 
@@ -164,6 +167,78 @@ def test_ldm4_unet_step(dev):
     for i in range(4):
         assert torch.equal(e4[i], e4[0])            # same input in every slot -> identical results
     assert (e4[0] - e[0]).abs().max().item() < FREE * sens
+
+
+def test_sdmini_spatial_transformer_step(dev):
+    """SpatialTransformer UNet (QuantBasicTransformerBlock, cross-attention over a context, GEGLU) through
+    the step engine: LayerNorm / GEGLU token producers, w4a8 token linears, fp32 attention core."""
+    from oracle import unet_ref as U
+    g = load_golden("sdmini_w4a8.pt")
+    x, t, ctx = g["x"], g["t"], g["context"]
+    qnn, sd = _quantised("sdmini", dev, g, x, t, ctx)
+    eng = qnn.build_engine(batch=x.shape[0], context_shape=ctx.shape[1:])
+    eng.set_schedule([float(t[0])], _act_dicts(g))
+    assert sorted(eng.aq_names) == g["act_names"]
+    e = eng.forward(x.to(dev), t, ctx.to(dev)).cpu()
+    err = (e - g["eps"]).abs().max().item()
+    spec = oracle_spec(sd, g["seed"])
+    rec = {}
+    with torch.no_grad():
+        e_orc = U.ldm_unet_forward(sd, SDMINI_CFG, x, t, spec, U.ActParams(g["act_names"], g["act_table"][0]), rec,
+                                   context=ctx)
+    assert (e_orc - g["eps"]).abs().max().item() < 1e-1          # this host's oracle vs the golden's host
+    flips = _flip_report(eng, rec, "sdmini")
+    tf = (eng.forward_teacher_forced(x.to(dev), t, rec, ctx.to(dev)).cpu() - e_orc).abs().max().item()
+    if tf >= TOL_EPS:
+        _block_report(eng, rec, "sdmini")
+    print(f"[sdmini] eps max-abs err vs reference: teacher-forced {tf:.3e}, free-running {err:.3e} "
+          f"(|eps| max {g['eps'].abs().max():.3f})")
+    assert tf < TOL_EPS
+    # free-running: the same flip cascade as the other UNets (no fp64 sensitivity recorded for this fixture)
+    assert torch.isfinite(e).all() and flips < 0.5 and err < 0.25 * g["eps"].abs().max().item()
+    # QuantModel.forward(x, t, context) is the same path, and graph replay is deterministic
+    with torch.no_grad():
+        e2 = qnn(x.to(dev), t.to(dev), ctx.to(dev)).cpu()
+    assert torch.equal(e2, e)
+
+
+@pytest.mark.parametrize("name", ["sd_v14", "cin256"])
+def test_full_size_spatial_transformer_unets(dev, name):
+    """BASELINE configs[2] / [4] at full size (SD v1.4: 8 heads of 40 / 80 / 160 channels, 77-token context of 768;
+    cin256: one head of 384 / 576 / 960 channels, 1-token context of 512), classifier-free-guidance batch of 2.  The CPU
+    oracle needs minutes for these, so the engine is checked against the product's own module path (torch fake-quant on
+    the GPU, the calibration-time graph, itself parity-tested against the oracle at the small size): free-running
+    agreement within the flip-cascade band, identical activation-quantiser sets, deterministic replay."""
+    from tfmq_b200.host import ldm_unet as H
+    from tfmq_b200.quant.quant_layer import QMODE, QuantLayer, Scaler
+    from tfmq_b200.quant.quant_model import QuantModel
+    cfg = dict(sd_v14=H.sd_v14_config, cin256=H.cin256_config)[name]()
+    tk = 77 if name == "sd_v14" else 1
+    fp = H.UNetModel(**cfg).eval()
+    synth.fill_state_dict(fp, 7)
+    fp = fp.to(dev)
+    wq = dict(bits=4, channel_wise=True, scaler=Scaler.MINMAX)
+    aq = dict(bits=8, channel_wise=False, scaler=Scaler.MINMAX, leaf_param=True)
+    qnn = QuantModel(fp, wq, aq, cali=False, softmax_a_bit=8, aq_mode=[QMODE.NORMAL.value, QMODE.QDIFF.value])
+    qnn.eval()
+    nq = sum(isinstance(m, QuantLayer) for m in qnn.model.modules())
+    assert nq == 265                                          # SURVEY section 8(a): QuantLayers of SD v1.4 / cin256
+    x = synth.latents((2, cfg["in_channels"], 64, 64), 21).to(dev)
+    t = torch.tensor([601.0, 601.0], device=dev)
+    ctx = synth.latents((2, tk, cfg["context_dim"]), 22).to(dev)
+    qnn.set_quant_state(True, True)
+    qnn.disable_out_quantization()                            # as every entry point does (sample_diffusion_ldm.py:459)
+    with torch.no_grad():
+        qnn(x, t, ctx)                                        # lazy quantiser initialisation (MINMAX)
+        ref = qnn(x, t, ctx).cpu()                            # module path, frozen parameters
+        eng = qnn.build_engine(batch=2, context_shape=(tk, cfg["context_dim"]))
+        e = qnn(x, t, ctx).cpu()                              # engine path
+        e2 = qnn(x, t, ctx).cpu()
+    assert torch.equal(e, e2) and torch.isfinite(e).all()
+    rel = ((e - ref).norm() / ref.norm()).item()
+    print(f"[{name}] engine vs module path: rel L2 {rel:.3e}, max-abs {(e - ref).abs().max():.3e}, |eps| max "
+          f"{ref.abs().max():.3f}; {eng.launches_per_step} launches per step, {len(eng.aq_names)} act-quantised layers")
+    assert rel < 0.25
 
 
 def test_product_refuses_cpu():

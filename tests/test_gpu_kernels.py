@@ -306,6 +306,47 @@ def test_act_prepare_upsample_and_offset(dev):
     assert (got[:, 0, :, 32:] == int(zp.item())).all()
 
 
+def test_token_producers_layernorm_and_geglu(dev):
+    """LayerNorm -> quantise and GEGLU -> quantise on token rows (BasicTransformerBlock inputs): fp32 output within
+    fp32 rounding of torch's, codes equal except where the pre-rounding value sits on a rounding boundary."""
+    ops, q = _ops(), _qref()
+    g = torch.Generator().manual_seed(21)
+    n, t, c = 2, 64, 320
+    x = torch.randn(n, t, c, generator=g) * 1.7 + 0.2
+    gamma = 1 + 0.1 * torch.randn(c, generator=g)
+    beta = 0.1 * torch.randn(c, generator=g)
+    y = F.layer_norm(x, (c,), gamma, beta, 1e-5)
+    xd = x.reshape(n, 1, t, c).to(dev)
+    out = torch.empty_like(xd)
+    ops.act_prepare(xd, dst_f32=out, ln=(gamma.to(dev), beta.to(dev), 1e-5))
+    torch.cuda.synchronize()
+    assert (out.cpu().reshape(n, t, c) - y).abs().max().item() < 2e-6
+    da, za = q.minmax_scale(y, 256)
+    aq = torch.tensor([da.item(), za.item()], device=dev)
+    u8 = torch.empty((n, 1, t, c), dtype=torch.uint8, device=dev)
+    ops.act_prepare(xd, aq=aq, dst_u8=u8, ln=(gamma.to(dev), beta.to(dev), 1e-5))
+    torch.cuda.synchronize()
+    ref = q.uaq_codes(y, da, za, 256)
+    diff = (u8.cpu().reshape(n, t, c).float() - ref).abs()
+    assert diff.max().item() <= 1 and (diff > 0).float().mean().item() < 2e-3
+    # GEGLU: rows are [value | gate]
+    h = torch.randn(n, t, 2 * c, generator=g) * 1.5
+    a, gate = h.chunk(2, dim=-1)
+    z = a * F.gelu(gate)
+    hd = h.reshape(n, 1, t, 2 * c).to(dev)
+    outg = torch.empty((n, 1, t, c), device=dev)
+    ops.act_prepare(hd, dst_f32=outg, geglu=True)
+    torch.cuda.synchronize()
+    assert (outg.cpu().reshape(n, t, c) - z).abs().max().item() < 2e-6
+    dz, zz = q.minmax_scale(z, 256)
+    aqz = torch.tensor([dz.item(), zz.item()], device=dev)
+    ops.act_prepare(hd, aq=aqz, dst_u8=u8, geglu=True)
+    torch.cuda.synchronize()
+    refz = q.uaq_codes(z, dz, zz, 256)
+    diffz = (u8.cpu().reshape(n, t, c).float() - refz).abs()
+    assert diffz.max().item() <= 1 and (diffz > 0).float().mean().item() < 2e-3
+
+
 # ------------------------------------------------------------------ small kernels
 def test_linear_small_variants(dev):
     ops, q = _ops(), _qref()

@@ -2,7 +2,7 @@
 (tests/golden/make_golden.py).  No GPU, no product compute."""
 import torch
 
-from helpers import CIFAR_CFG, LDM4_CFG, fp_model, load_golden, oracle_spec, synth
+from helpers import CIFAR_CFG, LDM4_CFG, SDMINI_CFG, fp_model, load_golden, oracle_spec, synth
 from oracle import quant_ref as Q
 from oracle import unet_ref as U
 
@@ -96,6 +96,19 @@ def test_ldm4_unet_step():
     assert sorted(n for n, s in spec.items() if s["aq"]) == g["act_names"]
     with torch.no_grad():
         e = U.ldm_unet_forward(sd, LDM4_CFG, g["x"], g["t"], spec, U.ActParams(g["act_names"], g["act_table"][0]))
+    assert (e - g["eps"]).abs().max().item() < 2e-5
+
+
+def test_sdmini_spatial_transformer_unet_step():
+    """SpatialTransformer path (QuantBasicTransformerBlock / cross_attn_forward / GEGLU) against the reference's output."""
+    g = load_golden("sdmini_w4a8.pt")
+    assert g["block_attention_quantisers_inert"]          # SURVEY F3, observed when the fixture was made
+    sd = fp_model("sdmini", g["seed"]).state_dict()
+    spec = oracle_spec(sd, g["seed"])
+    assert sorted(n for n, s in spec.items() if s["aq"]) == g["act_names"]
+    with torch.no_grad():
+        e = U.ldm_unet_forward(sd, SDMINI_CFG, g["x"], g["t"], spec, U.ActParams(g["act_names"], g["act_table"][0]),
+                               context=g["context"])
     assert (e - g["eps"]).abs().max().item() < 2e-5
 
 

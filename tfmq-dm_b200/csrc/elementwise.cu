@@ -121,6 +121,8 @@ __device__ __forceinline__ void split_h16x4(const float (&t)[4], uint2& hi, uint
   lo = make_uint2(lb[0] | (lb[1] << 16), lb[2] | (lb[3] << 16));
 }
 
+__device__ __forceinline__ float gelu_f(float g) { return 0.5f * g * (1.f + erff(g * 0.70710678118654752440f)); }
+
 // One warp per destination pixel (lanes = float4 channel vectors): the pixel decode / border test is per
 // warp, not per element, and every global access is a full row.
 __global__ void __launch_bounds__(ACT_THREADS) act_prepare_kernel(const ActParams P) {
@@ -184,12 +186,54 @@ __global__ void __launch_bounds__(ACT_THREADS) act_prepare_kernel(const ActParam
                           : nullptr;
     uint2* olo = d.dst_hi ? reinterpret_cast<uint2*>(static_cast<__half*>(d.dst_lo) + ((long long)n * npix + pp) * d.dst_h_ld)
                           : nullptr;
+    float ln_scale = 1.f, ln_shift = 0.f;
+    if (d.ln_gamma) {
+      // LayerNorm over the c channels of this token (nn.LayerNorm in BasicTransformerBlock, attention.py:205-207):
+      // row moments in double, then y = (x * rstd - rstd * mean) * gamma + beta
+      double s1 = 0.0, s2 = 0.0;
+      for (int v = lane; v < nvec; v += 32) {
+        const float4 f = src[v];
+        s1 += (double)f.x + (double)f.y + (double)f.z + (double)f.w;
+        s2 += (double)f.x * f.x + (double)f.y * f.y + (double)f.z * f.z + (double)f.w * f.w;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+      }
+      const double mean = s1 / c;
+      double var = s2 / c - mean * mean;
+      if (var < 0) var = 0;
+      ln_scale = (float)(1.0 / sqrt(var + (double)d.ln_eps));
+      ln_shift = -ln_scale * (float)mean;
+    }
     for (int v0 = lane; v0 < nvec; v0 += 64) {
       const int v1 = v0 + 32;
       const bool has1 = v1 < nvec;
       const float4 f0 = src[v0];
       const float4 f1 = has1 ? src[v1] : make_float4(0.f, 0.f, 0.f, 0.f);
       float t0[4] = {f0.x, f0.y, f0.z, f0.w}, t1[4] = {f1.x, f1.y, f1.z, f1.w};
+      if (d.ln_gamma) {
+        const float4 g0 = *reinterpret_cast<const float4*>(d.ln_gamma + v0 * 4), b0 = *reinterpret_cast<const float4*>(d.ln_beta + v0 * 4);
+        t0[0] = fmaf(fmaf(t0[0], ln_scale, ln_shift), g0.x, b0.x), t0[1] = fmaf(fmaf(t0[1], ln_scale, ln_shift), g0.y, b0.y);
+        t0[2] = fmaf(fmaf(t0[2], ln_scale, ln_shift), g0.z, b0.z), t0[3] = fmaf(fmaf(t0[3], ln_scale, ln_shift), g0.w, b0.w);
+        if (has1) {
+          const float4 g1 = *reinterpret_cast<const float4*>(d.ln_gamma + v1 * 4), b1 = *reinterpret_cast<const float4*>(d.ln_beta + v1 * 4);
+          t1[0] = fmaf(fmaf(t1[0], ln_scale, ln_shift), g1.x, b1.x), t1[1] = fmaf(fmaf(t1[1], ln_scale, ln_shift), g1.y, b1.y);
+          t1[2] = fmaf(fmaf(t1[2], ln_scale, ln_shift), g1.z, b1.z), t1[3] = fmaf(fmaf(t1[3], ln_scale, ln_shift), g1.w, b1.w);
+        }
+      }
+      if (d.geglu) {
+        // GEGLU (attention.py:37-44): the source row holds [value (c) | gate (c)]; out = value * gelu(gate), exact erf form
+        const float4 q0 = src[nvec + v0];
+        const float4 q1 = has1 ? src[nvec + v1] : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float gq0[4] = {q0.x, q0.y, q0.z, q0.w}, gq1[4] = {q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          t0[j] *= gelu_f(gq0[j]);
+          t1[j] *= gelu_f(gq1[j]);
+        }
+      }
       if (gn) {
         const float4 a0 = *reinterpret_cast<const float4*>(sp + v0 * 4), b0 = *reinterpret_cast<const float4*>(sp + c + v0 * 4);
         t0[0] = fmaf(t0[0], a0.x, b0.x), t0[1] = fmaf(t0[1], a0.y, b0.y);
@@ -336,6 +380,11 @@ extern "C" int tfmq_act_prepare(tfmq_ctx* ctx, const tfmq_act_desc* d, void* str
   } else if (d->dst_f32) {
     TFMQ_REQUIRE(d->dst_ld % 4 == 0 && ((uintptr_t)d->dst_f32 & 15) == 0, TFMQ_ERR_SHAPE, "act_prepare: dst_ld/align");
   }
+  TFMQ_REQUIRE(!d->ln_gamma || (d->ln_beta && !d->gn_stats && !d->upsample && ((uintptr_t)d->ln_gamma & 15) == 0 &&
+                                ((uintptr_t)d->ln_beta & 15) == 0),
+               TFMQ_ERR_ARG, "act_prepare: LayerNorm needs ln_beta, 16-byte aligned parameters, no GN / upsample");
+  TFMQ_REQUIRE(!d->geglu || (!d->gn_stats && !d->ln_gamma && !d->upsample && !d->silu), TFMQ_ERR_ARG,
+               "act_prepare: GEGLU excludes GN / LN / SiLU / upsample");
   if (d->gn_stats) {
     TFMQ_REQUIRE(d->gamma && d->beta && d->groups > 0 && d->groups <= 64 && d->c % d->groups == 0, TFMQ_ERR_ARG,
                  "act_prepare: GroupNorm parameters (groups <= 64)");

@@ -31,6 +31,7 @@ class ActDesc(C.Structure):
         ("halo", C.c_int), ("dst_c", C.c_int), ("dst_c_off", C.c_int),
         ("dst_f32", C.c_void_p), ("dst_ld", i64),
         ("dst_hi", C.c_void_p), ("dst_lo", C.c_void_p), ("dst_h_ld", i64),
+        ("ln_gamma", C.c_void_p), ("ln_beta", C.c_void_p), ("ln_eps", C.c_float), ("geglu", C.c_int),
     ]
 
 

@@ -98,22 +98,30 @@ class _QL:
             self.codes, self.packed, self.wsum = ops.pack_w4(w2d, delta, zp, alpha)
             self.wdelta, self.wzp_f = delta.contiguous(), zp.contiguous()
             self.wzp_u8 = zp.to(torch.uint8).contiguous()
-            if aq_index is None and self.is_conv:
-                # weight-only quantised conv with fp activations: exact integer weights on the fp paths
-                self.w_hi = (self.codes.float() - zp[:, None]).contiguous()
-                self.w_lo = None
-                self.h_hi, self.h_lo, self.h_scale = ops.split_h16(self.w_hi, self.wdelta)
         else:
             self.w_f32 = w2d
-            if self.is_conv and self.cin > 4 and self.cout > 4:
-                self.w_hi, self.w_lo = ops.split_tf32(w2d)
-                self.h_hi, self.h_lo, self.h_scale = ops.split_h16(w2d)
+        self._fp_ready = False
+
+    def ensure_fp(self):
+        """Operand planes for the floating-point conv paths, made on first use (only layers that run with fp
+        activations need them): fp weights split for tf32 / fp16; weight-only-quantised layers use their exact
+        integer weights (code - zp) with delta as the epilogue scale."""
+        if self._fp_ready:
+            return
+        if self.quant_w:
+            self.w_hi = (self.codes.float() - self.wzp_f[:, None]).contiguous()
+            self.w_lo = None
+            self.h_hi, self.h_lo, self.h_scale = ops.split_h16(self.w_hi, self.wdelta)
+        else:
+            self.w_hi, self.w_lo = ops.split_tf32(self.w_f32)
+            self.h_hi, self.h_lo, self.h_scale = ops.split_h16(self.w_f32)
+        self._fp_ready = True
 
 
 class StepEngine:
     def __init__(self, qnn, batch: int, act_tables: Optional[Sequence[Dict[str, torch.Tensor]]] = None,
                  timesteps: Optional[Sequence[int]] = None, fp_passes: int = 3, device=None, use_graph: bool = True,
-                 fuse_gn: bool = True, fp_mode: str = "h16"):
+                 fuse_gn: bool = True, fp_mode: str = "h16", context_shape: Optional[Sequence[int]] = None):
         model = qnn.model
         self.dev = torch.device(device) if device is not None else next(model.parameters()).device
         if self.dev.type != "cuda":
@@ -164,6 +172,11 @@ class StepEngine:
         self.x_in = torch.zeros((N, model.in_channels, res, res), dtype=torch.float32, device=self.dev)
         self.t_in = torch.zeros((N,), dtype=torch.float32, device=self.dev)
         self.noise = None
+        # SpatialTransformer UNets: the conditioning tokens [batch, tokens, context_dim] (fp32, resident)
+        self.ctx_in = None
+        if context_shape is not None:
+            self.ctx_in = torch.zeros((N, int(context_shape[0]), int(context_shape[1])), dtype=torch.float32,
+                                      device=self.dev)
         if self.kind == "ddim":
             self._trace_ddim(model, N, res)
         else:
@@ -184,7 +197,8 @@ class StepEngine:
             aqt = mods[name].aqtizer
             if aqt.delta is not None:
                 self.cur[2 * i] = float(aqt.delta.detach())
-                self.cur[2 * i + 1] = float(aqt.zero_point)
+                zp = aqt.zero_point
+                self.cur[2 * i + 1] = float(zp.detach()) if torch.is_tensor(zp) else float(zp)
 
     def timestep_embedding_cpu(self, t: torch.Tensor) -> torch.Tensor:
         """Bit-identical to the reference's CPU embedding (same torch ops, on the host)."""
@@ -267,10 +281,17 @@ class StepEngine:
     _consts: Dict[int, torch.Tensor]
 
     def _qconv(self, layer: QuantLayer, x: T, gn=None, silu=False, upsample=False, emb: Optional[torch.Tensor] = None,
-               res: Optional[T] = None, out: Optional[T] = None) -> T:
-        """One QuantLayer conv with its input transform and fused epilogue."""
+               res: Optional[T] = None, out: Optional[T] = None, ln: Optional[nn.LayerNorm] = None,
+               geglu: bool = False) -> T:
+        """One QuantLayer conv / token linear with its input transform and fused epilogue.
+        ln: LayerNorm applied to every token first; geglu: x holds [value | gate], the layer sees value * gelu(gate)."""
         q = self.ql[id(layer)]
         oh, ow = (2 * x.h, 2 * x.w) if upsample else (x.h, x.w)
+        tok = {}
+        if ln is not None:
+            tok["ln"] = (self._const(ln.weight), self._const(ln.bias), float(ln.eps))
+        if geglu:
+            tok["geglu"] = True
         if out is None:
             out = self._new(x.n, oh, ow, q.cout)
         if q.quant_w and q.aq_index is not None:
@@ -283,34 +304,40 @@ class StepEngine:
             out.producer = rec
 
             def run():
-                ops.act_prepare(x.view, aq=aq, dst_u8=u8, halo=halo, silu=silu, upsample=upsample, **self._gn_args(gn))
+                ops.act_prepare(x.view, aq=aq, dst_u8=u8, halo=halo, silu=silu, upsample=upsample, **tok,
+                                **self._gn_args(gn))
                 if self.teacher is not None and q.name in self.teacher:
-                    forced = self.teacher[q.name].to(self.dev).permute(0, 2, 3, 1)
+                    forced = self.teacher[q.name].to(self.dev)
+                    # conv inputs are recorded [b, c, h, w], token / context inputs [b, tokens, c]
+                    forced = forced.permute(0, 2, 3, 1) if forced.dim() == 4 else forced.reshape(u8.shape)
                     (u8[:, 1:-1, 1:-1] if halo else u8).copy_(forced)
                 ops.conv_w4a8(u8, q.ksize, q.packed, q.wzp_u8, q.wdelta, q.wsum, q.bias, aq, out.view, emb=emb,
                               res=res.view if res is not None else None, stats=self._stats_of(rec))
             self.ops.append(run)
         else:
             assert not upsample
-            src = self._fp_input(x, gn, silu)
+            src = self._fp_input(x, gn, silu, tok)
             self._fp_conv(q, src, out, res, pad_lo=q.ksize // 2, emb=emb)
         return out
 
-    def _fp_input(self, x: T, gn=None, silu: bool = False):
+    def _fp_input(self, x: T, gn=None, silu: bool = False, tok: Optional[dict] = None):
         """Input of a floating-point conv: x itself, or [GN][SiLU](x).  h16 mode: the fp16 hi / lo planes of it (one
         act_prepare launch, which is also where GN / SiLU are applied); tf32 mode: an fp32 tensor."""
+        tok = tok or {}
+        c_out = x.c // 2 if tok.get("geglu") else x.c
         if self.fp_mode == "h16":
-            key = (id(x), id(gn[0]) if gn is not None else None, silu)
+            key = (id(x), id(gn[0]) if gn is not None else None, silu, id(tok["ln"][0]) if "ln" in tok else None,
+                   bool(tok.get("geglu")))
             if key not in self._h16:
-                hi = torch.empty((x.n, x.h, x.w, x.c), dtype=torch.float16, device=self.dev)
+                hi = torch.empty((x.n, x.h, x.w, c_out), dtype=torch.float16, device=self.dev)
                 lo = torch.empty_like(hi)
                 self._h16[key] = (hi, lo)
-                self.ops.append(lambda: ops.act_prepare(x.view, dst_h16=(hi, lo), silu=silu, **self._gn_args(gn)))
+                self.ops.append(lambda: ops.act_prepare(x.view, dst_h16=(hi, lo), silu=silu, **tok, **self._gn_args(gn)))
             return self._h16[key]
-        if gn is None and not silu:
+        if gn is None and not silu and not tok:
             return x
-        src = self._new(x.n, x.h, x.w, x.c)
-        self.ops.append(lambda: ops.act_prepare(x.view, dst_f32=src.view, silu=silu, **self._gn_args(gn)))
+        src = self._new(x.n, x.h, x.w, c_out)
+        self.ops.append(lambda: ops.act_prepare(x.view, dst_f32=src.view, silu=silu, **tok, **self._gn_args(gn)))
         return src
 
     def _fp_launch(self, src, ksize, stride, pad_lo, w_tf32, w_h16, out: T, res: Optional[T], bias, wscale, emb, rec):
@@ -326,6 +353,7 @@ class StepEngine:
 
     def _fp_conv(self, q: _QL, src, out: T, res: Optional[T], pad_lo: int, stride: int = 1, emb=None):
         wscale = q.wdelta if q.quant_w else None
+        q.ensure_fp()
         rec = {"stats": []}
         out.producer = rec
         self.ops.append(lambda: self._fp_launch(src, q.ksize, stride, pad_lo, (q.w_hi, q.w_lo),
@@ -396,6 +424,16 @@ class StepEngine:
                     if ("out:" + q.name) in self.teacher:
                         kw["out"].copy_(self.teacher["out:" + q.name].to(self.dev))
         self.ops[self._lin_group_slot] = run
+
+    def _ctx_tokens(self) -> T:
+        """The conditioning tokens as a [batch * tokens, 1, 1, context_dim] NHWC tensor (one "image" per token), the
+        shape the 1x1 implicit GEMM takes for a plain linear layer."""
+        if getattr(self, "_ctx_T", None) is None:
+            n, tk, c = self.ctx_in.shape
+            t = T(n * tk, 1, 1, c)
+            t.buf = self.ctx_in.reshape(n * tk, 1, 1, c)
+            self._ctx_T = t
+        return self._ctx_T
 
     def _attention(self, q_t, k_t, v_t, o: T, heads: int, d: int, scale: float, strides):
         b, tq = o.n, o.h * o.w
@@ -533,11 +571,55 @@ class StepEngine:
             self.block_out[self._names[id(blk)]] = out
             return out
 
+        def cross_attention(att, norm: nn.LayerNorm, tok: T, ctx: Optional[T]) -> T:
+            """quant_block.cross_attn_forward (reference :212-245) on tokens = NHWC pixels: LayerNorm + quantise feeds the
+            q (and, for self-attention, k / v) projections; the attention core is fp32 (the block's own quantisers
+            are inert); to_out adds the residual in its epilogue."""
+            qt = self._qconv(att.to_q, tok, ln=norm)
+            if ctx is None:
+                kt, vt = self._qconv(att.to_k, tok, ln=norm), self._qconv(att.to_v, tok, ln=norm)
+                tk = tok.h * tok.w
+            else:
+                kt, vt = self._qconv(att.to_k, ctx), self._qconv(att.to_v, ctx)
+                tk = self.ctx_in.shape[1]
+            heads = att.heads
+            inner = qt.c
+            d = inner // heads
+            o = self._new(tok.n, tok.h, tok.w, inner)
+            tq = tok.h * tok.w
+            b = tok.n
+
+            def strides():
+                return dict(q=(tq * qt.view.stride(2), d, qt.view.stride(2)), k=(tk * kt.view.stride(2), d, kt.view.stride(2)),
+                            v=(tk * vt.view.stride(2), d, vt.view.stride(2)), o=(tq * o.view.stride(2), d, o.view.stride(2)))
+            self.ops.append(lambda: ops.attention(qt.view, kt.view, vt.view, o.view, b, heads, tq, tk, d, float(att.scale),
+                                                  strides()))
+            return self._qconv(att.to_out[0], o, res=tok)
+
+        def spatial_transformer(blk, x: T) -> T:
+            """SpatialTransformer (ldm/modules/attention.py:250-261) with QuantBasicTransformerBlock (quant_block.py:
+            248-299).  NHWC activations ARE the [b, hw, c] token layout, so the two rearranges cost nothing."""
+            if self.ctx_in is None:
+                raise RuntimeError("StepEngine: this UNet needs context_shape=(tokens, context_dim)")
+            ctx = self._ctx_tokens()
+            tok = self._qconv(blk.proj_in, x, gn=self._gn(x, blk.norm))
+            for tb in blk.transformer_blocks:
+                tok = cross_attention(tb.attn1, tb.norm1, tok, None)
+                tok = cross_attention(tb.attn2, tb.norm2, tok, ctx)
+                y = self._qconv(tb.ff.net[0].proj, tok, ln=tb.norm3)
+                tok = self._qconv(tb.ff.net[2], y, geglu=True, res=tok)
+                self.block_out[self._names[id(tb)]] = tok
+            out = self._qconv(blk.proj_out, tok, res=x)
+            self.block_out[self._names[id(blk)]] = out
+            return out
+
         def run_seq(seq, h: T) -> T:
             for layer in seq:
                 name = layer.__class__.__name__
                 if isinstance(layer, QuantResBlock):
                     h = resblock(layer, h)
+                elif name == "SpatialTransformer":
+                    h = spatial_transformer(layer, h)
                 elif isinstance(layer, QuantAttentionBlock) or name == "AttentionBlock":
                     h = attnblock(layer, h)
                 elif name == "Downsample":
@@ -629,9 +711,11 @@ class StepEngine:
         return ctx.launches - before
 
     @torch.no_grad()
-    def forward(self, x: torch.Tensor, t=None) -> torch.Tensor:
-        """eps = UNet(x, t) with the currently selected activation-quant row (QuantModel.forward)."""
+    def forward(self, x: torch.Tensor, t=None, context: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """eps = UNet(x, t[, context]) with the currently selected activation-quant row (QuantModel.forward)."""
         self.x_in.copy_(x)
+        if context is not None:
+            self.ctx_in.copy_(context)
         if t is not None:
             t = torch.as_tensor(t, dtype=torch.float32, device=self.dev).reshape(-1)
             t = t.expand(self.batch) if t.numel() == 1 else t
@@ -643,11 +727,14 @@ class StepEngine:
         return self.eps.clone()
 
     @torch.no_grad()
-    def forward_teacher_forced(self, x: torch.Tensor, t, record: Dict[str, torch.Tensor]) -> torch.Tensor:
+    def forward_teacher_forced(self, x: torch.Tensor, t, record: Dict[str, torch.Tensor],
+                               context: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Test hook: eager run in which every activation quantiser's output codes (and the time-
         embedding MLP outputs) are replaced by the oracle's, so that the comparison isolates the
         arithmetic of the kernels from the flip cascade of the quantised network (Parity)."""
         self.x_in.copy_(x)
+        if context is not None:
+            self.ctx_in.copy_(context)
         t = torch.as_tensor(t, dtype=torch.float32).reshape(-1)
         t = t.expand(self.batch) if t.numel() == 1 else t
         self.emb_rows.copy_(self.timestep_embedding_cpu(t.cpu()).to(self.dev))

@@ -90,13 +90,20 @@ def fill_zero(t: torch.Tensor):
 def act_prepare(src: torch.Tensor, *, aq: torch.Tensor | None = None, dst_u8: torch.Tensor | None = None,
                 halo: int = 0, dst_c_off: int = 0, dst_f32: torch.Tensor | None = None,
                 gn_stats_t: torch.Tensor | None = None, gamma=None, beta=None, groups: int = 32,
-                eps: float = 1e-5, silu: bool = False, upsample: bool = False, dst_h16=None):
+                eps: float = 1e-5, silu: bool = False, upsample: bool = False, dst_h16=None,
+                ln=None, geglu: bool = False):
     """[GN] -> [SiLU] -> u8 codes into a halo-padded NHWC buffer, or fp32 NHWC, or (dst_h16 = (hi, lo)) the fp16
     hi / lo planes `conv_h16` reads."""
     ctx = _ctx(src)
     n, h, w, c, ld = _nhwc(src)
     d = ActDesc()
     d.src, d.src_ld = src.data_ptr(), ld
+    if geglu:                    # src rows are [value | gate]
+        assert c % 2 == 0
+        c //= 2
+        d.geglu = 1
+    if ln is not None:           # (gamma, beta, eps): LayerNorm over the channels of every token
+        d.ln_gamma, d.ln_beta, d.ln_eps = ln[0].data_ptr(), ln[1].data_ptr(), float(ln[2])
     d.n, d.h, d.w, d.c = n, h, w, c
     d.upsample = int(upsample)
     d.gn_stats = gn_stats_t.data_ptr() if gn_stats_t is not None else None

@@ -129,17 +129,21 @@ class QuantModel(nn.Module):
                 m.set_running_stat(running_stat)
 
     # ------------------------------------------------------------------ forward
-    def build_engine(self, batch: int, act_tables=None, timesteps=None, fp_passes: int = 3):
-        """Freeze the calibrated model into the fused sm_100a step program (engine.StepEngine)."""
+    def build_engine(self, batch: int, act_tables=None, timesteps=None, fp_passes: int = 3, context_shape=None,
+                     fp_mode: str = "h16"):
+        """Freeze the calibrated model into the fused sm_100a step program (engine.StepEngine).
+        context_shape = (tokens, context_dim) for SpatialTransformer UNets."""
         from ..engine import StepEngine
-        self._engine = StepEngine(self, batch=batch, act_tables=act_tables, timesteps=timesteps, fp_passes=fp_passes)
+        self._engine = StepEngine(self, batch=batch, act_tables=act_tables, timesteps=timesteps, fp_passes=fp_passes,
+                                  context_shape=context_shape, fp_mode=fp_mode)
         return self._engine
 
     def forward(self, x: torch.Tensor, timestep=None, context: torch.Tensor = None) -> torch.Tensor:
         eng = self._engine
         if eng is not None and not torch.is_grad_enabled() and x.is_cuda and x.shape[0] == eng.batch \
-                and context is None:
-            return eng.forward(x, timestep)
+                and (context is None) == (eng.ctx_in is None) \
+                and (context is None or tuple(context.shape) == tuple(eng.ctx_in.shape)):
+            return eng.forward(x, timestep, context)
         if context is None:
             return self.model(x, timestep)
         return self.model(x, timestep, context)
