@@ -662,6 +662,16 @@ class StepEngine:
         self.coef = self.cur[self.off_coef:self.off_coef + 5]
         self.x_next = torch.zeros_like(self.x_in)
         self.x0_pred = torch.zeros_like(self.x_in)
+        self.cfg_scale: Optional[float] = None
+        self.eps_cfg = torch.zeros_like(self.x_in[: max(self.batch // 2, 1)])
+
+    def set_guidance(self, scale: Optional[float]):
+        """Classifier-free guidance for `step` / `sample`: batch slots [0, B) = unconditional, [B, 2B) = conditional."""
+        if scale is not None and self.batch % 2:
+            raise ValueError("classifier-free guidance needs an even engine batch (unconditional + conditional halves)")
+        if scale != self.cfg_scale:
+            self.cfg_scale = scale
+            self.g_upd = None      # the captured step graph depends on it
 
     def _emb_rows_from_cur(self):
         src = self.cur[self.off_emb:self.off_emb + self.emb_dim]
@@ -673,7 +683,14 @@ class StepEngine:
         ops.fill_zero(self.gn_ws)
         for op in self.ops:
             op()
-        if with_update:
+        if with_update and self.cfg_scale is not None:
+            # classifier-free guidance (ldm/models/diffusion/ddim.py:171-180): slots [0, B) hold the unconditional
+            # half, [B, 2B) the conditional half of the SAME latents; e = e_u + s (e_c - e_u), one update, both halves
+            h = self.batch // 2
+            ops.cfg_combine(self.eps[:h], self.eps[h:], self.cfg_scale, self.eps_cfg)
+            ops.ddim_update(self.x_in[:h], self.eps_cfg, self.coef, self.x_in[h:], None, noise=self.noise)
+            ops.ddim_update(self.x_in[:h], self.eps_cfg, self.coef, self.x_in[:h], self.x0_pred[:h], noise=self.noise)
+        elif with_update:
             ops.ddim_update(self.x_in, self.eps, self.coef, self.x_in, self.x0_pred, noise=self.noise)
 
     def _launch(self, with_update: bool):

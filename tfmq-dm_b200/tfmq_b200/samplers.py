@@ -96,7 +96,8 @@ def make_ddim_timesteps(num_ddim_timesteps: int, num_ddpm_timesteps: int = 1000)
 
 
 class DDIMSampler:
-    """Unconditional DDIM sampling for the LDM UNets (ldm/models/diffusion/ddim.py:57-212).
+    """DDIM sampling for the LDM UNets, unconditional or conditional with classifier-free guidance
+    (ldm/models/diffusion/ddim.py:57-212).
     `model` is the QuantModel (what the reference installs as model.model.diffusion_model);
     the noise schedule comes from linear_start / linear_end of the LDM config."""
 
@@ -131,17 +132,28 @@ class DDIMSampler:
     @torch.no_grad()
     def sample(self, S, batch_size, shape, conditioning=None, eta=0.0, x_T=None, verbose=False,
                unconditional_guidance_scale=1.0, unconditional_conditioning=None, untill_fake_t=None, **kwargs):
-        if conditioning is not None or unconditional_conditioning is not None:
-            raise NotImplementedError("conditional sampling (SD / cin256) is the next widening step")
         if eta != 0:
             raise NotImplementedError("eta > 0")
         self.make_schedule(S, eta)
         dev = next(self.model.parameters()).device
         C, H, W = shape
         img = torch.randn((batch_size, C, H, W), device=dev) if x_T is None else x_T.to(dev)
+        # conditional sampling (ddim.py:171-180): with guidance the UNet sees [x | x], [uncond | cond] as one 2B batch
+        cfg = conditioning is not None and unconditional_conditioning is not None and unconditional_guidance_scale != 1.0
+        ctx = None
+        if conditioning is not None:
+            ctx = conditioning.to(dev).float()
+            if cfg:
+                ctx = torch.cat([unconditional_conditioning.to(dev).float(), ctx], dim=0)
+        nb = batch_size * (2 if cfg else 1)
         eng = getattr(self.model, "_engine", None)
-        if eng is None or eng.batch != batch_size:
-            eng = self.model.build_engine(batch=batch_size)
+        want_ctx = tuple(ctx.shape) if ctx is not None else None
+        have_ctx = tuple(eng.ctx_in.shape) if (eng is not None and eng.ctx_in is not None) else None
+        if eng is None or eng.batch != nb or want_ctx != have_ctx:
+            eng = self.model.build_engine(batch=nb, context_shape=ctx.shape[1:] if ctx is not None else None)
+        eng.set_guidance(float(unconditional_guidance_scale) if cfg else None)
+        if ctx is not None:
+            eng.ctx_in.copy_(ctx)
         ts = [float(t) for t in np.flip(self.ddim_timesteps)]
         tables = None
         if self.ckpt is not None:
@@ -149,9 +161,9 @@ class DDIMSampler:
             tot, t_max = self.ddpm_num_timesteps // S, S - 1
             tables = [self.ckpt[f"act_{int(t_max - (int(t) - 1) // tot)}"] for t in ts]
         eng.set_schedule(ts, tables, self.coefficient_rows())
-        eng.x_in.copy_(img)
+        eng.x_in.copy_(torch.cat([img, img], dim=0) if cfg else img)
         n_run = S if not untill_fake_t else min(S, untill_fake_t - 1)
         for k in range(n_run):
             eng.step(k)
-        out = eng.x_in.clone()
-        return out, {"x_inter": [img, out], "pred_x0": [img, eng.x0_pred.clone()]}
+        out = eng.x_in[:batch_size].clone()
+        return out, {"x_inter": [img, out], "pred_x0": [img, eng.x0_pred[:batch_size].clone()]}
