@@ -1,6 +1,8 @@
 // HBM-bound producer / consumer kernels around the tcgen05 GEMMs:
 // GroupNorm statistics, the fused GN-apply + SiLU + activation-quantise producer,
 // DDIM update, classifier-free-guidance combine, timestep embedding.
+#include <cstdlib>
+
 #include <cuda_fp16.h>
 
 #include "ctx.h"
@@ -397,7 +399,8 @@ extern "C" int tfmq_act_prepare(tfmq_ctx* ctx, const tfmq_act_desc* d, void* str
   P.out_w = d->upsample ? 2 * d->w : d->w;
   const int halo = d->dst_u8 ? d->halo : 0;
   const int npix = (P.out_h + 2 * halo) * (P.out_w + 2 * halo);
-  int chunks = (ctx->sm_count * 8 + d->n - 1) / d->n;
+  static const int cta_mult = getenv("TFMQ_ACT_CTAS") ? atoi(getenv("TFMQ_ACT_CTAS")) : 4;   // CTAs per SM (tuning aid)
+  int chunks = (ctx->sm_count * cta_mult + d->n - 1) / d->n;
   if (chunks > npix) chunks = npix;
   const int ppc = (npix + chunks - 1) / chunks;
   chunks = (npix + ppc - 1) / ppc;
