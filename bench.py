@@ -273,7 +273,9 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout (one JSON line only)
+        # one JSON line on stdout: NCCL prints its version banner there at NCCL_DEBUG=VERSION and above (WARN included)
+        os.environ.pop("NCCL_DEBUG", None)
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     from tfmq_b200 import _lib
     from helpers import synth

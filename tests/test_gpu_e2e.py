@@ -160,6 +160,10 @@ def test_ldm4_unet_step(dev):
           f"(reference's own fp64-accumulation sensitivity {sens:.3e}; |eps| max {g['eps'].abs().max():.3f})")
     assert tf < TOL_EPS
     assert err < FREE * sens and flips < 0.5
+    # what a sampling rank receives from rank 0 (the one broadcast of the multi-GPU path): tensors only, all on the device
+    from tfmq_b200.dist_utils import engine_constants
+    consts = engine_constants(eng)
+    assert len(consts) > 300 and all(torch.is_tensor(c) and c.is_cuda for c in consts)
     # batch independence: a batch-4 engine reproduces the batch-1 result in every slot
     eng4 = qnn.build_engine(batch=4)
     eng4.set_schedule([float(g["t"][0])], _act_dicts(g))

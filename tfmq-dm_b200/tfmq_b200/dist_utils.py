@@ -70,11 +70,12 @@ def engine_constants(eng) -> List[torch.Tensor]:
     """Every device constant a sampling rank needs from rank 0."""
     out = [eng.table] if eng.table is not None else []
     for q in eng.ql.values():
-        for name in ("packed", "codes", "wdelta", "wzp_f", "wzp_u8", "wsum", "bias", "w_hi", "w_lo", "w_f32", "w_oihw"):
+        for name in ("packed", "codes", "wdelta", "wzp_f", "wzp_u8", "wsum", "bias", "w_hi", "w_lo", "w_f32", "w_oihw",
+                     "h_hi", "h_lo", "h_scale"):
             t = getattr(q, name, None)
-            if t is not None:
+            if torch.is_tensor(t):
                 out.append(t)
-    for hi, lo, b, _ in eng._plain.values():
-        out += [hi, lo] + ([b] if b is not None else [])
-    out += list(eng._consts.values())
+    for w_tf32, w_h16, b, _ in eng._plain.values():
+        out += [t for t in (*w_tf32, *w_h16, b) if torch.is_tensor(t)]
+    out += [t for t in eng._consts.values() if torch.is_tensor(t)]
     return out
