@@ -268,9 +268,11 @@ __global__ void __launch_bounds__(128) attn_mma_kernel(const AttnP P) {
 // Same algorithm with m16n8k16 fp16 MMAs: every fp32 operand is split into two fp16 terms
 // (hi = half(x), lo = half(x - hi): 22 significand bits, the same as the tf32 hi/lo split) and each product
 // is hi*hi + lo*hi + hi*lo with fp32 accumulation.  One k16 instruction covers twice the depth of a k8 tf32
-// instruction, so the tensor-pipe work halves.  K is staged [key][D+8] and V transposed [dim][64+8] (fp16) so
-// every B fragment is one conflict-free 32-bit load; the S accumulator fragment is directly the A fragment of
-// the PV product (no permutation needed for k16).
+// instruction, so the tensor-pipe work halves.  K and V are both staged [key][D+8] (fp16 hi / lo planes, conflict-free
+// 8-byte stores); the K fragments of S = Q K^T are plain 32-bit loads, the V fragments of O += P V come transposed out of
+// `ldmatrix.x4.trans` (no scattered 2-byte transpose stores).  The raw fp32 K/V rows of the NEXT key tile are fetched into
+// registers while the current tile is being multiplied.  The S accumulator fragment is directly the A fragment of the PV
+// product (no permutation needed for k16).
 __device__ __forceinline__ void mma_f16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
       "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -289,17 +291,27 @@ __device__ __forceinline__ void split1_h(float x, __half& hi, __half& lo) {
   lo = __float2half_rn(x - __half2float(hi));
 }
 
+// four 8x8 b16 matrices, transposed on the way out: thread (g, t) of matrix i gets elements (row 2t, col g), (row 2t+1, col g)
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* smem_row) {
+  const uint32_t addr = static_cast<uint32_t>(__cvta_generic_to_shared(smem_row));
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+
 template <int D>
 __global__ void __launch_bounds__(128) attn_h16_kernel(const AttnP P) {
-  constexpr int KP = D + 8;          // K row pitch (halves)
-  constexpr int VP = ATT_TK + 8;     // V^T row pitch (halves)
+  constexpr int KP = D + 8;          // K / V row pitch (halves): 16-byte aligned rows, conflict-free ldmatrix
   constexpr int KS = D / 16;         // k-steps of Q K^T
   constexpr int NT = D / 8;          // n-tiles of P V
+  constexpr int ITEMS = ATT_TK * (D / 4) / 128;    // float4 pieces of a K (or V) tile per thread
+  constexpr bool PREFETCH = ITEMS <= 4;            // registers for the next tile's raw rows (D = 32)
+  static_assert(ATT_TK * (D / 4) % 128 == 0 && NT % 2 == 0, "tile geometry");
   extern __shared__ __half smh[];
   __half* Khi = smh;
   __half* Klo = Khi + ATT_TK * KP;
-  __half* Vhi = Klo + ATT_TK * KP;   // transposed: [D][VP]
-  __half* Vlo = Vhi + D * VP;
+  __half* Vhi = Klo + ATT_TK * KP;   // [key][KP] like K
+  __half* Vlo = Vhi + ATT_TK * KP;
   const tfmq_attn_desc& a = P.a;
   const int bh = blockIdx.y, b = bh / a.heads, h = bh % a.heads;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -331,31 +343,55 @@ __global__ void __launch_bounds__(128) attn_h16_kernel(const AttnP P) {
   for (int i = 0; i < NT; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
 
+  float4 kreg[PREFETCH ? ITEMS : 1], vreg[PREFETCH ? ITEMS : 1];
+  auto fetch = [&](int k0, int it, float4& kv, float4& vv) {
+    const int i = threadIdx.x + it * 128;
+    const int j = i / (D / 4), c4 = (i - j * (D / 4)) * 4;
+    kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
+    if (k0 + j < a.tk) {
+      kv = *reinterpret_cast<const float4*>(kb + (long long)(k0 + j) * a.k_st + c4);
+      vv = *reinterpret_cast<const float4*>(vb + (long long)(k0 + j) * a.v_st + c4);
+    }
+  };
+  auto stage = [&](int it, const float4& kv, const float4& vv) {
+    const int i = threadIdx.x + it * 128;
+    const int j = i / (D / 4), c4 = (i - j * (D / 4)) * 4;
+    uint32_t h01, l01, h23, l23;
+    split2_h(kv.x, kv.y, h01, l01);
+    split2_h(kv.z, kv.w, h23, l23);
+    *reinterpret_cast<uint2*>(Khi + j * KP + c4) = make_uint2(h01, h23);
+    *reinterpret_cast<uint2*>(Klo + j * KP + c4) = make_uint2(l01, l23);
+    split2_h(vv.x, vv.y, h01, l01);
+    split2_h(vv.z, vv.w, h23, l23);
+    *reinterpret_cast<uint2*>(Vhi + j * KP + c4) = make_uint2(h01, h23);
+    *reinterpret_cast<uint2*>(Vlo + j * KP + c4) = make_uint2(l01, l23);
+  };
+  if (PREFETCH) {
+#pragma unroll
+    for (int it = 0; it < ITEMS; ++it) fetch(0, it, kreg[it], vreg[it]);
+  }
+  // ldmatrix row of this lane: matrix (lane >> 3) = (key half, n-tile parity), row (lane & 7)
+  const int lm_key = ((lane >> 3) & 1) * 8 + (lane & 7), lm_dim = (lane >> 4) * 8;
+
   for (int k0 = 0; k0 < a.tk; k0 += ATT_TK) {
     __syncthreads();
     const int kn = min(ATT_TK, a.tk - k0);
-    for (int i = threadIdx.x; i < ATT_TK * (D / 4); i += 128) {
-      const int j = i / (D / 4), c4 = (i - j * (D / 4)) * 4;
-      float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
-      if (j < kn) {
-        kv = *reinterpret_cast<const float4*>(kb + (long long)(k0 + j) * a.k_st + c4);
-        vv = *reinterpret_cast<const float4*>(vb + (long long)(k0 + j) * a.v_st + c4);
-      }
-      uint32_t h01, l01, h23, l23;
-      split2_h(kv.x, kv.y, h01, l01);
-      split2_h(kv.z, kv.w, h23, l23);
-      *reinterpret_cast<uint2*>(Khi + j * KP + c4) = make_uint2(h01, h23);
-      *reinterpret_cast<uint2*>(Klo + j * KP + c4) = make_uint2(l01, l23);
-      const float ve[4] = {vv.x, vv.y, vv.z, vv.w};
+    if (PREFETCH) {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        __half vh, vl;
-        split1_h(ve[e], vh, vl);
-        Vhi[(c4 + e) * VP + j] = vh;
-        Vlo[(c4 + e) * VP + j] = vl;
+      for (int it = 0; it < ITEMS; ++it) stage(it, kreg[it], vreg[it]);
+    } else {
+#pragma unroll 2
+      for (int it = 0; it < ITEMS; ++it) {
+        float4 kv, vv;
+        fetch(k0, it, kv, vv);
+        stage(it, kv, vv);
       }
     }
     __syncthreads();
+    if (PREFETCH && k0 + ATT_TK < a.tk) {      // the next tile's rows travel while this one is multiplied
+#pragma unroll
+      for (int it = 0; it < ITEMS; ++it) fetch(k0 + ATT_TK, it, kreg[it], vreg[it]);
+    }
 
     // ---- S = Q K^T
     float s[8][4];
@@ -414,14 +450,17 @@ __global__ void __launch_bounds__(128) attn_h16_kernel(const AttnP P) {
       split2_h(s[2 * kt + 1][0], s[2 * kt + 1][1], ph[2], pl[2]);
       split2_h(s[2 * kt + 1][2], s[2 * kt + 1][3], ph[3], pl[3]);
 #pragma unroll
-      for (int nt = 0; nt < NT; ++nt) {
-        const uint32_t* vh = reinterpret_cast<const uint32_t*>(Vhi + (nt * 8 + g) * VP) + kt * 8 + t;
-        const uint32_t* vl = reinterpret_cast<const uint32_t*>(Vlo + (nt * 8 + g) * VP) + kt * 8 + t;
-        const uint32_t bh0 = vh[0], bh1 = vh[4];
-        const uint32_t bl0 = vl[0], bl1 = vl[4];
-        mma_f16(o[nt], pl, bh0, bh1);
-        mma_f16(o[nt], ph, bl0, bl1);
-        mma_f16(o[nt], ph, bh0, bh1);
+      for (int nt = 0; nt < NT; nt += 2) {
+        // matrices: (keys kt*16 + 0..7, dims nt*8..), (keys +8.., same dims), then the same two for n-tile nt + 1
+        uint32_t bh[4], bl[4];
+        ldmatrix_x4_trans(bh, Vhi + (kt * 16 + lm_key) * KP + nt * 8 + lm_dim);
+        ldmatrix_x4_trans(bl, Vlo + (kt * 16 + lm_key) * KP + nt * 8 + lm_dim);
+        mma_f16(o[nt], pl, bh[0], bh[1]);
+        mma_f16(o[nt], ph, bl[0], bl[1]);
+        mma_f16(o[nt], ph, bh[0], bh[1]);
+        mma_f16(o[nt + 1], pl, bh[2], bh[3]);
+        mma_f16(o[nt + 1], ph, bl[2], bl[3]);
+        mma_f16(o[nt + 1], ph, bh[2], bh[3]);
       }
     }
   }
@@ -445,7 +484,7 @@ __global__ void __launch_bounds__(128) attn_h16_kernel(const AttnP P) {
 
 template <int D>
 static int launch_h16(tfmq_ctx* ctx, const AttnP& P, cudaStream_t st) {
-  const size_t smem = (size_t)(2 * ATT_TK * (D + 8) + 2 * D * (ATT_TK + 8)) * sizeof(__half);
+  const size_t smem = (size_t)(4 * ATT_TK * (D + 8)) * sizeof(__half);
   auto kern = attn_h16_kernel<D>;
   static size_t smem_set = 0;
   if (smem > smem_set) {
