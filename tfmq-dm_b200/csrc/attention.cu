@@ -291,6 +291,13 @@ __device__ __forceinline__ void split1_h(float x, __half& hi, __half& lo) {
   lo = __float2half_rn(x - __half2float(hi));
 }
 
+// 2^x on the SFU (MUFU.EX2, about 2 ulp); ex2(-inf) = 0
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // four 8x8 b16 matrices, transposed on the way out: thread (g, t) of matrix i gets elements (row 2t, col g), (row 2t+1, col g)
 __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* smem_row) {
   const uint32_t addr = static_cast<uint32_t>(__cvta_generic_to_shared(smem_row));
@@ -322,6 +329,7 @@ __global__ void __launch_bounds__(128) attn_h16_kernel(const AttnP P) {
   const float* vb = a.v + (long long)b * a.v_sb + (long long)h * a.v_sh;
 
   uint32_t qh[KS][4], ql[KS][4];
+  const float qs = a.scale * 1.4426950408889634f;
   {
     const int r0 = min(q0 + g, a.tq - 1), r1 = min(q0 + g + 8, a.tq - 1);
     const float* p0 = qb + (long long)r0 * a.q_st;
@@ -332,10 +340,11 @@ __global__ void __launch_bounds__(128) attn_h16_kernel(const AttnP P) {
       const float2 x1 = *reinterpret_cast<const float2*>(p1 + ks * 16 + 2 * t);
       const float2 x2 = *reinterpret_cast<const float2*>(p0 + ks * 16 + 2 * t + 8);
       const float2 x3 = *reinterpret_cast<const float2*>(p1 + ks * 16 + 2 * t + 8);
-      split2_h(x0.x * a.scale, x0.y * a.scale, qh[ks][0], ql[ks][0]);
-      split2_h(x1.x * a.scale, x1.y * a.scale, qh[ks][1], ql[ks][1]);
-      split2_h(x2.x * a.scale, x2.y * a.scale, qh[ks][2], ql[ks][2]);
-      split2_h(x3.x * a.scale, x3.y * a.scale, qh[ks][3], ql[ks][3]);
+      // scores are kept in the log2 domain (scale * log2 e folded into q): softmax is then one MUFU.EX2 per element
+      split2_h(x0.x * qs, x0.y * qs, qh[ks][0], ql[ks][0]);
+      split2_h(x1.x * qs, x1.y * qs, qh[ks][1], ql[ks][1]);
+      split2_h(x2.x * qs, x2.y * qs, qh[ks][2], ql[ks][2]);
+      split2_h(x3.x * qs, x3.y * qs, qh[ks][3], ql[ks][3]);
     }
   }
   float o[NT][4];
@@ -422,15 +431,15 @@ __global__ void __launch_bounds__(128) attn_h16_kernel(const AttnP P) {
     mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-    const float c0 = expf(m0 - mx0), c1 = expf(m1 - mx1);
+    const float c0 = ex2f(m0 - mx0), c1 = ex2f(m1 - mx1);
     m0 = mx0, m1 = mx1;
     float rs0 = 0.f, rs1 = 0.f;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
-      s[nt][0] = expf(s[nt][0] - mx0);
-      s[nt][1] = expf(s[nt][1] - mx0);
-      s[nt][2] = expf(s[nt][2] - mx1);
-      s[nt][3] = expf(s[nt][3] - mx1);
+      s[nt][0] = ex2f(s[nt][0] - mx0);
+      s[nt][1] = ex2f(s[nt][1] - mx0);
+      s[nt][2] = ex2f(s[nt][2] - mx1);
+      s[nt][3] = ex2f(s[nt][3] - mx1);
       rs0 += s[nt][0] + s[nt][1];
       rs1 += s[nt][2] + s[nt][3];
     }
