@@ -96,3 +96,42 @@ def test_block_reconstruction_reduces_the_loss(dev):
     after = err()
     print(f"block reconstruction: lp_loss nearest {before:.5f} -> AdaRound {after:.5f}")
     assert after < before
+
+
+def test_cali_model_spatial_transformer_unet(dev):
+    """cali_model on a conditional UNet (SD / cin256 structure): calibration data are (x, t, context) triples
+    (quant/calibration.py:62-67, sample_diffusion_ldm.py:486-538), QuantBasicTransformerBlock units go through
+    block_reconstruction, and the checkpoint drives guided sampling through a freshly built model."""
+    from tfmq_b200.quant.calibration import act_tables_from_ckpt, cali_model, load_cali_model
+    from tfmq_b200.quant.quant_layer import QMODE, Scaler
+    from tfmq_b200.quant.quant_model import QuantModel
+    from tfmq_b200.quant.reconstruction_util import RLOSS
+    from tfmq_b200.samplers import DDIMSampler
+
+    def build(cali):
+        wq = dict(bits=4, channel_wise=True, scaler=Scaler.MINMAX)
+        aq = dict(bits=8, channel_wise=False, scaler=Scaler.MINMAX, leaf_param=True)
+        q = QuantModel(fp_model("sdmini").to(dev), wq, aq, cali=cali, softmax_a_bit=8,
+                       aq_mode=[QMODE.NORMAL.value, QMODE.QDIFF.value])
+        q.eval()
+        return q
+
+    g = torch.Generator().manual_seed(3)
+    w_cali = (synth.latents((8, 4, 16, 16), 61), torch.randint(0, 1000, (8,), generator=g).float(),
+              synth.latents((8, 7, 96), 62))
+    a_cali = (synth.latents((16, 4, 16, 16), 63), torch.cat([torch.full((8,), 751.0), torch.full((8,), 501.0)]),
+              synth.latents((16, 7, 96), 64))
+    qnn = build(True)
+    torch.manual_seed(0)
+    ckpt = cali_model(qnn, w_cali, a_cali, use_aq=True, path=None, running_stat=True, interval=8, iters=2, batch_size=4,
+                      w=0.01, asym=True, warmup=0.2, opt_mode=RLOSS.MSE, multi_gpu=False)
+    alphas = [k for k in ckpt["weight"] if k.endswith("wqtizer.alpha")]
+    assert any("transformer_blocks.0.attn2.to_k" in k for k in alphas) and any("ff.net.0.proj" in k for k in alphas)
+    assert len(act_tables_from_ckpt(ckpt)) == 2
+    q2 = build(False)
+    x = synth.latents((2, 4, 16, 16), 65)
+    c, uc = synth.latents((2, 7, 96), 66), synth.latents((2, 7, 96), 67)
+    load_cali_model(q2, (x, torch.full((2,), 751.0), c), use_aq=True, ckpt=ckpt)
+    out, _ = DDIMSampler(q2, ckpt=ckpt).sample(2, 2, (4, 16, 16), conditioning=c, unconditional_conditioning=uc,
+                                              unconditional_guidance_scale=3.0, x_T=x)
+    assert torch.isfinite(out).all() and out.shape == x.shape
