@@ -76,6 +76,7 @@ struct ActParams {
   tfmq_act_desc d;
   int out_h, out_w;     // destination interior extent
   int pix_per_cta;      // destination pixels (incl. halo) per CTA
+  double inv_cnt;       // GroupNorm: 1 / (channels per group * h * w)
 };
 
 // x*sigmoid(x); __expf / __frcp_rn keep the result within ~2 ulp of the accurate form, far below the
@@ -93,11 +94,13 @@ __device__ __forceinline__ float silu_f(float v) { return v * rcp_approx(1.f + _
 // case and only then the correctly rounded division is evaluated.
 // Rounding and the float -> integer move use the 1.5*2^23 / 2^23 add tricks (full-rate FADD, round-half-even
 // like rintf) instead of FRND / F2I, which share the quarter-rate pipe with the SiLU's EX2 / RCP.
+__device__ __noinline__ float quant_slow(float t, float delta) { return rintf(__fdiv_rn(t, delta)); }
 __device__ __forceinline__ uint32_t quant1(float t, float delta, float inv, float zp) {
   const float q = fminf(fmaxf(t * inv, -1024.f), 1024.f);   // beyond +-1024 steps the code saturates either way
   float nq = __fsub_rn(__fadd_rn(q, 12582912.f), 12582912.f);
-  const float rem = fmaf(-nq, delta, t);
-  if (fabsf(fabsf(rem) * inv - 0.5f) < 1e-6f * fmaxf(fabsf(nq), 1.f)) nq = rintf(__fdiv_rn(t, delta));
+  // |q| <= 1024: both t * inv and RN(t / delta) lie within 1.3e-4 of the real quotient, so their roundings can only
+  // differ when q is within 2.6e-4 of a half-integer; 5e-4 of margin sends 0.1 % of the elements to the exact path
+  if (fabsf(q - nq) > 0.4995f) nq = quant_slow(t, delta);
   const float code = fminf(fmaxf(nq + zp, 0.f), 255.f);
   return __float_as_uint(__fadd_rn(code, 8388608.f)) & 0xFFu;
 }
@@ -127,23 +130,29 @@ __device__ __forceinline__ float gelu_f(float g) { return 0.5f * g * (1.f + erff
 
 // One warp per destination pixel (lanes = float4 channel vectors): the pixel decode / border test is per
 // warp, not per element, and every global access is a full row.
+// Specialised at compile time on (normalisation, SiLU, GEGLU, output kind): the kernel is instruction-issue bound
+// (ncu: issue slots 70 % busy at 30 % of the DRAM rate), so per-element mode tests are not free.
+enum { ACT_NORM_NONE = 0, ACT_NORM_GN = 1, ACT_NORM_LN = 2 };
+enum { ACT_OUT_U8 = 0, ACT_OUT_F32 = 1, ACT_OUT_H16 = 2 };
+template <int NORM, bool SILU, bool GEGLU, int OUT>
 __global__ void __launch_bounds__(ACT_THREADS) act_prepare_kernel(const ActParams P) {
   extern __shared__ float sp[];  // [c] a = rstd*gamma, [c] b = beta - a*mean
   const tfmq_act_desc& d = P.d;
   const int n = blockIdx.y;
   const int c = d.c;
-  if (d.gn_stats) {
-    // the double-precision part (mean, 1/sqrt(var+eps)) once per group, not per channel
+  if (NORM == ACT_NORM_GN) {
+    // Group moments from the double sums: three double multiply-adds per group (1 / count comes from the host; the
+    // double-precision divide and square root this replaced cost ~200 DP instructions per group in EVERY CTA, on a part
+    // with a 1/64-rate DP pipe), then rstd in fp32 as torch's own GroupNorm computes it.
     __shared__ float sg[2 * 64];
     const int cpg = c / d.groups;
-    const double cnt = (double)cpg * d.h * d.w;
     for (int g = threadIdx.x; g < d.groups; g += ACT_THREADS) {
       const double su = d.gn_stats[((long long)n * d.groups + g) * 2];
       const double sq = d.gn_stats[((long long)n * d.groups + g) * 2 + 1];
-      const double mean = su / cnt;
-      double var = sq / cnt - mean * mean;
+      const double mean = su * P.inv_cnt;
+      double var = fma(-mean, mean, sq * P.inv_cnt);
       if (var < 0) var = 0;
-      sg[2 * g] = (float)(1.0 / sqrt(var + (double)d.eps));
+      sg[2 * g] = 1.f / sqrtf((float)var + d.eps);
       sg[2 * g + 1] = (float)mean;
     }
     __syncthreads();
@@ -156,12 +165,12 @@ __global__ void __launch_bounds__(ACT_THREADS) act_prepare_kernel(const ActParam
     __syncthreads();
   }
   float delta = 1.f, zp = 0.f;
-  if (d.dst_u8) {
+  if (OUT == ACT_OUT_U8) {
     delta = d.aq[0];
     zp = d.aq[1];
   }
   const float inv = __frcp_rn(delta);
-  const int halo = d.dst_u8 ? d.halo : 0;
+  const int halo = (OUT == ACT_OUT_U8) ? d.halo : 0;
   const int Wp = P.out_w + 2 * halo, Hp = P.out_h + 2 * halo;
   const int npix = Wp * Hp;
   const int nvec = c >> 2;
@@ -170,26 +179,29 @@ __global__ void __launch_bounds__(ACT_THREADS) act_prepare_kernel(const ActParam
   const int p0 = blockIdx.x * P.pix_per_cta;
   const int p1 = min(p0 + P.pix_per_cta, npix);
   const uint32_t zfill = (uint32_t)zp * 0x01010101u;
-  const bool gn = d.gn_stats != nullptr;
+  constexpr bool gn = NORM == ACT_NORM_GN;
   for (int pp = p0 + warp; pp < p1; pp += NW) {
     const int yy = pp / Wp, xx = pp - yy * Wp;
     const int y = yy - halo, x = xx - halo;
     const bool border = (y < 0) | (x < 0) | (y >= P.out_h) | (x >= P.out_w);
-    uint32_t* o8 = d.dst_u8 ? reinterpret_cast<uint32_t*>(d.dst_u8 + ((long long)n * npix + pp) * d.dst_c + d.dst_c_off)
-                            : nullptr;
-    if (border) {
+    uint32_t* o8 = (OUT == ACT_OUT_U8)
+                       ? reinterpret_cast<uint32_t*>(d.dst_u8 + ((long long)n * npix + pp) * d.dst_c + d.dst_c_off)
+                       : nullptr;
+    if (OUT == ACT_OUT_U8 && border) {
       for (int v = lane; v < nvec; v += 32) o8[v] = zfill;
       continue;
     }
     const int sy = d.upsample ? (y >> 1) : y, sx = d.upsample ? (x >> 1) : x;
     const float4* src = reinterpret_cast<const float4*>(d.src + (((long long)n * d.h + sy) * d.w + sx) * d.src_ld);
-    float4* o32 = d.dst_f32 ? reinterpret_cast<float4*>(d.dst_f32 + ((long long)n * npix + pp) * d.dst_ld) : nullptr;
-    uint2* ohi = d.dst_hi ? reinterpret_cast<uint2*>(static_cast<__half*>(d.dst_hi) + ((long long)n * npix + pp) * d.dst_h_ld)
-                          : nullptr;
-    uint2* olo = d.dst_hi ? reinterpret_cast<uint2*>(static_cast<__half*>(d.dst_lo) + ((long long)n * npix + pp) * d.dst_h_ld)
-                          : nullptr;
+    float4* o32 = (OUT == ACT_OUT_F32) ? reinterpret_cast<float4*>(d.dst_f32 + ((long long)n * npix + pp) * d.dst_ld) : nullptr;
+    uint2* ohi = (OUT == ACT_OUT_H16)
+                     ? reinterpret_cast<uint2*>(static_cast<__half*>(d.dst_hi) + ((long long)n * npix + pp) * d.dst_h_ld)
+                     : nullptr;
+    uint2* olo = (OUT == ACT_OUT_H16)
+                     ? reinterpret_cast<uint2*>(static_cast<__half*>(d.dst_lo) + ((long long)n * npix + pp) * d.dst_h_ld)
+                     : nullptr;
     float ln_scale = 1.f, ln_shift = 0.f;
-    if (d.ln_gamma) {
+    if (NORM == ACT_NORM_LN) {
       // LayerNorm over the c channels of this token (nn.LayerNorm in BasicTransformerBlock, attention.py:205-207):
       // row moments in double, then y = (x * rstd - rstd * mean) * gamma + beta
       double s1 = 0.0, s2 = 0.0;
@@ -215,7 +227,7 @@ __global__ void __launch_bounds__(ACT_THREADS) act_prepare_kernel(const ActParam
       const float4 f0 = src[v0];
       const float4 f1 = has1 ? src[v1] : make_float4(0.f, 0.f, 0.f, 0.f);
       float t0[4] = {f0.x, f0.y, f0.z, f0.w}, t1[4] = {f1.x, f1.y, f1.z, f1.w};
-      if (d.ln_gamma) {
+      if (NORM == ACT_NORM_LN) {
         const float4 g0 = *reinterpret_cast<const float4*>(d.ln_gamma + v0 * 4), b0 = *reinterpret_cast<const float4*>(d.ln_beta + v0 * 4);
         t0[0] = fmaf(fmaf(t0[0], ln_scale, ln_shift), g0.x, b0.x), t0[1] = fmaf(fmaf(t0[1], ln_scale, ln_shift), g0.y, b0.y);
         t0[2] = fmaf(fmaf(t0[2], ln_scale, ln_shift), g0.z, b0.z), t0[3] = fmaf(fmaf(t0[3], ln_scale, ln_shift), g0.w, b0.w);
@@ -225,7 +237,7 @@ __global__ void __launch_bounds__(ACT_THREADS) act_prepare_kernel(const ActParam
           t1[2] = fmaf(fmaf(t1[2], ln_scale, ln_shift), g1.z, b1.z), t1[3] = fmaf(fmaf(t1[3], ln_scale, ln_shift), g1.w, b1.w);
         }
       }
-      if (d.geglu) {
+      if (GEGLU) {
         // GEGLU (attention.py:37-44): the source row holds [value (c) | gate (c)]; out = value * gelu(gate), exact erf form
         const float4 q0 = src[nvec + v0];
         const float4 q1 = has1 ? src[nvec + v1] : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -246,14 +258,14 @@ __global__ void __launch_bounds__(ACT_THREADS) act_prepare_kernel(const ActParam
           t1[2] = fmaf(t1[2], a1.z, b1.z), t1[3] = fmaf(t1[3], a1.w, b1.w);
         }
       }
-      if (d.silu) {
+      if (SILU) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) t0[j] = silu_f(t0[j]), t1[j] = silu_f(t1[j]);
       }
-      if (o8) {
+      if (OUT == ACT_OUT_U8) {
         o8[v0] = quant4(t0, delta, inv, zp);
         if (has1) o8[v1] = quant4(t1, delta, inv, zp);
-      } else if (ohi) {
+      } else if (OUT == ACT_OUT_H16) {
         uint2 h, l;
         split_h16x4(t0, h, l);
         ohi[v0] = h, olo[v0] = l;
@@ -405,8 +417,32 @@ extern "C" int tfmq_act_prepare(tfmq_ctx* ctx, const tfmq_act_desc* d, void* str
   const int ppc = (npix + chunks - 1) / chunks;
   chunks = (npix + ppc - 1) / ppc;
   P.pix_per_cta = ppc;
+  P.inv_cnt = d->gn_stats ? 1.0 / ((double)(d->c / d->groups) * d->h * d->w) : 0.0;
   const size_t smem = d->gn_stats ? 2 * (size_t)d->c * sizeof(float) : 0;
-  act_prepare_kernel<<<dim3(chunks, d->n), ACT_THREADS, smem, tfmq_stream(stream)>>>(P);
+  const dim3 grid(chunks, d->n);
+  cudaStream_t st = tfmq_stream(stream);
+  const int out = d->dst_u8 ? ACT_OUT_U8 : d->dst_hi ? ACT_OUT_H16 : ACT_OUT_F32;
+#define ACT_LAUNCH(NORM, SILU, GEGLU, OUT) \
+  act_prepare_kernel<NORM, SILU, GEGLU, OUT><<<grid, ACT_THREADS, smem, st>>>(P)
+#define ACT_BY_OUT(NORM, SILU, GEGLU)                         \
+  do {                                                        \
+    if (out == ACT_OUT_U8) ACT_LAUNCH(NORM, SILU, GEGLU, ACT_OUT_U8);        \
+    else if (out == ACT_OUT_H16) ACT_LAUNCH(NORM, SILU, GEGLU, ACT_OUT_H16); \
+    else ACT_LAUNCH(NORM, SILU, GEGLU, ACT_OUT_F32);          \
+  } while (0)
+  if (d->geglu) ACT_BY_OUT(ACT_NORM_NONE, false, true);
+  else if (d->ln_gamma) {
+    TFMQ_REQUIRE(!d->silu, TFMQ_ERR_ARG, "act_prepare: LayerNorm + SiLU is not a combination of the path");
+    ACT_BY_OUT(ACT_NORM_LN, false, false);
+  } else if (d->gn_stats) {
+    if (d->silu) ACT_BY_OUT(ACT_NORM_GN, true, false);
+    else ACT_BY_OUT(ACT_NORM_GN, false, false);
+  } else {
+    if (d->silu) ACT_BY_OUT(ACT_NORM_NONE, true, false);
+    else ACT_BY_OUT(ACT_NORM_NONE, false, false);
+  }
+#undef ACT_BY_OUT
+#undef ACT_LAUNCH
   TFMQ_LAUNCH_CHECK("act_prepare");
   return TFMQ_OK;
 }
