@@ -361,6 +361,23 @@ def sdmini_golden():
     print("sdmini_w4a8.pt written", len(names), "act-quantised layers; inert:", inert, time.time() - t0)
 
 
+def unet_keys():
+    """state_dict keys / shapes of the REFERENCE UNetModel for every supported LDM config (meta device: no weights are
+    materialised), and the module list of the reference QuantModel on the small transformer UNet."""
+    from ldm.modules.diffusionmodules.openaimodel import UNetModel
+    from tfmq_b200.host import ldm_unet as H
+    out = {}
+    for name, cfg in (("ldm4", H.celebahq_ldm4_config()), ("sd_mini", H.sd_mini_config()), ("sd_v14", H.sd_v14_config()),
+                      ("cin256", H.cin256_config())):
+        with torch.device("meta"):
+            m = UNetModel(**cfg)
+        out[name] = [(k, tuple(v.shape)) for k, v in m.state_dict().items()]
+    qnn, _ = build_ref_qnn("sdmini")
+    out["sd_mini_quant_modules"] = [(n, type(m).__name__) for n, m in qnn.named_modules()]
+    torch.save(out, os.path.join(HERE, "unet_keys.pt"))
+    print("unet_keys.pt written", {k: len(v) for k, v in out.items()})
+
+
 def cali_schema():
     """G9: run the reference's cali_model on a tiny synthetic set and record the checkpoint's key set and
     shapes (the on-disk format the drop-in must read and write)."""
@@ -399,3 +416,5 @@ if __name__ == "__main__":
         cali_schema()
     if "sdmini" in what:
         sdmini_golden()
+    if "keys" in what:
+        unet_keys()

@@ -119,3 +119,37 @@ def test_adaround_quantizer_matches_oracle_on_cpu_math():
     assert torch.equal(a(w), Q.adaround_fake_quant(w, d, z, a.alpha.detach(), 16))
     a.soft_tgt = True
     assert torch.equal(a(w).detach(), Q.adaround_fake_quant(w, d, z, a.alpha.detach(), 16, soft=True))
+
+
+def test_ldm_unets_have_the_reference_state_dict_keys():
+    """Reference checkpoints must load unchanged: same keys, same shapes, same order, for every supported LDM config
+    (fixture written by tests/golden/make_golden.py from the reference's own UNetModel)."""
+    import torch
+    from helpers import load_golden
+    from tfmq_b200.host import ldm_unet as H
+    g = load_golden("unet_keys.pt")
+    for name, cfg in (("ldm4", H.celebahq_ldm4_config()), ("sd_mini", H.sd_mini_config()), ("sd_v14", H.sd_v14_config()),
+                      ("cin256", H.cin256_config())):
+        with torch.device("meta"):
+            m = H.UNetModel(**cfg)
+        mine = [(k, tuple(v.shape)) for k, v in m.state_dict().items()]
+        assert mine == g[name], name
+
+
+def test_quant_model_surgery_on_transformer_unet_matches_reference():
+    """QuantModel's module surgery on a SpatialTransformer UNet: the same QuantLayer / QuantBasicTransformerBlock /
+    QuantResBlock placement as the reference's QuantModel (module names and classes; Identity placement aside)."""
+    from helpers import fp_model, load_golden
+    from tfmq_b200.quant.quant_layer import QMODE, Scaler
+    from tfmq_b200.quant.quant_model import QuantModel
+    g = load_golden("unet_keys.pt")
+    wq = dict(bits=4, channel_wise=True, scaler=Scaler.MINMAX)
+    aq = dict(bits=8, channel_wise=False, scaler=Scaler.MINMAX, leaf_param=True)
+    qnn = QuantModel(fp_model("sdmini"), wq, aq, cali=False, softmax_a_bit=8, aq_mode=[QMODE.NORMAL.value, QMODE.QDIFF.value])
+    mine = {n: type(m).__name__ for n, m in qnn.named_modules()}
+    ref = dict(g["sd_mini_quant_modules"])
+    interesting = ("QuantLayer", "QuantBasicTransformerBlock", "QuantResBlock", "UniformAffineQuantizer")
+    want = {n: c for n, c in ref.items() if c in interesting}
+    got = {n: c for n, c in mine.items() if c in interesting}
+    assert got == want
+    assert sum(c == "QuantLayer" for c in got.values()) > 100
