@@ -300,6 +300,13 @@ int tfmq_ddim_update(tfmq_ctx* ctx, const float* x, const float* e, const float*
 int tfmq_cfg_combine(tfmq_ctx* ctx, const float* e_uncond, const float* e_cond, float s, int64_t count, float* out,
                      void* stream);
 
+/* PLMS sampler (ldm/models/diffusion/plms.py:226-238): the Adams-Bashforth combination of the current noise prediction e0
+ * with the stored ones (e1 = old_eps[-1], e2, e3), in the reference's operation order.  order 0: e0; 1: (e0 + e1) / 2 (second
+ * half of the first, pseudo improved Euler, step); 2: (3 e0 - e1) / 2; 3: (23 e0 - 16 e1 + 5 e2) / 12;
+ * 4: (55 e0 - 59 e1 + 37 e2 - 9 e3) / 24.  The latent update itself is tfmq_ddim_update with the combined prediction. */
+int tfmq_plms_eps(tfmq_ctx* ctx, const float* e0, const float* e1, const float* e2, const float* e3, int order,
+                  int64_t count, float* out, void* stream);
+
 /* ------------------------------------------------------------------------- *
  * Calibration primitives.
  * ------------------------------------------------------------------------- */

@@ -38,8 +38,10 @@ _orig_to = torch.Tensor.to
 
 
 def _to(self, *a, **k):
-    a = tuple("cpu" if (isinstance(x, str) and x.startswith("cuda")) else x for x in a)
-    if isinstance(k.get("device"), str) and k["device"].startswith("cuda"):
+    def is_cuda(x):
+        return (isinstance(x, str) and x.startswith("cuda")) or (isinstance(x, torch.device) and x.type == "cuda")
+    a = tuple("cpu" if is_cuda(x) else x for x in a)
+    if is_cuda(k.get("device")):
         k["device"] = "cpu"
     return _orig_to(self, *a, **k)
 
@@ -378,6 +380,59 @@ def unet_keys():
     print("unet_keys.pt written", {k: len(v) for k, v in out.items()})
 
 
+def stub_eps(x, t, c=None):
+    """A UNet stand-in made of exactly-rounded fp32 ops only (roll, mul, sub, add): the same bits on CPU and GPU, so a
+    sampler trajectory pins the UPDATE RULE, not a network."""
+    e = 0.3 * x.roll(1, -1) - (0.2 * x) * (t.float() / 1000.0)[:, None, None, None]
+    if c is not None:
+        e = e + 0.05 * c.reshape(c.shape[0], -1)[:, :1, None, None]
+    return e
+
+
+def plms_golden():
+    """Trajectories of the reference's PLMSSampler / DDIMSampler (ldm/models/diffusion/{plms,ddim}.py) driven by `stub_eps`
+    through a minimal LatentDiffusion stand-in (betas / alphas_cumprod buffers + apply_model), incl. guidance and the
+    `untill_fake_t` early stop."""
+    import numpy as np
+    from ldm.models.diffusion.ddim import DDIMSampler
+    from ldm.models.diffusion.plms import PLMSSampler
+    from ldm.modules.diffusionmodules.util import make_beta_schedule
+
+    class Stub(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            betas = make_beta_schedule("linear", 1000, linear_start=0.00085, linear_end=0.012)
+            ac = np.cumprod(1.0 - betas, axis=0)
+            f = lambda a: torch.tensor(a, dtype=torch.float32)  # noqa: E731
+            self.num_timesteps = 1000
+            self.register_buffer("betas", f(betas))
+            self.register_buffer("alphas_cumprod", f(ac))
+            self.register_buffer("alphas_cumprod_prev", f(np.append(1.0, ac[:-1])))
+            self.register_buffer("sqrt_alphas_cumprod", f(np.sqrt(ac)))
+            self.register_buffer("sqrt_one_minus_alphas_cumprod", f(np.sqrt(1.0 - ac)))
+            self.register_buffer("log_one_minus_alphas_cumprod", f(np.log(1.0 - ac)))
+            self.register_buffer("sqrt_recip_alphas_cumprod", f(np.sqrt(1.0 / ac)))
+            self.register_buffer("sqrt_recipm1_alphas_cumprod", f(np.sqrt(1.0 / ac - 1)))
+            self.device = torch.device("cpu")
+
+        def apply_model(self, x, t, c):
+            return stub_eps(x, t, c)
+
+    m = Stub()
+    x_T = synth.latents((2, 4, 8, 8), 81)
+    c, uc = synth.latents((2, 3, 5), 82), synth.latents((2, 3, 5), 83)
+    out = dict(x_T=x_T, c=c, uc=uc, linear_start=0.00085, linear_end=0.012)
+    for name, cls in (("plms", PLMSSampler), ("ddim", DDIMSampler)):
+        s10, _ = cls(m).sample(S=10, batch_size=2, shape=[4, 8, 8], eta=0.0, x_T=x_T.clone(), verbose=False)
+        s10c, _ = cls(m).sample(S=10, batch_size=2, shape=[4, 8, 8], eta=0.0, x_T=x_T.clone(), verbose=False, conditioning=c,
+                               unconditional_conditioning=uc, unconditional_guidance_scale=3.0)
+        s4, _ = cls(m).sample(S=10, batch_size=2, shape=[4, 8, 8], eta=0.0, x_T=x_T.clone(), verbose=False, untill_fake_t=5)
+        out[name] = dict(full=s10, guided=s10c, stop5=s4)
+    torch.save(out, os.path.join(HERE, "samplers_stub.pt"))
+    print("samplers_stub.pt written", {k: (v["full"].abs().max().item() if isinstance(v, dict) else None) for k, v in out.items()
+                                        if isinstance(v, dict)})
+
+
 def cali_schema():
     """G9: run the reference's cali_model on a tiny synthetic set and record the checkpoint's key set and
     shapes (the on-disk format the drop-in must read and write)."""
@@ -418,3 +473,5 @@ if __name__ == "__main__":
         sdmini_golden()
     if "keys" in what:
         unet_keys()
+    if "plms" in what:
+        plms_golden()

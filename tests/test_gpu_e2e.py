@@ -287,3 +287,59 @@ def test_product_refuses_cpu():
     qnn.set_quant_state(True, True)
     with pytest.raises(RuntimeError):
         qnn(torch.zeros(1, 3, 32, 32), torch.zeros(1))
+
+
+def _stub_eps(x, t, c=None):
+    """tests/golden/make_golden.py::stub_eps (exactly-rounded ops only: identical bits on CPU and GPU)."""
+    e = 0.3 * x.roll(1, -1) - (0.2 * x) * (t.float() / 1000.0)[:, None, None, None]
+    if c is not None:
+        e = e + 0.05 * c.reshape(c.shape[0], -1)[:, :1, None, None]
+    return e
+
+
+@pytest.mark.parametrize("name", ["plms", "ddim"])
+def test_sampler_update_rules_match_the_reference_samplers(dev, name):
+    """PLMS (pseudo improved Euler + Adams-Bashforth 2/3/4) and DDIM update rules, guidance and the `untill_fake_t`
+    early stop against trajectories of the reference's own PLMSSampler / DDIMSampler driven by the same stand-in UNet."""
+    from tfmq_b200.samplers import DDIMSampler, PLMSSampler
+    g = load_golden("samplers_stub.pt")
+    cls = PLMSSampler if name == "plms" else DDIMSampler
+    mk = lambda: cls(_stub_eps, linear_start=g["linear_start"], linear_end=g["linear_end"])  # noqa: E731
+    x_T, c, uc = g["x_T"].to(dev), g["c"].to(dev), g["uc"].to(dev)
+    full, _ = mk().sample(10, 2, (4, 8, 8), x_T=x_T)
+    guided, _ = mk().sample(10, 2, (4, 8, 8), x_T=x_T, conditioning=c, unconditional_conditioning=uc,
+                            unconditional_guidance_scale=3.0)
+    stop5, _ = mk().sample(10, 2, (4, 8, 8), x_T=x_T, untill_fake_t=5)
+    for tag, got in (("full", full), ("guided", guided), ("stop5", stop5)):
+        ref = g[name][tag]
+        err = (got.cpu() - ref).abs().max().item()
+        print(f"[{name}] {tag}: max-abs {err:.3e} (|x| max {ref.abs().max():.2f})")
+        assert err <= 1e-5 * max(1.0, ref.abs().max().item())
+
+
+def test_fp_engine_and_calibration_data_generation(dev):
+    """calibration-data generation = the FULL-PRECISION sampler with early stops, on the same engine in its
+    all-floating-point state.  The fp engine must agree with the fp host UNet, and the generated (x_t, t) pairs must have
+    the reference's shapes and time stamps (quant/data_generate.py:74-113)."""
+    from tfmq_b200.quant.data_generate import generate_cali_data_ldm
+    from tfmq_b200.quant.quant_layer import QMODE, Scaler
+    from tfmq_b200.quant.quant_model import QuantModel
+    fp = fp_model("ldm")
+    x = synth.latents((2, 3, 64, 64), 91)
+    t = torch.tensor([301.0, 301.0])
+    with torch.no_grad():
+        ref = fp(x, t)                      # fp32 on the CPU (torch's GPU convs would run in TF32)
+    fp, x, t = fp.to(dev), x.to(dev), t.to(dev)
+    wq = dict(bits=4, channel_wise=True, scaler=Scaler.MINMAX)
+    aq = dict(bits=8, channel_wise=False, scaler=Scaler.MINMAX, leaf_param=True)
+    qnn = QuantModel(fp, wq, aq, cali=True, softmax_a_bit=8, aq_mode=[QMODE.NORMAL.value, QMODE.QDIFF.value])
+    qnn.eval()
+    qnn.set_quant_state(False, False)
+    eng = qnn.build_engine(batch=2)
+    e = eng.forward(x, t).cpu()
+    err = (e - ref).abs().max().item()
+    print(f"[fp engine] LDM-4 eps vs the fp32 host UNet on the CPU: max-abs {err:.3e} (|eps| max {ref.abs().max():.2f})")
+    assert err < 2e-4
+    T, c = 10, 5
+    xs, ts = generate_cali_data_ldm(qnn, T=T, c=c, batch_size=2, shape=[3, 64, 64])
+    assert xs.shape == (4, 3, 64, 64) and ts.tolist() == [501, 501, 1, 1] and torch.isfinite(xs).all()

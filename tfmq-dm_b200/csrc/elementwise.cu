@@ -308,6 +308,33 @@ __global__ void cfg_combine_kernel(const float* __restrict__ eu, const float* __
     out[i] = __fadd_rn(eu[i], __fmul_rn(s, __fsub_rn(ec[i], eu[i])));
 }
 
+// PLMS multistep combination of the current and stored noise predictions (ldm/models/diffusion/plms.py:226-238), with the
+// reference's operation order so the fp32 roundings agree:
+//   order 0: e0                       (first half of the pseudo improved Euler step, and plain DDIM)
+//   order 1: (e0 + e1) / 2            (second half: e1 = model output at x_prev)
+//   order 2: (3 e0 - e1) / 2          order 3: (23 e0 - 16 e1 + 5 e2) / 12
+//   order 4: (55 e0 - 59 e1 + 37 e2 - 9 e3) / 24        with e1, e2, e3 = old_eps[-1], [-2], [-3]
+__global__ void plms_eps_kernel(const float* __restrict__ e0, const float* __restrict__ e1, const float* __restrict__ e2,
+                                const float* __restrict__ e3, int order, long long count, float* __restrict__ out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float a = e0[i];
+    float r = a;
+    if (order == 1) {
+      r = __fdiv_rn(__fadd_rn(a, e1[i]), 2.f);
+    } else if (order == 2) {
+      r = __fdiv_rn(__fsub_rn(__fmul_rn(3.f, a), e1[i]), 2.f);
+    } else if (order == 3) {
+      r = __fdiv_rn(__fadd_rn(__fsub_rn(__fmul_rn(23.f, a), __fmul_rn(16.f, e1[i])), __fmul_rn(5.f, e2[i])), 12.f);
+    } else if (order >= 4) {
+      r = __fdiv_rn(__fsub_rn(__fadd_rn(__fsub_rn(__fmul_rn(55.f, a), __fmul_rn(59.f, e1[i])), __fmul_rn(37.f, e2[i])),
+                              __fmul_rn(9.f, e3[i])),
+                    24.f);
+    }
+    out[i] = r;
+  }
+}
+
 __global__ void timestep_embedding_kernel(const float* __restrict__ t, int m, int dim, int style,
                                           float* __restrict__ out) {
   const int half = dim / 2;
@@ -456,6 +483,19 @@ extern "C" int tfmq_ddim_update(tfmq_ctx* ctx, const float* x, const float* e, c
   if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
   ddim_update_kernel<<<blocks, 256, 0, tfmq_stream(stream)>>>(x, e, noise, coef, count, x_prev, x0_out);
   TFMQ_LAUNCH_CHECK("ddim_update");
+  return TFMQ_OK;
+}
+
+extern "C" int tfmq_plms_eps(tfmq_ctx* ctx, const float* e0, const float* e1, const float* e2, const float* e3,
+                             int order, int64_t count, float* out, void* stream) {
+  if (!ctx) return TFMQ_ERR_ARG;
+  TFMQ_REQUIRE(e0 && out && order >= 0 && order <= 4, TFMQ_ERR_ARG, "plms_eps: null pointer / order");
+  TFMQ_REQUIRE((order < 1 || e1) && (order < 3 || e2) && (order < 4 || e3), TFMQ_ERR_ARG,
+               "plms_eps: order %d needs more stored predictions", order);
+  if (count <= 0) return TFMQ_OK;
+  const int blocks = (int)((count + 255) / 256 < 1184 ? (count + 255) / 256 : 1184);
+  plms_eps_kernel<<<blocks, 256, 0, tfmq_stream(stream)>>>(e0, e1, e2, e3, order, count, out);
+  TFMQ_LAUNCH_CHECK("plms_eps");
   return TFMQ_OK;
 }
 

@@ -315,7 +315,8 @@ class StepEngine:
                               res=res.view if res is not None else None, stats=self._stats_of(rec))
             self.ops.append(run)
         else:
-            assert not upsample
+            # floating-point layer (also every layer of the un-quantised model, e.g. calibration-data generation)
+            tok = dict(tok, upsample=True) if upsample else tok
             src = self._fp_input(x, gn, silu, tok)
             self._fp_conv(q, src, out, res, pad_lo=q.ksize // 2, emb=emb)
         return out
@@ -325,18 +326,19 @@ class StepEngine:
         act_prepare launch, which is also where GN / SiLU are applied); tf32 mode: an fp32 tensor."""
         tok = tok or {}
         c_out = x.c // 2 if tok.get("geglu") else x.c
+        up = 2 if tok.get("upsample") else 1
         if self.fp_mode == "h16":
             key = (id(x), id(gn[0]) if gn is not None else None, silu, id(tok["ln"][0]) if "ln" in tok else None,
-                   bool(tok.get("geglu")))
+                   bool(tok.get("geglu")), up)
             if key not in self._h16:
-                hi = torch.empty((x.n, x.h, x.w, c_out), dtype=torch.float16, device=self.dev)
+                hi = torch.empty((x.n, x.h * up, x.w * up, c_out), dtype=torch.float16, device=self.dev)
                 lo = torch.empty_like(hi)
                 self._h16[key] = (hi, lo)
                 self.ops.append(lambda: ops.act_prepare(x.view, dst_h16=(hi, lo), silu=silu, **tok, **self._gn_args(gn)))
             return self._h16[key]
         if gn is None and not silu and not tok:
             return x
-        src = self._new(x.n, x.h, x.w, c_out)
+        src = self._new(x.n, x.h * up, x.w * up, c_out)
         self.ops.append(lambda: ops.act_prepare(x.view, dst_f32=src.view, silu=silu, **tok, **self._gn_args(gn)))
         return src
 

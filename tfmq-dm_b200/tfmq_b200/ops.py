@@ -340,6 +340,18 @@ def cfg_combine(e_u, e_c, s: float, out):
     _ctx(out).call("tfmq_cfg_combine", _p(e_u), _p(e_c), C.c_float(s), out.numel(), _p(out), _stream())
 
 
+def plms_eps(e0, olds, out):
+    """Adams-Bashforth combination of e0 with the stored predictions `olds` = [old_eps[-1], old_eps[-2], ...] (up to 3);
+    `olds` = ["euler", e_next] selects the (e0 + e_next) / 2 of the first step."""
+    ctx = _ctx(out)
+    if len(olds) == 2 and isinstance(olds[0], str):
+        order, es = 1, [olds[1], None, None]
+    else:
+        order = 0 if not olds else min(len(olds), 3) + 1
+        es = (list(olds) + [None, None, None])[:3]
+    ctx.call("tfmq_plms_eps", _p(e0), _p(es[0]), _p(es[1]), _p(es[2]), order, out.numel(), _p(out), _stream())
+
+
 # --------------------------------------------------------------------------- calibration
 def minmax_rows(x2d: torch.Tensor) -> torch.Tensor:
     rows, cols = x2d.shape

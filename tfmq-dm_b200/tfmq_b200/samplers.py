@@ -3,7 +3,9 @@
 * generalized_steps(x, seq, model, b, **kwargs) -> (xs, x0_preds, xt, t)
       reference ddim/functions/denoising.py:10-41 (used by Diffusion.sample_image, runners/diffusion.py:429-476)
 * DDIMSampler(model).sample(S, batch_size, shape, eta=0., x_T=None, ...) -> (samples, intermediates)
-      reference ldm/models/diffusion/ddim.py:57-212, unconditional path (LDM-4 CelebA-HQ / LSUN)
+      reference ldm/models/diffusion/ddim.py:57-212, unconditional or conditional with classifier-free guidance
+* PLMSSampler(model).sample(...)  -- same call shape, Adams-Bashforth multistep update
+      reference ldm/models/diffusion/plms.py:57-242 (the README's Stable Diffusion command samples with --plms)
 
 What changes underneath: the latent stays resident on the GPU for the whole trajectory (the reference
 hops GPU<->CPU every step, denoising.py:23,38), the FSC parameter switch is one device-side row
@@ -135,6 +137,9 @@ class DDIMSampler:
         if eta != 0:
             raise NotImplementedError("eta > 0")
         self.make_schedule(S, eta)
+        if not hasattr(self.model, "build_engine"):
+            return self._sample_callable(S, batch_size, shape, conditioning, x_T, unconditional_guidance_scale,
+                                         unconditional_conditioning, untill_fake_t)
         dev = next(self.model.parameters()).device
         C, H, W = shape
         img = torch.randn((batch_size, C, H, W), device=dev) if x_T is None else x_T.to(dev)
@@ -167,3 +172,116 @@ class DDIMSampler:
             eng.step(k)
         out = eng.x_in[:batch_size].clone()
         return out, {"x_inter": [img, out], "pred_x0": [img, eng.x0_pred[:batch_size].clone()]}
+
+
+def _callable_eps(model, batch_size, ctx, cfg, scale):
+    """eps(x, t) from any callable (x, t, context) -> eps on CUDA tensors, with the guidance formula of ddim.py:171-180."""
+    from . import ops
+
+    def fn(x, t, k):
+        tt = torch.full((x.shape[0],), float(t), device=x.device)
+        if not cfg:
+            return model(x, tt, ctx)
+        e = model(torch.cat([x, x]), torch.cat([tt, tt]), ctx)
+        out = torch.empty_like(e[:batch_size])
+        ops.cfg_combine(e[:batch_size].contiguous(), e[batch_size:].contiguous(), scale, out)
+        return out
+    return fn
+
+
+def _sample_callable(self, S, batch_size, shape, conditioning, x_T, scale, uncond, untill_fake_t):
+    """DDIM with a plain callable as the UNet (update-rule parity tests): same kernels for guidance and the update."""
+    from . import ops
+    dev = x_T.device
+    img = x_T.clone()
+    cfg = conditioning is not None and uncond is not None and scale != 1.0
+    ctx = None
+    if conditioning is not None:
+        ctx = torch.cat([uncond.to(dev).float(), conditioning.to(dev).float()]) if cfg else conditioning.to(dev).float()
+    eps_fn = _callable_eps(self.model, batch_size, ctx, cfg, float(scale))
+    rows = torch.tensor(self.coefficient_rows(), dtype=torch.float32, device=dev)
+    ts = [float(t) for t in np.flip(self.ddim_timesteps)]
+    x0 = torch.empty_like(img)
+    for k in range(S if not untill_fake_t else min(S, untill_fake_t - 1)):
+        ops.ddim_update(img, eps_fn(img, ts[k], k).contiguous(), rows[k], img, x0)
+    return img, {"x_inter": [x_T, img], "pred_x0": [x_T, x0]}
+
+
+DDIMSampler._sample_callable = _sample_callable
+
+
+class PLMSSampler(DDIMSampler):
+    """Pseudo linear multistep sampling (ldm/models/diffusion/plms.py:57-242), eta = 0: the UNet output of a step is
+    combined with up to three stored ones (Adams-Bashforth, `tfmq_plms_eps`) before the DDIM-form update; the first
+    step is the pseudo improved Euler step with a second UNet evaluation at x_prev.  Same schedule, FSC indexing,
+    conditioning and guidance handling as DDIMSampler.  `model` is a QuantModel, or any callable
+    (x, t, context) -> eps on CUDA tensors (used by the update-rule parity test)."""
+
+    def _eps_fn(self, batch_size, ctx, cfg, scale):
+        from . import ops
+        model = self.model
+        if hasattr(model, "build_engine"):
+            nb = batch_size * (2 if cfg else 1)
+            eng = getattr(model, "_engine", None)
+            want = tuple(ctx.shape) if ctx is not None else None
+            have = tuple(eng.ctx_in.shape) if (eng is not None and eng.ctx_in is not None) else None
+            if eng is None or eng.batch != nb or want != have:
+                eng = model.build_engine(batch=nb, context_shape=ctx.shape[1:] if ctx is not None else None)
+            eng.set_guidance(None)
+            self._eng = eng
+
+            def fn(x, t, k):
+                if self._tables is not None:
+                    eng.select_step(k)
+                e = eng.forward(torch.cat([x, x]) if cfg else x, torch.full((nb,), float(t)), ctx)
+                if not cfg:
+                    return e
+                out = torch.empty_like(e[:batch_size])
+                ops.cfg_combine(e[:batch_size], e[batch_size:], scale, out)
+                return out
+            return fn
+
+        return _callable_eps(model, batch_size, ctx, cfg, scale)
+
+    @torch.no_grad()
+    def sample(self, S, batch_size, shape, conditioning=None, eta=0.0, x_T=None, verbose=False,
+               unconditional_guidance_scale=1.0, unconditional_conditioning=None, untill_fake_t=None, **kwargs):
+        from . import ops
+        if eta != 0:
+            raise ValueError("ddim_eta must be 0 for PLMS (plms.py:27-28)")
+        self.make_schedule(S, eta)
+        dev = x_T.device if x_T is not None and x_T.is_cuda else next(self.model.parameters()).device
+        C, H, W = shape
+        img = torch.randn((batch_size, C, H, W), device=dev) if x_T is None else x_T.to(dev).clone()
+        cfg = conditioning is not None and unconditional_conditioning is not None and unconditional_guidance_scale != 1.0
+        ctx = None
+        if conditioning is not None:
+            ctx = conditioning.to(dev).float()
+            if cfg:
+                ctx = torch.cat([unconditional_conditioning.to(dev).float(), ctx], dim=0)
+        ts = [float(t) for t in np.flip(self.ddim_timesteps)]
+        self._tables = None
+        if self.ckpt is not None:
+            tot, t_max = self.ddpm_num_timesteps // S, S - 1
+            self._tables = [self.ckpt[f"act_{int(t_max - (int(t) - 1) // tot)}"] for t in ts]
+        eps_fn = self._eps_fn(batch_size, ctx, cfg, float(unconditional_guidance_scale))
+        if self._tables is not None and hasattr(self.model, "build_engine"):
+            self._eng.set_schedule(ts, self._tables)
+        rows = torch.tensor(self.coefficient_rows(), dtype=torch.float32, device=dev)   # [S, 5] in sampling order
+        old = []                                     # newest first
+        x0 = torch.empty_like(img)
+        e_comb = torch.empty_like(img)
+        n_run = S if not untill_fake_t else min(S, untill_fake_t - 1)
+        for k in range(n_run):
+            e_t = eps_fn(img, ts[k], k).contiguous()
+            if not old:
+                # pseudo improved Euler: x_prev from e_t, second evaluation there, average
+                x_prev = torch.empty_like(img)
+                ops.ddim_update(img, e_t, rows[k], x_prev)
+                e_next = eps_fn(x_prev, ts[min(k + 1, S - 1)], min(k + 1, S - 1)).contiguous()
+                ops.plms_eps(e_t, ["euler", e_next], e_comb)
+            else:
+                ops.plms_eps(e_t, old[:3], e_comb)
+            ops.ddim_update(img, e_comb, rows[k], img, x0)
+            old = [e_t] + old[:2]
+        return img, {"x_inter": [x_T, img], "pred_x0": [x_T, x0]}
