@@ -613,7 +613,10 @@ def test_adaround_kernels_vs_autograd(dev):
 @pytest.mark.parametrize("n,h,w,cin,cout,cpg,ch_off,groups", [
     (2, 32, 32, 64, 224, 7, 0, 32),        # plain: 32 groups of 7 channels
     (2, 16, 16, 64, 448, 35, 672, 32),     # second part of a 672+448 concat: groups of 35 straddle the boundary
-    (3, 8, 8, 64, 64, 2, 0, 32),           # tile spans two images: the launcher falls back to a separate pass
+    (3, 8, 8, 64, 64, 2, 0, 32),           # tile spans two images (per-image sums in the epilogue), odd batch tail
+    (16, 8, 8, 96, 896, 28, 0, 32),        # LDM-4 lowest resolution: CTA pairs, tiles of two images
+    (5, 4, 4, 64, 256, 8, 0, 32),          # CIFAR lowest resolution: eight images per tile, batch tail
+    (4, 8, 8, 64, 1792, 56, 0, 32),        # wide layer: 2 x tile_n x 8 B may exceed the smem budget -> separate pass
 ])
 def test_conv_epilogue_gn_stats(dev, n, h, w, cin, cout, cpg, ch_off, groups):
     ops, q = _ops(), _qref()

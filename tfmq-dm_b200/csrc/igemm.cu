@@ -81,9 +81,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint8_t* p_ring = u_ring + (size_t)SU * p.u_bytes;
   uint8_t* ebuf = W4 ? p_ring + (size_t)SP * p.p_bytes : smem + (size_t)S * p.stage_bytes;   // 2 epilogue chunks
   float4* chp = reinterpret_cast<float4*>(ebuf + 2 * 128 * 32 * 4);        // [tile_n] per-channel constants
-  float2* cstat = reinterpret_cast<float2*>(ebuf + 2 * 128 * 32 * 4 + p.tile_n * 16);  // [tile_n] per-channel (sum, sumsq)
-  float2* cpart = cstat + p.tile_n;     // [2][parts][chunk_w] row-block partials of the last two chunks
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ebuf + 2 * 128 * 32 * 4 + p.tile_n * 24 + 2 * 256 * 8);
+  // [stat_imgs][tile_n] per-image, per-channel (sum, sumsq): a tile of a small feature map spans several images
+  float2* cstat = reinterpret_cast<float2*>(ebuf + 2 * 128 * 32 * 4 + p.tile_n * 16);
+  float2* cpart = cstat + p.stat_imgs * p.tile_n;     // [2][parts][chunk_w] row-block partials of the last two chunks
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ebuf + 2 * 128 * 32 * 4 + p.tile_n * 16 + p.stat_imgs * p.tile_n * 8 +
+                                               2 * 256 * 8);
   // barrier slots (8 bytes each, 32 slots): the two pipelines use the first 24 differently
   uint64_t* full_tma = bars;            // [<=8] TMA bytes landed (w4a8: the A tile; CTA pair: of both CTAs, at the leader)
   uint64_t* empty = bars + 8;           // [<=8] UMMAs that read the stage (w4a8: the A slot) retired
@@ -620,11 +622,13 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (p.n_stat > 0) {
           // GroupNorm statistics of the finished output values: thread = (column, block of rows) sums its rows;
           // the partials of the previous chunk are combined here too, in a fixed order (bit-reproducible)
-          if (ci > 0 && et < CW) {
-            const float2* pp = cpart + ((g - 1) & 1) * ET + et;
+          if (ci > 0 && et < CW * p.stat_imgs) {
+            // image `im` of the tile owns the row blocks [im * ppi, (im + 1) * ppi)
+            const int im = et / CW, col = et - im * CW, ppi = (ET / CW) / p.stat_imgs;
+            const float2* pp = cpart + ((g - 1) & 1) * ET + im * ppi * CW + col;
             float a1 = 0.f, a2 = 0.f;
-            for (int k = 0; k < ET / CW; ++k) a1 += pp[k * CW].x, a2 += pp[k * CW].y;
-            cstat[(ci - 1) * CW + et] = make_float2(a1, a2);
+            for (int k = 0; k < ppi; ++k) a1 += pp[k * CW].x, a2 += pp[k * CW].y;
+            cstat[im * p.tile_n + (ci - 1) * CW + col] = make_float2(a1, a2);
           }
           cpart[(g & 1) * ET + et] = (CW == 32) ? chunk_col_partial<32>(buf, et) : chunk_col_partial<16>(buf, et);   // [part][col]
         }
@@ -647,27 +651,31 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       }
       if (p.n_stat > 0) {
         named_bar_sync(1, ET);                // the last chunk's partials are written
-        if (et < CW) {
-          const float2* pp = cpart + ((g - 1) & 1) * ET + et;
+        if (et < CW * p.stat_imgs) {
+          const int im = et / CW, col = et - im * CW, ppi = (ET / CW) / p.stat_imgs;
+          const float2* pp = cpart + ((g - 1) & 1) * ET + im * ppi * CW + col;
           float a1 = 0.f, a2 = 0.f;
-          for (int k = 0; k < ET / CW; ++k) a1 += pp[k * CW].x, a2 += pp[k * CW].y;
-          cstat[(nchunks - 1) * CW + et] = make_float2(a1, a2);
+          for (int k = 0; k < ppi; ++k) a1 += pp[k * CW].x, a2 += pp[k * CW].y;
+          cstat[im * p.tile_n + (nchunks - 1) * CW + col] = make_float2(a1, a2);
         }
         named_bar_sync(1, ET);                // every chunk's sums are in cstat
         for (int k = 0; k < p.n_stat; ++k) {
           const tfmq_gn_target tg = p.stat[k];
           const int g_lo = (tg.ch_off + c_out0) / tg.cpg;
           const int g_hi = (tg.ch_off + c_out0 + p.tile_n - 1) / tg.cpg;
-          for (int gi = g_lo + et; gi <= g_hi; gi += ET) {
+          const int ng = g_hi - g_lo + 1;
+          for (int idx = et; idx < ng * p.stat_imgs; idx += ET) {
+            const int im = idx / ng, gi = g_lo + (idx - im * ng);
+            if (n0 + im >= p.n_img) continue;       // batch tail: rows past the batch carry no image
             const int ch_lo = max(gi * tg.cpg - tg.ch_off, c_out0) - c_out0;
             const int ch_hi = min((gi + 1) * tg.cpg - tg.ch_off, c_out0 + p.tile_n) - c_out0;
             double a1 = 0.0, a2 = 0.0;
             for (int ch = ch_lo; ch < ch_hi; ++ch) {
-              const float2 v2 = cstat[ch];
+              const float2 v2 = cstat[im * p.tile_n + ch];
               a1 += (double)v2.x;
               a2 += (double)v2.y;
             }
-            double* dst = tg.stats + ((long long)n0 * tg.groups + gi) * 2;
+            double* dst = tg.stats + ((long long)(n0 + im) * tg.groups + gi) * 2;
             atomicAdd(dst, a1);
             atomicAdd(dst + 1, a2);
           }
@@ -749,9 +757,10 @@ static int launch_igemm(tfmq_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap
                         const CUtensorMap& tmB2, IgemmParams& p, cudaStream_t stream, const char* name) {
   // shared-memory plan
   if (CG == 1) p.b_rows[0] = p.tile_n, p.b_row0[0] = 0, p.b_rows[1] = 0, p.b_row0[1] = 0;
+  if (p.stat_imgs < 1) p.stat_imgs = 1;
   const uint32_t extra = 1024u /*alignment slack*/ + 2u * 128u * 32u * 4u /*epilogue chunks*/ +
-                         (uint32_t)p.tile_n * 24u /*chp + GN channel sums*/ + 2u * 256u * 8u /*GN partials*/ +
-                         512u /*barriers*/;
+                         (uint32_t)p.tile_n * 16u /*chp*/ + (uint32_t)(p.stat_imgs * p.tile_n) * 8u /*GN channel sums*/ +
+                         2u * 256u * 8u /*GN partials*/ + 512u /*barriers*/;
   static const int stages_env = getenv("TFMQ_IGEMM_STAGES") ? atoi(getenv("TFMQ_IGEMM_STAGES")) : 0;   // experiments
   int stages;
   size_t smem;
@@ -937,9 +946,11 @@ extern "C" int tfmq_conv_w4a8(tfmq_ctx* ctx, const tfmq_conv_w4a8_desc* d, void*
   p.out = d->out, p.out_ld = d->out_ld, p.bias = d->bias, p.wscale = d->wdelta, p.wsum = d->wsum, p.wzp = d->wzp;
   p.aq = d->aq, p.emb = d->emb, p.emb_ld = d->emb_ld, p.res = d->res, p.res_ld = d->res_ld;
   TFMQ_REQUIRE(d->n_stat >= 0 && d->n_stat <= 2, TFMQ_ERR_ARG, "conv_w4a8: n_stat");
-  const bool fuse_stats = d->n_stat > 0 && g.tn == 1;
+  // GroupNorm statistics in the epilogue; a tile of a small feature map spans tn images (per-image sums, <= 8 KB of smem)
+  const bool fuse_stats = d->n_stat > 0 && g.tn * p.tile_n * 8 <= 8192;
   if (fuse_stats) {
     p.n_stat = d->n_stat;
+    p.stat_imgs = g.tn;
     for (int i = 0; i < d->n_stat; ++i) p.stat[i] = d->stat[i];
   }
 
@@ -1013,9 +1024,11 @@ extern "C" int tfmq_conv_fp(tfmq_ctx* ctx, const tfmq_conv_fp_desc* d, void* str
   p.res = d->res, p.res_ld = d->res_ld;
   p.emb = d->emb, p.emb_ld = d->emb_ld;
   TFMQ_REQUIRE(d->n_stat >= 0 && d->n_stat <= 2, TFMQ_ERR_ARG, "conv_fp: n_stat");
-  const bool fuse_stats = d->n_stat > 0 && g.tn == 1;
+  // GroupNorm statistics in the epilogue; a tile of a small feature map spans tn images (per-image sums, <= 8 KB of smem)
+  const bool fuse_stats = d->n_stat > 0 && g.tn * p.tile_n * 8 <= 8192;
   if (fuse_stats) {
     p.n_stat = d->n_stat;
+    p.stat_imgs = g.tn;
     for (int i = 0; i < d->n_stat; ++i) p.stat[i] = d->stat[i];
   }
 
@@ -1088,9 +1101,11 @@ extern "C" int tfmq_conv_h16(tfmq_ctx* ctx, const tfmq_conv_h16_desc* d, void* s
   p.res = d->res, p.res_ld = d->res_ld;
   p.emb = d->emb, p.emb_ld = d->emb_ld;
   TFMQ_REQUIRE(d->n_stat >= 0 && d->n_stat <= 2, TFMQ_ERR_ARG, "conv_h16: n_stat");
-  const bool fuse_stats = d->n_stat > 0 && g.tn == 1;
+  // GroupNorm statistics in the epilogue; a tile of a small feature map spans tn images (per-image sums, <= 8 KB of smem)
+  const bool fuse_stats = d->n_stat > 0 && g.tn * p.tile_n * 8 <= 8192;
   if (fuse_stats) {
     p.n_stat = d->n_stat;
+    p.stat_imgs = g.tn;
     for (int i = 0; i < d->n_stat; ++i) p.stat[i] = d->stat[i];
   }
 

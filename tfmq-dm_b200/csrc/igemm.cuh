@@ -53,7 +53,8 @@ struct IgemmParams {
   const float* res;
   long long res_ld;
   int32_t* out_i32;  // MODE_I8: raw accumulators [pixels][cout]
-  int n_stat;        // fused GroupNorm statistics of the output (only when tn == 1)
+  int n_stat;        // fused GroupNorm statistics of the output
+  int stat_imgs;     // images a tile spans when statistics are fused (tn), else 1
   tfmq_gn_target stat[2];
   int dbg;           // debug: bit0 = producer skips the TMA loads (timing experiments only, TFMQ_IGEMM_DBG)
   long long* prof;   // debug: per-CTA phase cycle counters [grid][16] (TFMQ_IGEMM_PROF=1), else null
