@@ -474,6 +474,9 @@ def test_ddim_update_and_embedding(dev):
     (2, 1, 256, 256, 256, "ddim"),     # CIFAR single-head (generic path)
     (2, 8, 100, 77, 40, "tokens"),     # SD cross-attention shape, ragged tq / tk
     (1, 8, 64, 64, 160, "tokens"),
+    (2, 8, 200, 77, 160, "tokens"),    # SD deepest cross-attention, ragged (fp16-split kernel at d = 160)
+    (1, 8, 300, 300, 40, "tokens"),    # d = 40 zero-padded to three k16 steps, ragged tails
+    (2, 4, 130, 70, 80, "tokens"),
 ])
 def test_attention_fp32(dev, b, heads, tq, tk, d, layout):
     ops = _ops()

@@ -320,6 +320,7 @@ __global__ void __launch_bounds__(128) attn_h16_kernel(const AttnP P) {
   __half* Vhi = Klo + ATT_TK * KP;   // [key][KP] like K
   __half* Vlo = Vhi + ATT_TK * KP;
   const tfmq_attn_desc& a = P.a;
+  const int dr = a.d;                // real head dim <= D (d = 40 runs zero-padded as D = 48)
   const int bh = blockIdx.y, b = bh / a.heads, h = bh % a.heads;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
@@ -336,10 +337,12 @@ __global__ void __launch_bounds__(128) attn_h16_kernel(const AttnP P) {
     const float* p1 = qb + (long long)r1 * a.q_st;
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks) {
-      const float2 x0 = *reinterpret_cast<const float2*>(p0 + ks * 16 + 2 * t);
-      const float2 x1 = *reinterpret_cast<const float2*>(p1 + ks * 16 + 2 * t);
-      const float2 x2 = *reinterpret_cast<const float2*>(p0 + ks * 16 + 2 * t + 8);
-      const float2 x3 = *reinterpret_cast<const float2*>(p1 + ks * 16 + 2 * t + 8);
+      const float2 z2 = make_float2(0.f, 0.f);
+      const int ca = ks * 16 + 2 * t, cb = ca + 8;
+      const float2 x0 = ca < dr ? *reinterpret_cast<const float2*>(p0 + ca) : z2;
+      const float2 x1 = ca < dr ? *reinterpret_cast<const float2*>(p1 + ca) : z2;
+      const float2 x2 = cb < dr ? *reinterpret_cast<const float2*>(p0 + cb) : z2;
+      const float2 x3 = cb < dr ? *reinterpret_cast<const float2*>(p1 + cb) : z2;
       // scores are kept in the log2 domain (scale * log2 e folded into q): softmax is then one MUFU.EX2 per element
       split2_h(x0.x * qs, x0.y * qs, qh[ks][0], ql[ks][0]);
       split2_h(x1.x * qs, x1.y * qs, qh[ks][1], ql[ks][1]);
@@ -357,7 +360,7 @@ __global__ void __launch_bounds__(128) attn_h16_kernel(const AttnP P) {
     const int i = threadIdx.x + it * 128;
     const int j = i / (D / 4), c4 = (i - j * (D / 4)) * 4;
     kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
-    if (k0 + j < a.tk) {
+    if (k0 + j < a.tk && c4 < dr) {
       kv = *reinterpret_cast<const float4*>(kb + (long long)(k0 + j) * a.k_st + c4);
       vv = *reinterpret_cast<const float4*>(vb + (long long)(k0 + j) * a.v_st + c4);
     }
@@ -482,6 +485,7 @@ __global__ void __launch_bounds__(128) attn_h16_kernel(const AttnP P) {
   const int r0 = q0 + g, r1 = q0 + g + 8;
 #pragma unroll
   for (int nt = 0; nt < NT; ++nt) {
+    if (nt * 8 + 2 * t >= dr) continue;
     if (r0 < a.tq)
       *reinterpret_cast<float2*>(ob + (long long)r0 * a.o_st + nt * 8 + 2 * t) =
           make_float2(o[nt][0] * i0, o[nt][1] * i0);
@@ -569,9 +573,12 @@ extern "C" int tfmq_attention(tfmq_ctx* ctx, const tfmq_attn_desc* d, void* stre
   if (vec_ok) {
     switch (d->d) {
       case 32: return q_ok ? launch_h16<32>(ctx, P, st) : launch_mma<32>(ctx, P, st);
-      case 40: return launch_mma<40>(ctx, P, st);
+      case 40: return q_ok ? launch_h16<48>(ctx, P, st) : launch_mma<40>(ctx, P, st);   // zero-padded to 3 k16 steps
       case 64: return q_ok ? launch_h16<64>(ctx, P, st) : launch_mma<64>(ctx, P, st);
       case 80: return q_ok ? launch_h16<80>(ctx, P, st) : launch_mma<80>(ctx, P, st);
+      case 160:
+        if (q_ok) return launch_h16<160>(ctx, P, st);      // SD v1.4's deepest levels
+        break;
       default: break;
     }
   }

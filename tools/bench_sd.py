@@ -57,6 +57,7 @@ print(f"{name}: engine batch {nb} (guidance halves included): {ms:.2f} ms per st
 # eager per-op timing by kernel family
 names = ["act_prepare", "conv_w4a8", "conv_h16", "conv_fp", "attention", "gn_stats_part", "linear_small", "conv_in", "conv_out"]
 acc = collections.defaultdict(lambda: [0, []])
+attn_calls = []
 orig = {k: getattr(ops, k) for k in names}
 
 
@@ -68,6 +69,8 @@ def wrap(k):
         e_.record()
         acc[k][0] += 1
         acc[k][1].append((s_, e_))
+        if k == "attention":
+            attn_calls.append(((a[4], a[5], a[6], a[7], a[8]), s_, e_))      # (b, heads, tq, tk, d)
         return r
     return f
 
@@ -85,3 +88,11 @@ for k, (cnt, evs) in acc.items():
     tot += us
 for us, k, cnt in sorted(rows, reverse=True):
     print(f"  {k:16s} n={cnt:4d} {us:9.1f} us  {100 * us / tot:5.1f} %")
+
+by_shape = collections.defaultdict(lambda: [0, 0.0])
+for shape, a_, b_ in attn_calls:
+    by_shape[shape][0] += 1
+    by_shape[shape][1] += a_.elapsed_time(b_) * 1e3
+print("  attention by (batch, heads, Tq, Tk, d):")
+for shape, (cnt, us) in sorted(by_shape.items(), key=lambda kv: -kv[1][1]):
+    print(f"    {shape}  n={cnt:2d} {us:9.1f} us")
