@@ -477,6 +477,10 @@ def test_ddim_update_and_embedding(dev):
     (2, 8, 200, 77, 160, "tokens"),    # SD deepest cross-attention, ragged (fp16-split kernel at d = 160)
     (1, 8, 300, 300, 40, "tokens"),    # d = 40 zero-padded to three k16 steps, ragged tails
     (2, 4, 130, 70, 80, "tokens"),
+    (2, 1, 200, 200, 384, "tokens"),   # cin256: one wide head, warps split the head dimension
+    (2, 1, 70, 70, 576, "tokens"),
+    (1, 1, 64, 64, 960, "tokens"),
+    (3, 1, 100, 1, 384, "tokens"),     # cin256 cross-attention over a single class token
 ])
 def test_attention_fp32(dev, b, heads, tq, tk, d, layout):
     ops = _ops()

@@ -5,8 +5,9 @@
 //    two-term fp16 splits of the fp32 operands, 3 products per term pair: fp32-accurate.
 //  * attn_mma_kernel<D>  : head dim 40 (not a multiple of 16) or unaligned q: the same with m16n8k8 tf32.
 //    The tcgen05/TMEM version of these kernels is the next step.
-//  * attn_generic_kernel<G> : any head dim (CIFAR d=256, cin d=384..960): G lanes share one
-//    query, FFMA only.
+//  * attn_wide_kernel<DW, NW, KT> : one WIDE head (CIFAR d = 256, cin256 d = 384 / 576 / 960): the warps of a CTA split
+//    the head dimension; same fp16-split tensor-core arithmetic.
+//  * attn_generic_kernel<G> : any other head dim or unaligned operands: G lanes share one query, FFMA only.
 #include <cuda_fp16.h>
 
 #include "ctx.h"
@@ -495,6 +496,212 @@ __global__ void __launch_bounds__(128) attn_h16_kernel(const AttnP P) {
   }
 }
 
+// ------------------------------------------------------------------ tensor-core kernel for WIDE heads
+// One head of 256 ... 960 channels (cin256's single-head SpatialTransformers, CIFAR's AttnBlock): the accumulators of
+// a whole head do not fit one warp's registers, so the NW warps of a CTA split the HEAD DIMENSION instead of the
+// queries.  A CTA owns 16 queries; warp w owns channels [w DW, (w + 1) DW):
+//   * S = Q K^T : every warp multiplies its channel slice (a K-split of the product); the partial 16 x KT tiles go
+//     through shared memory and every warp sums all of them in the same order, so all warps hold the SAME scores
+//     and run the same online softmax (identical m, l);
+//   * O += P V  : every warp multiplies P with its DW columns of V and keeps only those DW accumulator columns.
+// No product is computed twice.  Same arithmetic as attn_h16_kernel (fp16 hi/lo split, 3 products, log2-domain softmax).
+template <int DW, int NW, int KT, int QG>
+__global__ void __launch_bounds__(NW * QG * 32) attn_wide_kernel(const AttnP P) {
+  constexpr int KS = DW / 16;        // k-steps of this warp's slice of Q K^T
+  constexpr int NT = DW / 8;         // n-tiles of this warp's slice of P V
+  constexpr int ST = KT / 8;         // n-tiles of the score tile
+  constexpr int THREADS = NW * QG * 32;   // QG groups of NW warps, one 16-query tile each, sharing the staged K / V tile
+  static_assert(DW % 16 == 0 && NT % 2 == 0 && KT % 16 == 0, "geometry");
+  const tfmq_attn_desc& a = P.a;
+  const int d = a.d;                 // == DW * NW
+  const int KP = d + 8;              // row pitch (halves): 16-byte aligned rows, conflict-free fragment loads
+  extern __shared__ __half smh[];
+  __half* Khi = smh;
+  __half* Klo = Khi + KT * KP;
+  __half* Vhi = Klo + KT * KP;
+  __half* Vlo = Vhi + KT * KP;
+  float* Sp_all = reinterpret_cast<float*>(Vlo + KT * KP);  // [QG][NW][16][KT] partial scores
+  const int bh = blockIdx.y, b = bh / a.heads, h = bh % a.heads;
+  const int qg = (threadIdx.x >> 5) / NW, warp = (threadIdx.x >> 5) % NW, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int q0 = (blockIdx.x * QG + qg) * 16;
+  float* Sp = Sp_all + qg * NW * 16 * KT;
+  const int dw0 = warp * DW;
+  const float* qb = a.q + (long long)b * a.q_sb + (long long)h * a.q_sh;
+  const float* kb = a.k + (long long)b * a.k_sb + (long long)h * a.k_sh;
+  const float* vb = a.v + (long long)b * a.v_sb + (long long)h * a.v_sh;
+
+  uint32_t qh[KS][4], ql[KS][4];
+  const float qs = a.scale * 1.4426950408889634f;
+  {
+    const int r0 = min(q0 + g, a.tq - 1), r1 = min(q0 + g + 8, a.tq - 1);
+    const float* p0 = qb + (long long)r0 * a.q_st + dw0;
+    const float* p1 = qb + (long long)r1 * a.q_st + dw0;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      const float2 x0 = *reinterpret_cast<const float2*>(p0 + ks * 16 + 2 * t);
+      const float2 x1 = *reinterpret_cast<const float2*>(p1 + ks * 16 + 2 * t);
+      const float2 x2 = *reinterpret_cast<const float2*>(p0 + ks * 16 + 2 * t + 8);
+      const float2 x3 = *reinterpret_cast<const float2*>(p1 + ks * 16 + 2 * t + 8);
+      split2_h(x0.x * qs, x0.y * qs, qh[ks][0], ql[ks][0]);
+      split2_h(x1.x * qs, x1.y * qs, qh[ks][1], ql[ks][1]);
+      split2_h(x2.x * qs, x2.y * qs, qh[ks][2], ql[ks][2]);
+      split2_h(x3.x * qs, x3.y * qs, qh[ks][3], ql[ks][3]);
+    }
+  }
+  float o[NT][4];
+#pragma unroll
+  for (int i = 0; i < NT; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+  const int lm_key = ((lane >> 3) & 1) * 8 + (lane & 7), lm_dim = (lane >> 4) * 8;
+  const int vec_per_row = d >> 2;
+
+  for (int k0 = 0; k0 < a.tk; k0 += KT) {
+    __syncthreads();
+    const int kn = min(KT, a.tk - k0);
+    // stage the K and V rows of this key tile (all channels) as fp16 hi / lo planes
+    for (int i = threadIdx.x; i < KT * vec_per_row; i += THREADS) {
+      const int j = i / vec_per_row, c4 = (i - j * vec_per_row) * 4;
+      float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
+      if (j < kn) {
+        kv = *reinterpret_cast<const float4*>(kb + (long long)(k0 + j) * a.k_st + c4);
+        vv = *reinterpret_cast<const float4*>(vb + (long long)(k0 + j) * a.v_st + c4);
+      }
+      uint32_t h01, l01, h23, l23;
+      split2_h(kv.x, kv.y, h01, l01);
+      split2_h(kv.z, kv.w, h23, l23);
+      *reinterpret_cast<uint2*>(Khi + j * KP + c4) = make_uint2(h01, h23);
+      *reinterpret_cast<uint2*>(Klo + j * KP + c4) = make_uint2(l01, l23);
+      split2_h(vv.x, vv.y, h01, l01);
+      split2_h(vv.z, vv.w, h23, l23);
+      *reinterpret_cast<uint2*>(Vhi + j * KP + c4) = make_uint2(h01, h23);
+      *reinterpret_cast<uint2*>(Vlo + j * KP + c4) = make_uint2(l01, l23);
+    }
+    __syncthreads();
+
+    // ---- partial S over this warp's channel slice
+    float s[ST][4];
+#pragma unroll
+    for (int nt = 0; nt < ST; ++nt) {
+      s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+      const uint32_t* kh = reinterpret_cast<const uint32_t*>(Khi + (nt * 8 + g) * KP + dw0) + t;
+      const uint32_t* kl = reinterpret_cast<const uint32_t*>(Klo + (nt * 8 + g) * KP + dw0) + t;
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        const uint32_t bh0 = kh[ks * 8], bh1 = kh[ks * 8 + 4];
+        const uint32_t bl0 = kl[ks * 8], bl1 = kl[ks * 8 + 4];
+        mma_f16(s[nt], ql[ks], bh0, bh1);
+        mma_f16(s[nt], qh[ks], bl0, bl1);
+        mma_f16(s[nt], qh[ks], bh0, bh1);
+      }
+    }
+    // exchange: Sp[w][row][col], fragment (rows g, g + 8; cols nt * 8 + 2t, + 1)
+    {
+      float* mine = Sp + warp * 16 * KT;
+#pragma unroll
+      for (int nt = 0; nt < ST; ++nt) {
+        *reinterpret_cast<float2*>(mine + g * KT + nt * 8 + 2 * t) = make_float2(s[nt][0], s[nt][1]);
+        *reinterpret_cast<float2*>(mine + (g + 8) * KT + nt * 8 + 2 * t) = make_float2(s[nt][2], s[nt][3]);
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int nt = 0; nt < ST; ++nt) {
+      float2 a0 = make_float2(0.f, 0.f), a1 = a0;
+      for (int w = 0; w < NW; ++w) {         // the same order in every warp: identical sums
+        const float2 p0 = *reinterpret_cast<const float2*>(Sp + w * 16 * KT + g * KT + nt * 8 + 2 * t);
+        const float2 p1 = *reinterpret_cast<const float2*>(Sp + w * 16 * KT + (g + 8) * KT + nt * 8 + 2 * t);
+        a0.x += p0.x, a0.y += p0.y, a1.x += p1.x, a1.y += p1.y;
+      }
+      s[nt][0] = a0.x, s[nt][1] = a0.y, s[nt][2] = a1.x, s[nt][3] = a1.y;
+    }
+    // ---- online softmax (log2 domain), identical in every warp
+    float mx0 = m0, mx1 = m1;
+#pragma unroll
+    for (int nt = 0; nt < ST; ++nt) {
+      const int c = nt * 8 + 2 * t;
+      if (c >= kn) s[nt][0] = -INFINITY, s[nt][2] = -INFINITY;
+      if (c + 1 >= kn) s[nt][1] = -INFINITY, s[nt][3] = -INFINITY;
+      mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+      mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float c0 = ex2f(m0 - mx0), c1 = ex2f(m1 - mx1);
+    m0 = mx0, m1 = mx1;
+    float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < ST; ++nt) {
+      s[nt][0] = ex2f(s[nt][0] - mx0);
+      s[nt][1] = ex2f(s[nt][1] - mx0);
+      s[nt][2] = ex2f(s[nt][2] - mx1);
+      s[nt][3] = ex2f(s[nt][3] - mx1);
+      rs0 += s[nt][0] + s[nt][1];
+      rs1 += s[nt][2] + s[nt][3];
+    }
+    l0 = l0 * c0 + rs0;
+    l1 = l1 * c1 + rs1;
+#pragma unroll
+    for (int i = 0; i < NT; ++i) {
+      o[i][0] *= c0, o[i][1] *= c0;
+      o[i][2] *= c1, o[i][3] *= c1;
+    }
+    // ---- O[:, slice] += P V[:, slice]
+#pragma unroll
+    for (int kt = 0; kt < KT / 16; ++kt) {
+      uint32_t ph[4], pl[4];
+      split2_h(s[2 * kt][0], s[2 * kt][1], ph[0], pl[0]);
+      split2_h(s[2 * kt][2], s[2 * kt][3], ph[1], pl[1]);
+      split2_h(s[2 * kt + 1][0], s[2 * kt + 1][1], ph[2], pl[2]);
+      split2_h(s[2 * kt + 1][2], s[2 * kt + 1][3], ph[3], pl[3]);
+#pragma unroll
+      for (int nt = 0; nt < NT; nt += 2) {
+        uint32_t bh[4], bl[4];
+        ldmatrix_x4_trans(bh, Vhi + (kt * 16 + lm_key) * KP + dw0 + nt * 8 + lm_dim);
+        ldmatrix_x4_trans(bl, Vlo + (kt * 16 + lm_key) * KP + dw0 + nt * 8 + lm_dim);
+        mma_f16(o[nt], pl, bh[0], bh[1]);
+        mma_f16(o[nt], ph, bl[0], bl[1]);
+        mma_f16(o[nt], ph, bh[0], bh[1]);
+        mma_f16(o[nt + 1], pl, bh[2], bh[3]);
+        mma_f16(o[nt + 1], ph, bl[2], bl[3]);
+        mma_f16(o[nt + 1], ph, bh[2], bh[3]);
+      }
+    }
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float i0 = 1.f / l0, i1 = 1.f / l1;
+  float* ob = a.o + (long long)b * a.o_sb + (long long)h * a.o_sh + dw0;
+  const int r0 = q0 + g, r1 = q0 + g + 8;
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+    if (r0 < a.tq)
+      *reinterpret_cast<float2*>(ob + (long long)r0 * a.o_st + nt * 8 + 2 * t) = make_float2(o[nt][0] * i0, o[nt][1] * i0);
+    if (r1 < a.tq)
+      *reinterpret_cast<float2*>(ob + (long long)r1 * a.o_st + nt * 8 + 2 * t) = make_float2(o[nt][2] * i1, o[nt][3] * i1);
+  }
+}
+
+template <int DW, int NW, int KT, int QG>
+static int launch_wide(tfmq_ctx* ctx, const AttnP& P, cudaStream_t st) {
+  const size_t smem = (size_t)(4 * KT * (P.a.d + 8)) * sizeof(__half) + (size_t)QG * NW * 16 * KT * sizeof(float);
+  auto kern = attn_wide_kernel<DW, NW, KT, QG>;
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return tfmq_fail(ctx, TFMQ_ERR_CUDA, "attention: smem attr: %s", cudaGetErrorString(e));
+    smem_set = smem;
+  }
+  dim3 grid((P.a.tq + 16 * QG - 1) / (16 * QG), P.a.b * P.a.heads);
+  kern<<<grid, NW * QG * 32, smem, st>>>(P);
+  TFMQ_LAUNCH_CHECK("attention_wide");
+  return TFMQ_OK;
+}
+
 template <int D>
 static int launch_h16(tfmq_ctx* ctx, const AttnP& P, cudaStream_t st) {
   const size_t smem = (size_t)(4 * ATT_TK * (D + 8)) * sizeof(__half);
@@ -579,6 +786,10 @@ extern "C" int tfmq_attention(tfmq_ctx* ctx, const tfmq_attn_desc* d, void* stre
       case 160:
         if (q_ok) return launch_h16<160>(ctx, P, st);      // SD v1.4's deepest levels
         break;
+      case 256: if (q_ok) return launch_wide<64, 4, 64, 2>(ctx, P, st); break;    // CIFAR AttnBlock (one head)
+      case 384: if (q_ok) return launch_wide<96, 4, 48, 2>(ctx, P, st); break;    // cin256, 32x32
+      case 576: if (q_ok) return launch_wide<96, 6, 32, 1>(ctx, P, st); break;    // cin256, 16x16
+      case 960: if (q_ok) return launch_wide<160, 6, 16, 1>(ctx, P, st); break;   // cin256, 8x8
       default: break;
     }
   }
