@@ -408,19 +408,20 @@ def test_linear_grouped_equals_separate_launches(dev):
         assert a["out"].abs().max().item() > 0
 
 
-def test_conv_in_out(dev):
+@pytest.mark.parametrize("hh,ww", [(16, 16), (12, 20), (40, 8)])     # widths that are / are not multiples of 8
+def test_conv_in_out(dev, hh, ww):
     ops = _ops()
     g = torch.Generator().manual_seed(2)
-    x = torch.randn(2, 3, 16, 16, generator=g)
+    x = torch.randn(2, 3, hh, ww, generator=g)
     w = torch.randn(64, 3, 3, 3, generator=g) * 0.2
     b = torch.randn(64, generator=g)
-    out = torch.empty((2, 16, 16, 64), device=dev)
+    out = torch.empty((2, hh, ww, 64), device=dev)
     ops.conv_in(x.to(dev), w.to(dev), b.to(dev), out)
     assert (out.cpu().permute(0, 3, 1, 2) - F.conv2d(x, w, b, padding=1)).abs().max().item() < 1e-5
-    h = torch.randn(2, 64, 16, 16, generator=g)
+    h = torch.randn(2, 64, hh, ww, generator=g)
     w2 = torch.randn(3, 64, 3, 3, generator=g) * 0.05
     b2 = torch.randn(3, generator=g)
-    o2 = torch.empty((2, 3, 16, 16), device=dev)
+    o2 = torch.empty((2, 3, hh, ww), device=dev)
     ops.conv_out(nhwc(h).to(dev), w2.to(dev), b2.to(dev), o2)
     assert (o2.cpu() - F.conv2d(h, w2, b2, padding=1)).abs().max().item() < 1e-5
 

@@ -129,6 +129,7 @@ __global__ void __launch_bounds__(LIN_THREADS) linear_grouped_kernel(const tfmq_
 // conv_in: NCHW (cin<=4) -> NHWC, 3x3 pad 1.  CTA = 16 pixels x 16 channel groups; weights transposed in
 // smem as ws[tap*cin][cout] so each thread reads float4 of 4 consecutive output channels.
 constexpr int CIN_PIX = 16;
+constexpr int CIN_GROUPS = 8;     // pixel groups per CTA: the transposed weight staging is shared by 128 pixels
 __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                       const float* __restrict__ bias, int n, int h, int wd, int cin,
                                                       int cout, float* __restrict__ out, long long out_ld) {
@@ -140,9 +141,10 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ 
   }
   __syncthreads();
   const long long total = (long long)n * h * wd;
-  const long long pix = blockIdx.x * (long long)CIN_PIX + (threadIdx.x >> 4);
-  if (pix >= total) return;
   const int cg = threadIdx.x & 15;
+  for (int grp = 0; grp < CIN_GROUPS; ++grp) {
+  const long long pix = ((long long)blockIdx.x * CIN_GROUPS + grp) * CIN_PIX + (threadIdx.x >> 4);
+  if (pix >= total) return;
   const int xx = (int)(pix % wd);
   const int yy = (int)((pix / wd) % h);
   const int nn = (int)(pix / ((long long)wd * h));
@@ -176,6 +178,7 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ 
       }
     }
     *reinterpret_cast<float4*>(out + pix * out_ld + co) = acc;
+  }
   }
 }
 
@@ -225,6 +228,63 @@ __global__ void __launch_bounds__(256) conv_out_kernel(const float* __restrict__
     const float r0 = warp_sum(acc.x), r1 = warp_sum(acc.y), r2 = warp_sum(acc.z), r3 = warp_sum(acc.w);
     const float rl = lane == 0 ? r0 : lane == 1 ? r1 : lane == 2 ? r2 : r3;
     if (lane < cout) out[(((long long)nn * cout + lane) * h + yy) * wd + xx] = rl + (bias ? bias[lane] : 0.f);
+  }
+}
+
+// conv_out for widths that are multiples of 8: a warp owns 8 consecutive pixels of one image row.  Per (input row,
+// channel) it loads the 10 input columns it needs ONCE and each weight float4 once, and applies them to all 8 pixels
+// (the pixel-at-a-time kernel above re-reads every input 9 times and every weight once per pixel).
+__global__ void __launch_bounds__(256) conv_out_row8_kernel(const float* __restrict__ x, long long x_ld,
+                                                            const float* __restrict__ w, const float* __restrict__ bias,
+                                                            int n, int h, int wd, int cin, int cout,
+                                                            float* __restrict__ out) {
+  extern __shared__ float4 w4s[];               // [9][cin]
+  for (int i = threadIdx.x; i < 9 * cin; i += 256) {
+    const int tap = i / cin, ci = i - tap * cin;
+    float t[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int co = 0; co < cout; ++co) t[co] = w[((long long)co * cin + ci) * 9 + tap];
+    w4s[i] = make_float4(t[0], t[1], t[2], t[3]);
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long total8 = (long long)n * h * (wd >> 3);          // groups of 8 pixels
+  const long long grp = blockIdx.x * 8LL + warp;
+  if (grp >= total8) return;
+  const int gx = (int)(grp % (wd >> 3));
+  const int yy = (int)((grp / (wd >> 3)) % h);
+  const int nn = (int)(grp / ((long long)(wd >> 3) * h));
+  const int x0 = gx * 8;
+  float4 acc[8];
+#pragma unroll
+  for (int p = 0; p < 8; ++p) acc[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int ky = 0; ky < 3; ++ky) {
+    const int y = yy + ky - 1;
+    if (y < 0 || y >= h) continue;
+    const float* row = x + (((long long)nn * h + y) * wd) * x_ld;
+    for (int ci = lane; ci < cin; ci += 32) {
+      float v[10];
+#pragma unroll
+      for (int j = 0; j < 10; ++j) {
+        const int xq = x0 + j - 1;
+        v[j] = (xq >= 0 && xq < wd) ? row[(long long)xq * x_ld + ci] : 0.f;
+      }
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const float4 w4 = w4s[(ky * 3 + kx) * cin + ci];
+#pragma unroll
+        for (int p = 0; p < 8; ++p) {
+          const float a = v[p + kx];
+          acc[p].x = fmaf(a, w4.x, acc[p].x), acc[p].y = fmaf(a, w4.y, acc[p].y);
+          acc[p].z = fmaf(a, w4.z, acc[p].z), acc[p].w = fmaf(a, w4.w, acc[p].w);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int p = 0; p < 8; ++p) {
+    const float r0 = warp_sum(acc[p].x), r1 = warp_sum(acc[p].y), r2 = warp_sum(acc[p].z), r3 = warp_sum(acc[p].w);
+    const float rl = lane == 0 ? r0 : lane == 1 ? r1 : lane == 2 ? r2 : r3;
+    if (lane < cout) out[(((long long)nn * cout + lane) * h + yy) * wd + x0 + p] = rl + (bias ? bias[lane] : 0.f);
   }
 }
 
@@ -292,7 +352,7 @@ extern "C" int tfmq_conv_in(tfmq_ctx* ctx, const float* x_nchw, const float* w, 
                "conv_in: out / bias must be 16-byte aligned");
   const long long total = (long long)n * h * wd;
   if (total == 0) return TFMQ_OK;
-  conv_in_kernel<<<(unsigned)((total + CIN_PIX - 1) / CIN_PIX), 256, (size_t)cout * cin * 9 * sizeof(float),
+  conv_in_kernel<<<(unsigned)((total + CIN_PIX * CIN_GROUPS - 1) / (CIN_PIX * CIN_GROUPS)), 256, (size_t)cout * cin * 9 * sizeof(float),
                    tfmq_stream(stream)>>>(x_nchw, w, bias, n, h, wd, cin, cout, out, out_ld);
   TFMQ_LAUNCH_CHECK("conv_in");
   return TFMQ_OK;
@@ -306,6 +366,13 @@ extern "C" int tfmq_conv_out(tfmq_ctx* ctx, const float* x, int64_t x_ld, const 
   TFMQ_REQUIRE(9 * cin * 16 <= 48 * 1024, TFMQ_ERR_SHAPE, "conv_out: cin %d too large", cin);
   const long long total = (long long)n * h * wd;
   if (total == 0) return TFMQ_OK;
+  if (wd % 8 == 0) {
+    const long long groups = total / 8;
+    conv_out_row8_kernel<<<(unsigned)((groups + 7) / 8), 256, (size_t)9 * cin * sizeof(float4), tfmq_stream(stream)>>>(
+        x, x_ld, w, bias, n, h, wd, cin, cout, out_nchw);
+    TFMQ_LAUNCH_CHECK("conv_out");
+    return TFMQ_OK;
+  }
   const long long per_cta = 8LL * COUT_PIX_PER_WARP;
   conv_out_kernel<<<(unsigned)((total + per_cta - 1) / per_cta), 256, (size_t)9 * cin * sizeof(float4),
                     tfmq_stream(stream)>>>(x, x_ld, w, bias, n, h, wd, cin, cout, out_nchw);
