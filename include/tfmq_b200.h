@@ -308,6 +308,23 @@ int tfmq_plms_eps(tfmq_ctx* ctx, const float* e0, const float* e1, const float* 
                   int64_t count, float* out, void* stream);
 
 /* ------------------------------------------------------------------------- *
+ * First-stage decode prologue: what happens to the sampled latent before the
+ * decoder's conv_in, as ONE launch.
+ *   z' = z * inv_scale                                   LatentDiffusion.decode_first_stage,
+ *                                                        ldm/models/diffusion/ddpm.py:706-713 (1/scale_factor)
+ *   codebook != NULL (VQModelInterface.decode, ldm/models/autoencoder.py:274-279; the quantiser is
+ *   taming-transformers' VectorQuantizer2.forward, a dependency the reference does not vendor):
+ *       j = argmin_j (|z'|^2 + |e_j|^2 - 2 z'.e_j) (first minimum), zq = z' + (e_j - z')
+ *   else zq = z'                                         (AutoencoderKL.decode, :330-333; force_not_quantize)
+ *   out[co] = bias[co] + sum_i w[co][i] zq[i]            post_quant_conv (1x1); w == NULL: out = zq
+ * z: NCHW fp32 [n][c][hw], out: NCHW fp32 [n][c_out][hw], c, c_out <= 4; codebook [n_embed][c];
+ * indices (optional): int32 [n*hw], the chosen code of every latent pixel.
+ * ------------------------------------------------------------------------- */
+int tfmq_first_stage_input(tfmq_ctx* ctx, const float* z, float inv_scale, const float* codebook, int n_embed,
+                           const float* w, const float* bias, int n, int hw, int c, int c_out, float* out,
+                           int32_t* indices, void* stream);
+
+/* ------------------------------------------------------------------------- *
  * Calibration primitives.
  * ------------------------------------------------------------------------- */
 /* per-row min/max of x[rows][cols] -> mm[rows][2] (rows=1: whole tensor) */

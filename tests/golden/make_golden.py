@@ -433,6 +433,65 @@ def plms_golden():
                                         if isinstance(v, dict)})
 
 
+def first_stage_golden():
+    """First-stage decode through the reference's own `VQModelInterface.decode` / `AutoencoderKL.decode`
+    (ldm/models/autoencoder.py:274-283,330-333 -> Decoder, ldm/modules/diffusionmodules/model.py:462-568) on small seeded
+    models.  `ldm.models.autoencoder` imports taming-transformers' VectorQuantizer2, which the reference does not vendor:
+    a stand-in module with its published forward (the same restatement as oracle/first_stage_ref.py::vq_lookup) is
+    registered, so the lookup itself is NOT pinned by this fixture -- post_quant_conv and the decoder are."""
+    from tfmq_b200.first_stage import first_stage_mini_config
+
+    class VectorQuantizer2(torch.nn.Module):
+        def __init__(self, n_e, e_dim, beta, remap=None, unknown_index="random", sane_index_shape=False, legacy=True):
+            super().__init__()
+            self.n_e, self.e_dim = n_e, e_dim
+            self.embedding = torch.nn.Embedding(n_e, e_dim)
+            self.embedding.weight.data.uniform_(-1.0 / n_e, 1.0 / n_e)
+
+        def forward(self, z):
+            z = z.permute(0, 2, 3, 1).contiguous()
+            zf = z.view(-1, self.e_dim)
+            d = torch.sum(zf ** 2, dim=1, keepdim=True) + torch.sum(self.embedding.weight ** 2, dim=1) - 2 * \
+                torch.einsum('bd,dn->bn', zf, self.embedding.weight.t())
+            idx = torch.argmin(d, dim=1)
+            z_q = self.embedding(idx).view(z.shape)
+            z_q = z + (z_q - z).detach()
+            return z_q.permute(0, 3, 1, 2).contiguous(), None, (None, None, idx)
+
+    for name in ("taming", "taming.modules", "taming.modules.vqvae"):
+        sys.modules[name] = types.ModuleType(name)
+    tq = types.ModuleType("taming.modules.vqvae.quantize")
+    tq.VectorQuantizer2 = VectorQuantizer2
+    sys.modules["taming.modules.vqvae.quantize"] = tq
+    from ldm.models.autoencoder import AutoencoderKL, VQModelInterface
+
+    t0 = time.time()
+    out = {}
+    for kind in ("vq", "vq-attn", "kl"):
+        cfg = first_stage_mini_config(kind)
+        loss = {"target": "torch.nn.Identity"}
+        if cfg["n_embed"] is not None:
+            m = VQModelInterface(embed_dim=cfg["embed_dim"], n_embed=cfg["n_embed"], ddconfig=dict(cfg["ddconfig"]),
+                                 lossconfig=loss)
+        else:
+            m = AutoencoderKL(ddconfig=dict(cfg["ddconfig"]), lossconfig=loss, embed_dim=cfg["embed_dim"])
+        m.eval()
+        synth.fill_state_dict(m, SEED)
+        if cfg["n_embed"] is not None:       # codes of the latent's own scale, so that the lookup moves the latent a little
+            m.quantize.embedding.weight.data.copy_(synth.latents((cfg["n_embed"], cfg["embed_dim"]), 91))
+        z = synth.latents((2, cfg["embed_dim"], 16, 16), 92)
+        zs = 1. / cfg["scale_factor"] * z                       # ddpm.py:713
+        with torch.no_grad():
+            rec = dict(z=z, image=m.decode(zs))
+            if cfg["n_embed"] is not None:
+                rec["image_not_quantized"] = m.decode(zs, force_not_quantize=True)
+        rec["decoder_keys"] = [(k, tuple(v.shape)) for k, v in m.state_dict().items()
+                               if k.startswith(("decoder.", "post_quant_conv.", "quantize."))]
+        out[kind] = rec
+    torch.save(out, os.path.join(HERE, "first_stage.pt"))
+    print("first_stage.pt written", {k: tuple(v["image"].shape) for k, v in out.items()}, time.time() - t0)
+
+
 def cali_schema():
     """G9: run the reference's cali_model on a tiny synthetic set and record the checkpoint's key set and
     shapes (the on-disk format the drop-in must read and write)."""
@@ -467,6 +526,8 @@ if __name__ == "__main__":
         cifar_golden()
     if "ldm" in what:
         ldm_golden()
+    if "first_stage" in what:
+        first_stage_golden()
     if "schema" in what:
         cali_schema()
     if "sdmini" in what:

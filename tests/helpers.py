@@ -34,6 +34,18 @@ def fp_model(kind: str, seed: int = 1234):
     return m
 
 
+def first_stage_model(kind: str, seed: int = 1234):
+    """Seeded first stage (product parameter container) matching tests/golden/make_golden.py::first_stage_golden."""
+    from tfmq_b200.first_stage import FirstStageModel, first_stage_mini_config
+    cfg = first_stage_mini_config(kind)
+    m = FirstStageModel(**cfg)
+    m.eval()
+    synth.fill_state_dict(m, seed)
+    if cfg["n_embed"] is not None:
+        m.quantize.embedding.weight.data.copy_(synth.latents((cfg["n_embed"], cfg["embed_dim"]), 91))
+    return m, cfg
+
+
 def oracle_spec(sd, seed: int = 1234):
     from oracle import unet_ref
     return unet_ref.build_spec(sd, alpha_fn=lambda n, w, d: synth.synth_alpha(n, w, d, seed))

@@ -479,6 +479,7 @@ def test_ddim_update_and_embedding(dev):
     (1, 8, 300, 300, 40, "tokens"),    # d = 40 zero-padded to three k16 steps, ragged tails
     (2, 4, 130, 70, 80, "tokens"),
     (2, 1, 200, 200, 384, "tokens"),   # cin256: one wide head, warps split the head dimension
+    (2, 1, 150, 150, 512, "tokens"),   # first-stage decoder mid.attn_1 (one 512-channel head)
     (2, 1, 70, 70, 576, "tokens"),
     (1, 1, 64, 64, 960, "tokens"),
     (3, 1, 100, 1, 384, "tokens"),     # cin256 cross-attention over a single class token

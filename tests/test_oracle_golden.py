@@ -137,3 +137,34 @@ def test_reference_path_is_chaotic_under_fp_reassociation():
     assert (g["alt_last"] - g["xs_last"]).abs().max().item() > 1e-1
     gl = load_golden("ldm4_w4a8.pt")
     assert (gl["alt_eps"] - gl["eps"]).abs().max().item() > 1e-2
+
+
+def test_first_stage_decode_against_reference():
+    """the oracle's decode_first_stage equals the reference's VQModelInterface.decode / AutoencoderKL.decode
+    (fixture first_stage.pt); the weights are re-created from the seeded fill on the product's parameter container, whose
+    state_dict keys must therefore be the reference's."""
+    import pytest
+    from helpers import first_stage_model
+    from oracle import first_stage_ref as FS
+    g = load_golden("first_stage.pt")
+    for kind in ("vq", "vq-attn", "kl"):
+        m, cfg = first_stage_model(kind)
+        sd = m.state_dict()
+        assert sorted((k, tuple(v.shape)) for k, v in sd.items()) == sorted(g[kind]["decoder_keys"])
+        z = g[kind]["z"]
+        quant = cfg["n_embed"] is not None
+        img = FS.decode_first_stage(z, sd, cfg["scale_factor"], quantize=quant)
+        assert (img - g[kind]["image"]).abs().max().item() < 2e-5
+        if quant:
+            img2 = FS.decode_first_stage(z, sd, cfg["scale_factor"], quantize=True, force_not_quantize=True)
+            assert (img2 - g[kind]["image_not_quantized"]).abs().max().item() < 2e-5
+            assert (img2 - img).abs().max().item() > 1e-2          # the codebook lookup is not a no-op in the fixture
+            # brute-force nearest code (float64) agrees with the restated lookup
+            zq, idx = FS.vq_lookup(z, sd["quantize.embedding.weight"])
+            zf = z.permute(0, 2, 3, 1).reshape(-1, z.shape[1]).double()
+            bf = torch.cdist(zf, sd["quantize.embedding.weight"].double()).argmin(1)
+            assert torch.equal(idx, bf)
+        with pytest.raises(RuntimeError):
+            m(z)                                                   # parameter container: no torch / CPU forward
+        with pytest.raises(RuntimeError):
+            m.decode_first_stage(z)                                # CPU latent: no CPU path

@@ -788,6 +788,7 @@ extern "C" int tfmq_attention(tfmq_ctx* ctx, const tfmq_attn_desc* d, void* stre
         break;
       case 256: if (q_ok) return launch_wide<64, 4, 64, 2>(ctx, P, st); break;    // CIFAR AttnBlock (one head)
       case 384: if (q_ok) return launch_wide<96, 4, 48, 2>(ctx, P, st); break;    // cin256, 32x32
+      case 512: if (q_ok) return launch_wide<128, 4, 32, 2>(ctx, P, st); break;   // first-stage decoder mid.attn_1 (one head)
       case 576: if (q_ok) return launch_wide<96, 6, 32, 1>(ctx, P, st); break;    // cin256, 16x16
       case 960: if (q_ok) return launch_wide<160, 6, 16, 1>(ctx, P, st); break;   // cin256, 8x8
       default: break;

@@ -288,6 +288,73 @@ __global__ void __launch_bounds__(256) conv_out_row8_kernel(const float* __restr
   }
 }
 
+// First-stage decode prologue: latent scaling, optional nearest-codebook lookup with the straight-through arithmetic of
+// the reference's quantiser, and the 1x1 post_quant_conv, NCHW -> NCHW with <= 4 channels.  One thread per latent pixel; the
+// codebook is staged through shared memory in chunks of FS_CHUNK codes as (e0, e1, e2, e3) + |e|^2.
+constexpr int FS_CHUNK = 1024;
+__global__ void __launch_bounds__(128) first_stage_input_kernel(const float* __restrict__ z, float inv_scale,
+                                                                const float* __restrict__ codebook, int n_embed,
+                                                                const float* __restrict__ w, const float* __restrict__ bias,
+                                                                long long total, int hw, int c, int c_out,
+                                                                float* __restrict__ out, int* __restrict__ indices) {
+  __shared__ float4 es[FS_CHUNK];
+  __shared__ float ee[FS_CHUNK];
+  const long long pix = (long long)blockIdx.x * 128 + threadIdx.x;
+  const bool valid = pix < total;
+  const long long nn = valid ? pix / hw : 0;
+  const int p = valid ? (int)(pix - nn * hw) : 0;
+  float v[4] = {0.f, 0.f, 0.f, 0.f};
+  if (valid)
+    for (int i = 0; i < c; ++i) v[i] = z[(nn * c + i) * hw + p] * inv_scale;
+  if (codebook) {
+    float zz = 0.f;
+    for (int i = 0; i < c; ++i) zz += v[i] * v[i];
+    float best = INFINITY;
+    int best_j = 0;
+    for (int j0 = 0; j0 < n_embed; j0 += FS_CHUNK) {
+      __syncthreads();
+      for (int j = threadIdx.x; j < FS_CHUNK; j += 128) {
+        float e[4] = {0.f, 0.f, 0.f, 0.f};
+        float s = 0.f;
+        if (j0 + j < n_embed)
+          for (int i = 0; i < c; ++i) {
+            e[i] = codebook[(long long)(j0 + j) * c + i];
+            s += e[i] * e[i];
+          }
+        es[j] = make_float4(e[0], e[1], e[2], e[3]);
+        ee[j] = s;
+      }
+      __syncthreads();
+      const int cnt = min(FS_CHUNK, n_embed - j0);
+      for (int j = 0; j < cnt; ++j) {
+        const float4 e = es[j];
+        float dot = v[0] * e.x;
+        dot = fmaf(v[1], e.y, dot), dot = fmaf(v[2], e.z, dot), dot = fmaf(v[3], e.w, dot);
+        const float d = (zz + ee[j]) - 2.f * dot;
+        if (d < best) best = d, best_j = j0 + j;      // strict <: the first minimum, as torch.argmin
+      }
+    }
+    if (valid) {
+      if (indices) indices[pix] = best_j;
+      for (int i = 0; i < c; ++i) {
+        const float e = codebook[(long long)best_j * c + i];
+        v[i] = v[i] + (e - v[i]);                       // z + (z_q - z).detach()
+      }
+    }
+  }
+  if (!valid) return;
+  for (int co = 0; co < c_out; ++co) {
+    float acc = 0.f;
+    if (w) {
+      for (int i = 0; i < c; ++i) acc = fmaf(v[i], w[co * c + i], acc);
+      if (bias) acc += bias[co];
+    } else {
+      acc = v[co];
+    }
+    out[(nn * c_out + co) * hw + p] = acc;
+  }
+}
+
 }  // namespace tfmq
 
 using namespace tfmq;
@@ -346,13 +413,19 @@ extern "C" int tfmq_conv_in(tfmq_ctx* ctx, const float* x_nchw, const float* w, 
   if (!ctx) return TFMQ_ERR_ARG;
   TFMQ_REQUIRE(x_nchw && w && out, TFMQ_ERR_ARG, "conv_in: null pointer");
   TFMQ_REQUIRE(cin >= 1 && cin <= 4, TFMQ_ERR_SHAPE, "conv_in: cin %d > 4", cin);
-  TFMQ_REQUIRE(cout % 4 == 0 && out_ld % 4 == 0 && cout * cin * 9 * 4 <= 48 * 1024, TFMQ_ERR_SHAPE,
-               "conv_in: cout %d", cout);
+  const size_t smem_in = (size_t)cout * cin * 9 * sizeof(float);
+  TFMQ_REQUIRE(cout % 4 == 0 && out_ld % 4 == 0 && smem_in <= 160 * 1024, TFMQ_ERR_SHAPE, "conv_in: cout %d", cout);
+  static size_t smem_in_set = 48 * 1024;
+  if (smem_in > smem_in_set) {      // the first-stage decoder's conv_in (z -> 512 channels) needs 54 / 72 KB
+    cudaError_t e = cudaFuncSetAttribute(conv_in_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_in);
+    if (e != cudaSuccess) return tfmq_fail(ctx, TFMQ_ERR_CUDA, "conv_in: smem attr: %s", cudaGetErrorString(e));
+    smem_in_set = smem_in;
+  }
   TFMQ_REQUIRE(((uintptr_t)out & 15) == 0 && (!bias || ((uintptr_t)bias & 15) == 0), TFMQ_ERR_ARG,
                "conv_in: out / bias must be 16-byte aligned");
   const long long total = (long long)n * h * wd;
   if (total == 0) return TFMQ_OK;
-  conv_in_kernel<<<(unsigned)((total + CIN_PIX * CIN_GROUPS - 1) / (CIN_PIX * CIN_GROUPS)), 256, (size_t)cout * cin * 9 * sizeof(float),
+  conv_in_kernel<<<(unsigned)((total + CIN_PIX * CIN_GROUPS - 1) / (CIN_PIX * CIN_GROUPS)), 256, smem_in,
                    tfmq_stream(stream)>>>(x_nchw, w, bias, n, h, wd, cin, cout, out, out_ld);
   TFMQ_LAUNCH_CHECK("conv_in");
   return TFMQ_OK;
@@ -377,5 +450,22 @@ extern "C" int tfmq_conv_out(tfmq_ctx* ctx, const float* x, int64_t x_ld, const 
   conv_out_kernel<<<(unsigned)((total + per_cta - 1) / per_cta), 256, (size_t)9 * cin * sizeof(float4),
                     tfmq_stream(stream)>>>(x, x_ld, w, bias, n, h, wd, cin, cout, out_nchw);
   TFMQ_LAUNCH_CHECK("conv_out");
+  return TFMQ_OK;
+}
+
+extern "C" int tfmq_first_stage_input(tfmq_ctx* ctx, const float* z, float inv_scale, const float* codebook, int n_embed,
+                                      const float* w, const float* bias, int n, int hw, int c, int c_out, float* out,
+                                      int32_t* indices, void* stream) {
+  if (!ctx) return TFMQ_ERR_ARG;
+  TFMQ_REQUIRE(z && out, TFMQ_ERR_ARG, "first_stage_input: null pointer");
+  TFMQ_REQUIRE(c >= 1 && c <= 4 && c_out >= 1 && c_out <= 4, TFMQ_ERR_SHAPE, "first_stage_input: channels %d -> %d (<= 4)", c,
+               c_out);
+  TFMQ_REQUIRE(w || c_out == c, TFMQ_ERR_SHAPE, "first_stage_input: no post_quant_conv but %d -> %d channels", c, c_out);
+  TFMQ_REQUIRE(!codebook || n_embed >= 1, TFMQ_ERR_SHAPE, "first_stage_input: empty codebook");
+  const long long total = (long long)n * hw;
+  if (total == 0) return TFMQ_OK;
+  first_stage_input_kernel<<<(unsigned)((total + 127) / 128), 128, 0, tfmq_stream(stream)>>>(
+      z, inv_scale, codebook, n_embed, w, bias, total, hw, c, c_out, out, indices);
+  TFMQ_LAUNCH_CHECK("first_stage_input");
   return TFMQ_OK;
 }

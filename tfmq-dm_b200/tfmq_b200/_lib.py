@@ -126,6 +126,7 @@ _SIGS = {
     "tfmq_ddim_update": (C.c_int, [P, P, P, P, P, i64, P, P, P]),
     "tfmq_cfg_combine": (C.c_int, [P, P, P, C.c_float, i64, P, P]),
     "tfmq_plms_eps": (C.c_int, [P, P, P, P, P, C.c_int, i64, P, P]),
+    "tfmq_first_stage_input": (C.c_int, [P, P, C.c_float, P, C.c_int, P, P, C.c_int, C.c_int, C.c_int, C.c_int, P, P, P]),
     "tfmq_minmax_rows": (C.c_int, [P, P, i64, i64, P, P]),
     "tfmq_mse_scale_search": (C.c_int, [P, P, i64, i64, C.c_int, P, P, P]),
     "tfmq_act_range_update": (C.c_int, [P, P, i64, i64, C.c_int, C.c_float, C.c_int, P, P, P]),

@@ -352,6 +352,22 @@ def plms_eps(e0, olds, out):
     ctx.call("tfmq_plms_eps", _p(e0), _p(es[0]), _p(es[1]), _p(es[2]), order, out.numel(), _p(out), _stream())
 
 
+def first_stage_input(z: torch.Tensor, inv_scale: float, out: torch.Tensor, codebook=None, w=None, bias=None,
+                      indices=None):
+    """Latent -> decoder input: z / scale_factor, [nearest-codebook lookup], [post_quant_conv 1x1]; NCHW fp32 in and out."""
+    ctx = _ctx(out)
+    n, c, h, wd = z.shape
+    assert z.is_contiguous() and out.is_contiguous() and out.shape[0] == n and tuple(out.shape[2:]) == (h, wd)
+    if codebook is not None:
+        assert codebook.is_contiguous() and codebook.shape[1] == c
+    if w is not None:
+        w = w.reshape(out.shape[1], c)
+        assert w.is_contiguous()
+    ctx.call("tfmq_first_stage_input", _p(z), C.c_float(inv_scale), _p(codebook),
+             codebook.shape[0] if codebook is not None else 0, _p(w), _p(bias), n, h * wd, c, out.shape[1], _p(out),
+             _p(indices), _stream())
+
+
 # --------------------------------------------------------------------------- calibration
 def minmax_rows(x2d: torch.Tensor) -> torch.Tensor:
     rows, cols = x2d.shape
