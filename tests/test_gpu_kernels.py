@@ -124,6 +124,9 @@ def _w4a8_case(dev, n, h, w, cin, cout, ksize, use_emb, use_res, seed, ld_extra=
     (5, 1, 1, 512, 256, 1, False, False),      # linear, M = 5 rows
     (16, 4, 4, 512, 256, 3, True, True),       # CIFAR lowest resolution
     (2, 32, 32, 448, 448, 3, True, True),      # two N tiles
+    (8, 64, 64, 32, 96, 3, True, True),        # several units per persistent CTA pair, 3 residual chunks each
+    (6, 64, 64, 64, 224, 1, False, True),      # 7 residual chunks per unit, residual loads two chunks ahead across units
+    (6, 64, 64, 64, 224, 1, False, False),
 ])
 def test_conv_w4a8_exact(dev, n, h, w, cin, cout, ks, emb, res):
     _w4a8_case(dev, n, h, w, cin, cout, ks, emb, res, seed=n * 1000 + cin + cout + ks)

@@ -79,12 +79,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const int SP = p.p_stages;
   uint8_t* u_ring = smem + (size_t)S * IGEMM_A_BYTES;
   uint8_t* p_ring = u_ring + (size_t)SU * p.u_bytes;
-  uint8_t* ebuf = W4 ? p_ring + (size_t)SP * p.p_bytes : smem + (size_t)S * p.stage_bytes;   // 2 epilogue chunks
-  float4* chp = reinterpret_cast<float4*>(ebuf + 2 * 128 * 32 * 4);        // [tile_n] per-channel constants
+  // NB epilogue chunk buffers: 2, or 3 when a residual is folded in (its TMA load then runs two chunks ahead)
+  const int NB = p.epi_bufs;
+  uint8_t* ebuf = W4 ? p_ring + (size_t)SP * p.p_bytes : smem + (size_t)S * p.stage_bytes;
+  float4* chp = reinterpret_cast<float4*>(ebuf + NB * 128 * 32 * 4);        // [tile_n] per-channel constants
   // [stat_imgs][tile_n] per-image, per-channel (sum, sumsq): a tile of a small feature map spans several images
-  float2* cstat = reinterpret_cast<float2*>(ebuf + 2 * 128 * 32 * 4 + p.tile_n * 16);
+  float2* cstat = reinterpret_cast<float2*>(ebuf + NB * 128 * 32 * 4 + p.tile_n * 16);
   float2* cpart = cstat + p.stat_imgs * p.tile_n;     // [2][parts][chunk_w] row-block partials of the last two chunks
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ebuf + 2 * 128 * 32 * 4 + p.tile_n * 16 + p.stat_imgs * p.tile_n * 8 +
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ebuf + NB * 128 * 32 * 4 + p.tile_n * 16 + p.stat_imgs * p.tile_n * 8 +
                                                2 * 256 * 8);
   // barrier slots (8 bytes each, 32 slots): the two pipelines use the first 24 differently
   uint64_t* full_tma = bars;            // [<=8] TMA bytes landed (w4a8: the A tile; CTA pair: of both CTAs, at the leader)
@@ -93,7 +95,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint64_t* empty_u = bars + 20;        // w4a8 [<=4]: UMMAs that read the s8 B slot retired
   uint64_t* acc_full = bars + 24;       // [2] accumulator stage complete
   uint64_t* acc_empty = bars + 26;      // [2] accumulator stage drained by the epilogue
-  uint64_t* res_full = bars + 28;       // [2] residual chunk landed in the epilogue buffer
+  uint64_t* res_full = bars + 40;       // [<=3] residual chunk landed in the epilogue buffer
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 30);
   uint64_t* full_p = bars + 32;         // w4a8 [<=4]: packed int4 tile landed
   uint64_t* empty_p = bars + 36;        // w4a8 [<=4]: the transform warps hold the packed tile in registers
@@ -139,8 +141,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
       mbar_init(&acc_empty[s], IGEMM_EPI_WARPS * CG);
-      mbar_init(&res_full[s], 1);
     }
+    for (int s = 0; s < NB; ++s) mbar_init(&res_full[s], 1);
     mbar_fence_init();
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -492,6 +494,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       za = (int)p.aq[1];
     }
     uint32_t tcount = 0, g = 0;             // tiles / chunks processed by this CTA
+    uint32_t gb = 0, gph = 0;               // g % NB (chunk buffer) and (g / NB) & 1 (phase of its residual barrier)
+    const int LA = NB - 1;                  // residual loads run LA chunks ahead of the fold
     const bool prof_on = p.prof != nullptr && et == 0;
     long long prof_acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     long long prof_t = prof_on ? clock64() : 0;
@@ -510,10 +514,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       if (et == 0) {
         tma_store_wait_read<1>();             // the store that last used this buffer has read it
         if (p.res) {
-          mbar_expect_tx(&res_full[g & 1], chunk_bytes);
-          tma_load_4d(ebuf + (g & 1) * chunk_bytes, &tmRes, &res_full[g & 1], c_out0, x0, y0, n0);
+          // all stores but the last one have been read, so the LA buffers after the last one's are free
+          for (int j = 0; j < LA && j < nchunks; ++j) {
+            const uint32_t b = (gb + (uint32_t)j) % (uint32_t)NB;
+            mbar_expect_tx(&res_full[b], chunk_bytes);
+            tma_load_4d(ebuf + b * chunk_bytes, &tmRes, &res_full[b], c_out0 + j * CW, x0, y0, n0);
+          }
           // pull the rest of the residual tile into L2 while the main loop of this tile runs
-          for (int ci = 1; ci < nchunks; ++ci) tma_prefetch_l2_4d(&tmRes, c_out0 + ci * CW, x0, y0, n0);
+          for (int ci = LA; ci < nchunks; ++ci) tma_prefetch_l2_4d(&tmRes, c_out0 + ci * CW, x0, y0, n0);
         }
       }
       // per-channel constants of this N tile
@@ -548,9 +556,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         a_sum = (int)sv[0];
       }
 
-      for (int ci = 0; ci < nchunks; ++ci, ++g) {
+      for (int ci = 0; ci < nchunks; ++ci, ++g, gb = (gb + 1 == (uint32_t)NB) ? 0u : gb + 1, gph ^= (gb == 0u)) {
         const int c0 = ci * CW + half * HC;   // first column (within the tile) this thread handles
-        uint8_t* buf = ebuf + (g & 1) * chunk_bytes;
+        uint8_t* buf = ebuf + gb * chunk_bytes;
         uint32_t v[16];
         if (CW == 32) {
           tmem_ld16(tmem_d + (uint32_t)c0, v);
@@ -579,7 +587,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           }
         }
         PROF_T(2)
-        if (p.res) mbar_wait(&res_full[g & 1], (g >> 1) & 1u);
+        if (p.res) mbar_wait(&res_full[gb], gph);
         PROF_T(3)
         const float* embp = (p.emb && !emb_folded) ? p.emb + (long long)n_l * p.emb_ld + c_out0 + c0 : nullptr;
         const int npiece = HC >> 2;           // 16-byte pieces per thread: 4 (CW 32) or 2 (CW 16)
@@ -638,10 +646,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           tma_store_commit();
           if (ci + 1 < nchunks) {
             tma_store_wait_read<1>();         // the other buffer's store has finished reading
-            if (p.res) {
-              mbar_expect_tx(&res_full[(g + 1) & 1], chunk_bytes);
-              tma_load_4d(ebuf + ((g + 1) & 1) * chunk_bytes, &tmRes, &res_full[(g + 1) & 1], c_out0 + (ci + 1) * CW,
-                          x0, y0, n0);
+            if (p.res && ci + LA < nchunks) {
+              // chunk ci + LA goes into the buffer of chunk ci - 1 (NB = 3) / ci - 1 (NB = 2), whose store was just awaited
+              const uint32_t b = (gb + (uint32_t)LA) % (uint32_t)NB;
+              mbar_expect_tx(&res_full[b], chunk_bytes);
+              tma_load_4d(ebuf + b * chunk_bytes, &tmRes, &res_full[b], c_out0 + (ci + LA) * CW, x0, y0, n0);
             }
           }
         }
@@ -758,9 +767,15 @@ static int launch_igemm(tfmq_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap
   // shared-memory plan
   if (CG == 1) p.b_rows[0] = p.tile_n, p.b_row0[0] = 0, p.b_rows[1] = 0, p.b_row0[1] = 0;
   if (p.stat_imgs < 1) p.stat_imgs = 1;
-  const uint32_t extra = 1024u /*alignment slack*/ + 2u * 128u * 32u * 4u /*epilogue chunks*/ +
-                         (uint32_t)p.tile_n * 16u /*chp*/ + (uint32_t)(p.stat_imgs * p.tile_n) * 8u /*GN channel sums*/ +
-                         2u * 256u * 8u /*GN partials*/ + 512u /*barriers*/;
+  // epilogue chunk buffers: a third one lets the residual's TMA loads run two chunks ahead of the fold (the K = 2016 layers
+  // with a residual are epilogue-bound and spent a quarter of the epilogue waiting for it) -- if the main loop keeps its depth
+  static const int eb_env = getenv("TFMQ_IGEMM_EPI_BUFS") ? atoi(getenv("TFMQ_IGEMM_EPI_BUFS")) : 0;
+  p.epi_bufs = (eb_env == 2 || eb_env == 3) ? eb_env : (p.res ? 3 : 2);
+  const uint32_t extra_base = 1024u /*alignment slack*/ + (uint32_t)p.tile_n * 16u /*chp*/ +
+                              (uint32_t)(p.stat_imgs * p.tile_n) * 8u /*GN channel sums*/ + 2u * 256u * 8u /*GN partials*/ +
+                              512u /*barriers*/;
+  const uint32_t chunk_buf = 128u * 32u * 4u;
+  uint32_t extra = extra_base + (uint32_t)p.epi_bufs * chunk_buf;
   static const int stages_env = getenv("TFMQ_IGEMM_STAGES") ? atoi(getenv("TFMQ_IGEMM_STAGES")) : 0;   // experiments
   int stages;
   size_t smem;
@@ -778,6 +793,11 @@ static int launch_igemm(tfmq_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap
     const long long left = (long long)ctx->max_smem_optin - extra - (long long)p.u_stages * p.u_bytes -
                            (long long)p.p_stages * p.p_bytes;
     stages = (int)(left / (long long)IGEMM_A_BYTES);
+    if (p.epi_bufs == 3 && stages < 4 && !eb_env) {      // keep the A ring at least 4 deep (or as deep as it was)
+      p.epi_bufs = 2;
+      extra = extra_base + 2u * chunk_buf;
+      stages = (int)((left + (long long)chunk_buf) / (long long)IGEMM_A_BYTES);
+    }
     if (stages > 8) stages = 8;
     if (stages_env > 0 && stages_env < stages) stages = stages_env;
     if (stages < 2) return tfmq_fail(ctx, TFMQ_ERR_SHAPE, "%s: tile does not fit shared memory", name);
@@ -799,6 +819,14 @@ static int launch_igemm(tfmq_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap
     }
     p.stage_bytes = (off + 1023u) & ~1023u;
     stages = (int)(((uint32_t)ctx->max_smem_optin - extra) / p.stage_bytes);
+    if (p.epi_bufs == 3 && !eb_env) {
+      const int stages2 = (int)(((uint32_t)ctx->max_smem_optin - extra + chunk_buf) / p.stage_bytes);
+      if (stages2 > stages && stages < 4) {              // the third buffer would cost a pipeline stage
+        p.epi_bufs = 2;
+        extra -= chunk_buf;
+        stages = stages2;
+      }
+    }
     if (stages > 8) stages = 8;
     if (stages_env > 0 && stages_env < stages) stages = stages_env;
     if (stages < 1) return tfmq_fail(ctx, TFMQ_ERR_SHAPE, "%s: tile does not fit shared memory", name);
