@@ -262,6 +262,29 @@ def int8_pipeline_tops(dev):
         return f"failed: {exc}"
 
 
+def time_first_stage(dev, batch):
+    """The step after the path: vq-f4 first-stage decode of one batch of latents (latent -> 256x256 image),
+    so that images/s can also be read as "including the decode".  Reported next to the headline, not folded into it."""
+    from helpers import synth
+    from tfmq_b200.first_stage import FirstStageModel, vq_f4_config
+    cfg = vq_f4_config()
+    fs = FirstStageModel(**cfg).eval()
+    synth.fill_state_dict(fs, SEED)
+    fs.quantize.embedding.weight.data.copy_(synth.latents((cfg["n_embed"], cfg["embed_dim"]), 91))
+    fs = fs.to(dev)
+    z = synth.latents((batch, 3, 64, 64), 77).to(dev)
+    for _ in range(3):
+        fs.decode_first_stage(z)
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(5):
+        fs.decode_first_stage(z)
+    e.record()
+    torch.cuda.synchronize()
+    return s.elapsed_time(e) / 5, fs.engine(batch, 64, 64, dev).launches_per_decode
+
+
 def run_ours(args):
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -385,6 +408,15 @@ def run_ours(args):
                          "step_frac": GFLOP_PER_SAMPLE * BATCH / ms_per_step / int8_peak},
             "clocks": sampler.summary() if sampler else None,
         }
+        if world == 1:
+            try:
+                fs_ms, fs_launches = time_first_stage(dev, BATCH)
+                line["first_stage"] = {
+                    "workload": "vq-f4 decode_first_stage, 16 latents 3x64x64 -> 3x256x256 (SURVEY f3; not part of `value`)",
+                    "ms_per_decode": fs_ms, "launches": fs_launches,
+                    "images_per_s_with_decode": BATCH / (DDIM_STEPS * ms_per_step * 1e-3 + fs_ms * 1e-3)}
+            except Exception as exc:      # noqa: BLE001
+                line["first_stage"] = f"failed: {exc}"
         if cpu_line:
             line["cpu_baseline"] = cpu_line
         print(json.dumps(line), flush=True)
