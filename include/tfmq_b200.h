@@ -284,6 +284,12 @@ typedef struct {
   float* o;       int64_t o_sb, o_sh, o_st;
   int b, heads, tq, tk, d;
   float scale;
+  /* optional: write o as the fp16 hi / lo planes `tfmq_conv_h16` reads (same split as tfmq_act_prepare's dst_hi / dst_lo),
+   * addressed with o_sb / o_sh / o_st, INSTEAD of fp32 `o` (which may then be NULL).  Saves the split launch between an
+   * attention core and a floating-point proj_out conv.  Tensor-core kernels only (head dims 32, 40, 64, 80, 160, 256,
+   * 384, 512, 576, 960 with 8-byte aligned operands); other shapes return TFMQ_ERR_SHAPE. */
+  void* o_hi;
+  void* o_lo;
 } tfmq_attn_desc;
 int tfmq_attention(tfmq_ctx* ctx, const tfmq_attn_desc* d, void* stream);
 

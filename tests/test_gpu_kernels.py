@@ -524,6 +524,28 @@ def test_attention_fp32(dev, b, heads, tq, tk, d, layout):
     assert err < 2e-5, f"attention max err {err}"
 
 
+@pytest.mark.parametrize("b,heads,tq,d", [(2, 14, 256, 32), (1, 8, 100, 40), (2, 1, 90, 512), (1, 2, 70, 160)])
+def test_attention_fp16_plane_output(dev, b, heads, tq, d):
+    """o_hi / o_lo output == the fp32 output pushed through tfmq_act_prepare's split, bit for bit."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(d)
+    c = heads * d
+    q, k, v = (torch.randn(b, tq, c, generator=g).to(dev) for _ in range(3))
+    st = dict(q=(tq * c, d, c), k=(tq * c, d, c), v=(tq * c, d, c), o=(tq * c, d, c))
+    o = torch.empty((b, tq, c), device=dev)
+    ops.attention(q, k, v, o, b, heads, tq, tq, d, d ** -0.5, st)
+    hi = torch.zeros((b, tq, c), dtype=torch.float16, device=dev)
+    lo = torch.zeros_like(hi)
+    ops.attention(q, k, v, None, b, heads, tq, tq, d, d ** -0.5, st, o_h16=(hi, lo))
+    rhi = torch.empty((b, tq, 1, c), dtype=torch.float16, device=dev)
+    rlo = torch.empty_like(rhi)
+    ops.act_prepare(o.view(b, tq, 1, c), dst_h16=(rhi, rlo))
+    assert torch.equal(hi.view(-1), rhi.view(-1)) and torch.equal(lo.view(-1), rlo.view(-1))
+    assert (hi.float() + lo.float() - o).abs().max().item() <= 2.0 ** -21 * o.abs().max().item()
+    with pytest.raises(RuntimeError):      # FFMA kernel (head dim 24): no plane output
+        ops.attention(q, k, v, None, b, 1, tq, tq, 24, 0.2, st, o_h16=(hi, lo))
+
+
 # ------------------------------------------------------------------ calibration kernels
 def test_minmax_and_mse_search(dev):
     ops, q = _ops(), _qref()

@@ -287,6 +287,28 @@ __device__ __forceinline__ void split2_h(float x0, float x1, uint32_t& hi, uint3
   hi = *reinterpret_cast<const uint32_t*>(&h);
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
+// the saturating split tfmq_act_prepare writes (elementwise.cu::split_h16x4), for two values: bits of (hi0, hi1), (lo0, lo1)
+__device__ __forceinline__ void split2_sat(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  uint16_t h0, h1, l0, l1;
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h0) : "f"(x0));
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h1) : "f"(x1));
+  const float r0 = x0 - __half2float(__ushort_as_half(h0)), r1 = x1 - __half2float(__ushort_as_half(h1));
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(l0) : "f"(r0));
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(l1) : "f"(r1));
+  hi = (uint32_t)h0 | ((uint32_t)h1 << 16);
+  lo = (uint32_t)l0 | ((uint32_t)l1 << 16);
+}
+// one (row, column pair) of the output: fp32, or the fp16 hi / lo planes a floating-point conv reads next
+__device__ __forceinline__ void store_o2(const tfmq_attn_desc& a, long long off, float x0, float x1) {
+  if (a.o_hi) {
+    uint32_t hi, lo;
+    split2_sat(x0, x1, hi, lo);
+    *reinterpret_cast<uint32_t*>(static_cast<__half*>(a.o_hi) + off) = hi;
+    *reinterpret_cast<uint32_t*>(static_cast<__half*>(a.o_lo) + off) = lo;
+  } else {
+    *reinterpret_cast<float2*>(a.o + off) = make_float2(x0, x1);
+  }
+}
 __device__ __forceinline__ void split1_h(float x, __half& hi, __half& lo) {
   hi = __float2half_rn(x);
   lo = __float2half_rn(x - __half2float(hi));
@@ -482,17 +504,13 @@ __global__ void __launch_bounds__(128) attn_h16_kernel(const AttnP P) {
   l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
   l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
   const float i0 = 1.f / l0, i1 = 1.f / l1;
-  float* ob = a.o + (long long)b * a.o_sb + (long long)h * a.o_sh;
+  const long long ob = (long long)b * a.o_sb + (long long)h * a.o_sh;
   const int r0 = q0 + g, r1 = q0 + g + 8;
 #pragma unroll
   for (int nt = 0; nt < NT; ++nt) {
     if (nt * 8 + 2 * t >= dr) continue;
-    if (r0 < a.tq)
-      *reinterpret_cast<float2*>(ob + (long long)r0 * a.o_st + nt * 8 + 2 * t) =
-          make_float2(o[nt][0] * i0, o[nt][1] * i0);
-    if (r1 < a.tq)
-      *reinterpret_cast<float2*>(ob + (long long)r1 * a.o_st + nt * 8 + 2 * t) =
-          make_float2(o[nt][2] * i1, o[nt][3] * i1);
+    if (r0 < a.tq) store_o2(a, ob + (long long)r0 * a.o_st + nt * 8 + 2 * t, o[nt][0] * i0, o[nt][1] * i0);
+    if (r1 < a.tq) store_o2(a, ob + (long long)r1 * a.o_st + nt * 8 + 2 * t, o[nt][2] * i1, o[nt][3] * i1);
   }
 }
 
@@ -675,14 +693,12 @@ __global__ void __launch_bounds__(NW * QG * 32) attn_wide_kernel(const AttnP P) 
   l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
   l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
   const float i0 = 1.f / l0, i1 = 1.f / l1;
-  float* ob = a.o + (long long)b * a.o_sb + (long long)h * a.o_sh + dw0;
+  const long long ob = (long long)b * a.o_sb + (long long)h * a.o_sh + dw0;
   const int r0 = q0 + g, r1 = q0 + g + 8;
 #pragma unroll
   for (int nt = 0; nt < NT; ++nt) {
-    if (r0 < a.tq)
-      *reinterpret_cast<float2*>(ob + (long long)r0 * a.o_st + nt * 8 + 2 * t) = make_float2(o[nt][0] * i0, o[nt][1] * i0);
-    if (r1 < a.tq)
-      *reinterpret_cast<float2*>(ob + (long long)r1 * a.o_st + nt * 8 + 2 * t) = make_float2(o[nt][2] * i1, o[nt][3] * i1);
+    if (r0 < a.tq) store_o2(a, ob + (long long)r0 * a.o_st + nt * 8 + 2 * t, o[nt][0] * i0, o[nt][1] * i0);
+    if (r1 < a.tq) store_o2(a, ob + (long long)r1 * a.o_st + nt * 8 + 2 * t, o[nt][2] * i1, o[nt][3] * i1);
   }
 }
 
@@ -762,7 +778,9 @@ using namespace tfmq;
 
 extern "C" int tfmq_attention(tfmq_ctx* ctx, const tfmq_attn_desc* d, void* stream) {
   if (!ctx) return TFMQ_ERR_ARG;
-  TFMQ_REQUIRE(d && d->q && d->k && d->v && d->o, TFMQ_ERR_ARG, "attention: null pointer");
+  TFMQ_REQUIRE(d && d->q && d->k && d->v && (d->o || d->o_hi), TFMQ_ERR_ARG, "attention: null pointer");
+  TFMQ_REQUIRE(!d->o_hi || (d->o_lo && (((uintptr_t)d->o_hi | (uintptr_t)d->o_lo) & 3) == 0), TFMQ_ERR_ARG,
+               "attention: o_lo missing or fp16 planes not 4-byte aligned");
   TFMQ_REQUIRE(d->d > 0 && d->d <= 1024, TFMQ_ERR_SHAPE, "attention: head dim %d", d->d);
   if (d->b == 0 || d->heads == 0 || d->tq == 0) return TFMQ_OK;
   TFMQ_REQUIRE(d->tk > 0, TFMQ_ERR_SHAPE, "attention: empty key set");
@@ -776,13 +794,14 @@ extern "C" int tfmq_attention(tfmq_ctx* ctx, const tfmq_attn_desc* d, void* stre
   };
   const bool vec_ok = al16(d->k, d->k_sb, d->k_sh, d->k_st) && al16(d->v, d->v_sb, d->v_sh, d->v_st) &&
                       (((uintptr_t)d->o & 7) == 0) && d->o_sb % 2 == 0 && d->o_sh % 2 == 0 && d->o_st % 2 == 0;
+  const bool planes = d->o_hi != nullptr;     // only the kernels below the next `if` write fp16 planes
   const bool q_ok = (((uintptr_t)d->q & 7) == 0) && d->q_sb % 2 == 0 && d->q_sh % 2 == 0 && d->q_st % 2 == 0;
   if (vec_ok) {
     switch (d->d) {
-      case 32: return q_ok ? launch_h16<32>(ctx, P, st) : launch_mma<32>(ctx, P, st);
-      case 40: return q_ok ? launch_h16<48>(ctx, P, st) : launch_mma<40>(ctx, P, st);   // zero-padded to 3 k16 steps
-      case 64: return q_ok ? launch_h16<64>(ctx, P, st) : launch_mma<64>(ctx, P, st);
-      case 80: return q_ok ? launch_h16<80>(ctx, P, st) : launch_mma<80>(ctx, P, st);
+      case 32: if (q_ok) return launch_h16<32>(ctx, P, st); if (!planes) return launch_mma<32>(ctx, P, st); break;
+      case 40: if (q_ok) return launch_h16<48>(ctx, P, st); if (!planes) return launch_mma<40>(ctx, P, st); break;   // zero-padded to 3 k16 steps
+      case 64: if (q_ok) return launch_h16<64>(ctx, P, st); if (!planes) return launch_mma<64>(ctx, P, st); break;
+      case 80: if (q_ok) return launch_h16<80>(ctx, P, st); if (!planes) return launch_mma<80>(ctx, P, st); break;
       case 160:
         if (q_ok) return launch_h16<160>(ctx, P, st);      // SD v1.4's deepest levels
         break;
@@ -794,6 +813,8 @@ extern "C" int tfmq_attention(tfmq_ctx* ctx, const tfmq_attn_desc* d, void* stre
       default: break;
     }
   }
+  TFMQ_REQUIRE(!planes, TFMQ_ERR_SHAPE, "attention: fp16-plane output needs a tensor-core kernel (head dim %d, alignment)",
+               d->d);
   int G = 1;
   while (G <= 32 && !(d->d % G == 0 && d->d / G <= 32)) G <<= 1;
   TFMQ_REQUIRE(G <= 32, TFMQ_ERR_SHAPE, "attention: head dim %d not supported", d->d);

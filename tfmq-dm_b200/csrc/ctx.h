@@ -3,6 +3,7 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -46,3 +47,17 @@ static inline int tfmq_fail(tfmq_ctx* ctx, int status, const char* fmt, ...) {
   } while (0)
 
 static inline cudaStream_t tfmq_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// Programmatic dependent launch of the conv and producer kernels (TFMQ_PDL=0 switches it off): the next kernel's CTAs are
+// scheduled, and run their prologue (barrier init, TMEM allocation, descriptor prefetch), while the tail of the previous
+// kernel drains; every such kernel executes griddepcontrol.wait before it touches global memory.
+static inline bool tfmq_pdl() {
+  static const bool on = getenv("TFMQ_PDL") ? atoi(getenv("TFMQ_PDL")) != 0 : false;
+  return on;
+}
+static inline int tfmq_pdl_attr(cudaLaunchAttribute* a) {
+  if (!tfmq_pdl()) return 0;
+  a->id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  a->val.programmaticStreamSerializationAllowed = 1;
+  return 1;
+}

@@ -6,6 +6,7 @@
 #include <cuda_fp16.h>
 
 #include "ctx.h"
+#include "ptx.cuh"
 
 namespace tfmq {
 
@@ -137,6 +138,9 @@ enum { ACT_OUT_U8 = 0, ACT_OUT_F32 = 1, ACT_OUT_H16 = 2 };
 template <int NORM, bool SILU, bool GEGLU, int OUT>
 __global__ void __launch_bounds__(ACT_THREADS) act_prepare_kernel(const ActParams P) {
   extern __shared__ float sp[];  // [c] a = rstd*gamma, [c] b = beta - a*mean
+  // programmatic dependent launch: the CTAs may be scheduled while the producer of `src` / `gn_stats` still drains
+  griddep_launch_dependents();
+  griddep_wait();
   const tfmq_act_desc& d = P.d;
   const int n = blockIdx.y;
   const int c = d.c;
@@ -449,8 +453,12 @@ extern "C" int tfmq_act_prepare(tfmq_ctx* ctx, const tfmq_act_desc* d, void* str
   const dim3 grid(chunks, d->n);
   cudaStream_t st = tfmq_stream(stream);
   const int out = d->dst_u8 ? ACT_OUT_U8 : d->dst_hi ? ACT_OUT_H16 : ACT_OUT_F32;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid, cfg.blockDim = dim3(ACT_THREADS), cfg.dynamicSmemBytes = smem, cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  cfg.attrs = attr, cfg.numAttrs = (unsigned)tfmq_pdl_attr(&attr[0]);
 #define ACT_LAUNCH(NORM, SILU, GEGLU, OUT) \
-  act_prepare_kernel<NORM, SILU, GEGLU, OUT><<<grid, ACT_THREADS, smem, st>>>(P)
+  cudaLaunchKernelEx(&cfg, act_prepare_kernel<NORM, SILU, GEGLU, OUT>, P)
 #define ACT_BY_OUT(NORM, SILU, GEGLU)                         \
   do {                                                        \
     if (out == ACT_OUT_U8) ACT_LAUNCH(NORM, SILU, GEGLU, ACT_OUT_U8);        \

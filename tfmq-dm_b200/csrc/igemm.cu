@@ -172,6 +172,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // programmatic dependent launch: everything above overlapped the tail of the previous kernel; nothing below may touch
+  // global memory before that kernel has completed
+  griddep_launch_dependents();
+  griddep_wait();
 
   const bool need_a_lo = FP && (p.pass_flags & PASS_LO_HI);
   const bool need_b_lo = FP && (p.pass_flags & PASS_HI_LO);
@@ -495,6 +499,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
     uint32_t tcount = 0, g = 0;             // tiles / chunks processed by this CTA
     uint32_t gb = 0, gph = 0;               // g % NB (chunk buffer) and (g / NB) & 1 (phase of its residual barrier)
+    int chp_c0 = -1, chp_n0 = -1;           // N tile / image the per-channel constants in smem were computed for
     const int LA = NB - 1;                  // residual loads run LA chunks ahead of the fold
     const bool prof_on = p.prof != nullptr && et == 0;
     long long prof_acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -524,9 +529,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           for (int ci = LA; ci < nchunks; ++ci) tma_prefetch_l2_4d(&tmRes, c_out0 + ci * CW, x0, y0, n0);
         }
       }
-      // per-channel constants of this N tile
-      named_bar_sync(1, ET);                  // previous tile is done with chp / cstat
-      for (int ch = et; ch < p.tile_n; ch += ET) {
+      // per-channel constants of this N tile; a persistent CTA walks the units M-fastest, so consecutive units usually
+      // share the N tile (always, when one tile covers all output channels) and the constants are kept
+      const bool chp_keep = tcount > 0 && c_out0 == chp_c0 && (!emb_folded || n0 == chp_n0);
+      chp_c0 = c_out0, chp_n0 = n0;
+      if (!chp_keep) named_bar_sync(1, ET);   // previous tile is done with chp
+      for (int ch = et; ch < (chp_keep ? 0 : p.tile_n); ch += ET) {
         const int c = c_out0 + ch;
         float sc = 1.f, bi = 0.f;
         int ws = 0, zw = 0;
@@ -889,17 +897,20 @@ static int launch_igemm(tfmq_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap
     cudaEventCreate(&ev1);
     cudaEventRecord(ev0, stream);
   }
-  if (CG == 1) {
-    kern<<<grid, IGEMM_THREADS, smem, stream>>>(tmA, tmA2, tmB, tmB2, tmOut, tmRes, p);
-  } else {
+  {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid), cfg.blockDim = dim3(IGEMM_THREADS), cfg.dynamicSmemBytes = smem, cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr, cfg.numAttrs = 1;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (CG == 2) {
+      attr[na].id = cudaLaunchAttributeClusterDimension;
+      attr[na].val.clusterDim.x = 2, attr[na].val.clusterDim.y = 1, attr[na].val.clusterDim.z = 1;
+      ++na;
+    }
+    if (!(prof_env || time_env)) na += tfmq_pdl_attr(&attr[na]);
+    cfg.attrs = attr, cfg.numAttrs = (unsigned)na;
     cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmA2, tmB, tmB2, tmOut, tmRes, p);
-    if (e != cudaSuccess) return tfmq_fail(ctx, TFMQ_ERR_CUDA, "%s: cluster launch: %s", name, cudaGetErrorString(e));
+    if (e != cudaSuccess) return tfmq_fail(ctx, TFMQ_ERR_CUDA, "%s: launch: %s", name, cudaGetErrorString(e));
   }
   TFMQ_LAUNCH_CHECK(name);
   if (prof_env || time_env) {

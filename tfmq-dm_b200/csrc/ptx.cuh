@@ -288,4 +288,12 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+
+// Programmatic dependent launch: a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may be
+// scheduled while its predecessor in the stream still runs; `griddep_wait` blocks until the predecessor has completed and
+// its writes are visible (a no-op for a normally launched kernel), `griddep_launch_dependents` lets the successor be
+// scheduled early (its own `griddep_wait` still orders it after this grid).
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 }  // namespace tfmq

@@ -97,6 +97,7 @@ class AttnDesc(C.Structure):
         ("o", C.c_void_p), ("o_sb", i64), ("o_sh", i64), ("o_st", i64),
         ("b", C.c_int), ("heads", C.c_int), ("tq", C.c_int), ("tk", C.c_int), ("d", C.c_int),
         ("scale", C.c_float),
+        ("o_hi", C.c_void_p), ("o_lo", C.c_void_p),
     ]
 
 

@@ -437,9 +437,23 @@ class StepEngine:
             self._ctx_T = t
         return self._ctx_T
 
-    def _attention(self, q_t, k_t, v_t, o: T, heads: int, d: int, scale: float, strides):
+    def _attention(self, q_t, k_t, v_t, o: T, heads: int, d: int, scale: float, strides, o_h16=None):
+        """o_h16 = (hi, lo): the attention kernel writes the fp16 planes the following floating-point conv reads (no
+        fp32 output, no split launch); `o` then only carries the shape."""
         b, tq = o.n, o.h * o.w
-        self.ops.append(lambda: ops.attention(q_t(), k_t(), v_t(), o.view, b, heads, tq, tq, d, scale, strides()))
+        if o_h16 is not None:
+            self.ops.append(lambda: ops.attention(q_t(), k_t(), v_t(), None, b, heads, tq, tq, d, scale, strides(),
+                                                  o_h16=o_h16))
+        else:
+            self.ops.append(lambda: ops.attention(q_t(), k_t(), v_t(), o.view, b, heads, tq, tq, d, scale, strides()))
+
+    def _attn_out_planes(self, n, h, w, c, d):
+        """fp16 hi / lo planes for an attention output that feeds a floating-point conv, when the kernel for head dim d
+        can write them; else None (fp32 output + split launch)."""
+        if self.fp_mode != "h16" or d not in ops.ATTN_PLANE_DIMS:
+            return None
+        hi = torch.empty((n, h, w, c), dtype=torch.float16, device=self.dev)
+        return hi, torch.empty_like(hi)
 
     # ================================================================ DDIM UNet program
     def _trace_ddim(self, m, N, res):
@@ -556,20 +570,21 @@ class StepEngine:
             self._plain_conv(blk.qkv, xn, qkv, None, pad_lo=0, stride=1)
             heads = blk.num_heads
             d = x.c // heads
-            o = self._new(x.n, x.h, x.w, x.c)
+            planes = self._attn_out_planes(x.n, x.h, x.w, x.c, d)
+            o = T(x.n, x.h, x.w, x.c) if planes is not None else self._new(x.n, x.h, x.w, x.c)
             tq = x.h * x.w
 
             def strides():
                 s = (qkv.view.stride(0), 3 * d, qkv.view.stride(2))
-                return dict(q=s, k=s, v=s, o=(o.view.stride(0), d, o.view.stride(2)))
+                return dict(q=s, k=s, v=s, o=(tq * x.c, d, x.c))
 
             def part(i):
                 # per head the qkv conv writes (q | k | v) blocks of d channels (legacy order,
                 # openaimodel.py:386-389); q / k / v of head 0 start at channel 0 / d / 2d
                 return lambda: qkv.view.reshape(-1)[i * d:]
-            self._attention(part(0), part(1), part(2), o, heads, d, 1.0 / math.sqrt(d), strides)
+            self._attention(part(0), part(1), part(2), o, heads, d, 1.0 / math.sqrt(d), strides, o_h16=planes)
             out = self._new(x.n, x.h, x.w, x.c)
-            self._plain_conv(blk.proj_out, o, out, x, pad_lo=0, stride=1)
+            self._plain_conv(blk.proj_out, planes if planes is not None else o, out, x, pad_lo=0, stride=1)
             self.block_out[self._names[id(blk)]] = out
             return out
 

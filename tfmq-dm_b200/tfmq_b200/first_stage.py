@@ -251,17 +251,18 @@ class DecoderEngine(StepEngine):
             self._keep.append(qkv_conv)
             qkv = self._new(x.n, x.h, x.w, 3 * c)
             self._plain_conv(qkv_conv, self._fp_input(x, self._gn(x, blk.norm)), qkv, None, pad_lo=0, stride=1)
-            o = self._new(x.n, x.h, x.w, c)
+            planes = self._attn_out_planes(x.n, x.h, x.w, c, c)
+            o = T(x.n, x.h, x.w, c) if planes is not None else self._new(x.n, x.h, x.w, c)
 
             def strides():
                 s = (qkv.view.stride(0), 0, qkv.view.stride(2))
-                return dict(q=s, k=s, v=s, o=(o.view.stride(0), 0, o.view.stride(2)))
+                return dict(q=s, k=s, v=s, o=(x.h * x.w * c, 0, c))
 
             def part(i):
                 return lambda: qkv.view.reshape(-1)[i * c:]
-            self._attention(part(0), part(1), part(2), o, 1, c, float(int(c) ** -0.5), strides)
+            self._attention(part(0), part(1), part(2), o, 1, c, float(int(c) ** -0.5), strides, o_h16=planes)
             out = self._new(x.n, x.h, x.w, c)
-            self._conv(blk.proj_out, o, out, res=x)
+            self._conv(blk.proj_out, planes if planes is not None else o, out, res=x)
             self.block_out[self._names[id(blk)]] = out
             return out
 

@@ -318,13 +318,22 @@ def timestep_embedding(t: torch.Tensor, dim: int, style: int, out: torch.Tensor)
     _ctx(out).call("tfmq_timestep_embedding", _p(t), t.numel(), dim, style, _p(out), _stream())
 
 
-def attention(q, k, v, o, b: int, heads: int, tq: int, tk: int, d: int, scale: float, strides):
-    """strides: dict name -> (sb, sh, st) in elements for q, k, v, o."""
-    ctx = _ctx(o)
+ATTN_PLANE_DIMS = (32, 40, 64, 80, 160, 256, 384, 512, 576, 960)   # head dims whose kernels can write fp16 hi / lo planes
+
+
+def attention(q, k, v, o, b: int, heads: int, tq: int, tk: int, d: int, scale: float, strides, o_h16=None):
+    """strides: dict name -> (sb, sh, st) in elements for q, k, v, o.  o_h16 = (hi, lo): the output goes to these fp16
+    planes (o's strides) instead of fp32 `o`, which may then be None."""
+    ctx = _ctx(q)
     a = AttnDesc()
+    if o_h16 is not None:
+        assert o_h16[0].dtype == torch.float16 and o_h16[1].dtype == torch.float16
+        a.o_hi, a.o_lo = o_h16[0].data_ptr(), o_h16[1].data_ptr()
     for name, t in (("q", q), ("k", k), ("v", v), ("o", o)):
         sb, sh, st = strides[name]
-        setattr(a, name, t.data_ptr())
+        if t is None:
+            t = q.new_empty(0)
+        setattr(a, name, t.data_ptr() if t.numel() else None)
         setattr(a, name + "_sb", sb)
         setattr(a, name + "_sh", sh)
         setattr(a, name + "_st", st)
