@@ -686,15 +686,18 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             if (n0 + im >= p.n_img) continue;       // batch tail: rows past the batch carry no image
             const int ch_lo = max(gi * tg.cpg - tg.ch_off, c_out0) - c_out0;
             const int ch_hi = min((gi + 1) * tg.cpg - tg.ch_off, c_out0 + p.tile_n) - c_out0;
-            double a1 = 0.0, a2 = 0.0;
+            // the group's channels of this tile in fp32 (each term is already an fp32 sum over 128 rows), one conversion per
+            // group: the double-precision pipe is 1/64 rate and these adds sat on the epilogue's critical path; the running
+            // sums across tiles stay in double
+            float a1 = 0.f, a2 = 0.f;
             for (int ch = ch_lo; ch < ch_hi; ++ch) {
               const float2 v2 = cstat[im * p.tile_n + ch];
-              a1 += (double)v2.x;
-              a2 += (double)v2.y;
+              a1 += v2.x;
+              a2 += v2.y;
             }
             double* dst = tg.stats + ((long long)(n0 + im) * tg.groups + gi) * 2;
-            atomicAdd(dst, a1);
-            atomicAdd(dst + 1, a2);
+            atomicAdd(dst, (double)a1);
+            atomicAdd(dst + 1, (double)a2);
           }
         }
       }
