@@ -635,20 +635,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         fence_proxy_async_smem();
         named_bar_sync(1, ET);                // all 128 rows of the chunk are in smem
         PROF_T(5)
-        if (p.n_stat > 0) {
-          // GroupNorm statistics of the finished output values: thread = (column, block of rows) sums its rows;
-          // the partials of the previous chunk are combined here too, in a fixed order (bit-reproducible)
-          if (ci > 0 && et < CW * p.stat_imgs) {
-            // image `im` of the tile owns the row blocks [im * ppi, (im + 1) * ppi)
-            const int im = et / CW, col = et - im * CW, ppi = (ET / CW) / p.stat_imgs;
-            const float2* pp = cpart + ((g - 1) & 1) * ET + im * ppi * CW + col;
-            float a1 = 0.f, a2 = 0.f;
-            for (int k = 0; k < ppi; ++k) a1 += pp[k * CW].x, a2 += pp[k * CW].y;
-            cstat[im * p.tile_n + (ci - 1) * CW + col] = make_float2(a1, a2);
-          }
-          cpart[(g & 1) * ET + et] = (CW == 32) ? chunk_col_partial<32>(buf, et) : chunk_col_partial<16>(buf, et);   // [part][col]
-        }
-        PROF_T(6)
+        // the store (and the next residual load) go out BEFORE the statistics pass over the same buffer: the TMA engine
+        // works while the warps sum columns, and thread 0's warp is the one every other warp waits for at the next barrier
         if (et == 0) {
           tma_store_4d(&tmOut, buf, c_out0 + ci * CW, x0, y0, n0);
           tma_store_commit();
@@ -662,14 +650,31 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             }
           }
         }
+        if (p.n_stat > 0) {
+          // GroupNorm statistics of the finished output values: thread = (column, block of rows) sums its rows;
+          // the partials of the previous chunk are combined here too, in a fixed order (bit-reproducible)
+          // (done by the LAST warps of the group: thread 0 issues the TMA store and waits for buffers in this phase)
+          if (ci > 0 && et >= ET - CW * p.stat_imgs) {
+            // image `im` of the tile owns the row blocks [im * ppi, (im + 1) * ppi)
+            const int e2 = et - (ET - CW * p.stat_imgs);
+            const int im = e2 / CW, col = e2 - im * CW, ppi = (ET / CW) / p.stat_imgs;
+            const float2* pp = cpart + ((g - 1) & 1) * ET + im * ppi * CW + col;
+            float a1 = 0.f, a2 = 0.f;
+            for (int k = 0; k < ppi; ++k) a1 += pp[k * CW].x, a2 += pp[k * CW].y;
+            cstat[im * p.tile_n + (ci - 1) * CW + col] = make_float2(a1, a2);
+          }
+          cpart[(g & 1) * ET + et] = (CW == 32) ? chunk_col_partial<32>(buf, et) : chunk_col_partial<16>(buf, et);   // [part][col]
+        }
+        PROF_T(6)
         PROF_T(7)
         if (!p.res) named_bar_sync(1, ET);    // without a residual barrier, publish "next buffer is free"
         PROF_T(8)
       }
       if (p.n_stat > 0) {
         named_bar_sync(1, ET);                // the last chunk's partials are written
-        if (et < CW * p.stat_imgs) {
-          const int im = et / CW, col = et - im * CW, ppi = (ET / CW) / p.stat_imgs;
+        if (et >= ET - CW * p.stat_imgs) {
+          const int e2 = et - (ET - CW * p.stat_imgs);
+          const int im = e2 / CW, col = e2 - im * CW, ppi = (ET / CW) / p.stat_imgs;
           const float2* pp = cpart + ((g - 1) & 1) * ET + im * ppi * CW + col;
           float a1 = 0.f, a2 = 0.f;
           for (int k = 0; k < ppi; ++k) a1 += pp[k * CW].x, a2 += pp[k * CW].y;
