@@ -209,18 +209,20 @@ def time_w4a8_kernels(eng):
 
 def ncu_traffic():
     """DRAM bytes per launch of the w4a8 conv kernel from the committed `ncu --set full` capture
-    (profiles/r1f_ncu_full_igemm.csv: dram__bytes_read.sum + dram__bytes_write.sum, mean over the captured launches)."""
+    (profiles/r1j_ncu_full_igemm.csv: dram__bytes_read.sum + dram__bytes_write.sum, mean over the captured launches)."""
     import csv
-    path = os.path.join(ROOT, "profiles", "r1f_ncu_full_igemm.csv")
-    if not os.path.exists(path):
+    name = next((n for n in ("r1j_ncu_full_igemm.csv", "r1f_ncu_full_igemm.csv")
+                 if os.path.exists(os.path.join(ROOT, "profiles", n))), None)
+    if name is None:
         return None, "no ncu capture committed"
+    path = os.path.join(ROOT, "profiles", name)
     rows = list(csv.reader(open(path)))[1:]
     hdr = rows[0]
     k, r, w = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
     vals = [(float(x[r]) + float(x[w])) * 1e6 for x in rows[2:] if "igemm_kernel<0" in x[k]]
     if not vals:
         return None, "capture holds no w4a8 launch"
-    return sum(vals) / len(vals), f"mean over {len(vals)} captured w4a8 launches (profiles/r1f_ncu_full_igemm.csv)"
+    return sum(vals) / len(vals), f"mean over {len(vals)} captured w4a8 launches (profiles/{name})"
 
 
 def int8_cublas_tops(dev):
