@@ -153,3 +153,41 @@ def test_quant_model_surgery_on_transformer_unet_matches_reference():
     got = {n: c for n, c in mine.items() if c in interesting}
     assert got == want
     assert sum(c == "QuantLayer" for c in got.values()) > 100
+
+
+def test_first_stage_configs_and_decoder_program():
+    """First-stage decode, host side: the full-size configs build the reference's module tree, and the
+    DecoderEngine program traces with every kernel call recorded instead of launched (tools/dry_trace_first_stage.py, in a
+    subprocess because it redirects torch allocations)."""
+    import json
+    import os
+    import subprocess
+    import sys
+    from tfmq_b200.first_stage import FirstStageModel, kl_f8_config, vq_f4_config
+    with torch.device("meta"):
+        vq, kl = FirstStageModel(**vq_f4_config()), FirstStageModel(**kl_f8_config())
+    sd = vq.state_dict()
+    assert tuple(sd["quantize.embedding.weight"].shape) == (8192, 3)
+    assert tuple(sd["decoder.conv_in.weight"].shape) == (512, 3, 3, 3)
+    assert tuple(sd["decoder.mid.attn_1.q.weight"].shape) == (512, 512, 1, 1)
+    assert tuple(sd["decoder.up.0.block.2.conv2.weight"].shape) == (128, 128, 3, 3)
+    assert tuple(sd["decoder.up.1.block.0.nin_shortcut.weight"].shape) == (256, 512, 1, 1)
+    assert "decoder.up.0.upsample.conv.weight" not in sd and "decoder.up.2.upsample.conv.weight" in sd
+    assert tuple(sd["decoder.conv_out.weight"].shape) == (3, 128, 3, 3)
+    sk = kl.state_dict()
+    assert "quantize.embedding.weight" not in sk and tuple(sk["post_quant_conv.weight"].shape) == (4, 4, 1, 1)
+    assert len([k for k in sk if k.startswith("decoder.up.3.")]) > 0 and kl.scale_factor == 0.18215
+    # 3 (vq-f4) / 4 (kl-f8) levels x 3 ResnetBlocks + 2 mid blocks, 2 convs each, + shortcuts + attention + conv_in / out
+    assert sum(1 for k in sd if k.endswith("conv1.weight")) == 11 and sum(1 for k in sk if k.endswith("conv1.weight")) == 14
+    tool = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "dry_trace_first_stage.py")
+    out = subprocess.run([sys.executable, tool], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    got = {ln.split(" ", 2)[0]: (int(ln.split(" ", 2)[1]), json.loads(ln.split(" ", 2)[2])) for ln in out.stdout.strip().splitlines()}
+    for kind, n_attn in (("vq", 1), ("vq-attn", 3), ("kl", 1)):
+        n_ops, c = got[kind]
+        assert c["tfmq_first_stage_input"] == 1 and c["tfmq_conv_in"] == 1 and c["tfmq_conv_out"] == 1
+        assert c["tfmq_attention"] == n_attn
+        # 6 ResnetBlocks (2 convs each) + 1 nin_shortcut + 1 Upsample conv + (stacked qkv + proj_out) per attention
+        assert c["tfmq_conv_h16"] == 6 * 2 + 1 + 1 + 2 * n_attn
+        # the attention output reaches proj_out as fp16 planes written by the attention kernel: no split launch for it
+        assert c["tfmq_act_prepare"] == c["tfmq_conv_h16"] - n_attn + 1      # + the final GN + SiLU before conv_out

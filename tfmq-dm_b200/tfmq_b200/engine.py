@@ -10,9 +10,10 @@ ldm/modules/diffusionmodules/openaimodel.py:744-780) and the per-step host work 
   (delta, zero_point, sum(q - z)); the reference re-quantises all weights every forward;
 * activations live in HBM as fp32 NHWC; every QuantLayer input is produced by one fused
   GroupNorm-apply + SiLU + quantise kernel writing u8 codes with a zero-point halo;
-* conv / linear run on tcgen05 (int8 for w4a8 layers, 3-pass tf32 for the layers the reference keeps
-  in floating point) with bias / time-embedding / residual fused in the epilogue; skip
-  concatenations are free (producers write into windows of the concat buffer);
+* conv / linear run on tcgen05 (kind::i8 for w4a8 layers; kind::f16 on fp16 hi/lo split planes, three
+  error-compensated products, for the layers the reference keeps in floating point) with bias /
+  time-embedding / residual fused in the epilogue and the next GroupNorm's statistics reduced there;
+  skip concatenations are free (producers write into windows of the concat buffer);
 * the Finite-Set-Calibration switch is one device-to-device copy of a parameter row per step
   (activation (delta, zp) of every layer, the sinusoidal embedding, the DDIM coefficients) instead of
   ~184 `load_state_dict` tensor copies and a `.item()` sync.

@@ -298,6 +298,11 @@ class DecoderEngine(StepEngine):
         self.ops.append(lambda: ops.conv_out(f.view, w_out, b_out, self.image))
 
     # ---------------------------------------------------------------- execution
+    def _not_a_step_engine(self, *a, **k):
+        raise RuntimeError("DecoderEngine only decodes latents (decode); it shares StepEngine's op-emission helpers, not its "
+                           "sampling interface")
+    forward = forward_teacher_forced = step = sample = set_schedule = select_step = set_guidance = _not_a_step_engine
+
     def _run(self, quantize: bool, scale: bool):
         fs = self.fs
         inv = float(torch.tensor(1.0 / fs.scale_factor, dtype=torch.float32)) if scale else 1.0

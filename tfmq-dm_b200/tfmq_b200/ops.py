@@ -329,11 +329,11 @@ def attention(q, k, v, o, b: int, heads: int, tq: int, tk: int, d: int, scale: f
     if o_h16 is not None:
         assert o_h16[0].dtype == torch.float16 and o_h16[1].dtype == torch.float16
         a.o_hi, a.o_lo = o_h16[0].data_ptr(), o_h16[1].data_ptr()
+    if o is None and o_h16 is None:
+        raise ValueError("attention: give the fp32 output `o` or the fp16 planes `o_h16`")
     for name, t in (("q", q), ("k", k), ("v", v), ("o", o)):
         sb, sh, st = strides[name]
-        if t is None:
-            t = q.new_empty(0)
-        setattr(a, name, t.data_ptr() if t.numel() else None)
+        setattr(a, name, t.data_ptr() if t is not None else None)
         setattr(a, name + "_sb", sb)
         setattr(a, name + "_sh", sh)
         setattr(a, name + "_st", st)
