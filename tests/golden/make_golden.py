@@ -492,6 +492,30 @@ def first_stage_golden():
     print("first_stage.pt written", {k: tuple(v["image"].shape) for k, v in out.items()}, time.time() - t0)
 
 
+def runner_golden():
+    """The reference's DDIM runner (ddim/runners/diffusion.py): beta schedules, logvar, and `Diffusion.sample_image` driven by
+    `stub_eps` on the uniform and quadratic timestep sequences, with and without the `untill_fake_t` early stop.
+    (`ddim.datasets` imports lmdb for a dataset class that is never touched: an empty stand-in module is registered.)"""
+    sys.modules.setdefault("lmdb", types.ModuleType("lmdb"))
+    from ddim.runners.diffusion import Diffusion, get_beta_schedule
+    NS = types.SimpleNamespace
+    out = {"schedules": {k: torch.from_numpy(get_beta_schedule(k, beta_start=1e-4, beta_end=0.02, num_diffusion_timesteps=1000))
+                         for k in ("linear", "quad", "const", "jsd", "sigmoid")}}
+    x = synth.latents((2, 3, 8, 8), 61)
+    for var in ("fixedlarge", "fixedsmall"):
+        cfg = NS(model=NS(var_type=var), diffusion=NS(beta_schedule="linear", beta_start=1e-4, beta_end=0.02,
+                                                       num_diffusion_timesteps=1000))
+        for skip in ("uniform", "quad"):
+            r = Diffusion(NS(skip_type=skip, timesteps=10, sample_type="generalized", eta=0.0), cfg, device=torch.device("cpu"))
+            full, _, _ = r.sample_image(x.clone(), stub_eps)
+            _, x_t, t_t = r.sample_image(x.clone(), stub_eps, untill_fake_t=4)
+            out[(var, skip)] = dict(betas=r.betas.clone(), logvar=r.logvar.clone(), full=full, x_t=x_t, t_t=t_t)
+    out["x"] = x
+    torch.save(out, os.path.join(HERE, "runner_ddim.pt"))
+    print("runner_ddim.pt written", {k: (v["full"].abs().max().item(), v["t_t"].tolist()) for k, v in out.items()
+                                      if isinstance(k, tuple)})
+
+
 def cali_schema():
     """G9: run the reference's cali_model on a tiny synthetic set and record the checkpoint's key set and
     shapes (the on-disk format the drop-in must read and write)."""
@@ -526,6 +550,8 @@ if __name__ == "__main__":
         cifar_golden()
     if "ldm" in what:
         ldm_golden()
+    if "runner" in what:
+        runner_golden()
     if "first_stage" in what:
         first_stage_golden()
     if "schema" in what:

@@ -191,3 +191,62 @@ def test_first_stage_configs_and_decoder_program():
         assert c["tfmq_conv_h16"] == 6 * 2 + 1 + 1 + 2 * n_attn
         # the attention output reaches proj_out as fp16 planes written by the attention kernel: no split launch for it
         assert c["tfmq_act_prepare"] == c["tfmq_conv_h16"] - n_attn + 1      # + the final GN + SiLU before conv_out
+
+
+def test_ddim_runner_schedules_and_sample_image_plumbing(monkeypatch):
+    """runners.Diffusion against the reference's own runner (fixture runner_ddim.pt): beta schedules and logvar bit for bit;
+    `sample_image`'s timestep sequence / argument plumbing by routing its `generalized_steps` call to the oracle's CPU
+    restatement with the same stand-in UNet the fixture used (the product's generalized_steps itself needs the GPU engine and
+    is covered by the GPU tests)."""
+    from types import SimpleNamespace as NS
+    from helpers import load_golden
+    from tfmq_b200 import runners as R
+    g = load_golden("runner_ddim.pt")
+    for name, want in g["schedules"].items():
+        got = R.get_beta_schedule(name, beta_start=1e-4, beta_end=0.02, num_diffusion_timesteps=1000)
+        assert torch.equal(torch.from_numpy(got), want), name
+    with pytest.raises(NotImplementedError):
+        R.get_beta_schedule("cosine", beta_start=1e-4, beta_end=0.02, num_diffusion_timesteps=10)
+
+    def stub_eps(x, t, c=None):          # tests/golden/make_golden.py::stub_eps
+        return 0.3 * x.roll(1, -1) - (0.2 * x) * (t.float() / 1000.0)[:, None, None, None]
+
+    calls = []
+
+    def oracle_steps(x, seq, model, b, **kw):
+        calls.append(dict(kw, seq=list(seq)))
+        seq = list(seq)
+        stop = kw.get("untill_fake_t")
+        xs, x0 = U.generalized_steps(x, seq, lambda xt, t, k: model(xt, t), b, eta=kw.get("eta", 0.0))
+        x_t = t_t = None
+        if stop is not None and stop <= len(seq):            # the reference breaks before the stop-th UNet call
+            x_t, t_t = xs[stop - 1], torch.ones(x.size(0)) * list(reversed(seq))[stop - 1]
+        return xs, x0, x_t, t_t
+    monkeypatch.setattr(R, "generalized_steps", oracle_steps)
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="no CPU path"):
+            R.Diffusion(NS(), NS(diffusion=NS(), model=NS()))
+    for var in ("fixedlarge", "fixedsmall"):
+        cfg = NS(model=NS(var_type=var), diffusion=NS(beta_schedule="linear", beta_start=1e-4, beta_end=0.02,
+                                                       num_diffusion_timesteps=1000))
+        for skip in ("uniform", "quad"):
+            want = g[(var, skip)]
+            r = R.Diffusion(NS(skip_type=skip, timesteps=10, sample_type="generalized", eta=0.0), cfg, device="cpu")
+            assert torch.equal(r.betas, want["betas"]) and torch.equal(r.logvar, want["logvar"]) and r.num_timesteps == 1000
+            full, x_t, t_t = r.sample_image(g["x"].clone(), stub_eps)
+            assert torch.equal(full, want["full"]) and x_t is None
+            _, x_t, t_t = r.sample_image(g["x"].clone(), stub_eps, untill_fake_t=4, tot=7, cali_ckpt={"k": 1}, t_max=3)
+            assert torch.equal(x_t, want["x_t"]) and torch.equal(t_t, want["t_t"])
+            assert calls[-1]["tot"] == 7 and calls[-1]["t_max"] == 3 and calls[-1]["cali_ckpt"] == {"k": 1}
+            pair, _, _ = r.sample_image(g["x"].clone(), stub_eps, last=False)
+            assert len(pair) == 2 and torch.equal(pair[0][-1], want["full"]) and len(pair[1]) == 10
+    assert calls[0]["seq"] == list(range(0, 1000, 100))
+    r.args.sample_type = "ddpm_noisy"
+    with pytest.raises(NotImplementedError):
+        r.sample_image(g["x"], stub_eps)
+    # quantize() without --ptq hands the FP model back; image-space transform
+    r.args.ptq = False
+    m = torch.nn.Identity()
+    assert r.quantize(m) == (m, None, None, None)
+    img = R.inverse_data_transform(NS(data=NS(rescaled=True, logit_transform=False)), torch.tensor([-3.0, -1.0, 0.0, 1.0, 2.0]))
+    assert torch.equal(img, torch.tensor([0.0, 0.0, 0.5, 1.0, 1.0]))

@@ -25,18 +25,28 @@ def _fp_state(model):
 
 
 @torch.no_grad()
-def generate_cali_data_ddim(model, betas: torch.Tensor, T: int, c: int, batch_size: int, shape: List[int],
-                            num_timesteps: int = 1000, generator: torch.Generator = None) -> Tuple[torch.Tensor]:
-    """reference :52-71 (`runnr.sample_image(x, model, untill_fake_t=i)[1:]` -> (x_t, t))."""
+def generate_cali_data_ddim(model=None, betas: torch.Tensor = None, T: int = None, c: int = None, batch_size: int = None,
+                            shape: List[int] = None, num_timesteps: int = 1000, generator: torch.Generator = None,
+                            runnr=None) -> Tuple[torch.Tensor]:
+    """reference :52-71 (`runnr.sample_image(x, model, untill_fake_t=i)[1:]` -> (x_t, t)).  Two call shapes: the
+    reference's, `generate_cali_data_ddim(runnr=<runners.Diffusion>, model=qnn, T=, c=, batch_size=, shape=)`, which samples
+    through the runner (its skip_type / eta / betas); or without a runner, `(model, betas, T, c, batch_size, shape)` on the
+    uniform schedule.  `model` is the QuantModel; it is put in its all-floating-point state."""
     _fp_state(model)
     dev = next(model.parameters()).device
-    seq = list(range(0, num_timesteps, num_timesteps // T))
+    if runnr is None and betas is None:
+        raise ValueError("generate_cali_data_ddim: give the runner (runnr=) or the beta schedule (betas=)")
+    seq = list(range(0, num_timesteps, num_timesteps // T)) if runnr is None else None
     tmp = []
     for i in range(1, T + 1):
         if i % c == 0:
             x = torch.randn((batch_size, *shape), device=dev, generator=generator)
-            _, _, x_t, t_t = generalized_steps(x, seq, model, betas, eta=0.0, untill_fake_t=i)
+            if runnr is not None:
+                x_t, t_t = runnr.sample_image(x, model, untill_fake_t=i)[1:]
+            else:
+                _, _, x_t, t_t = generalized_steps(x, seq, model, betas, eta=0.0, untill_fake_t=i)
             tmp.append([x_t.cpu(), t_t.cpu()])
+    model._engine = None                # the all-fp engine must not outlive the state it was traced in
     return _cat(tmp)
 
 
