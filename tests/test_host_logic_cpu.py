@@ -250,3 +250,48 @@ def test_ddim_runner_schedules_and_sample_image_plumbing(monkeypatch):
     assert r.quantize(m) == (m, None, None, None)
     img = R.inverse_data_transform(NS(data=NS(rescaled=True, logit_transform=False)), torch.tensor([-3.0, -1.0, 0.0, 1.0, 2.0]))
     assert torch.equal(img, torch.tensor([0.0, 0.0, 0.5, 1.0, 1.0]))
+
+
+def test_ldm_script_shells():
+    """runners.LatentDiffusion / DiffusionWrapper: what sample_diffusion_ldm.py:438-479 and the samplers read."""
+    from types import SimpleNamespace as NS
+    import numpy as np
+    from helpers import first_stage_model
+    from tfmq_b200 import runners as R
+    from tfmq_b200.samplers import DDIMSampler, PLMSSampler
+    seen = []
+
+    def unet(x, t, context=None):
+        seen.append(context)
+        return x * 2
+
+    ld = R.LatentDiffusion(unet, scale_factor=0.18215, linear_start=0.00085, linear_end=0.012, conditioning_key="crossattn",
+                           image_size=64, channels=4)
+    x, t = torch.ones(2, 4, 8, 8), torch.tensor([5.0, 5.0])
+    assert torch.equal(ld.apply_model(x, t, [torch.zeros(2, 3, 7), torch.ones(2, 4, 7)]), x * 2)
+    assert tuple(seen[-1].shape) == (2, 7, 7)                       # c_crossattn concatenated along the token axis
+    # FSC attributes as the script installs them for a 50-table checkpoint (:473-479)
+    ckpt = {"weight": {}, **{f"act_{k}": {"k": k} for k in range(50)}}
+    n_tables = len(ckpt) - 1
+    ld.model.tot, ld.model.t_max, ld.model.ckpt, ld.model.iter = 1000 // n_tables, n_tables - 1, ckpt, 0
+    assert [ld.model.fsc_index(t_) for t_ in (981, 961, 21, 1)] == [0, 1, 48, 49]
+    with pytest.raises(RuntimeError, match="DDIMSampler"):
+        ld.model(x, t)
+    # the reference's call shape: DDIMSampler(<LatentDiffusion>) picks up UNet, FSC tables and noise schedule
+    for cls in (DDIMSampler, PLMSSampler):
+        s = cls(ld)
+        direct = cls(unet, linear_start=0.00085, linear_end=0.012, timesteps=1000, ckpt=ckpt)
+        assert s.model is unet and s.ckpt is ckpt and s.ddpm_num_timesteps == 1000
+        assert np.array_equal(s.alphas_cumprod, direct.alphas_cumprod)
+    assert DDIMSampler(unet).ddpm_num_timesteps == 1000 and DDIMSampler(unet).ckpt is None
+    # decode goes to the first stage with the model's scale factor (and there is no CPU path behind it)
+    with pytest.raises(RuntimeError, match="first_stage_model"):
+        ld.decode_first_stage(x)
+    fs, _ = first_stage_model("kl")
+    ld.first_stage_model = fs
+    with pytest.raises(RuntimeError):
+        ld.decode_first_stage(torch.zeros(1, 4, 16, 16))
+    assert fs.scale_factor == 0.18215
+    assert R.quantize_ldm(NS(ptq=False), ld) is ld
+    with pytest.raises(NotImplementedError):
+        R.DiffusionWrapper(unet, "concat")

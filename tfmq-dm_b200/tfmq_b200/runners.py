@@ -9,6 +9,10 @@ plumbing of `Diffusion.sample`, and batched sample generation -- the drop-in for
     Diffusion.sample_image       :429-476  (timestep sequence, generalized_steps with the FSC arguments)
     inverse_data_transform       ddim/datasets/__init__.py:206-215
 
+and the LDM side (`sample_diffusion_ldm.py:438-547`, `ldm/models/diffusion/ddpm.py:1385-1405`): `LatentDiffusion` /
+`DiffusionWrapper` shells that carry what the samplers and the decode read (`.model.diffusion_model`, the FSC attributes
+`.tot .t_max .ckpt .iter`, `.first_stage_model`, `.scale_factor`, the noise schedule) and `quantize_ldm`, the script's `--ptq` block.
+
 `args` / `config` are the namespaces the reference's `sample_diffusion_ddim.py` builds (argparse + YAML): the attributes
 read here are args.{ptq, wq, aq, use_aq, cali, cali_ckpt, cali_save_path, softmax_a_bit, q_mode, timesteps, interval_length,
 skip_type, sample_type, eta, asym, running_stat} and config.{diffusion.*, model.var_type, data.{channels, image_size,
@@ -26,7 +30,7 @@ import torch
 
 from . import dist_utils
 from .quant.calibration import cali_model, load_cali_model
-from .quant.data_generate import generate_cali_data_ddim
+from .quant.data_generate import generate_cali_data_ddim, generate_cali_data_ldm
 from .quant.quant_layer import Scaler
 from .quant.quant_model import QuantModel
 from .quant.reconstruction_util import RLOSS
@@ -160,3 +164,102 @@ class Diffusion:
             keep = min(n, total - r * n)
             out.append((x[:keep].permute(0, 2, 3, 1).cpu().numpy() * 255.).round().astype(np.uint8))
         return np.concatenate(out, axis=0) if out else np.zeros((0, size, size, ch), dtype=np.uint8)
+
+
+# ---------------------------------------------------------------------------------------------- LDM scripts
+class DiffusionWrapper(torch.nn.Module):
+    """Holder with the reference's attribute names: `.diffusion_model` (the UNet; the QuantModel after `--ptq`) and,
+    once activation quantisation is calibrated, the FSC attributes the script installs (`.tot .t_max .ckpt .iter`).
+    The per-call `load_state_dict` switch of the reference's forward (ddpm.py:1402-1405) is not reproduced: the samplers
+    read `.ckpt` and switch the activation parameters on the device, one row copy per step."""
+
+    def __init__(self, diffusion_model, conditioning_key: Optional[str] = None):
+        super().__init__()
+        if conditioning_key not in (None, "crossattn"):
+            raise NotImplementedError(f"conditioning_key {conditioning_key}: the configs of the path use None / crossattn")
+        self.diffusion_model, self.conditioning_key = diffusion_model, conditioning_key
+
+    def fsc_index(self, t: int) -> int:
+        """The `act_k` table the reference loads for DDPM time t: t_max - (t - 1) // tot."""
+        return int(self.t_max - (int(t) - 1) // self.tot)
+
+    def forward(self, x, t, c_concat: list = None, c_crossattn: list = None):
+        if hasattr(self, "tot"):
+            raise RuntimeError("DiffusionWrapper.forward with FSC tables: sample through DDIMSampler / PLMSSampler, which "
+                               "select the per-step activation parameters on the device")
+        if self.conditioning_key is None:
+            return self.diffusion_model(x, t)
+        return self.diffusion_model(x, t, context=torch.cat(c_crossattn, 1))
+
+
+class LatentDiffusion(torch.nn.Module):
+    """What the sampling scripts hold as `model`: `.model` (DiffusionWrapper), `.first_stage_model`, the noise schedule
+    and `decode_first_stage` -- without Lightning, the encoders, the losses or training (outside the path)."""
+
+    def __init__(self, unet, first_stage_model=None, scale_factor: float = 1.0, timesteps: int = 1000,
+                 linear_start: float = 0.0015, linear_end: float = 0.0195, conditioning_key: Optional[str] = None,
+                 image_size: Optional[int] = None, channels: Optional[int] = None):
+        super().__init__()
+        self.model = DiffusionWrapper(unet, conditioning_key)
+        self.first_stage_model = first_stage_model
+        self.scale_factor, self.num_timesteps = float(scale_factor), timesteps
+        self.linear_start, self.linear_end = linear_start, linear_end
+        self.image_size = image_size if image_size is not None else getattr(unet, "image_size", None)
+        self.channels = channels if channels is not None else getattr(unet, "in_channels", None)
+
+    def apply_model(self, x_noisy, t, cond=None):
+        if cond is None:
+            return self.model(x_noisy, t)
+        return self.model(x_noisy, t, c_crossattn=cond if isinstance(cond, list) else [cond])
+
+    @torch.no_grad()
+    def decode_first_stage(self, z, predict_cids: bool = False, force_not_quantize: bool = False):
+        fs = self.first_stage_model
+        if fs is None:
+            raise RuntimeError("LatentDiffusion.decode_first_stage: no first_stage_model (first_stage.FirstStageModel) was given")
+        fs.scale_factor = self.scale_factor
+        return fs.decode_first_stage(z, predict_cids=predict_cids, force_not_quantize=force_not_quantize)
+
+
+def quantize_ldm(opt, model: LatentDiffusion, device="cuda"):
+    """The `if opt.ptq:` block of sample_diffusion_ldm.py:456-547 on a `LatentDiffusion` shell.  Sampling (`not opt.cali`):
+    wraps the UNet in a QuantModel, loads opt.cali_ckpt, installs it as `model.model.diffusion_model` and, with
+    opt.use_aq, the FSC attributes `.tot .t_max .ckpt .iter`.  Calibration (`opt.cali`): generates the calibration data
+    with the FP sampler, runs `cali_model` (saves to opt.cali_save_path) and installs the calibrated QuantModel.
+    opt: ptq, cali, wq, aq, use_aq, softmax_a_bit, q_mode, cali_ckpt, cali_save_path, custom_steps, interval_length, plms,
+    eta, asym, running_stat."""
+    if not getattr(opt, "ptq", False):
+        return model
+    scaler = Scaler.MSE if opt.cali else Scaler.MINMAX
+    wq_params = dict(bits=opt.wq, channel_wise=True, scaler=scaler)
+    aq_params = dict(bits=opt.aq, channel_wise=False, scaler=scaler, leaf_param=opt.use_aq)
+    unet = model.model.diffusion_model
+    setattr(unet, "split", True)
+    qnn = QuantModel(model=unet, wq_params=wq_params, aq_params=aq_params, cali=bool(opt.cali),
+                     softmax_a_bit=opt.softmax_a_bit, aq_mode=opt.q_mode)
+    qnn.to(device)
+    qnn.eval()
+    shape = [model.channels, model.image_size, model.image_size]
+    if not opt.cali:
+        load_cali_model(qnn, (torch.randn(1, *shape), torch.randint(0, 1000, (1,))), use_aq=opt.use_aq, path=opt.cali_ckpt)
+        model.model.diffusion_model = qnn
+        if opt.use_aq:
+            cali_ckpt = torch.load(opt.cali_ckpt, map_location="cpu", weights_only=False)
+            n_tables = len(cali_ckpt) - 1
+            model.model.tot, model.model.t_max = 1000 // n_tables, n_tables - 1
+            model.model.ckpt, model.model.iter = cali_ckpt, 0
+        return model
+    logger.info("Generating calibration data...")
+    per_step = 256
+    xs, ts = generate_cali_data_ldm(qnn, T=opt.custom_steps, c=1, batch_size=per_step, shape=shape,
+                                    plms=getattr(opt, "plms", False), eta=opt.eta, linear_start=model.linear_start,
+                                    linear_end=model.linear_end, timesteps=model.num_timesteps)
+    qnn._engine = None
+    kept = [slice(i * per_step, (i + 1) * per_step) for i in range(0, opt.custom_steps, opt.interval_length)]
+    w_cali_data = [torch.cat([xs[s] for s in kept]), torch.cat([ts[s] for s in kept])]
+    logger.info("Calibration data generated.")
+    cali_model(qnn=qnn, use_aq=opt.use_aq, path=opt.cali_save_path, running_stat=opt.running_stat, interval=per_step,
+               w_cali_data=w_cali_data, a_cali_data=(xs, ts), iters=20000, batch_size=32, w=0.01, asym=opt.asym,
+               warmup=0.2, opt_mode=RLOSS.MSE, multi_gpu=False)
+    model.model.diffusion_model = qnn
+    return model

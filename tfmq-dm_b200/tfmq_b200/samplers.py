@@ -103,8 +103,21 @@ class DDIMSampler:
     `model` is the QuantModel (what the reference installs as model.model.diffusion_model);
     the noise schedule comes from linear_start / linear_end of the LDM config."""
 
-    def __init__(self, model, linear_start: float = 0.0015, linear_end: float = 0.0195, timesteps: int = 1000,
-                 ckpt: Optional[dict] = None):
+    def __init__(self, model, linear_start: Optional[float] = None, linear_end: Optional[float] = None,
+                 timesteps: Optional[int] = None, ckpt: Optional[dict] = None):
+        wrapper = getattr(model, "model", None)
+        if wrapper is not None and hasattr(wrapper, "diffusion_model"):
+            # the reference's call shape, DDIMSampler(<LatentDiffusion>) (runners.LatentDiffusion here): the UNet is
+            # model.model.diffusion_model, the FSC tables are the `.ckpt` the script installs on the wrapper, the noise
+            # schedule is the model's
+            ckpt = ckpt if ckpt is not None else getattr(wrapper, "ckpt", None)
+            linear_start = linear_start if linear_start is not None else getattr(model, "linear_start", None)
+            linear_end = linear_end if linear_end is not None else getattr(model, "linear_end", None)
+            timesteps = timesteps if timesteps is not None else getattr(model, "num_timesteps", None)
+            model = wrapper.diffusion_model
+        linear_start = 0.0015 if linear_start is None else linear_start
+        linear_end = 0.0195 if linear_end is None else linear_end
+        timesteps = 1000 if timesteps is None else timesteps
         self.model = model
         self.ddpm_num_timesteps = timesteps
         betas = make_beta_schedule("linear", timesteps, linear_start, linear_end)
