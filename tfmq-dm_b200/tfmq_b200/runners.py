@@ -221,13 +221,17 @@ class LatentDiffusion(torch.nn.Module):
         return fs.decode_first_stage(z, predict_cids=predict_cids, force_not_quantize=force_not_quantize)
 
 
-def quantize_ldm(opt, model: LatentDiffusion, device="cuda"):
+def quantize_ldm(opt, model: LatentDiffusion, device="cuda", context_shape=None, cali_data=None):
     """The `if opt.ptq:` block of sample_diffusion_ldm.py:456-547 on a `LatentDiffusion` shell.  Sampling (`not opt.cali`):
     wraps the UNet in a QuantModel, loads opt.cali_ckpt, installs it as `model.model.diffusion_model` and, with
     opt.use_aq, the FSC attributes `.tot .t_max .ckpt .iter`.  Calibration (`opt.cali`): generates the calibration data
     with the FP sampler, runs `cali_model` (saves to opt.cali_save_path) and installs the calibrated QuantModel.
     opt: ptq, cali, wq, aq, use_aq, softmax_a_bit, q_mode, cali_ckpt, cali_save_path, custom_steps, interval_length, plms,
-    eta, asym, running_stat."""
+    eta, asym, running_stat[, no_grad_ckpt].
+    Conditional UNets (txt2img.py:394-470, latent_imagenet_diffusion.py): context_shape = (tokens, context_dim) adds the
+    conditioning tensor to the dummy forward of `load_cali_model`; their calibration data come from guided sampling with
+    encoder outputs (quant.data_generate.generate_cali_data_conditional) and are passed in as `cali_data` = (x_t, t, c),
+    used for both the weight and the activation phase as those scripts do."""
     if not getattr(opt, "ptq", False):
         return model
     scaler = Scaler.MSE if opt.cali else Scaler.MINMAX
@@ -239,9 +243,14 @@ def quantize_ldm(opt, model: LatentDiffusion, device="cuda"):
                      softmax_a_bit=opt.softmax_a_bit, aq_mode=opt.q_mode)
     qnn.to(device)
     qnn.eval()
+    if getattr(opt, "no_grad_ckpt", False):
+        qnn.set_grad_ckpt(False)
     shape = [model.channels, model.image_size, model.image_size]
     if not opt.cali:
-        load_cali_model(qnn, (torch.randn(1, *shape), torch.randint(0, 1000, (1,))), use_aq=opt.use_aq, path=opt.cali_ckpt)
+        init = (torch.randn(1, *shape), torch.randint(0, 1000, (1,)))
+        if context_shape is not None:
+            init += (torch.randn(1, *context_shape),)
+        load_cali_model(qnn, init, use_aq=opt.use_aq, path=opt.cali_ckpt)
         model.model.diffusion_model = qnn
         if opt.use_aq:
             cali_ckpt = torch.load(opt.cali_ckpt, map_location="cpu", weights_only=False)
@@ -249,6 +258,15 @@ def quantize_ldm(opt, model: LatentDiffusion, device="cuda"):
             model.model.tot, model.model.t_max = 1000 // n_tables, n_tables - 1
             model.model.ckpt, model.model.iter = cali_ckpt, 0
         return model
+    if cali_data is not None:
+        cali_model(qnn=qnn, use_aq=opt.use_aq, path=opt.cali_save_path, running_stat=opt.running_stat, interval=256,
+                   w_cali_data=cali_data, a_cali_data=cali_data, iters=20000, batch_size=32, w=0.01, asym=opt.asym,
+                   warmup=0.2, opt_mode=RLOSS.MSE, multi_gpu=False)
+        model.model.diffusion_model = qnn
+        return model
+    if context_shape is not None:
+        raise ValueError("quantize_ldm: calibrating a conditional UNet needs cali_data=(x_t, t, c) "
+                         "(quant.data_generate.generate_cali_data_conditional)")
     logger.info("Generating calibration data...")
     per_step = 256
     xs, ts = generate_cali_data_ldm(qnn, T=opt.custom_steps, c=1, batch_size=per_step, shape=shape,
