@@ -43,6 +43,25 @@ def _worker(rank, world, port, ret):
     # calibration data: each rank takes its 1/world slice of every timestep interval
     idx = D.shard_interval_indices(8, 4, rank, world).tolist()
     ok &= idx == ([0, 1, 4, 5] if rank == 0 else [2, 3, 6, 7])
+    # runner: the rounds of `sample_batches` are split over the ranks (no collective); the union is the single-rank result
+    from types import SimpleNamespace as NS
+    from tfmq_b200 import runners as R
+    cfg = NS(model=NS(var_type="fixedlarge"), data=NS(channels=3, image_size=4, rescaled=True, logit_transform=False),
+             sampling=NS(batch_size=2), diffusion=NS(beta_schedule="linear", beta_start=1e-4, beta_end=0.02,
+                                                       num_diffusion_timesteps=1000))
+    run = R.Diffusion(NS(skip_type="uniform", timesteps=10, sample_type="generalized", eta=0.0), cfg, device="cpu")
+    rounds = []
+
+    def fake_sample_image(x, model, **kw):          # stands in for the GPU sampler: marks every image with its round
+        rounds.append(len(rounds))
+        return torch.full_like(x, -1.0 + 0.25 * (model["first"] + len(rounds) - 1)), None, None
+    run.sample_image = fake_sample_image
+    first = list(D.shard_range(4, rank, world))[0]                  # 7 images in batches of 2 = 4 rounds
+    imgs = run.sample_batches({"first": first}, total=7)
+    allr = [None] * world
+    dist.all_gather_object(allr, imgs[:, 0, 0, 0].tolist())
+    ok &= imgs.dtype == torch.zeros(1).numpy().astype("uint8").dtype and imgs.shape[1:] == (4, 4, 3)
+    ok &= sum(allr, []) == [0, 0, 32, 32, 64, 64, 96]               # round r -> value round(255 * r / 8); last round keeps 1
     ret[rank] = ok
     dist.destroy_process_group()
 
