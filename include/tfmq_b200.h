@@ -37,7 +37,8 @@ typedef enum {
   TFMQ_ERR_UNAVAILABLE = 4  /* no sm_100 device / driver entry point missing */
 } tfmq_status;
 
-/* context: one per device per process; not thread-safe */
+/* context: one per device per process, ONE DEVICE PER PROCESS (the launchers cache the kernels' opt-in shared-memory
+ * attribute per process, matching the one-process-per-GPU model of the path); not thread-safe */
 int tfmq_create(tfmq_ctx** out, int device);
 int tfmq_destroy(tfmq_ctx* ctx);
 const char* tfmq_last_error(tfmq_ctx* ctx);
