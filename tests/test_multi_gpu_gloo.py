@@ -62,6 +62,17 @@ def _worker(rank, world, port, ret):
     dist.all_gather_object(allr, imgs[:, 0, 0, 0].tolist())
     ok &= imgs.dtype == torch.zeros(1).numpy().astype("uint8").dtype and imgs.shape[1:] == (4, 4, 3)
     ok &= sum(allr, []) == [0, 0, 32, 32, 64, 64, 96]               # round r -> value round(255 * r / 8); last round keeps 1
+    # with an identically seeded generator the union over the ranks is bit-identical to the single-rank run
+    run.sample_image = lambda x, model, **kw: (torch.tanh(x), None, None)
+    part = run.sample_batches(None, total=7, generator=torch.Generator().manual_seed(11))
+    parts = [None] * world
+    dist.all_gather_object(parts, part)
+    saved = (D.rank, D.world)
+    D.rank, D.world = (lambda: 0), (lambda: 1)
+    single = run.sample_batches(None, total=7, generator=torch.Generator().manual_seed(11))
+    D.rank, D.world = saved
+    import numpy as np
+    ok &= single.shape == (7, 4, 4, 3) and np.array_equal(np.concatenate(parts, axis=0), single) and len(part) in (3, 4)
     ret[rank] = ok
     dist.destroy_process_group()
 

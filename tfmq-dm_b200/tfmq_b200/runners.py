@@ -152,19 +152,24 @@ class Diffusion:
     def sample_batches(self, model, total: int, untill_fake_t=114514, tot=None, cali_ckpt=None, t_max=None,
                        generator: Optional[torch.Generator] = None) -> np.ndarray:
         """`sample_fid` without the files: `total` images in rounds of config.sampling.batch_size, as uint8 [n, H, W, C].
-        Under torch.distributed every rank takes its contiguous share of the rounds (independent batches, no collective)."""
+        Under torch.distributed every rank takes its contiguous share of the rounds (independent batches, no collective).
+        With a `generator` seeded identically on every rank, each rank draws the x_T of ALL rounds and keeps its own, so
+        the union over the ranks is bit-identical to a single-GPU run with that seed; without one the ranks
+        draw independently."""
         n = self.config.sampling.batch_size
         ch, size = self.config.data.channels, self.config.data.image_size
-        rounds = dist_utils.shard_range(math.ceil(total / n), dist_utils.rank(), dist_utils.world())
+        n_rounds = math.ceil(total / n)
+        mine = dist_utils.shard_range(n_rounds, dist_utils.rank(), dist_utils.world())
         out = []
-        for r in rounds:
+        for r in (range(n_rounds) if generator is not None else mine):
             x = torch.randn(n, ch, size, size, device=self.device, generator=generator)
+            if r not in mine:
+                continue
             x = self.sample_image(x, model, untill_fake_t=untill_fake_t, tot=tot, cali_ckpt=cali_ckpt, t_max=t_max)[0]
             x = inverse_data_transform(self.config, x)
             keep = min(n, total - r * n)
             out.append((x[:keep].permute(0, 2, 3, 1).cpu().numpy() * 255.).round().astype(np.uint8))
         return np.concatenate(out, axis=0) if out else np.zeros((0, size, size, ch), dtype=np.uint8)
-
 
 # ---------------------------------------------------------------------------------------------- LDM scripts
 class DiffusionWrapper(torch.nn.Module):
