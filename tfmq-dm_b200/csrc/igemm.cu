@@ -88,17 +88,20 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   float2* cpart = cstat + p.stat_imgs * p.tile_n;     // [2][parts][chunk_w] row-block partials of the last two chunks
   uint64_t* bars = reinterpret_cast<uint64_t*>(ebuf + NB * 128 * 32 * 4 + p.tile_n * 16 + p.stat_imgs * p.tile_n * 8 +
                                                2 * 256 * 8);
-  // barrier slots (8 bytes each, 32 slots): the two pipelines use the first 24 differently
+  // barrier slots (8 bytes each, 64 slots; 128 when p.deep_bars): the two pipelines use the first 24 differently.
+  // deep_bars (w4a8 with more than 4 slots in the s8 B or packed ring, TFMQ_IGEMM_USTAGES / _PSTAGES up to 8): the four ring
+  // barrier arrays move to a second block of 64 slots; the default layout is untouched.
+  const bool deep = W4 && p.deep_bars != 0;
   uint64_t* full_tma = bars;            // [<=8] TMA bytes landed (w4a8: the A tile; CTA pair: of both CTAs, at the leader)
   uint64_t* empty = bars + 8;           // [<=8] UMMAs that read the stage (w4a8: the A slot) retired
-  uint64_t* full_xf = bars + 16;        // [<=8] transform warps done (w4a8: s8 B slot written, [<=4])
-  uint64_t* empty_u = bars + 20;        // w4a8 [<=4]: UMMAs that read the s8 B slot retired
+  uint64_t* full_xf = deep ? bars + 64 : bars + 16;   // [<=8] transform warps done (w4a8: s8 B slot written, [<=4], deep [<=8])
+  uint64_t* empty_u = deep ? bars + 72 : bars + 20;   // w4a8 [<=4], deep [<=8]: UMMAs that read the s8 B slot retired
   uint64_t* acc_full = bars + 24;       // [2] accumulator stage complete
   uint64_t* acc_empty = bars + 26;      // [2] accumulator stage drained by the epilogue
   uint64_t* res_full = bars + 40;       // [<=3] residual chunk landed in the epilogue buffer
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 30);
-  uint64_t* full_p = bars + 32;         // w4a8 [<=4]: packed int4 tile landed
-  uint64_t* empty_p = bars + 36;        // w4a8 [<=4]: the transform warps hold the packed tile in registers
+  uint64_t* full_p = deep ? bars + 80 : bars + 32;    // w4a8 [<=4], deep [<=8]: packed int4 tile landed
+  uint64_t* empty_p = deep ? bars + 88 : bars + 36;   // w4a8 [<=4], deep [<=8]: the transform warps hold the packed tile in registers
 
   const int tiles_x = p.W / p.tw;
   const int tiles_y = p.H / p.th;
@@ -792,6 +795,8 @@ static int launch_igemm(tfmq_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap
                               512u /*barriers*/;
   const uint32_t chunk_buf = 128u * 32u * 4u;
   uint32_t extra = extra_base + (uint32_t)p.epi_bufs * chunk_buf;
+  uint32_t deep_extra = 0;
+  p.deep_bars = 0;
   static const int stages_env = getenv("TFMQ_IGEMM_STAGES") ? atoi(getenv("TFMQ_IGEMM_STAGES")) : 0;   // experiments
   int stages;
   size_t smem;
@@ -806,12 +811,17 @@ static int launch_igemm(tfmq_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap
     p.p_bytes = ((uint32_t)(CG == 2 ? p.b_rows[0] : p.tile_n) * 64u + 1023u) & ~1023u;
     static const int sp_env = getenv("TFMQ_IGEMM_PSTAGES") ? atoi(getenv("TFMQ_IGEMM_PSTAGES")) : 0;
     p.p_stages = sp_env > 0 ? sp_env : 4;
+    if (p.u_stages < 2 || p.u_stages > 8 || (p.u_stages & 1) || p.p_stages < 1 || p.p_stages > 8)
+      return tfmq_fail(ctx, TFMQ_ERR_ARG, "%s: ring depths (s8 B %d: even, 2..8; packed %d: 1..8)", name, p.u_stages, p.p_stages);
+    p.deep_bars = (p.u_stages > 4 || p.p_stages > 4) ? 1 : 0;
+    deep_extra = p.deep_bars ? 512u : 0u;             // second block of 64 barrier slots
+    extra += deep_extra;
     const long long left = (long long)ctx->max_smem_optin - extra - (long long)p.u_stages * p.u_bytes -
                            (long long)p.p_stages * p.p_bytes;
     stages = (int)(left / (long long)IGEMM_A_BYTES);
     if (p.epi_bufs == 3 && stages < 4 && !eb_env) {      // keep the A ring at least 4 deep (or as deep as it was)
       p.epi_bufs = 2;
-      extra = extra_base + 2u * chunk_buf;
+      extra = extra_base + deep_extra + 2u * chunk_buf;
       stages = (int)((left + (long long)chunk_buf) / (long long)IGEMM_A_BYTES);
     }
     if (stages > 8) stages = 8;

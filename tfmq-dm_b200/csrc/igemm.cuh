@@ -33,6 +33,7 @@ struct IgemmParams {
   int th, tw, tn;          // tile = tn*th*tw = 128 output pixels
   int tile_n, stages, tmem_cols, acc_stages, chunk_w;
   int epi_bufs;              // epilogue chunk buffers (2, or 3: residual loads two chunks ahead)
+  int deep_bars;             // w4a8: ring barrier arrays of 8 slots in a second barrier block (ring depths > 4)
   int kchunk, kslice;  // channels per k-block / per UMMA
   int u_stages;              // w4a8: slots of the s8 B ring
   uint32_t u_bytes;          // w4a8: bytes per s8 B slot
