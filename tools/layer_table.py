@@ -1,7 +1,7 @@
 """Per-layer table of the w4a8 conv launches of one LDM-4 step (batch 16): shape, algorithmic int8 ops, the duration of the
 corresponding launch in an ncu launch list (`--metrics gpu__time_duration.sum`, program order), achieved TOP/s and the
 fraction of the int8 peak bench.py uses.  Runs on the CPU: shapes come from one FP forward of the host model with hooks.
-  python tools/layer_table.py profiles/r1j_launches_step.csv > profiles/r1j_w4a8_layers.md"""
+  python tools/layer_table.py profiles/r1j_launches_step.csv > profiles/r1j_conv_layers.md"""
 import csv
 import json
 import os
@@ -26,7 +26,7 @@ fp = fp_model("ldm").eval()
 order = []
 hooks = []
 for n, m in fp.named_modules():
-    if isinstance(m, torch.nn.Conv2d):
+    if isinstance(m, (torch.nn.Conv2d, torch.nn.Conv1d)):
         hooks.append(m.register_forward_hook(lambda mod, inp, out, n=n: order.append((n, tuple(inp[0].shape), tuple(out.shape),
                                                                                      tuple(mod.weight.shape)))))
 with torch.no_grad():
@@ -38,6 +38,9 @@ qnn.set_quant_state(True, True)
 qnn.disable_out_quantization()
 flags = {n: (m.use_wq, m.use_aq and not m.disable_aq) for n, m in qnn.model.named_modules() if isinstance(m, QuantLayer)}
 layers = [(n, i, o, w) for n, i, o, w in order if flags.get(n) == (True, True)]
+# everything else that is a tensor-core conv runs on the fp16-split path: un-wrapped convs (skip / op / Conv1d qkv, proj_out) and
+# weight-only-quantised layers; the first / last conv (3 or fewer channels on one side) have their own FFMA kernels
+fp_layers = [(n, i, o, w) for n, i, o, w in order if flags.get(n) != (True, True) and min(w[0], w[1]) > 4]
 
 rows = [l for l in open(path) if not l.startswith("==")]
 durs = []
@@ -69,3 +72,30 @@ print("\n| map | launches | GOP | us | share of kernel time | TOP/s | of peak |"
 print("|---|---:|---:|---:|---:|---:|---:|")
 for m, (cnt, g, u) in by_map.items():
     print(f"| {m} | {cnt} | {g:.0f} | {u:.0f} | {100 * u / tot_us:.0f} % | {g / u * 1e3:.0f} | {g / u * 1e3 / peak:.2f} |")
+
+fdurs = []
+for r in csv.DictReader(rows):
+    if "igemm_kernel<3" in r["Kernel Name"] or "igemm_kernel<(int)3" in r["Kernel Name"]:
+        v = float(r["Metric Value"].replace(",", ""))
+        fdurs.append(v / 1e3 if r["Metric Unit"] == "ns" else v)
+if len(fdurs) == len(fp_layers):
+    fpeak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"] \
+        if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 1400.0
+    print(f"\n# fp32-accurate conv launches (kind::f16 on fp16 hi/lo planes, 3 products): algorithmic GFLOP, and the executed "
+          f"3 x GFLOP against the measured sustained f16/bf16 rate ({fpeak:.0f} TFLOP/s)\n")
+    print("| # | layer | conv | map | K | GFLOP | us | algorithmic TFLOP/s | executed (x3) of peak |")
+    print("|---:|---|---|---|---:|---:|---:|---:|---:|")
+    tg = tu = 0.0
+    for k, ((n, i, o, w), us) in enumerate(zip(fp_layers, fdurs)):
+        cout, cin = w[0], w[1]
+        taps = w[2] * (w[3] if len(w) == 4 else 1)
+        pix = o[2] * (o[3] if len(o) == 4 else 1)
+        gf = 2.0 * BATCH * pix * cout * cin * taps / 1e9
+        tg += gf
+        tu += us
+        shape = f"{o[2]}x{o[3]}" if len(o) == 4 else f"{o[2]} tok"
+        print(f"| {k} | {n} | {cin}->{cout} k{w[2]} | {shape} | {cin * taps} | {gf:.1f} | {us:.1f} | {gf / us * 1e3:.0f} | "
+              f"{3 * gf / us * 1e3 / fpeak:.2f} |")
+    print(f"\ntotal {tg:.0f} GFLOP algorithmic in {tu:.0f} us = {tg / tu * 1e3:.0f} TFLOP/s; executed x3 = {3 * tg / tu * 1e3 / fpeak:.2f} of peak")
+else:
+    print(f"\n# fp conv table skipped: {len(fdurs)} launches vs {len(fp_layers)} layers")
