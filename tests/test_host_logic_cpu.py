@@ -191,6 +191,13 @@ def test_first_stage_configs_and_decoder_program():
         assert c["tfmq_conv_h16"] == 6 * 2 + 1 + 1 + 2 * n_attn
         # the attention output reaches proj_out as fp16 planes written by the attention kernel: no split launch for it
         assert c["tfmq_act_prepare"] == c["tfmq_conv_h16"] - n_attn + 1      # + the final GN + SiLU before conv_out
+    # the same program EXECUTED on the CPU by torch stand-ins with the kernels' semantics (tests/emulated_ops.py): the host
+    # logic (op order, strides, residual aliasing, GroupNorm statistics through conv epilogues, fp16 planes) reproduces the
+    # oracle and the reference fixture
+    out = subprocess.run([sys.executable, tool, "--emulate"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    errs = {ln.split()[0]: float(ln.split()[-1]) for ln in out.stdout.strip().splitlines()}
+    assert set(errs) == {"vq", "vq-attn", "kl"} and max(errs.values()) < 2e-5, errs
 
 
 def test_ddim_runner_schedules_and_sample_image_plumbing(monkeypatch):
