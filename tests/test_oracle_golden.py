@@ -168,3 +168,40 @@ def test_first_stage_decode_against_reference():
             m(z)                                                   # parameter container: no torch / CPU forward
         with pytest.raises(RuntimeError):
             m.decode_first_stage(z)                                # CPU latent: no CPU path
+
+
+def test_oracle_size_independent_properties():
+    """Properties of the restated arithmetic that hold at any size (the GPU tests use the same ones at BASELINE sizes):
+    fake-quant is idempotent on its own output, codes stay on the grid, hard AdaRound at the analytic alpha is
+    round-to-nearest, the DDIM update is linear in (x, eps), and the nearest-code lookup is a projection."""
+    from oracle import first_stage_ref as FS
+    g = torch.Generator().manual_seed(3)
+    for shape, level, cw in (((7, 5, 3, 3), 16, True), ((4, 33), 16, True), ((2, 6, 9, 9), 256, False)):
+        x = torch.randn(shape, generator=g) * 3
+        d, z = (Q.channel_wise(Q.minmax_scale, x, level) if cw else Q.minmax_scale(x, level))
+        xq = Q.uaq_fake_quant(x, d, z, level)
+        assert torch.equal(Q.uaq_fake_quant(xq, d, z, level), xq)                       # idempotent
+        codes = Q.uaq_codes(x, d, z, level)
+        assert codes.min() >= 0 and codes.max() <= level - 1 and torch.equal(codes, codes.round())
+        # the zero point is rounded, so the grid need not reach the extreme values: "in range" = not clipped
+        inside = ((x / d + z) >= 0) & ((x / d + z) <= level - 1)
+        assert inside.float().mean() > 0.9
+        assert ((xq - x).abs() <= 0.5001 * d)[inside].all()                             # in-range values move <= delta / 2
+        if cw:
+            a0 = Q.adaround_init_alpha(x, d)
+            assert torch.equal(Q.adaround_fake_quant(x, d, z, a0, level), xq)
+            soft = Q.adaround_fake_quant(x, d, z, a0, level, soft=True)
+            assert ((soft - x).abs() <= 1e-5 * x.abs().max())[inside].all()             # soft rounding starts at the FP weight
+    # DDIM update: x_prev(a x1 + b x2, a e1 + b e2) = a x_prev(x1, e1) + b x_prev(x2, e2)
+    sa, s1, sn, c2, _ = Q.ddim_coefficients(0.37, 0.52)
+    upd = lambda x, e: sn * ((x - e * s1) / sa) + c2 * e  # noqa: E731
+    x1, x2, e1, e2 = (torch.randn(2, 3, 8, 8, generator=g).double() for _ in range(4))
+    assert torch.allclose(upd(0.3 * x1 - 1.7 * x2, 0.3 * e1 - 1.7 * e2), 0.3 * upd(x1, e1) - 1.7 * upd(x2, e2), atol=1e-12)
+    # VQ lookup: a projection onto the codebook (looking up its own output changes nothing), and never farther than any code
+    cb = torch.randn(50, 3, generator=g)
+    zz = torch.randn(2, 3, 5, 5, generator=g)
+    zq, idx = FS.vq_lookup(zz, cb)
+    zq2, idx2 = FS.vq_lookup(zq, cb)
+    assert torch.equal(idx2, idx) and (zq2 - zq).abs().max() < 1e-6
+    dmin = (zz.permute(0, 2, 3, 1).reshape(-1, 1, 3) - cb[None]).pow(2).sum(-1)
+    assert torch.equal(dmin.argmin(1), idx)
