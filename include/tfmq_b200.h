@@ -223,6 +223,12 @@ typedef struct {
   int64_t emb_ld;
   int n_stat;
   tfmq_gn_target stat[2];
+  /* optional: write the result as fp16 hi / lo planes (the split tfmq_act_prepare makes) INSTEAD of fp32 `out`, which may
+   * then be NULL: the consumer is another tfmq_conv_h16 or tfmq_attention_h16 (the qkv projection of an attention block).
+   * Pixel pitch out_h_ld in halves (multiple of 8).  Not combinable with res / n_stat. */
+  void* out_hi;
+  void* out_lo;
+  int64_t out_h_ld;
 } tfmq_conv_h16_desc;
 int tfmq_conv_h16(tfmq_ctx* ctx, const tfmq_conv_h16_desc* d, void* stream);
 
@@ -293,6 +299,28 @@ typedef struct {
   void* o_lo;
 } tfmq_attn_desc;
 int tfmq_attention(tfmq_ctx* ctx, const tfmq_attn_desc* d, void* stream);
+
+/* The same attention core on tcgen05 (UMMA, accumulators in tensor memory): S = Q K^T with both operands from shared
+ * memory, O += P V with P read from TENSOR MEMORY (written there by the softmax warps, never staged in shared memory)
+ * and V read as stored ([key][dim], MN-major).  Replaces the same reference code as tfmq_attention
+ * (openaimodel.py:383-405, quant_block.py:212-245,474-505); fp32-accurate: q, k, v arrive PRE-SPLIT as fp16 hi / lo
+ * planes (hi = half(x), lo = half(x - hi)) -- written once per tensor by tfmq_conv_h16 (out_hi / out_lo) or
+ * tfmq_act_prepare (dst_hi / dst_lo) -- and every product is hi*hi + lo*hi + hi*lo with fp32 accumulation; softmax in
+ * fp32.  Planes are addressed like tfmq_attn_desc (base + b*sb + h*sh + t*st + dim, in halves; strides multiples of 8,
+ * bases 16-byte aligned).  Head dims: multiples of 8 from 16 to 64 (32 for LDM-4, 40 for SD v1.4's first level).
+ * Output: fp32 `o`, or (o_hi, o_lo) planes for a following tfmq_conv_h16. */
+typedef struct {
+  const void* q_hi; const void* q_lo; int64_t q_sb, q_sh, q_st;
+  const void* k_hi; const void* k_lo; int64_t k_sb, k_sh, k_st;
+  const void* v_hi; const void* v_lo; int64_t v_sb, v_sh, v_st;
+  float* o;       /* or NULL when o_hi / o_lo are given */
+  void* o_hi;
+  void* o_lo;
+  int64_t o_sb, o_sh, o_st;
+  int b, heads, tq, tk, d;
+  float scale;
+} tfmq_attn_h16_desc;
+int tfmq_attention_h16(tfmq_ctx* ctx, const tfmq_attn_h16_desc* d, void* stream);
 
 /* ------------------------------------------------------------------------- *
  * DDIM update (ddim/functions/denoising.py:31-37; ldm/models/diffusion/ddim.py:

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in the header but not exported"
     assert sorted(_lib.EXPORTS) == names, "ctypes binding and header disagree"
-    assert lib.tfmq_abi_version() == 3
+    assert lib.tfmq_abi_version() == 4
 
 
 def test_struct_layouts_match_c():
@@ -35,8 +35,8 @@ def test_struct_layouts_match_c():
 #include <stdio.h>
 #include "tfmq_b200.h"
 int main(void) {
-  printf("%zu %zu %zu %zu %zu\n", sizeof(tfmq_act_desc), sizeof(tfmq_conv_w4a8_desc), sizeof(tfmq_conv_fp_desc),
-         sizeof(tfmq_linear_desc), sizeof(tfmq_attn_desc));
+  printf("%zu %zu %zu %zu %zu %zu %zu\n", sizeof(tfmq_act_desc), sizeof(tfmq_conv_w4a8_desc), sizeof(tfmq_conv_fp_desc),
+         sizeof(tfmq_linear_desc), sizeof(tfmq_attn_desc), sizeof(tfmq_conv_h16_desc), sizeof(tfmq_attn_h16_desc));
   return 0;
 }'''
     with tempfile.TemporaryDirectory() as td:
@@ -45,7 +45,8 @@ int main(void) {
         exe = os.path.join(td, "s")
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
         sizes = [int(x) for x in subprocess.check_output([exe]).split()]
-    want = [ctypes.sizeof(t) for t in (_lib.ActDesc, _lib.ConvW4A8Desc, _lib.ConvFpDesc, _lib.LinearDesc, _lib.AttnDesc)]
+    want = [ctypes.sizeof(t) for t in (_lib.ActDesc, _lib.ConvW4A8Desc, _lib.ConvFpDesc, _lib.LinearDesc, _lib.AttnDesc,
+                                     _lib.ConvH16Desc, _lib.AttnH16Desc)]
     assert sizes == want
 
 

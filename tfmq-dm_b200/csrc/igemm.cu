@@ -4,6 +4,8 @@
 #include <cstdlib>
 #include <vector>
 
+#include <cuda_fp16.h>
+
 #include "igemm.cuh"
 
 #include "ctx.h"
@@ -603,9 +605,36 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const float* embp = (p.emb && !emb_folded) ? p.emb + (long long)n_l * p.emb_ld + c_out0 + c0 : nullptr;
         const int npiece = HC >> 2;           // 16-byte pieces per thread: 4 (CW 32) or 2 (CW 16)
         const int k0 = half * npiece;
+        if (FP && p.out_planes) {
+          // output as fp16 hi / lo planes (CW == 32): the chunk buffer holds a [128][32] half tile of each plane, 64-byte
+          // rows under the 64B swizzle; this thread converts its 16 columns and writes two 16-byte pieces per plane
+          uint32_t hw[8], lw[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 ca = chp[c0 + 2 * j], cb = chp[c0 + 2 * j + 1];
+            const float f0 = __uint_as_float(v[2 * j]) * ca.x + ca.y, f1 = __uint_as_float(v[2 * j + 1]) * cb.x + cb.y;
+            uint16_t h0, h1, l0, l1;      // the saturating split of tfmq_act_prepare (elementwise.cu::split_h16x4)
+            asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h0) : "f"(f0));
+            asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h1) : "f"(f1));
+            const float r0 = f0 - __half2float(__ushort_as_half(h0)), r1 = f1 - __half2float(__ushort_as_half(h1));
+            asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(l0) : "f"(r0));
+            asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(l1) : "f"(r1));
+            hw[j] = (uint32_t)h0 | ((uint32_t)h1 << 16);
+            lw[j] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+          }
+          const uint32_t sw4 = (uint32_t)((r >> 1) & 3);
+          uint8_t* rh = buf + (uint32_t)r * 64u;
+          uint8_t* rl = rh + 128u * 64u;
+          const uint32_t pa = (((uint32_t)(2 * half)) ^ sw4) << 4, pb = (((uint32_t)(2 * half + 1)) ^ sw4) << 4;
+          *reinterpret_cast<uint4*>(rh + pa) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+          *reinterpret_cast<uint4*>(rh + pb) = make_uint4(hw[4], hw[5], hw[6], hw[7]);
+          *reinterpret_cast<uint4*>(rl + pa) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+          *reinterpret_cast<uint4*>(rl + pb) = make_uint4(lw[4], lw[5], lw[6], lw[7]);
+        }
+        const bool fold_f32 = !(FP && p.out_planes);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          if (k < npiece) {
+          if (k < npiece && fold_f32) {
             float4* slot = reinterpret_cast<float4*>(buf + row_off + ((uint32_t)((k0 + k) << 4) ^ sw16));
             float4 o;
             if (MODE == MODE_I8) {
@@ -642,6 +671,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         // works while the warps sum columns, and thread 0's warp is the one every other warp waits for at the next barrier
         if (et == 0) {
           tma_store_4d(&tmOut, buf, c_out0 + ci * CW, x0, y0, n0);
+          if (FP && p.out_planes) tma_store_4d(&tmRes, buf + 128u * 64u, c_out0 + ci * CW, x0, y0, n0);   // lo plane
           tma_store_commit();
           if (ci + 1 < nchunks) {
             tma_store_wait_read<1>();         // the other buffer's store has finished reading
@@ -740,14 +770,17 @@ static int pick_tile_n(int cout, int limit = 256) {
 // N tile for a persistent grid: the widest tile has the best operand reuse, but small feature maps then
 // leave most SMs idle (8x8x16 images = 8 M tiles).  Pick the divisor of cout that minimises
 //   waves(tiles) x (k-blocks x (k_fix + k_col * tile_n) + epilogue(tile_n))   [cycles, fitted to the phase counters]
-static int pick_tile_n_balanced(int cout, int limit, int tiles_m, int nkb, int sm_count, double k_fix, double k_col) {
+//   a tile that is not a multiple of 32 wide runs its epilogue in 16-column chunks (64B swizzle): twice the chunk iterations
+static int pick_tile_n_balanced(int cout, int limit, int tiles_m, int nkb, int sm_count, double k_fix, double k_col,
+                                int step = 16) {
+  static const double cw16 = getenv("TFMQ_IGEMM_CW16_PENALTY") ? atof(getenv("TFMQ_IGEMM_CW16_PENALTY")) : 2.0;
   int best = 0;
   double best_cost = 0.0;
-  for (int t = limit; t >= 16; t -= 16) {
+  for (int t = limit - limit % step; t >= step; t -= step) {
     if (cout % t) continue;
     const long long tiles = (long long)tiles_m * (cout / t);
     const double waves = (double)((tiles + sm_count - 1) / sm_count);
-    const double cost = waves * (nkb * (k_fix + k_col * t) + 3000.0 + 30.0 * t);
+    const double cost = waves * (nkb * (k_fix + k_col * t) + 3000.0 + 30.0 * t * (t % 32 ? cw16 : 1.0));
     if (!best || cost < best_cost * 0.97) best = t, best_cost = cost;   // prefer the wider tile on near-ties
   }
   return best;
@@ -876,7 +909,19 @@ static int launch_igemm(tfmq_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap
   // epilogue tensor maps: output (and residual) as [cout][W][H][N] fp32 / s32 with pixel pitch ld
   p.chunk_w = (p.tile_n % 32 == 0) ? 32 : 16;
   CUtensorMap tmOut, tmRes;
-  {
+  if (p.out_planes) {
+    // fp16 hi / lo planes: tmOut = hi, tmRes = lo, [cout][W][H][N] halves with pixel pitch out_h_ld, 64-byte chunk rows
+    if (p.chunk_w != 32) return tfmq_fail(ctx, TFMQ_ERR_SHAPE, "%s: plane output needs an N tile in multiples of 32", name);
+    cuuint64_t dims[4] = {(cuuint64_t)p.cout, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.n_img};
+    const cuuint64_t ld = (cuuint64_t)p.out_h_ld;
+    cuuint64_t str[3] = {ld * 2, (cuuint64_t)p.W * ld * 2, (cuuint64_t)p.H * p.W * ld * 2};
+    cuuint32_t box[4] = {32, (cuuint32_t)p.tw, (cuuint32_t)p.th, (cuuint32_t)p.tn};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    int rc = encode(ctx, &tmOut, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, p.out_hi, dims, str, box, es, CU_TENSOR_MAP_SWIZZLE_64B);
+    if (rc) return rc;
+    rc = encode(ctx, &tmRes, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, p.out_lo, dims, str, box, es, CU_TENSOR_MAP_SWIZZLE_64B);
+    if (rc) return rc;
+  } else {
     const bool i32 = (MODE == MODE_I8);
     const void* base = i32 ? (const void*)p.out_i32 : (const void*)p.out;
     const cuuint64_t ld = i32 ? (cuuint64_t)p.cout : (cuuint64_t)p.out_ld;
@@ -1126,14 +1171,19 @@ extern "C" int tfmq_conv_fp(tfmq_ctx* ctx, const tfmq_conv_fp_desc* d, void* str
 
 extern "C" int tfmq_conv_h16(tfmq_ctx* ctx, const tfmq_conv_h16_desc* d, void* stream) {
   if (!ctx) return TFMQ_ERR_ARG;
-  TFMQ_REQUIRE(d && d->x_hi && d->x_lo && d->w_hi && d->out, TFMQ_ERR_ARG, "conv_h16: null pointer");
+  TFMQ_REQUIRE(d && d->x_hi && d->x_lo && d->w_hi && (d->out || d->out_hi), TFMQ_ERR_ARG, "conv_h16: null pointer");
+  const bool planes = d->out_hi != nullptr;
+  TFMQ_REQUIRE(!planes || (d->out_lo && !d->res && !d->emb && d->n_stat == 0 && d->out_h_ld % 8 == 0 && d->cout % 32 == 0 &&
+                           (((uintptr_t)d->out_hi | (uintptr_t)d->out_lo) & 15) == 0),
+               TFMQ_ERR_ARG, "conv_h16: plane output needs out_lo, 16-byte alignment, out_h_ld %% 8 == 0, cout %% 32 == 0 and "
+                             "no residual / embedding / statistics");
   TFMQ_REQUIRE(d->ksize == 1 || d->ksize == 3, TFMQ_ERR_SHAPE, "conv_h16: ksize %d", d->ksize);
   TFMQ_REQUIRE(d->stride == 1 || d->stride == 2, TFMQ_ERR_SHAPE, "conv_h16: stride %d", d->stride);
   TFMQ_REQUIRE(d->cin % 16 == 0 && d->cin >= 16, TFMQ_ERR_SHAPE, "conv_h16: cin %d not a multiple of 16", d->cin);
   TFMQ_REQUIRE(d->cout % 16 == 0, TFMQ_ERR_SHAPE, "conv_h16: cout %d not a multiple of 16", d->cout);
-  TFMQ_REQUIRE(d->x_ld % 8 == 0 && d->out_ld % 4 == 0 && (!d->res || d->res_ld % 4 == 0), TFMQ_ERR_SHAPE,
+  TFMQ_REQUIRE(d->x_ld % 8 == 0 && (planes || d->out_ld % 4 == 0) && (!d->res || d->res_ld % 4 == 0), TFMQ_ERR_SHAPE,
                "conv_h16: x_ld must be a multiple of 8 halves, out_ld / res_ld of 4 floats");
-  TFMQ_REQUIRE(((uintptr_t)d->out & 15) == 0 && ((uintptr_t)d->x_hi & 15) == 0 && ((uintptr_t)d->x_lo & 15) == 0 &&
+  TFMQ_REQUIRE((planes || ((uintptr_t)d->out & 15) == 0) && ((uintptr_t)d->x_hi & 15) == 0 && ((uintptr_t)d->x_lo & 15) == 0 &&
                    ((uintptr_t)d->w_hi & 15) == 0 && (!d->w_lo || ((uintptr_t)d->w_lo & 15) == 0) &&
                    (!d->res || ((uintptr_t)d->res & 15) == 0),
                TFMQ_ERR_ARG, "conv_h16: pointers must be 16-byte aligned");
@@ -1150,8 +1200,10 @@ extern "C" int tfmq_conv_h16(tfmq_ctx* ctx, const tfmq_conv_h16_desc* d, void* s
     // two accumulator stages (each main + small-terms) need tile_n <= 128
     const int tiles_m = (d->out_w / g.tw) * (d->out_h / g.th) * ((d->n + g.tn - 1) / g.tn);
     const int limit = nkb_est < 24 ? 128 : 256;
-    p.tile_n = pick_tile_n_balanced(d->cout, limit, tiles_m, nkb_est, ctx->sm_count, 300.0, 6.0);
+    p.tile_n = pick_tile_n_balanced(d->cout, limit, tiles_m, nkb_est, ctx->sm_count, 300.0, 6.0, planes ? 32 : 16);
   }
+  p.out_planes = planes ? 1 : 0;
+  p.out_hi = d->out_hi, p.out_lo = d->out_lo, p.out_h_ld = d->out_h_ld;
   p.kchunk = 64, p.kslice = 16;
   p.pass_flags = PASS_HI_HI | PASS_LO_HI | (d->w_lo ? PASS_HI_LO : 0);
   p.out = d->out, p.out_ld = d->out_ld, p.bias = d->bias, p.wscale = d->wscale;

@@ -55,6 +55,10 @@ struct IgemmParams {
   const float* res;
   long long res_ld;
   int32_t* out_i32;  // MODE_I8: raw accumulators [pixels][cout]
+  int out_planes;    // fp modes: write fp16 hi / lo planes (out_hi, out_lo, pitch out_h_ld halves) instead of fp32 `out`
+  void* out_hi;
+  void* out_lo;
+  long long out_h_ld;
   int n_stat;        // fused GroupNorm statistics of the output
   int stat_imgs;     // images a tile spans when statistics are fused (tn), else 1
   tfmq_gn_target stat[2];

@@ -75,6 +75,7 @@ class ConvH16Desc(C.Structure):
         ("out", C.c_void_p), ("out_ld", i64),
         ("emb", C.c_void_p), ("emb_ld", i64),
         ("n_stat", C.c_int), ("stat", GnTarget * 2),
+        ("out_hi", C.c_void_p), ("out_lo", C.c_void_p), ("out_h_ld", i64),
     ]
 
 
@@ -101,6 +102,17 @@ class AttnDesc(C.Structure):
     ]
 
 
+class AttnH16Desc(C.Structure):
+    _fields_ = [
+        ("q_hi", C.c_void_p), ("q_lo", C.c_void_p), ("q_sb", i64), ("q_sh", i64), ("q_st", i64),
+        ("k_hi", C.c_void_p), ("k_lo", C.c_void_p), ("k_sb", i64), ("k_sh", i64), ("k_st", i64),
+        ("v_hi", C.c_void_p), ("v_lo", C.c_void_p), ("v_sb", i64), ("v_sh", i64), ("v_st", i64),
+        ("o", C.c_void_p), ("o_hi", C.c_void_p), ("o_lo", C.c_void_p), ("o_sb", i64), ("o_sh", i64), ("o_st", i64),
+        ("b", C.c_int), ("heads", C.c_int), ("tq", C.c_int), ("tk", C.c_int), ("d", C.c_int),
+        ("scale", C.c_float),
+    ]
+
+
 P = C.c_void_p
 _SIGS = {
     # name: (restype, argtypes)
@@ -124,6 +136,7 @@ _SIGS = {
     "tfmq_linear_grouped": (C.c_int, [P, P, P, C.c_int, C.c_int, C.c_int, C.c_int, P]),
     "tfmq_timestep_embedding": (C.c_int, [P, P, C.c_int, C.c_int, C.c_int, P, P]),
     "tfmq_attention": (C.c_int, [P, C.POINTER(AttnDesc), P]),
+    "tfmq_attention_h16": (C.c_int, [P, C.POINTER(AttnH16Desc), P]),
     "tfmq_ddim_update": (C.c_int, [P, P, P, P, P, i64, P, P, P]),
     "tfmq_cfg_combine": (C.c_int, [P, P, P, C.c_float, i64, P, P]),
     "tfmq_plms_eps": (C.c_int, [P, P, P, P, P, C.c_int, i64, P, P]),

@@ -21,6 +21,7 @@ ldm/modules/diffusionmodules/openaimodel.py:744-780) and the per-step host work 
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, List, Optional, Sequence
 
 import torch
@@ -134,6 +135,7 @@ class StepEngine:
         assert fp_mode in ("h16", "tf32")
         self.fp_mode = fp_mode if fp_passes == 3 else "tf32"
         self._h16: Dict[int, tuple] = {}
+        self.attn_tc = os.environ.get("TFMQ_ATTN_TC", "1") != "0"     # 0: the mma.sync attention kernels (comparison runs)
         self.kind = "ddim" if hasattr(model, "temb") else "ldm"
         self.model = model
         self.ops: List = []
@@ -343,9 +345,15 @@ class StepEngine:
         self.ops.append(lambda: ops.act_prepare(x.view, dst_f32=src.view, silu=silu, **tok, **self._gn_args(gn)))
         return src
 
-    def _fp_launch(self, src, ksize, stride, pad_lo, w_tf32, w_h16, out: T, res: Optional[T], bias, wscale, emb, rec):
-        """src: what `_fp_input` returned; w_tf32 = (hi, lo) fp32 planes, w_h16 = (hi, lo, scale) fp16 planes."""
-        if self.fp_mode == "h16":
+    def _fp_launch(self, src, ksize, stride, pad_lo, w_tf32, w_h16, out: T, res: Optional[T], bias, wscale, emb, rec,
+                   out_h16=None):
+        """src: what `_fp_input` returned; w_tf32 = (hi, lo) fp32 planes, w_h16 = (hi, lo, scale) fp16 planes.
+        out_h16 = (hi, lo): the conv writes fp16 planes for a tensor-core consumer instead of fp32 `out`."""
+        if out_h16 is not None:
+            hi, lo = src
+            ops.conv_h16(hi, lo, ksize, stride, pad_lo, w_h16[0], w_h16[1], None, bias=bias, wscale=w_h16[2],
+                         out_h16=out_h16)
+        elif self.fp_mode == "h16":
             hi, lo = src
             ops.conv_h16(hi, lo, ksize, stride, pad_lo, w_h16[0], w_h16[1], out.view, bias=bias, wscale=w_h16[2],
                          res=res.view if res is not None else None, emb=emb, stats=self._stats_of(rec))
@@ -362,9 +370,9 @@ class StepEngine:
         self.ops.append(lambda: self._fp_launch(src, q.ksize, stride, pad_lo, (q.w_hi, q.w_lo),
                                                 (q.h_hi, q.h_lo, q.h_scale), out, res, q.bias, wscale, emb, rec))
 
-    def _plain_conv(self, conv: nn.Module, src, out: T, res: Optional[T], pad_lo: int, stride: int):
+    def _plain_conv(self, conv: nn.Module, src, out: Optional[T], res: Optional[T], pad_lo: int, stride: int, out_h16=None):
         """An nn.Conv2d / nn.Conv1d the reference never wraps (skip / op / shortcut / qkv / proj_out).
-        src: a T (split here if needed) or what `_fp_input` returned."""
+        src: a T (split here if needed) or what `_fp_input` returned.  out_h16: fp16 hi / lo planes instead of `out`."""
         if isinstance(src, T):
             src = self._fp_input(src)
         key = id(conv)
@@ -378,8 +386,10 @@ class StepEngine:
             self._plain[key] = (ops.split_tf32(w2d), ops.split_h16(w2d), b, k)
         w_tf32, w_h16, b, k = self._plain[key]
         rec = {"stats": []}
-        out.producer = rec
-        self.ops.append(lambda: self._fp_launch(src, k, stride, pad_lo, w_tf32, w_h16, out, res, b, None, None, rec))
+        if out is not None:
+            out.producer = rec
+        self.ops.append(lambda: self._fp_launch(src, k, stride, pad_lo, w_tf32, w_h16, out, res, b, None, None, rec,
+                                                out_h16=out_h16))
 
     def _linear_kw(self, q: _QL, xin: torch.Tensor, out: torch.Tensor, silu_in: bool) -> dict:
         aq = self._aq_ptr(q) if (q.quant_w and q.aq_index is not None) else None
@@ -567,10 +577,28 @@ class StepEngine:
         def attnblock(blk: QuantAttentionBlock, x: T) -> T:
             gn = self._gn(x, blk.norm)
             xn = self._fp_input(x, gn)
-            qkv = self._new(x.n, x.h, x.w, 3 * x.c)
-            self._plain_conv(blk.qkv, xn, qkv, None, pad_lo=0, stride=1)
             heads = blk.num_heads
             d = x.c // heads
+            if self.fp_mode == "h16" and self.attn_tc and d in ops.ATTN_TC_DIMS and (3 * x.c) % 32 == 0:
+                # tcgen05 path: the qkv projection writes fp16 hi / lo planes (no fp32 qkv tensor, no split in the attention
+                # kernel), the attention core reads them by TMA and writes the planes the proj_out conv reads
+                qh = torch.empty((x.n, x.h, x.w, 3 * x.c), dtype=torch.float16, device=self.dev)
+                ql = torch.empty_like(qh)
+                self._plain_conv(blk.qkv, xn, None, None, pad_lo=0, stride=1, out_h16=(qh, ql))
+                oh = torch.empty((x.n, x.h, x.w, x.c), dtype=torch.float16, device=self.dev)
+                ol = torch.empty_like(oh)
+                tq, c3 = x.h * x.w, 3 * x.c
+                fh, fl = qh.view(-1), ql.view(-1)
+                st = dict(q=(tq * c3, 3 * d, c3), k=(tq * c3, 3 * d, c3), v=(tq * c3, 3 * d, c3), o=(tq * x.c, d, x.c))
+                b_, scale = x.n, 1.0 / math.sqrt(d)
+                self.ops.append(lambda: ops.attention_h16((fh, fl), (fh[d:], fl[d:]), (fh[2 * d:], fl[2 * d:]), None, b_, heads,
+                                                          tq, tq, d, scale, st, o_h16=(oh, ol)))
+                out = self._new(x.n, x.h, x.w, x.c)
+                self._plain_conv(blk.proj_out, (oh, ol), out, x, pad_lo=0, stride=1)
+                self.block_out[self._names[id(blk)]] = out
+                return out
+            qkv = self._new(x.n, x.h, x.w, 3 * x.c)
+            self._plain_conv(blk.qkv, xn, qkv, None, pad_lo=0, stride=1)
             planes = self._attn_out_planes(x.n, x.h, x.w, x.c, d)
             o = T(x.n, x.h, x.w, x.c) if planes is not None else self._new(x.n, x.h, x.w, x.c)
             tq = x.h * x.w

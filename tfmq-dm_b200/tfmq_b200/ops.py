@@ -11,7 +11,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import ActDesc, AttnDesc, ConvFpDesc, ConvH16Desc, ConvW4A8Desc, GnTarget, LinearDesc
+from ._lib import ActDesc, AttnDesc, AttnH16Desc, ConvFpDesc, ConvH16Desc, ConvW4A8Desc, GnTarget, LinearDesc
 
 
 def _ctx(t: torch.Tensor) -> _lib.Context:
@@ -184,16 +184,26 @@ def conv_fp(x: torch.Tensor, ksize: int, stride: int, pad_lo: int, w_hi, w_lo, o
     ctx.call("tfmq_conv_fp", C.byref(d), _stream())
 
 
-def conv_h16(x_hi: torch.Tensor, x_lo: torch.Tensor, ksize: int, stride: int, pad_lo: int, w_hi, w_lo, out: torch.Tensor,
-             bias=None, wscale=None, res=None, emb=None, stats=None):
-    """fp32-accurate conv on kind::f16 from pre-split fp16 hi / lo planes (see include/tfmq_b200.h)."""
-    ctx = _ctx(out)
+def conv_h16(x_hi: torch.Tensor, x_lo: torch.Tensor, ksize: int, stride: int, pad_lo: int, w_hi, w_lo, out,
+             bias=None, wscale=None, res=None, emb=None, stats=None, out_h16=None):
+    """fp32-accurate conv on kind::f16 from pre-split fp16 hi / lo planes (see include/tfmq_b200.h).
+    out_h16 = (hi, lo): the result is written as fp16 hi / lo planes instead of fp32 `out` (which may be None)."""
+    ctx = _ctx(x_hi)
     assert x_hi.dtype == torch.float16 and x_lo.dtype == torch.float16 and w_hi.dtype == torch.float16
     n, h, w, cin, x_ld = _nhwc(x_hi)
     assert _nhwc(x_lo) == (n, h, w, cin, x_ld)
-    on, oh, ow, cout, out_ld = _nhwc(out)
-    assert on == n
     d = ConvH16Desc()
+    if out_h16 is not None:
+        assert res is None and emb is None and not stats
+        ph, pl = out_h16
+        assert ph.dtype == torch.float16 and pl.dtype == torch.float16
+        on, oh, ow, cout, h_ld = _nhwc(ph)
+        assert _nhwc(pl) == (on, oh, ow, cout, h_ld)
+        d.out_hi, d.out_lo, d.out_h_ld = ph.data_ptr(), pl.data_ptr(), h_ld
+        out_ld = 0
+    else:
+        on, oh, ow, cout, out_ld = _nhwc(out)
+    assert on == n
     d.x_hi, d.x_lo, d.x_ld = x_hi.data_ptr(), x_lo.data_ptr(), x_ld
     d.n, d.h, d.w, d.cin, d.cout = n, h, w, cin, cout
     d.ksize, d.stride, d.pad_lo, d.out_h, d.out_w = ksize, stride, pad_lo, oh, ow
@@ -205,7 +215,7 @@ def conv_h16(x_hi: torch.Tensor, x_lo: torch.Tensor, ksize: int, stride: int, pa
         rn, rh, rw, rc, rld = _nhwc(res)
         assert (rn, rh, rw, rc) == (n, oh, ow, cout)
         d.res, d.res_ld = res.data_ptr(), rld
-    d.out, d.out_ld = out.data_ptr(), out_ld
+    d.out, d.out_ld = (out.data_ptr() if out_h16 is None else None), out_ld
     if emb is not None:
         assert emb.stride(-1) == 1
         d.emb, d.emb_ld = emb.data_ptr(), (emb.stride(0) if emb.dim() == 2 and emb.shape[0] > 1 else 0)
@@ -339,6 +349,34 @@ def attention(q, k, v, o, b: int, heads: int, tq: int, tk: int, d: int, scale: f
         setattr(a, name + "_st", st)
     a.b, a.heads, a.tq, a.tk, a.d, a.scale = b, heads, tq, tk, d, scale
     ctx.call("tfmq_attention", C.byref(a), _stream())
+
+
+ATTN_TC_DIMS = tuple(range(16, 65, 8))    # head dims of the tcgen05 kernel (tfmq_attention_h16)
+
+
+def attention_h16(q, k, v, o, b: int, heads: int, tq: int, tk: int, d: int, scale: float, strides, o_h16=None):
+    """The attention core on tcgen05 / TMEM from pre-split operands: q, k, v = (hi, lo) fp16 plane pairs; strides as in
+    `attention` (in halves for q / k / v; in elements of the output for o).  Output: fp32 `o` or the planes `o_h16`."""
+    ctx = _ctx(q[0])
+    a = AttnH16Desc()
+    for name, t in (("q", q), ("k", k), ("v", v)):
+        assert t[0].dtype == torch.float16 and t[1].dtype == torch.float16
+        sb, sh, st = strides[name]
+        setattr(a, name + "_hi", t[0].data_ptr())
+        setattr(a, name + "_lo", t[1].data_ptr())
+        setattr(a, name + "_sb", sb)
+        setattr(a, name + "_sh", sh)
+        setattr(a, name + "_st", st)
+    if o_h16 is not None:
+        assert o_h16[0].dtype == torch.float16 and o_h16[1].dtype == torch.float16
+        a.o_hi, a.o_lo = o_h16[0].data_ptr(), o_h16[1].data_ptr()
+    elif o is None:
+        raise ValueError("attention_h16: give the fp32 output `o` or the fp16 planes `o_h16`")
+    else:
+        a.o = o.data_ptr()
+    a.o_sb, a.o_sh, a.o_st = strides["o"]
+    a.b, a.heads, a.tq, a.tk, a.d, a.scale = b, heads, tq, tk, d, scale
+    ctx.call("tfmq_attention_h16", C.byref(a), _stream())
 
 
 def ddim_update(x, e, coef, x_prev, x0_out=None, noise=None):

@@ -60,6 +60,7 @@ def _demote(module, with_delta: bool) -> None:
 
 
 def _reset_aqtizers(qnn: QuantModel) -> None:
+    qnn.invalidate_engine()
     for name, module in qnn.model.named_modules():
         if "aqtizer" in name and isinstance(module, UniformAffineQuantizer):
             if module.delta is not None:
@@ -83,6 +84,16 @@ def _collect_act(qnn: QuantModel) -> dict:
 def cali_model(qnn: QuantModel, w_cali_data: Tuple[torch.Tensor], a_cali_data: Tuple[torch.Tensor],
                use_aq: bool = False, path: str = None, running_stat: bool = False, interval: int = 128,
                **kwargs) -> dict:
+    """reference quant/calibration.py:45-155.  Runs inside `qnn.calibrating()`: every forward here is the torch module
+    graph (hooks, autograd, lazy quantiser initialisation); the step engine is re-traced afterwards."""
+    with qnn.calibrating():
+        return _cali_model(qnn, w_cali_data, a_cali_data, use_aq=use_aq, path=path, running_stat=running_stat,
+                           interval=interval, **kwargs)
+
+
+def _cali_model(qnn: QuantModel, w_cali_data: Tuple[torch.Tensor], a_cali_data: Tuple[torch.Tensor],
+                use_aq: bool = False, path: str = None, running_stat: bool = False, interval: int = 128,
+                **kwargs) -> dict:
     """Phases of reference :45-155: W0 weight-quantiser init, W1 reconstruction (TIB / layers /
     blocks in definition order), W2 parameter promotion, A per-timestep activation ranges (FSC).
     Returns (and, if `path`, saves) the checkpoint dict."""
@@ -160,6 +171,13 @@ def cali_model(qnn: QuantModel, w_cali_data: Tuple[torch.Tensor], a_cali_data: T
 
 def load_cali_model(qnn: QuantModel, init_data: Tuple[torch.Tensor], use_aq: bool = False, path: str = None,
                     ckpt: dict = None) -> None:
+    """reference quant/calibration.py:158-224, inside `qnn.calibrating()` (its dummy forwards run the module graph)."""
+    with qnn.calibrating():
+        _load_cali_model(qnn, init_data, use_aq=use_aq, path=path, ckpt=ckpt)
+
+
+def _load_cali_model(qnn: QuantModel, init_data: Tuple[torch.Tensor], use_aq: bool = False, path: str = None,
+                     ckpt: dict = None) -> None:
     """reference :158-224: dummy forward to materialise the lazily created quantiser tensors,
     first / last layer exemptions, AdaRound detection by 'alpha' in the key, strict=False load of the
     'weight' part, optional second forward that creates the activation quantiser parameters."""
@@ -236,7 +254,8 @@ def cali_model_multi(gpu: int, dist_backend: str, world_size: int, dist_url: str
     ckpt = cali_model(qnn, w_shard, a_shard, use_aq=False, path=None, running_stat=running_stat,
                       interval=interval // world_size, **kwargs)
     if use_aq:
-        ckpt = _fsc_multi(qnn, a_shard, interval // world_size, running_stat, ckpt)
+        with qnn.calibrating():
+            ckpt = _fsc_multi(qnn, a_shard, interval // world_size, running_stat, ckpt)
     if rank == 0 and path:
         torch.save(ckpt, path)
 

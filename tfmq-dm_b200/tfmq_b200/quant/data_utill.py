@@ -2,6 +2,7 @@
 `quant/data_utill.py` (save_inout, GetLayerInpOut, DataSaverHook, StopForwardException)."""
 from __future__ import annotations
 
+import contextlib
 import logging
 from typing import Dict, Tuple, Union
 
@@ -45,10 +46,13 @@ class GetLayerInpOut:
         self.data_saver = DataSaverHook(store_input=True, store_output=True, stop_forward=True)
 
     def _forward(self, args):
-        try:
-            self.model(*(a.to(self.device) for a in args))
-        except StopForwardException:
-            pass
+        # the hooked forward is a calibration forward: torch module graph (QuantModel.calibrating), never the step engine
+        ctx = self.model.calibrating() if hasattr(self.model, "calibrating") else contextlib.nullcontext()
+        with ctx:
+            try:
+                self.model(*(a.to(self.device) for a in args))
+            except StopForwardException:
+                pass
 
     def __call__(self, xs, ts, cs=None):
         args = (xs, ts) if cs is None else (xs, ts, cs)

@@ -7,6 +7,7 @@ runs the fused sm_100a step engine (engine.py) instead of the module graph.
 """
 from __future__ import annotations
 
+import contextlib
 from typing import List
 
 import torch
@@ -33,7 +34,9 @@ class QuantModel(nn.Module):
         self.quant_block(self.model, wq_params, aq_params)
         if cali:
             self.get_tib(self.model, wq_params, aq_params)
-        self._engine = None   # fused step engine, built on demand by build_engine()
+        self._engine = None   # fused step engine, built on demand by build_engine() / forward()
+        self._cali_depth = 0  # > 0 inside `with qnn.calibrating():` -- forward runs the torch module graph
+        self._init_ok = False # every quantiser in use has been initialised (checked lazily, reset with the engine)
 
     # ------------------------------------------------------------------ surgery
     def get_tib(self, module: nn.Module, wq_params: dict = {}, aq_params: dict = {}):
@@ -81,7 +84,52 @@ class QuantModel(nn.Module):
                 setattr(module, name, cls(aq_params))
 
     # ------------------------------------------------------------------ state
+    def invalidate_engine(self) -> None:
+        """The step engine freezes weights, alpha and the quant state of every layer at trace time: anything that changes
+        them drops it, and the next sampling forward re-traces."""
+        self._engine = None
+        self._init_ok = False
+
+    @contextlib.contextmanager
+    def calibrating(self):
+        """Inside this context `forward` executes the torch module graph (hooks fire, autograd works, quantisers
+        initialise lazily and track running statistics): the calibration-time graph of quant/calibration.py,
+        quant/reconstruction.py and quant/data_utill.py.  Leaving it drops the step engine (the state has changed)."""
+        self._cali_depth += 1
+        try:
+            yield self
+        finally:
+            self._cali_depth -= 1
+            self.invalidate_engine()
+
+    def load_state_dict(self, state_dict, strict: bool = True, **kw):
+        """FSC swaps `act_k` (aqtizer delta / zero_point only) per timestep (ddim/functions/denoising.py:26-29): the engine
+        just re-reads the activation parameters; any other key changes what was frozen at trace time."""
+        out = super().load_state_dict(state_dict, strict=strict, **kw)
+        if self._engine is not None:
+            if all(".aqtizer." in k for k in state_dict):
+                self._engine._load_current_aq()
+            else:
+                self.invalidate_engine()
+        return out
+
+    def _apply(self, fn, *a, **kw):
+        self.invalidate_engine()
+        return super()._apply(fn, *a, **kw)
+
+    def _uninitialised(self) -> bool:
+        """True while a quantiser that the current state uses has not seen data yet: that forward IS the reference's lazy
+        initialisation (quant/quant_layer.py:213-216) and runs through the modules."""
+        for m in self.model.modules():
+            if isinstance(m, QuantLayer):
+                if m.use_wq and not getattr(m.wqtizer, "init", True):
+                    return True
+                if m.use_aq and not m.disable_aq and not getattr(m.aqtizer, "init", True):
+                    return True
+        return False
+
     def set_quant_state(self, use_wq: bool = False, use_aq: bool = False) -> None:
+        self.invalidate_engine()
         for m in self.model.modules():
             if isinstance(m, (BaseQuantBlock, QuantLayer)):
                 m.set_quant_state(use_wq=use_wq, use_aq=use_aq)
@@ -92,6 +140,7 @@ class QuantModel(nn.Module):
     def disable_out_quantization(self) -> None:
         """First / last layer exemptions in module-enumeration order (reference :103-120):
         layers #0, #2 and the last stay fp for good; #1 and #3 keep weight quant but no act quant."""
+        self.invalidate_engine()
         ql = self.quant_layers()
         for i in (0, 2, -1):
             ql[i].use_wq = False
@@ -113,6 +162,7 @@ class QuantModel(nn.Module):
                      if isinstance(m, QuantLayer) and m.aqtizer.delta is not None])
 
     def set_running_stat(self, running_stat: bool = False) -> None:
+        self.invalidate_engine()
         for m in self.model.modules():
             if isinstance(m, QuantBasicTransformerBlock):
                 for attn in (m.attn1, m.attn2):
@@ -139,11 +189,28 @@ class QuantModel(nn.Module):
         return self._engine
 
     def forward(self, x: torch.Tensor, timestep=None, context: torch.Tensor = None) -> torch.Tensor:
+        """Sampling forward = the fused sm_100a step engine, (re)built for this batch / context shape when needed.
+        The torch module graph runs only where the reference's semantics need modules: inside `calibrating()`, under
+        autograd (reconstruction), and for the lazy-initialisation forward of un-initialised quantisers.  There is no
+        other route: a CPU tensor outside those cases raises (no CPU path, no eager fallback)."""
+        module_graph = self._cali_depth > 0 or torch.is_grad_enabled()
+        if not module_graph and not self._init_ok:
+            self._init_ok = not self._uninitialised()
+            module_graph = not self._init_ok
+        if module_graph:
+            self.invalidate_engine()
+            if context is None:
+                return self.model(x, timestep)
+            return self.model(x, timestep, context)
+        if not x.is_cuda:
+            raise RuntimeError("QuantModel.forward outside calibration runs the sm_100a step engine: the input must be a "
+                               "CUDA tensor (no CPU path; use `with qnn.calibrating():` for the torch module graph)")
         eng = self._engine
-        if eng is not None and not torch.is_grad_enabled() and x.is_cuda and x.shape[0] == eng.batch \
-                and (context is None) == (eng.ctx_in is None) \
-                and (context is None or tuple(context.shape) == tuple(eng.ctx_in.shape)):
-            return eng.forward(x, timestep, context)
-        if context is None:
-            return self.model(x, timestep)
-        return self.model(x, timestep, context)
+        want_ctx = tuple(context.shape[1:]) if context is not None else None
+        if eng is not None:
+            have_ctx = tuple(eng.ctx_in.shape[1:]) if eng.ctx_in is not None else None
+            if eng.batch != x.shape[0] or have_ctx != want_ctx:
+                eng = None
+        if eng is None:
+            eng = self.build_engine(batch=x.shape[0], context_shape=want_ctx)
+        return eng.forward(x, timestep, context)

@@ -123,6 +123,21 @@ class DDIMSampler:
         betas = make_beta_schedule("linear", timesteps, linear_start, linear_end)
         self.alphas_cumprod = np.cumprod(1.0 - betas, axis=0)
         self.ckpt = ckpt         # FSC tables: {'act_k': ...} as saved by cali_model
+        # FSC indexing constants as the scripts install them on the wrapper (sample_diffusion_ldm.py:473-479)
+        self.tot = getattr(wrapper, "tot", None) if wrapper is not None else None
+        self.t_max = getattr(wrapper, "t_max", None) if wrapper is not None else None
+
+    def fsc_tables(self, ts):
+        """The `act_k` dict DiffusionWrapper.forward would load before the UNet call at timestep t
+        (ldm/models/diffusion/ddpm.py:1402-1405): k = t_max - (t - 1) // tot, where the scripts set tot = 1000 // n_tables and
+        t_max = n_tables - 1 from the NUMBER OF CALIBRATED TABLES (sample_diffusion_ldm.py:475-477), not from S."""
+        if self.ckpt is None:
+            return None
+        tot, t_max = self.tot, self.t_max
+        if tot is None or t_max is None:
+            n_tables = sum(1 for k in self.ckpt if str(k).startswith("act_"))
+            tot, t_max = self.ddpm_num_timesteps // n_tables, n_tables - 1
+        return [self.ckpt[f"act_{int(t_max - (int(t) - 1) // tot)}"] for t in ts]
 
     def make_schedule(self, ddim_num_steps: int, ddim_eta: float = 0.0):
         self.ddim_timesteps = make_ddim_timesteps(ddim_num_steps, self.ddpm_num_timesteps)
@@ -173,11 +188,7 @@ class DDIMSampler:
         if ctx is not None:
             eng.ctx_in.copy_(ctx)
         ts = [float(t) for t in np.flip(self.ddim_timesteps)]
-        tables = None
-        if self.ckpt is not None:
-            # FSC index of DiffusionWrapper.forward (ddpm.py:1402-1405): t_max - (t-1)//tot
-            tot, t_max = self.ddpm_num_timesteps // S, S - 1
-            tables = [self.ckpt[f"act_{int(t_max - (int(t) - 1) // tot)}"] for t in ts]
+        tables = self.fsc_tables(ts)
         eng.set_schedule(ts, tables, self.coefficient_rows())
         eng.x_in.copy_(torch.cat([img, img], dim=0) if cfg else img)
         n_run = S if not untill_fake_t else min(S, untill_fake_t - 1)
@@ -273,10 +284,7 @@ class PLMSSampler(DDIMSampler):
             if cfg:
                 ctx = torch.cat([unconditional_conditioning.to(dev).float(), ctx], dim=0)
         ts = [float(t) for t in np.flip(self.ddim_timesteps)]
-        self._tables = None
-        if self.ckpt is not None:
-            tot, t_max = self.ddpm_num_timesteps // S, S - 1
-            self._tables = [self.ckpt[f"act_{int(t_max - (int(t) - 1) // tot)}"] for t in ts]
+        self._tables = self.fsc_tables(ts)
         eps_fn = self._eps_fn(batch_size, ctx, cfg, float(unconditional_guidance_scale))
         if self._tables is not None and hasattr(self.model, "build_engine"):
             self._eng.set_schedule(ts, self._tables)
