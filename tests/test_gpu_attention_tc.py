@@ -114,3 +114,19 @@ def test_conv_h16_plane_output(dev, n, h, w, cin, cout):
     ref = F.linear(x.cpu().double(), wt.double(), bias.double())
     assert (out.cpu().double() - ref).abs().max().item() < 1e-4
     assert torch.equal(ph, wh) and torch.equal(pl, wl)
+
+
+@pytest.mark.parametrize("dbg", [32, 128, 256, 512, 768])
+def test_attention_h16_tc_skewed_warps(dbg):
+    """Race hunting: the kernel's debug switches put one softmax warp (or the rescale path) to sleep for 20 us at chosen
+    points, so the other warps, the UMMA warps and the TMA producer run as far ahead as the barriers let them.  Every
+    result must be unchanged (a parity wait that can alias, or a TMEM buffer handed over too early, shows up here).
+    The switch is read once per process: the cases run in a child process."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, TFMQ_ATTN_DBG=str(dbg))
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", os.path.join(here, "test_gpu_attention_tc.py"), "-k",
+                        "test_attention_h16_tc and not skewed"], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:]

@@ -18,6 +18,11 @@
 //              O += P V  (A = P from TENSOR MEMORY, B = V from shared memory, MN-major: V is read as stored, [key][dim]).
 //              The small cross terms of O accumulate in their own TMEM columns (the tensor-core accumulator truncates).
 // TMEM columns: [0, KT) S / P, [KT, KT + D) O main, [KT + D, KT + 2 D) O small terms.
+#include <algorithm>
+#include <cstdio>
+#include <utility>
+#include <vector>
+
 #include <cuda_fp16.h>
 
 #include "ctx.h"
@@ -32,12 +37,19 @@ struct AttnTcP {
   long long o_sb, o_sh, o_st;
   int heads, tq, tk, d;
   float scale_log2e;       // softmax scale * log2(e)
+  int dbg;                 // TFMQ_ATTN_DBG.  timing experiments: 2 = no P V UMMAs, 4 = no Q K^T UMMAs, 16 = predicated softmax path, 64 = no S
+                           // prefetch; race hunting (a 20 us sleep): 32 / 128 = in the rescale path, 256 / 512 = one slow warp per group
+  long long* prof;         // per-CTA phase cycle counters [grid][16] (TFMQ_ATTN_PROF=1), else null
 };
 
-constexpr int ATC_SOFTMAX_WARPS = 4;
-constexpr int ATC_WARP_TMA = 4, ATC_WARP_MMA = 5;
-constexpr int ATC_THREADS = 6 * 32;
-constexpr int ATC_STAGES = 2;
+// (counters are accumulated in global memory by one thread: no registers held when profiling is off)
+#define ATC_PROF(idx)                                       \
+  if (prof_on) {                                            \
+    const long long now_ = clock64();                       \
+    prof_dst[idx] += now_ - prof_t;                         \
+    prof_t = now_;                                          \
+  }
+
 constexpr float ATC_LAZY = 8.f;     // rescale only when the running max (log2 domain) grew by more than this
 
 // A from tensor memory, B from shared memory
@@ -81,8 +93,29 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
       "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
       : "memory");
 }
+// TMEM allocation with the column count as an IMMEDIATE: with a register operand the toolchain cannot tell how many
+// columns a CTA takes and the launch is limited to one CTA per SM (measured: occupancy 1 at any shared-memory size)
+template <uint32_t COLS>
+__device__ __forceinline__ void tmem_alloc_imm(uint32_t* slot_in_smem) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot_in_smem)), "n"(COLS)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <uint32_t COLS>
+__device__ __forceinline__ void tmem_dealloc_imm(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+__device__ __forceinline__ float fmax3(float a, float b, float c) {      // FMNMX3
+#ifdef ATC_NO_FMAX3
+  return fmaxf(a, fmaxf(b, c));
+#else
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+#endif
+}
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -103,62 +136,82 @@ __device__ __forceinline__ uint64_t smem_desc_rows(uint32_t saddr) {
 }
 
 // D = head dim as the tensor cores see it (a multiple of 16; a real head dim of 40 runs as 48 with TMA zero fill),
-// ROWB = bytes of one operand row in shared memory (64 for D = 32, 128 for D <= 64), KT = keys per tile.
-template <int D, int ROWB, int KT>
-__global__ void __launch_bounds__(ATC_THREADS, 2)
+// ROWB = bytes of one operand row in shared memory (64 for D = 32, 128 for D <= 64), KT = keys per tile,
+// NQ = 128-query blocks per CTA, ST = K / V ring depth.  One CTA per SM (a kernel that allocates tensor memory is given
+// one CTA per SM by the launch machinery: measured occupancy 1 at any shared-memory size), so the concurrency an SM needs
+// lives INSIDE the CTA: every query block has its own S / P and O columns in tensor memory, its own group of four softmax
+// warps and its own UMMA warp, and all blocks share each K / V tile in shared memory.
+//   warps [0, 4 NQ)       softmax, group g = query block g
+//   warps [4 NQ, 5 NQ)    UMMA issuers, one per query block (the issue cost of a UMMA, ~50 clocks, is what bounds a
+//                         single issuing warp: the P V products are only 16-32 clocks of tensor work each)
+//   warp  5 NQ            TMA producer
+// S is DOUBLE-BUFFERED per query block: Q K^T of tile j + 1 is issued before the warp waits for P of tile j, so the softmax
+// warps (bound by the SFU: one ex2 per score) go from tile to tile without waiting for the tensor pipe.
+// UMMA count per key tile and query block: 3 D / 16 for S, KT / 16 x 2 for O: the hi and lo planes of V lie next to each
+// other in a stage, so ONE MN-major descriptor (leading byte offset = plane size) presents [V_hi | V_lo] as an N = 2 DN operand
+// and P_hi [V_hi | V_lo] lands in the adjacent "main" and "small terms" accumulator columns; P_lo V_hi is the second product.
+template <int D, int ROWB, int KT, int NQ, int ST>
+__global__ void __launch_bounds__((5 * NQ + 1) * 32, 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUtensorMap tmQl,
                const __grid_constant__ CUtensorMap tmKh, const __grid_constant__ CUtensorMap tmKl,
                const __grid_constant__ CUtensorMap tmVh, const __grid_constant__ CUtensorMap tmVl, const AttnTcP p) {
   static_assert(D % 16 == 0 && D * 2 <= ROWB && (ROWB == 64 || ROWB == 128), "operand geometry");
   static_assert(KT == 64 || KT == 128, "key tile");
-  constexpr uint32_t Q_BYTES = 128u * ROWB;           // one plane of the 128-query tile
+  constexpr int DN = ROWB / 2;                        // columns of one V plane as the stacked operand sees it (>= D)
+  constexpr uint32_t Q_BYTES = 128u * ROWB;           // one plane of a 128-query block
   constexpr uint32_t KV_BYTES = (uint32_t)KT * ROWB;  // one plane of a key tile
   constexpr uint32_t STAGE_BYTES = 4u * KV_BYTES;     // K hi, K lo, V hi, V lo
-  constexpr uint32_t TMEM_COLS = (KT + 2 * D <= 128) ? 128u : (KT + 2 * D <= 256) ? 256u : 512u;
-  constexpr int NCH = KT / 32;                        // 32-column chunks of a score tile
+  constexpr uint32_t QB_COLS = 2 * KT + 2 * DN;       // TMEM columns of one query block: S / P x 2, O main, O small terms
+  constexpr uint32_t TMEM_COLS = (NQ * QB_COLS <= 128) ? 128u : (NQ * QB_COLS <= 256) ? 256u : 512u;
+  static_assert(NQ * QB_COLS <= 512, "tensor memory");
+  constexpr int WARP_MMA0 = 4 * NQ, WARP_TMA = 5 * NQ;
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* q_hi = smem;
-  uint8_t* q_lo = smem + Q_BYTES;
-  uint8_t* ring = smem + 2 * Q_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + ATC_STAGES * STAGE_BYTES);
-  uint64_t* q_full = bars;                 // Q planes landed
-  uint64_t* kv_full = bars + 1;            // [ATC_STAGES] K / V planes of the stage landed
-  uint64_t* kv_empty = kv_full + ATC_STAGES;   // [ATC_STAGES] the UMMAs that read the stage retired
-  uint64_t* s_full = kv_empty + ATC_STAGES;    // S tile complete in TMEM (and every earlier UMMA retired)
-  uint64_t* p_full = s_full + 1;           // P written over S (and O rescaled) by all four softmax warps
-  uint64_t* o_full = p_full + 1;           // last P V retired
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+  uint8_t* q_smem = smem;                              // [NQ][hi, lo]
+  uint8_t* ring = smem + NQ * 2 * Q_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + ST * STAGE_BYTES);
+  uint64_t* q_full = bars;                 // Q planes of all query blocks landed
+  uint64_t* kv_full = bars + 1;            // [ST] K / V planes of the stage landed
+  uint64_t* kv_empty = kv_full + ST;       // [ST] the UMMAs of every query block that read the stage retired
+  uint64_t* s_full = kv_empty + ST;        // [NQ][2] S tile complete in TMEM buffer 0 / 1
+  uint64_t* p_full = s_full + 2 * NQ;      // [NQ][2] P written over S (and O rescaled) by the block's four softmax warps
+  uint64_t* pv_done = p_full + 2 * NQ;     // [NQ] the block's P V of a tile retired (one phase per tile; waited for only by the
+                                           // in-loop rescale, which is never more than one phase behind)
+  uint64_t* o_full = pv_done + NQ;         // [NQ] the block's LAST P V retired (the softmax warps may reach the epilogue two
+                                           // phases ahead of pv_done: a parity wait on it would alias)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + NQ);
 
+  const long long t_entry = p.prof ? clock64() : 0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bh = blockIdx.y, b = bh / p.heads, h = bh - b * p.heads;
-  const int q0 = blockIdx.x * 128;
+  const int q0 = blockIdx.x * 128 * NQ;
+  const int nqv = min(NQ, (p.tq - q0 + 127) / 128);   // query blocks of this CTA that hold rows
   const int ntiles = (p.tk + KT - 1) / KT;
 
   if (threadIdx.x == 0) {
     mbar_init(q_full, 1);
-    for (int s = 0; s < ATC_STAGES; ++s) mbar_init(&kv_full[s], 1), mbar_init(&kv_empty[s], 1);
-    mbar_init(s_full, 1);
-    mbar_init(p_full, ATC_SOFTMAX_WARPS);
-    mbar_init(o_full, 1);
+    for (int s = 0; s < ST; ++s) mbar_init(&kv_full[s], 1), mbar_init(&kv_empty[s], (uint32_t)nqv);
+    for (int i = 0; i < 2 * NQ; ++i) mbar_init(&s_full[i], 1), mbar_init(&p_full[i], 4);
+    for (int i = 0; i < NQ; ++i) mbar_init(&pv_done[i], 1), mbar_init(&o_full[i], 1);
     mbar_fence_init();
     tma_prefetch_desc(&tmQh), tma_prefetch_desc(&tmQl), tma_prefetch_desc(&tmKh);
     tma_prefetch_desc(&tmKl), tma_prefetch_desc(&tmVh), tma_prefetch_desc(&tmVl);
   }
-  if (warp == ATC_WARP_MMA) tmem_alloc(tmem_slot, TMEM_COLS);
+  if (warp == WARP_TMA) tmem_alloc_imm<TMEM_COLS>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_o = tmem_base + (uint32_t)KT, tmem_o2 = tmem_o + (uint32_t)D;
 
-  if (warp == ATC_WARP_TMA) {
+  if (warp == WARP_TMA) {
     // ===================================================== TMA producer
     if (elect_one_sync()) {
-      mbar_expect_tx(q_full, 2 * Q_BYTES);
-      tma_load_4d(q_hi, &tmQh, q_full, 0, h, q0, b);
-      tma_load_4d(q_lo, &tmQl, q_full, 0, h, q0, b);
+      mbar_expect_tx(q_full, (uint32_t)nqv * 2 * Q_BYTES);
+      for (int i = 0; i < nqv; ++i) {
+        tma_load_4d(q_smem + (size_t)(2 * i) * Q_BYTES, &tmQh, q_full, 0, h, q0 + 128 * i, b);
+        tma_load_4d(q_smem + (size_t)(2 * i + 1) * Q_BYTES, &tmQl, q_full, 0, h, q0 + 128 * i, b);
+      }
     }
     __syncwarp();
     int s = 0;
@@ -174,195 +227,285 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__
         tma_load_4d(st + 3 * KV_BYTES, &tmVl, &kv_full[s], 0, h, j * KT, b);
       }
       __syncwarp();
-      if (++s == ATC_STAGES) s = 0, par ^= 1u;
+      if (++s == ST) s = 0, par ^= 1u;
     }
-  } else if (warp == ATC_WARP_MMA) {
-    // ===================================================== UMMA issuer
-    const uint32_t idesc_pv = idesc_f16(128, D) | (1u << 16);     // B (= V) is MN-major
-    const uint64_t d_qh = smem_desc_rows<ROWB>(smem_u32(q_hi)), d_ql = smem_desc_rows<ROWB>(smem_u32(q_lo));
-    const uint64_t d_ring = smem_desc_rows<ROWB>(smem_u32(ring));
-    constexpr uint32_t KV_U = KV_BYTES >> 4, STAGE_U = STAGE_BYTES >> 4;    // descriptor address units
-    constexpr uint32_t V_KSTEP_U = (16u * ROWB) >> 4;                       // 16 keys further down an MN-major tile
-    mbar_wait(q_full, 0);
-    int s = 0;
-    uint32_t par = 0;
-    for (int j = 0; j < ntiles; ++j) {
-      const int kn = min(KT, p.tk - j * KT);           // valid keys of this tile
-      const int nks = (kn + 15) >> 4;                  // 16-key steps of P V
-      const uint32_t idesc_qk = idesc_f16(128, (uint32_t)(nks * 16));
-      mbar_wait(&kv_full[s], par);
-      tc_fence_after();
-      const uint64_t d_kh = d_ring + (uint32_t)s * STAGE_U, d_kl = d_kh + KV_U;
-      const uint64_t d_vh = d_kh + 2 * KV_U, d_vl = d_kh + 3 * KV_U;
-      if (elect_one_sync()) {
-        // S = Q_lo K_hi + Q_hi K_lo + Q_hi K_hi   (the in-order tensor pipe has finished reading P_{j-1} by then)
+  } else if (warp >= WARP_MMA0) {
+    // ===================================================== UMMA issuer of query block i
+    const int i = warp - WARP_MMA0;
+    if (i < nqv) {
+      // every operand below is warp-uniform and computed outside the elected region: the descriptors stay in uniform
+      // registers and the UTCHMMAs issue back to back
+      const uint32_t idesc_pv2 = idesc_f16(128, 2 * DN) | (1u << 16);   // B = [V_hi | V_lo], MN-major
+      const uint32_t idesc_pv1 = idesc_f16(128, D) | (1u << 16);        // B = V_hi
+      constexpr uint32_t Q_U = Q_BYTES >> 4, KV_U = KV_BYTES >> 4, STAGE_U = STAGE_BYTES >> 4;   // descriptor address units
+      constexpr uint32_t V_KSTEP_U = (16u * ROWB) >> 4;                 // 16 keys further down an MN-major tile
+      const uint64_t d_qh = smem_desc_rows<ROWB>(smem_u32(q_smem)) + (uint32_t)(2 * i) * Q_U, d_ql = d_qh + Q_U;
+      const uint64_t d_ring = smem_desc_rows<ROWB>(smem_u32(ring));
+      const uint64_t lbo_planes = (uint64_t)KV_U << 16;                 // leading byte offset: V_lo plane = next N atom
+      const uint32_t t_q = tmem_base + (uint32_t)i * QB_COLS, t_o = t_q + 2u * KT, t_o2 = t_o + (uint32_t)DN;
+      // S_buf = Q_lo K_hi + Q_hi K_lo + Q_hi K_hi of the key tile in stage s
+      auto issue_qk = [&](int s, int kn, int buf) {
+        const uint32_t idesc_qk = idesc_f16(128, (uint32_t)(((kn + 15) >> 4) * 16));
+        const uint64_t d_kh = d_ring + (uint32_t)s * STAGE_U, d_kl = d_kh + KV_U;
+        const uint32_t t_s = t_q + (uint32_t)(buf * KT);
+        if (elect_one_sync()) {
+          if (!(p.dbg & 4)) {
 #pragma unroll
-        for (int k = 0; k < D / 16; ++k) umma_f16(tmem_base, d_ql + 2 * k, d_kh + 2 * k, idesc_qk, k > 0);
+            for (int k = 0; k < D / 16; ++k) umma_f16(t_s, d_ql + 2 * k, d_kh + 2 * k, idesc_qk, k > 0);
 #pragma unroll
-        for (int k = 0; k < D / 16; ++k) umma_f16(tmem_base, d_qh + 2 * k, d_kl + 2 * k, idesc_qk, 1);
+            for (int k = 0; k < D / 16; ++k) umma_f16(t_s, d_qh + 2 * k, d_kl + 2 * k, idesc_qk, 1);
 #pragma unroll
-        for (int k = 0; k < D / 16; ++k) umma_f16(tmem_base, d_qh + 2 * k, d_kh + 2 * k, idesc_qk, 1);
-        umma_commit(s_full);
-      }
-      __syncwarp();
-      mbar_wait(p_full, (uint32_t)j & 1u);
-      tc_fence_after();
-      if (elect_one_sync()) {
-        // P of 32-key chunk c sits at columns [32 c, 32 c + 16) (hi) and [32 c + 16, 32 c + 32) (lo), two halves per column
-        for (int ks = 0; ks < nks; ++ks) {
-          const uint32_t a_hi = tmem_base + (uint32_t)(32 * (ks >> 1) + 8 * (ks & 1)), a_lo = a_hi + 16u;
-          const uint64_t vh = d_vh + (uint32_t)ks * V_KSTEP_U, vl = d_vl + (uint32_t)ks * V_KSTEP_U;
-          const uint32_t acc = (j > 0 || ks > 0) ? 1u : 0u;
-          umma_f16_ts(tmem_o2, a_lo, vh, idesc_pv, acc);
-          umma_f16_ts(tmem_o2, a_hi, vl, idesc_pv, 1);
-          umma_f16_ts(tmem_o, a_hi, vh, idesc_pv, acc);
+            for (int k = 0; k < D / 16; ++k) umma_f16(t_s, d_qh + 2 * k, d_kh + 2 * k, idesc_qk, 1);
+          }
+          umma_commit(&s_full[2 * i + buf]);
         }
-        umma_commit(&kv_empty[s]);
-        if (j == ntiles - 1) umma_commit(o_full);
+        __syncwarp();
+      };
+      const bool prof_on = p.prof != nullptr && i == 0 && lane == 0;
+      long long* prof_dst = p.prof + ((long long)blockIdx.y * gridDim.x + blockIdx.x) * 16 + 7;
+      long long prof_t = prof_on ? clock64() : 0;
+      mbar_wait(q_full, 0);
+      mbar_wait(&kv_full[0], 0);
+      tc_fence_after();
+      issue_qk(0, min(KT, p.tk), 0);
+      ATC_PROF(0)
+      int s = 0;
+      uint32_t par = 0;
+      for (int j = 0; j < ntiles; ++j) {
+        const int kn = min(KT, p.tk - j * KT);           // valid keys of this tile
+        const int nks = (kn + 15) >> 4;                  // 16-key steps of P V
+        const int buf = j & 1;
+        const int s1 = (s + 1 == ST) ? 0 : s + 1;
+        const uint32_t par1 = (s + 1 == ST) ? par ^ 1u : par;
+        if (j + 1 < ntiles && !(p.dbg & 64)) {
+          // S of the NEXT tile into the other buffer (behind this block's P V of tile j - 1, which read P from it) before
+          // waiting for the softmax warps: they find it ready when they finish tile j
+          mbar_wait(&kv_full[s1], par1);
+          tc_fence_after();
+          ATC_PROF(0)
+          issue_qk(s1, min(KT, p.tk - (j + 1) * KT), buf ^ 1);
+          ATC_PROF(1)
+        }
+        const uint64_t d_vh = d_ring + (uint32_t)s * STAGE_U + 2 * KV_U, d_vhl = d_vh | lbo_planes;
+        const uint32_t t_p = t_q + (uint32_t)(buf * KT);
+        mbar_wait(&p_full[2 * i + buf], (uint32_t)(j >> 1) & 1u);
+        tc_fence_after();
+        ATC_PROF(2)
+        const uint32_t acc0 = j > 0 ? 1u : 0u;
+        if (elect_one_sync()) {
+          // P of 16-key group ks sits at columns [16 ks, 16 ks + 8) (hi) and [16 ks + 8, 16 ks + 16) (lo), two halves per column
+          if (!(p.dbg & 2)) {
+#pragma unroll
+            for (int ks = 0; ks < KT / 16; ++ks) {
+              if (ks < nks) {
+                // [O main | O small] (+)= P_hi [V_hi | V_lo];   O small += P_lo V_hi
+                umma_f16_ts(t_o, t_p + (uint32_t)(16 * ks), d_vhl + (uint32_t)ks * V_KSTEP_U, idesc_pv2, ks > 0 ? 1u : acc0);
+                umma_f16_ts(t_o2, t_p + (uint32_t)(16 * ks + 8), d_vh + (uint32_t)ks * V_KSTEP_U, idesc_pv1, 1);
+              }
+            }
+          }
+          umma_commit(&kv_empty[s]);
+          umma_commit(&pv_done[i]);
+          if (j == ntiles - 1) umma_commit(&o_full[i]);
+        }
+        __syncwarp();
+        if (j + 1 < ntiles && (p.dbg & 64)) {
+          mbar_wait(&kv_full[s1], par1);
+          tc_fence_after();
+          issue_qk(s1, min(KT, p.tk - (j + 1) * KT), buf ^ 1);
+        }
+        ATC_PROF(3)
+        s = s1, par = par1;
       }
-      __syncwarp();
-      if (++s == ATC_STAGES) s = 0, par ^= 1u;
     }
   } else {
-    // ===================================================== softmax warps: thread = query row = TMEM lane
-    const int r = warp * 32 + lane;
-    const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
-    const uint32_t t_s = tmem_base + lane_addr;
-    const float c = p.scale_log2e;
-    float m = -INFINITY, l = 0.f;          // running max (raw score units) and row sum
-    for (int j = 0; j < ntiles; ++j) {
-      const int kn = min(KT, p.tk - j * KT);
-      mbar_wait(s_full, (uint32_t)j & 1u);
-      tc_fence_after();
-      // ---- pass 1: row maximum of the valid columns
-      float mx = -INFINITY;
+    // ===================================================== softmax warps: group = query block, thread = query row = TMEM lane
+    const int qb = warp >> 2, wq = warp & 3;
+    if (qb < nqv) {
+      const int r = wq * 32 + lane;
+      const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
+      const uint32_t t_q = tmem_base + (uint32_t)qb * QB_COLS + lane_addr;
+      const uint32_t t_o = t_q + 2u * KT, t_o2 = t_o + (uint32_t)DN;
+      const float c = p.scale_log2e;
+      float m = -INFINITY, l = 0.f;          // running max (raw score units) and row sum
+      const bool prof_on = p.prof != nullptr && threadIdx.x == 0;
+      long long* prof_dst = p.prof + ((long long)blockIdx.y * gridDim.x + blockIdx.x) * 16;
+      long long prof_t = prof_on ? clock64() : 0;
+      if (prof_on) prof_dst[6] = -prof_t, prof_dst[12] = prof_t - t_entry;     // [12]: CTA entry -> roles start (prologue)
+      for (int j = 0; j < ntiles; ++j) {
+        const int kn = min(KT, p.tk - j * KT);
+        const int buf = j & 1;
+        const uint32_t t_s = t_q + (uint32_t)(buf * KT);
+        if ((p.dbg & 256) && wq == 3 && (j & 3) == 1) __nanosleep(20000);      // one slow warp per group (race hunting)
+        mbar_wait(&s_full[2 * qb + buf], (uint32_t)(j >> 1) & 1u);
+        tc_fence_after();
+        if ((p.dbg & 512) && wq == 2 && (j & 3) == 2) __nanosleep(20000);
+        if (prof_on && j == 0) prof_dst[13] = clock64() - prof_t;               // [13]: roles start -> first S tile
+        ATC_PROF(0)
+        // ---- the whole score row into registers (one TMEM round trip), row maximum of the valid columns
+        uint32_t sv[KT];
 #pragma unroll
-      for (int ch = 0; ch < NCH; ++ch) {
-        if (ch * 32 < kn) {
-          uint32_t v[32];
-          tmem_ld32(t_s + (uint32_t)(ch * 32), v);
-          tmem_ld_wait();
-          if (ch * 32 + 32 <= kn) {
+        for (int ch = 0; ch < KT / 32; ++ch)
+          if (ch * 32 < kn) tmem_ld32(t_s + (uint32_t)(ch * 32), *reinterpret_cast<uint32_t(*)[32]>(&sv[ch * 32]));
+        tmem_ld_wait();
+        float mx = -INFINITY;
+        const bool full = kn == KT && !(p.dbg & 16);
+        if (full) {
+          float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
-          } else {
+          for (int k = 0; k < KT; k += 8) {
+            m4[0] = fmax3(m4[0], __uint_as_float(sv[k]), __uint_as_float(sv[k + 1]));
+            m4[1] = fmax3(m4[1], __uint_as_float(sv[k + 2]), __uint_as_float(sv[k + 3]));
+            m4[2] = fmax3(m4[2], __uint_as_float(sv[k + 4]), __uint_as_float(sv[k + 5]));
+            m4[3] = fmax3(m4[3], __uint_as_float(sv[k + 6]), __uint_as_float(sv[k + 7]));
+          }
+          mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+        } else {
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (ch * 32 + i < kn) mx = fmaxf(mx, __uint_as_float(v[i]));
+          for (int k = 0; k < KT; ++k)
+            if (k < kn) mx = fmaxf(mx, __uint_as_float(sv[k]));
+        }
+        // ---- lazy rescale of the accumulators, once the P V of tile j - 1 has retired (S of this tile was issued ahead of it)
+        float alpha = 1.f;
+        bool grow = false;
+        if (j == 0) {
+          m = mx;
+        } else if ((mx - m) * c > ATC_LAZY) {
+          alpha = ex2_approx((m - mx) * c);
+          m = mx;
+          grow = true;
+        }
+        if (__any_sync(0xffffffffu, grow)) {
+          if (p.dbg & 128) __nanosleep(20000);
+          mbar_wait(&pv_done[qb], (uint32_t)(j - 1) & 1u);
+          if (p.dbg & 32) __nanosleep(20000);
+          tc_fence_after();
+          l *= alpha;
+#pragma unroll
+          for (int part = 0; part < 2 * DN / 16; ++part) {   // O main and O small terms: 2 DN consecutive columns
+            uint32_t v[16];
+            tmem_ld16(t_o + (uint32_t)(part * 16), v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int k = 0; k < 16; ++k) v[k] = __float_as_uint(__uint_as_float(v[k]) * alpha);
+            tmem_st16(t_o + (uint32_t)(part * 16), v);
           }
         }
-      }
-      // ---- lazy rescale of the accumulators (everything issued before S_j, i.e. P V of tile j - 1, has retired)
-      float alpha = 1.f;
-      bool grow = false;
-      if (j == 0) {
-        m = mx;
-      } else if ((mx - m) * c > ATC_LAZY) {
-        alpha = ex2_approx((m - mx) * c);
-        m = mx;
-        grow = true;
-      }
-      if (__any_sync(0xffffffffu, grow)) {
-        l *= alpha;
+        ATC_PROF(1)
+        // ---- p = 2^(s c - m c), row sum, fp16 hi / lo split; per 16-key group (= one K step of P V) written over S in place
+        // as [8 columns hi | 8 columns lo].  hi = p with the low 13 significand bits cleared (exact in fp16 above its
+        // subnormal range), lo = p - hi: one logic op and one add per element, and the SFU stays the busiest pipe.
+        const float mc = m * c;
+        float rs0 = 0.f, rs1 = 0.f;
+        auto split_store = [&](int g, float (&pv)[16]) {
+          uint32_t w[16];
 #pragma unroll
-        for (int part = 0; part < 2 * D / 16; ++part) {     // O main and O small terms: 2 D consecutive columns
-          uint32_t v[16];
-          tmem_ld16(tmem_o + lane_addr + (uint32_t)(part * 16), v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-          tmem_st16(tmem_o + lane_addr + (uint32_t)(part * 16), v);
-        }
-      }
-      // ---- pass 2: p = 2^(s c - m c), row sum, fp16 hi / lo split, written over S in place
-      const float mc = m * c;
-      float rs = 0.f;
-#pragma unroll
-      for (int ch = 0; ch < NCH; ++ch) {
-        if (ch * 32 < kn) {
-          uint32_t v[32], w[32];
-          tmem_ld32(t_s + (uint32_t)(ch * 32), v);
-          tmem_ld_wait();
-          const bool tail = ch * 32 + 32 > kn;
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * i]), c, -mc));
-            float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), c, -mc));
-            if (tail) {
-              if (ch * 32 + 2 * i >= kn) p0 = 0.f;
-              if (ch * 32 + 2 * i + 1 >= kn) p1 = 0.f;
-            }
-            rs += p0 + p1;
-            // column i of the packed A operand holds keys 2i (low half) and 2i + 1 (high half)
-            const __half2 hh = __floats2half2_rn(p0, p1);
-            const float2 hf = __half22float2(hh);
-            const __half2 ll = __floats2half2_rn(p0 - hf.x, p1 - hf.y);
-            w[i] = *reinterpret_cast<const uint32_t*>(&hh);
-            w[16 + i] = *reinterpret_cast<const uint32_t*>(&ll);
+          for (int k = 0; k < 8; ++k) {
+            const float p0 = pv[2 * k], p1 = pv[2 * k + 1];
+            rs0 += p0, rs1 += p1;
+            const float h0 = __uint_as_float(__float_as_uint(p0) & 0xFFFFE000u);
+            const float h1 = __uint_as_float(__float_as_uint(p1) & 0xFFFFE000u);
+            // a packed column of the A operand holds keys 2k (low half) and 2k + 1 (high half)
+            const __half2 hh = __floats2half2_rn(h0, h1);
+            const __half2 ll = __floats2half2_rn(p0 - h0, p1 - h1);
+            w[k] = *reinterpret_cast<const uint32_t*>(&hh);
+            w[8 + k] = *reinterpret_cast<const uint32_t*>(&ll);
           }
-          tmem_st32(t_s + (uint32_t)(ch * 32), w);
-        }
-      }
-      l += rs;
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(p_full);
-    }
-    // ---- epilogue: O = (O_main + O_small) / l
-    mbar_wait(o_full, 0);
-    tc_fence_after();
-    const float inv = 1.f / l;
-    const int t = q0 + r;
-    const long long off = (long long)b * p.o_sb + (long long)h * p.o_sh + (long long)t * p.o_st;
+          tmem_st16(t_s + (uint32_t)(g * 16), w);
+        };
+        if (full) {                      // the common case: no per-element predicates
 #pragma unroll
-    for (int part = 0; part < D / 16; ++part) {
-      uint32_t v[16], v2[16];
-      tmem_ld16(tmem_o + lane_addr + (uint32_t)(part * 16), v);
-      tmem_ld16(tmem_o2 + lane_addr + (uint32_t)(part * 16), v2);
-      tmem_ld_wait();
-      float f[16];
+          for (int g = 0; g < KT / 16; ++g) {
+            float pv[16];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) f[i] = (__uint_as_float(v[i]) + __uint_as_float(v2[i])) * inv;
-      if (t < p.tq && part * 16 < p.d) {
-        if (p.o_hi) {
-          uint32_t hi[8], lo[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            // the saturating split tfmq_act_prepare writes (elementwise.cu::split_h16x4)
-            uint16_t h0, h1, l0, l1;
-            asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h0) : "f"(f[2 * i]));
-            asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h1) : "f"(f[2 * i + 1]));
-            const float r0 = f[2 * i] - __half2float(__ushort_as_half(h0));
-            const float r1 = f[2 * i + 1] - __half2float(__ushort_as_half(h1));
-            asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(l0) : "f"(r0));
-            asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(l1) : "f"(r1));
-            hi[i] = (uint32_t)h0 | ((uint32_t)h1 << 16);
-            lo[i] = (uint32_t)l0 | ((uint32_t)l1 << 16);
-          }
-          if (part * 16 + 16 <= p.d) {
-            uint4* dh = reinterpret_cast<uint4*>(p.o_hi + off + part * 16);
-            uint4* dl = reinterpret_cast<uint4*>(p.o_lo + off + part * 16);
-            dh[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]), dh[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-            dl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]), dl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
-          } else {                                          // head dim 40: the last 16-column part holds 8 real columns
-            *reinterpret_cast<uint4*>(p.o_hi + off + part * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            *reinterpret_cast<uint4*>(p.o_lo + off + part * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            for (int k = 0; k < 16; ++k) pv[k] = ex2_approx(fmaf(__uint_as_float(sv[g * 16 + k]), c, -mc));
+            split_store(g, pv);
           }
         } else {
-          float4* dst = reinterpret_cast<float4*>(p.o + off + part * 16);
-          const int nv = (part * 16 + 16 <= p.d) ? 4 : 2;
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
-            if (i < nv) dst[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+          for (int g = 0; g < KT / 16; ++g) {
+            if (g * 16 < kn) {
+              float pv[16];
+#pragma unroll
+              for (int k = 0; k < 16; ++k)
+                pv[k] = (g * 16 + k < kn) ? ex2_approx(fmaf(__uint_as_float(sv[g * 16 + k]), c, -mc)) : 0.f;
+              split_store(g, pv);
+            }
+          }
+        }
+        l += rs0 + rs1;
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[2 * qb + buf]);
+        ATC_PROF(2)
+      }
+      // ---- epilogue: O = (O_main + O_small) / l
+      mbar_wait(&o_full[qb], 0);
+      tc_fence_after();
+      ATC_PROF(3)
+      const float inv = 1.f / l;
+      const int t = q0 + qb * 128 + r;
+      const long long off = (long long)b * p.o_sb + (long long)h * p.o_sh + (long long)t * p.o_st;
+#pragma unroll
+      for (int part = 0; part < D / 16; ++part) {
+        uint32_t v[16], v2[16];
+        tmem_ld16(t_o + (uint32_t)(part * 16), v);
+        tmem_ld16(t_o2 + (uint32_t)(part * 16), v2);
+        tmem_ld_wait();
+        float f[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) f[k] = (__uint_as_float(v[k]) + __uint_as_float(v2[k])) * inv;
+        if (t < p.tq && part * 16 < p.d) {
+          if (p.o_hi) {
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              // the saturating split tfmq_act_prepare writes (elementwise.cu::split_h16x4)
+              uint16_t h0, h1, l0, l1;
+              asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h0) : "f"(f[2 * k]));
+              asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h1) : "f"(f[2 * k + 1]));
+              const float r0 = f[2 * k] - __half2float(__ushort_as_half(h0));
+              const float r1 = f[2 * k + 1] - __half2float(__ushort_as_half(h1));
+              asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(l0) : "f"(r0));
+              asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(l1) : "f"(r1));
+              hi[k] = (uint32_t)h0 | ((uint32_t)h1 << 16);
+              lo[k] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+            }
+            if (part * 16 + 16 <= p.d) {
+              uint4* dh = reinterpret_cast<uint4*>(p.o_hi + off + part * 16);
+              uint4* dl = reinterpret_cast<uint4*>(p.o_lo + off + part * 16);
+              dh[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]), dh[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+              dl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]), dl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+            } else {                                          // head dim 40: the last 16-column part holds 8 real columns
+              *reinterpret_cast<uint4*>(p.o_hi + off + part * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+              *reinterpret_cast<uint4*>(p.o_lo + off + part * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
+          } else {
+            float4* dst = reinterpret_cast<float4*>(p.o + off + part * 16);
+            const int nv = (part * 16 + 16 <= p.d) ? 4 : 2;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (k < nv) dst[k] = make_float4(f[4 * k], f[4 * k + 1], f[4 * k + 2], f[4 * k + 3]);
+          }
         }
       }
+      ATC_PROF(4)
+      if (prof_on) prof_dst[6] += clock64();
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == ATC_WARP_MMA) tmem_dealloc(tmem_base, TMEM_COLS);
+  if (warp == WARP_TMA) tmem_dealloc_imm<TMEM_COLS>(tmem_base);
+  if (p.prof && threadIdx.x == 0) {
+    long long* prof_dst = p.prof + ((long long)blockIdx.y * gridDim.x + blockIdx.x) * 16;
+    prof_dst[14] = clock64() - t_entry;                                          // [14]: CTA entry -> exit
+    prof_dst[11] = t_entry;
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    prof_dst[15] = smid;
+  }
 }
 
 // 4-D map of one fp16 plane addressed as base + b*sb + h*sh + t*st + dim (halves): dims {d, heads, tokens, b}
@@ -383,7 +526,7 @@ static int encode_plane(tfmq_ctx* ctx, CUtensorMap* m, const void* base, int d, 
   return TFMQ_OK;
 }
 
-template <int D, int ROWB, int KT>
+template <int D, int ROWB, int KT, int NQ, int ST>
 static int launch_attn_tc(tfmq_ctx* ctx, const tfmq_attn_h16_desc* d, cudaStream_t st) {
   CUtensorMap tm[6];
   const void* base[6] = {d->q_hi, d->q_lo, d->k_hi, d->k_lo, d->v_hi, d->v_lo};
@@ -400,17 +543,97 @@ static int launch_attn_tc(tfmq_ctx* ctx, const tfmq_attn_h16_desc* d, cudaStream
   p.o_sb = d->o_sb, p.o_sh = d->o_sh, p.o_st = d->o_st;
   p.heads = d->heads, p.tq = d->tq, p.tk = d->tk, p.d = d->d;
   p.scale_log2e = d->scale * 1.4426950408889634f;
-  const size_t smem = 1024 + 2 * 128 * ROWB + (size_t)ATC_STAGES * 4 * KT * ROWB + 128;
-  auto kern = attn_tc_kernel<D, ROWB, KT>;
+  static const int dbg_env = getenv("TFMQ_ATTN_DBG") ? atoi(getenv("TFMQ_ATTN_DBG")) : 0;
+  static const bool prof_env = getenv("TFMQ_ATTN_PROF") != nullptr;   // debug aid: in-kernel phase counters, synchronous
+  p.dbg = dbg_env;
+  p.prof = nullptr;
+  const size_t smem = 1024 + (size_t)NQ * 2 * 128 * ROWB + (size_t)ST * 4 * KT * ROWB + 256;
+  auto kern = attn_tc_kernel<D, ROWB, KT, NQ, ST>;
   static size_t smem_set = 0;
   if (smem > smem_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return tfmq_fail(ctx, TFMQ_ERR_CUDA, "attention_h16: smem attr: %s", cudaGetErrorString(e));
+    // several CTAs per SM are the design point: ask for the full shared-memory carve-out
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
     smem_set = smem;
   }
-  dim3 grid((d->tq + 127) / 128, d->b * d->heads);
-  kern<<<grid, ATC_THREADS, smem, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], p);
+  if (prof_env) {
+    int occ = -1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, (5 * NQ + 1) * 32, smem);
+    fprintf(stderr, "[attn prof] occupancy %d CTAs / SM (%zu B dynamic smem, %d threads)\n", occ, smem, (5 * NQ + 1) * 32);
+    cudaFuncAttributes fa;
+    cudaFuncGetAttributes(&fa, kern);
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, ctx->device);
+    fprintf(stderr, "[attn prof] regs %d static smem %zu local %zu maxthreads %d maxdyn %d carveout %d | SM: smem %zu regs %d "
+            "blocks %d reserved %zu\n", fa.numRegs, fa.sharedSizeBytes, fa.localSizeBytes, fa.maxThreadsPerBlock,
+            fa.maxDynamicSharedSizeBytes, fa.preferredShmemCarveout, prop.sharedMemPerMultiprocessor, prop.regsPerMultiprocessor,
+            prop.maxBlocksPerMultiProcessor, prop.reservedSharedMemPerBlock);
+    for (size_t sm = 8192; sm <= smem; sm += 8192) {
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, (5 * NQ + 1) * 32, sm);
+      fprintf(stderr, " %zuK:%d", sm / 1024, occ);
+    }
+    fprintf(stderr, "\n");
+  }
+  dim3 grid((d->tq + 128 * NQ - 1) / (128 * NQ), d->b * d->heads);
+  const size_t nctas = (size_t)grid.x * grid.y;
+  if (prof_env) {
+    cudaMalloc(&p.prof, nctas * 16 * sizeof(long long));
+    cudaMemsetAsync(p.prof, 0, nctas * 16 * sizeof(long long), st);
+  }
+  static const bool time_env = getenv("TFMQ_ATTN_TIME") != nullptr;   // debug aid: per-launch device time, synchronous
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  if (time_env) {
+    cudaEventCreate(&ev0), cudaEventCreate(&ev1);
+    cudaEventRecord(ev0, st);
+  }
+  kern<<<grid, (5 * NQ + 1) * 32, smem, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], p);
   TFMQ_LAUNCH_CHECK("attention_h16");
+  if (time_env) {
+    cudaEventRecord(ev1, st);
+    cudaStreamSynchronize(st);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ev0, ev1);
+    cudaEventDestroy(ev0), cudaEventDestroy(ev1);
+    fprintf(stderr, "[attn time] b %d heads %d tq %d tk %d d %d NQ %d: %.1f us\n", d->b, d->heads, d->tq, d->tk, d->d, NQ, ms * 1e3f);
+  }
+  if (prof_env) {
+    std::vector<long long> hb(nctas * 16);
+    cudaMemcpy(hb.data(), p.prof, hb.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+    cudaFree(p.prof);
+    double avg[16] = {0};
+    for (size_t c = 0; c < nctas; ++c)
+      for (int i = 0; i < 16; ++i) avg[i] += (double)hb[c * 16 + i] / (double)nctas;
+    const double nt = (double)((d->tk + KT - 1) / KT);
+    {
+      double per_sm[256] = {0};
+      for (size_t c = 0; c < nctas; ++c) per_sm[hb[c * 16 + 15] & 255] += (double)hb[c * 16 + 14];
+      double mx = 0, sum = 0;
+      for (int i = 0; i < 256; ++i) mx = per_sm[i] > mx ? per_sm[i] : mx, sum += per_sm[i];
+      fprintf(stderr, "[attn prof] CTA lifetime avg %.0f clocks (prologue %.0f, first S after %.0f); busiest SM holds %.0f clocks "
+              "of CTA lifetime, mean SM %.0f\n", avg[14], avg[12], avg[13], mx, sum / ctx->sm_count);
+      // gaps between consecutive CTAs of one SM (clock64 is per SM)
+      std::vector<std::vector<std::pair<long long, long long>>> tl(256);
+      for (size_t c = 0; c < nctas; ++c) tl[hb[c * 16 + 15] & 255].push_back({hb[c * 16 + 11], hb[c * 16 + 14]});
+      double gap_sum = 0, span_sum = 0;
+      long long ngap = 0, nsm = 0;
+      for (auto& v : tl) {
+        if (v.empty()) continue;
+        std::sort(v.begin(), v.end());
+        for (size_t k = 1; k < v.size(); ++k) gap_sum += (double)(v[k].first - (v[k - 1].first + v[k - 1].second)), ++ngap;
+        span_sum += (double)(v.back().first + v.back().second - v.front().first);
+        ++nsm;
+      }
+      fprintf(stderr, "[attn prof] per SM: first entry -> last exit %.0f clocks on average; gap between a CTA's exit and the next "
+              "CTA's entry %.0f clocks on average (%lld gaps)\n", span_sum / nsm, ngap ? gap_sum / ngap : 0.0, ngap);
+    }
+    fprintf(stderr,
+            "[attn prof] b %d heads %d tq %d tk %d d %d KT %d NQ %d | softmax warp 0 per key tile (each phase includes ~250 clocks of "
+            "counter overhead): wait_s %.0f max+rescale %.0f exp+store %.0f | wait_o %.0f epilogue %.0f | loop total %.0f | "
+            "UMMA warp 0 per key tile: wait_kv %.0f issue_qk %.0f wait_p %.0f issue_pv %.0f\n",
+            d->b, d->heads, d->tq, d->tk, d->d, KT, NQ, avg[0] / nt, avg[1] / nt, avg[2] / nt, avg[3], avg[4], avg[6],
+            avg[7] / nt, avg[8] / nt, avg[9] / nt, avg[10] / nt);
+  }
   return TFMQ_OK;
 }
 
@@ -441,10 +664,21 @@ extern "C" int tfmq_attention_h16(tfmq_ctx* ctx, const tfmq_attn_h16_desc* d, vo
     TFMQ_REQUIRE(((uintptr_t)d->o & 15) == 0 && d->o_sb % 4 == 0 && d->o_sh % 4 == 0 && d->o_st % 4 == 0, TFMQ_ERR_ARG,
                  "attention_h16: fp32 output must be 16-byte aligned with strides in multiples of 4");
   cudaStream_t st = tfmq_stream(stream);
-  if (d->d <= 32) {
-    if (d->d == 32) return launch_attn_tc<32, 64, 128>(ctx, d, st);
-    return launch_attn_tc<32, 128, 64>(ctx, d, st);      // 16, 24: zero-filled up to the 128-byte operand row
+  // Two 128-query blocks per CTA (one CTA per SM) over key tiles of 64 keys, S double-buffered in tensor memory; a single
+  // query block when there is only one.  TFMQ_ATTN_NQ overrides (experiments).
+  static const int nq_env = getenv("TFMQ_ATTN_NQ") ? atoi(getenv("TFMQ_ATTN_NQ")) : 0;
+  const int qblocks = (d->tq + 127) / 128;
+  const int nq = nq_env ? nq_env : (qblocks >= 2 ? 2 : 1);
+  if (d->d == 32) {
+    if (nq >= 2) return launch_attn_tc<32, 64, 64, 2, 6>(ctx, d, st);
+    return launch_attn_tc<32, 64, 64, 1, 6>(ctx, d, st);
   }
-  if (d->d <= 48) return launch_attn_tc<48, 128, 64>(ctx, d, st);
-  return launch_attn_tc<64, 128, 64>(ctx, d, st);
+  // 128-byte operand rows: head dims 16, 24 (zero-filled), 40 (runs as 48), 48, 56, 64
+  if (d->d < 32) return launch_attn_tc<32, 128, 64, 1, 3>(ctx, d, st);
+  if (d->d <= 48) {
+    if (nq >= 2) return launch_attn_tc<48, 128, 64, 2, 4>(ctx, d, st);
+    return launch_attn_tc<48, 128, 64, 1, 4>(ctx, d, st);
+  }
+  if (nq >= 2) return launch_attn_tc<64, 128, 64, 2, 4>(ctx, d, st);
+  return launch_attn_tc<64, 128, 64, 1, 4>(ctx, d, st);
 }
