@@ -78,7 +78,7 @@ def build_quantised(dev, batch):
     ts = ldm_timesteps(DDIM_STEPS)
     load_cali_model(qnn, (x, torch.full((2,), ts[0], device=dev)), use_aq=True, ckpt={"weight": {}})
     anchors = []
-    with torch.no_grad():
+    with torch.no_grad(), qnn.calibrating():        # synthetic Phase A: torch module graph, lazily initialised quantisers
         for i in range(8):
             k = i * (DDIM_STEPS - 1) // 7
             _reset_aqtizers(qnn)

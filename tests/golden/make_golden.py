@@ -211,34 +211,11 @@ def promote_zero_points(qnn):
 
 
 def alt_arithmetic():
-    """Context manager: evaluate the oracle with every conv / linear accumulated in float64 (and rounded
-    once) instead of fp32 -- a strictly more accurate evaluation of the SAME fake-quant network, used
-    to measure how far fp re-association alone moves the reference's outputs (flip cascade)."""
-    import contextlib
-    import torch.nn.functional as F
+    """The oracle with every conv / linear accumulated in float64 (oracle/quant_ref.py::float64_accumulation): measures how
+    far fp re-association alone moves the reference's outputs (flip cascade)."""
     sys.path.insert(0, os.path.join(HERE, "..", ".."))
     from oracle import quant_ref as Q
-
-    @contextlib.contextmanager
-    def cm():
-        orig = Q.quant_layer_forward
-
-        def qlf64(x, w, bias, wq=None, aq=None, conv=None):
-            if aq is not None:
-                x = Q.uaq_fake_quant(x, aq[0], aq[1], 256)
-            if wq is not None:
-                w = Q.adaround_fake_quant(w, wq[0], wq[1], wq[2], 16) if wq[2] is not None \
-                    else Q.uaq_fake_quant(w, wq[0], wq[1], 16)
-            b = bias.double() if bias is not None else None
-            if conv is None:
-                return F.linear(x.double(), w.double(), b).float()
-            return F.conv2d(x.double(), w.double(), b, **conv).float()
-        Q.quant_layer_forward = qlf64
-        try:
-            yield
-        finally:
-            Q.quant_layer_forward = orig
-    return cm()
+    return Q.float64_accumulation()
 
 
 def oracle_alt_cifar(g):
@@ -361,6 +338,45 @@ def sdmini_golden():
                     block_attention_quantisers_inert=inert),
                os.path.join(HERE, "sdmini_w4a8.pt"))
     print("sdmini_w4a8.pt written", len(names), "act-quantised layers; inert:", inert, time.time() - t0)
+
+
+def full_size_golden(name):
+    """BASELINE configs[2] / [4] at FULL size through the reference's own QuantModel (w4a8, synthetic AdaRound checkpoint,
+    classifier-free-guidance batch of 2): SD v1.4 (configs/stable-diffusion/v1-inference.yaml:29-44, 77-token context of 768)
+    and cin256-v2 (configs/latent-diffusion/cin256-v2.yaml:19-39, one class token of 512).  Inputs are seeded (the tests
+    regenerate them); the fixture holds the activation-quantiser table and eps only."""
+    from ldm.modules.diffusionmodules.openaimodel import UNetModel
+    from tfmq_b200.host import ldm_unet as H
+    t0 = time.time()
+    cfg = dict(sd_v14=H.sd_v14_config, cin256=H.cin256_config)[name]()
+    tk = 77 if name == "sd_v14" else 1
+    seed = 7
+    fp = UNetModel(**cfg).eval()
+    synth.fill_state_dict(fp, seed)
+    wq, aq = wq_aq()
+    qnn = QuantModel(fp, wq, aq, cali=False, softmax_a_bit=8, aq_mode=[QMODE.NORMAL.value, QMODE.QDIFF.value])
+    qnn.eval()
+    x = synth.latents((2, cfg["in_channels"], 64, 64), 21)
+    t = torch.tensor([601.0, 601.0])
+    ctx = synth.latents((2, tk, cfg["context_dim"]), 22)
+    global SEED
+    saved, SEED = SEED, seed
+    try:
+        attach_alpha(qnn, (x, t, ctx))
+    finally:
+        SEED = saved
+    print(name, ": load_cali_model done", time.time() - t0)
+    with torch.no_grad():
+        reset_aq(qnn)
+        e = qnn(x, t, ctx)
+        act = collect_aq(qnn)
+        t1 = time.time()
+        e2 = qnn(x, t, ctx)
+        print(name, ": one reference w4a8 forward at batch 2 on", torch.get_num_threads(), "threads:", time.time() - t1, "s")
+    names, tab = pack_act([act])
+    torch.save(dict(seed=seed, x_seed=21, ctx_seed=22, t=t, tokens=tk, act_names=names, act_table=tab, eps=e2),
+               os.path.join(HERE, f"{name}_w4a8.pt"))
+    print(f"{name}_w4a8.pt written", len(names), "act-quantised layers", time.time() - t0)
 
 
 def unet_keys():
@@ -562,3 +578,6 @@ if __name__ == "__main__":
         unet_keys()
     if "plms" in what:
         plms_golden()
+    for full in ("sd_v14", "cin256"):
+        if full in what:
+            full_size_golden(full)

@@ -13,6 +13,8 @@ import synth  # noqa: E402
 CIFAR_CFG = dict(ch=128, ch_mult=[1, 2, 2, 2], num_res_blocks=2)
 LDM4_CFG = dict(model_channels=224, num_head_channels=32)
 SDMINI_CFG = dict(model_channels=64, num_heads=2)
+SD_V14_CFG = dict(model_channels=320, num_heads=8)       # BASELINE configs[2]
+CIN256_CFG = dict(model_channels=192, num_heads=1)       # BASELINE configs[4]
 
 
 def load_golden(name):
@@ -26,6 +28,9 @@ def fp_model(kind: str, seed: int = 1234):
     elif kind == "sdmini":
         from tfmq_b200.host.ldm_unet import UNetModel, sd_mini_config
         m = UNetModel(**sd_mini_config())
+    elif kind in ("sd_v14", "cin256"):
+        from tfmq_b200.host import ldm_unet as H
+        m = H.UNetModel(**dict(sd_v14=H.sd_v14_config, cin256=H.cin256_config)[kind]())
     else:
         from tfmq_b200.host.ldm_unet import UNetModel, celebahq_ldm4_config
         m = UNetModel(**celebahq_ldm4_config())
@@ -49,3 +54,13 @@ def first_stage_model(kind: str, seed: int = 1234):
 def oracle_spec(sd, seed: int = 1234):
     from oracle import unet_ref
     return unet_ref.build_spec(sd, alpha_fn=lambda n, w, d: synth.synth_alpha(n, w, d, seed))
+
+
+def full_size_inputs(name: str, g: dict):
+    """(x, t, context) of the full-size SpatialTransformer goldens (tests/golden/make_golden.py::full_size_golden): seeded,
+    regenerated here instead of stored."""
+    from tfmq_b200.host import ldm_unet as H
+    cfg = dict(sd_v14=H.sd_v14_config, cin256=H.cin256_config)[name]()
+    x = synth.latents((2, cfg["in_channels"], 64, 64), g["x_seed"])
+    ctx = synth.latents((2, g["tokens"], cfg["context_dim"]), g["ctx_seed"])
+    return x, g["t"], ctx

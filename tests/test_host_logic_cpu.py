@@ -302,3 +302,52 @@ def test_ldm_script_shells():
     assert R.quantize_ldm(NS(ptq=False), ld) is ld
     with pytest.raises(NotImplementedError):
         R.DiffusionWrapper(unet, "concat")
+
+
+def test_fsc_table_index_follows_the_number_of_calibrated_tables():
+    """DiffusionWrapper.forward picks act_k with k = t_max - (t - 1) // tot where the scripts set tot = 1000 // n_tables and
+    t_max = n_tables - 1 (sample_diffusion_ldm.py:475-477, ldm/models/diffusion/ddpm.py:1402-1405): the index depends on the
+    number of CALIBRATED tables, not on the number of sampling steps S."""
+    from tfmq_b200.samplers import DDIMSampler
+
+    class _Stub:                      # only .model / attribute lookups are touched before sampling
+        pass
+    ckpt = {"weight": {}}
+    for k in range(4):
+        ckpt[f"act_{k}"] = {"k": k}
+    smp = DDIMSampler(_Stub(), ckpt=ckpt)
+    for S in (4, 8, 20, 2):
+        smp.make_schedule(S)
+        ts = [float(t) for t in reversed(smp.ddim_timesteps.tolist())]
+        got = [d["k"] for d in smp.fsc_tables(ts)]
+        want = [int(3 - (int(t) - 1) // 250) for t in ts]        # tot = 1000 // 4, t_max = 3
+        assert got == want and all(0 <= k <= 3 for k in got), (S, got, want)
+    # the attributes the scripts install on the wrapper win over the table count
+    smp.tot, smp.t_max = 500, 1
+    smp.make_schedule(4)
+    ts = [float(t) for t in reversed(smp.ddim_timesteps.tolist())]
+    assert [d["k"] for d in smp.fsc_tables(ts)] == [int(1 - (int(t) - 1) // 500) for t in ts]
+
+
+def test_quant_model_engine_invalidation_and_calibration_context():
+    """QuantModel.forward has two routes and no silent third one: the torch module graph inside `calibrating()` / under
+    autograd / for the lazy-initialisation forward, the sm_100a step engine otherwise (a CPU tensor then raises).  Anything
+    that changes what the engine froze at trace time drops it."""
+    qnn = _qnn("cifar", cali=False)
+    qnn.set_quant_state(False, False)
+    x, t = synth.latents((1, 3, 32, 32), 5), torch.tensor([10.0])
+    with qnn.calibrating(), torch.no_grad(), pytest.raises(RuntimeError, match="no CPU fallback"):
+        qnn(x, t)                                       # module graph: its QuantLayers refuse CPU tensors themselves
+    with torch.no_grad(), pytest.raises(RuntimeError, match="no CPU path"):
+        qnn(x, t)                                       # outside: the engine route, which needs a CUDA tensor
+    sentinel = object()
+    for mutate in (lambda: qnn.set_quant_state(False, False), lambda: qnn.disable_out_quantization(),
+                   lambda: qnn.set_running_stat(False), lambda: qnn.load_state_dict(qnn.state_dict()),
+                   lambda: qnn.float()):
+        qnn._engine = sentinel
+        mutate()
+        assert qnn._engine is None
+    qnn._engine = sentinel
+    with qnn.calibrating():
+        pass
+    assert qnn._engine is None

@@ -112,6 +112,22 @@ def test_sdmini_spatial_transformer_unet_step():
     assert (e - g["eps"]).abs().max().item() < 2e-5
 
 
+def test_cin256_full_size_unet_step():
+    """BASELINE configs[4] at FULL size (cin256-v2: 265 QuantLayers, one head of 384 / 576 / 960 channels, class-token
+    context) against the reference's own QuantModel output (tests/golden/cin256_w4a8.pt).  The SD v1.4 fixture
+    (configs[2], 4x the work) is pinned the same way on the GPU box, tests/test_gpu_e2e.py."""
+    from helpers import CIN256_CFG, full_size_inputs
+    g = load_golden("cin256_w4a8.pt")
+    sd = fp_model("cin256", g["seed"]).state_dict()
+    spec = oracle_spec(sd, g["seed"])
+    assert len(U.wrapped_layer_names(sd)) == 265
+    assert sorted(n for n, s in spec.items() if s["aq"]) == g["act_names"]
+    x, t, ctx = full_size_inputs("cin256", g)
+    with torch.no_grad():
+        e = U.ldm_unet_forward(sd, CIN256_CFG, x, t, spec, U.ActParams(g["act_names"], g["act_table"][0]), context=ctx)
+    assert (e - g["eps"]).abs().max().item() < 2e-5
+
+
 def test_ddim_coef_table_matches_sampler():
     betas = synth.ddim_betas()
     seq = list(range(0, 1000, 20))

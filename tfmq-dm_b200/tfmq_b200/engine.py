@@ -86,8 +86,16 @@ class _QL:
         self.quant_w = bool(layer.use_wq)
         w2d = (w.permute(0, 2, 3, 1).reshape(self.cout, -1) if self.is_conv else w).float().contiguous().to(dev)
         self.w_oihw = w.float().contiguous().to(dev)    # conv_in / conv_out kernels read torch's layout
+        if aq_index is not None and int(getattr(layer.aqtizer, "level", 256)) != 256:
+            raise NotImplementedError(
+                f"StepEngine: layer {name} quantises its activations to {layer.aqtizer.level} levels; the sm_100a step program "
+                "implements the w4a8 path (u8 activation codes, --aq 8) only and does not fall back to another kernel")
         if self.quant_w:
             wq = layer.wqtizer
+            if int(getattr(wq, "level", getattr(getattr(wq, "uaqtizer", None), "level", 16))) != 16:
+                raise NotImplementedError(
+                    f"StepEngine: layer {name} has {getattr(wq, 'level', '?')}-level weights; the sm_100a step program packs "
+                    "4-bit codes (--wq 4) only -- 8-bit weights would be clamped to [0, 15] silently, so this is an error")
             delta = wq.delta.detach().reshape(-1).float().to(dev)
             zp = wq.zero_point
             zp = zp.detach().reshape(-1).float().to(dev) if torch.is_tensor(zp) else torch.full_like(delta, float(zp))
@@ -99,7 +107,10 @@ class _QL:
                 alpha = (a.permute(0, 2, 3, 1).reshape(self.cout, -1) if self.is_conv else a).float().contiguous().to(dev)
             self.codes, self.packed, self.wsum = ops.pack_w4(w2d, delta, zp, alpha)
             self.wdelta, self.wzp_f = delta.contiguous(), zp.contiguous()
-            self.wzp_u8 = zp.to(torch.uint8).contiguous()
+            # Scaler.MSE does not force the range to contain 0 (quant/quant_layer.py:38-64): a row whose weights share one
+            # sign gets a zero point outside [0, 255], which the u8 zero-point vector of the int8 epilogue cannot carry
+            self.wzp_in_range = bool(((zp >= 0) & (zp <= 255)).all())
+            self.wzp_u8 = zp.clamp(0, 255).to(torch.uint8).contiguous()
         else:
             self.w_f32 = w2d
         self._fp_ready = False
@@ -144,6 +155,7 @@ class StepEngine:
         self._u8_bufs: List = []
         self.u8_by_name: Dict[str, tuple] = {}
         self.teacher: Optional[Dict[str, torch.Tensor]] = None   # test hook: force quantiser decisions
+        self.tib_check: Dict[str, tuple] = {}                      # test hook: TIB outputs vs the oracle's, before forcing
         self.block_out: Dict[str, T] = {}                          # test hook: block name -> output tensor
         self._names = {id(m): n for n, m in model.named_modules()}
         self.graph = None
@@ -297,6 +309,10 @@ class StepEngine:
             tok["geglu"] = True
         if out is None:
             out = self._new(x.n, oh, ow, q.cout)
+        if q.quant_w and q.aq_index is not None and not q.wzp_in_range:
+            raise NotImplementedError(
+                f"StepEngine: layer {q.name} has a weight zero point outside [0, 255] (a channel whose weights share one sign "
+                "under Scaler.MSE); the w4a8 epilogue carries zero points as u8 -- refusing to run it with a wrapped value")
         if q.quant_w and q.aq_index is not None:
             halo = 1 if q.ksize == 3 else 0
             u8 = torch.empty((x.n, oh + 2 * halo, ow + 2 * halo, q.cin), dtype=torch.uint8, device=self.dev)
@@ -413,9 +429,17 @@ class StepEngine:
         def run():
             ops.linear_small(**kw)
             if self.teacher is not None and ("out:" + q.name) in self.teacher:
-                out.copy_(self.teacher["out:" + q.name].to(self.dev))
+                self._force_tib(q.name, out)
         self.ops.append(run)
         return out
+
+    def _force_tib(self, name: str, out: torch.Tensor):
+        """Teacher forcing of a time-embedding (Temporal Information Block) layer: the kernel's output is first COMPARED
+        with the oracle's (max-abs deviation and the oracle's magnitude go to `tib_check[name]`, asserted by the parity
+        tests), then replaced by it so the next layer sees the oracle's bits."""
+        forced = self.teacher["out:" + name].to(self.dev)
+        self.tib_check[name] = ((out - forced).abs().max(), forced.abs().max())
+        out.copy_(forced)
 
     def _open_linear_group(self):
         self._lin_group: List = []
@@ -435,7 +459,7 @@ class StepEngine:
             if self.teacher is not None:
                 for q, kw in members:
                     if ("out:" + q.name) in self.teacher:
-                        kw["out"].copy_(self.teacher["out:" + q.name].to(self.dev))
+                        self._force_tib(q.name, kw["out"])
         self.ops[self._lin_group_slot] = run
 
     def _ctx_tokens(self) -> T:
