@@ -379,6 +379,81 @@ def full_size_golden(name):
     print(f"{name}_w4a8.pt written", len(names), "act-quantised layers", time.time() - t0)
 
 
+def recon_golden(iters=50):
+    """the reference's own `tib_reconstruction` and `block_reconstruction` (quant/reconstruction.py:86-318) for
+    `iters` iterations with a fixed torch seed (it drives `randperm`): the loss of every iteration and a strided sample of
+    every alpha afterwards.  Sequence as in cali_model (quant/calibration.py:71-124): weight-quantiser initialisation,
+    first / last layer exemptions, TIB first, then the blocks.  Units: CIFAR UNet -- TIB (DDIM flavour) and an AttnBlock;
+    small SpatialTransformer UNet -- TIB (LDM flavour), a ResBlock and a BasicTransformerBlock.  (The reference leaves the
+    model in train() mode during reconstruction, so CIFAR's ResnetBlocks run with dropout 0.1 drawn from the CPU
+    generator: those are not reproducible on another device and are left out; the LDM configs have dropout 0.)"""
+    from ddim.models.diffusion import Model
+    from ldm.modules.diffusionmodules.openaimodel import UNetModel
+    from quant import reconstruction_util as RU
+    from quant.reconstruction import block_reconstruction, tib_reconstruction
+    from tfmq_b200.host.ddim_unet import cifar10_config
+    from tfmq_b200.host.ldm_unet import sd_mini_config
+    trace = []
+    for cls in (RU.LossFunc, RU.LossFuncTimeEmbedding):
+        orig = cls.__call__
+
+        def rec_call(self, *a, _orig=orig, **k):
+            out = _orig(self, *a, **k)
+            trace.append(float(out.detach()))
+            return out
+        cls.__call__ = rec_call
+    kw = dict(batch_size=8, iters=iters, w=0.01, opt_mode=RU.RLOSS.MSE, asym=True, b_range=(20, 2), warmup=0.2,
+              multi_gpu=False)
+    stride = 37
+    out = dict(seed=SEED, iters=iters, n=32, kw={k: v for k, v in kw.items() if k != "opt_mode"}, stride=stride, models={})
+
+    def sample(a):
+        a = a.detach()
+        return a.flatten()[::stride].clone(), float(a.double().sum()), float(a.double().abs().sum())
+
+    for kind, blocks in (("cifar", ["down.1.attn.0"]),
+                         ("sdmini", ["input_blocks.1.0", "input_blocks.1.1.transformer_blocks.0"])):
+        if kind == "cifar":
+            fp = Model(cifar10_config()).eval()
+            cali = (synth.latents((32, 3, 32, 32), 71),
+                    torch.randint(0, 1000, (32,), generator=torch.Generator().manual_seed(72)).float())
+        else:
+            fp = UNetModel(**sd_mini_config()).eval()
+            cali = (synth.latents((32, 4, 16, 16), 73),
+                    torch.randint(0, 1000, (32,), generator=torch.Generator().manual_seed(74)).float(),
+                    synth.latents((32, 7, 96), 75))
+        synth.fill_state_dict(fp, SEED)
+        wq, aq = wq_aq()
+        qnn = QuantModel(fp, wq, aq, cali=True, softmax_a_bit=8, aq_mode=[QMODE.NORMAL.value, QMODE.QDIFF.value])
+        qnn.eval()
+        qnn.set_quant_state(True, False)
+        with torch.no_grad():
+            qnn(*(d[:8] for d in cali))
+        qnn.disable_out_quantization()
+        rec = {}
+        trace.clear()
+        torch.manual_seed(0)
+        tib_reconstruction(qnn.tib, cali_data=cali, **kw)
+        rec["tib_loss"] = torch.tensor(trace)
+        rec["tib_alpha"] = {name: sample(m.wqtizer.alpha) for name, m in qnn.model.named_modules()
+                            if isinstance(m, QuantLayer) and isinstance(m.wqtizer, AdaRoundQuantizer)}
+        rec["blocks"] = {}
+        mods = dict(qnn.model.named_modules())
+        for i, bn in enumerate(blocks):
+            trace.clear()
+            torch.manual_seed(1 + i)
+            block_reconstruction(qnn, mods[bn], cali_data=cali, **kw)
+            rec["blocks"][bn] = dict(loss=torch.tensor(trace),
+                                     alpha={n: sample(m.wqtizer.alpha) for n, m in mods[bn].named_modules()
+                                            if isinstance(m, QuantLayer) and m.quant_emb is False})
+            print(kind, bn, "loss", rec["blocks"][bn]["loss"][:3].tolist(), "...", rec["blocks"][bn]["loss"][-2:].tolist(),
+                  "layers", list(rec["blocks"][bn]["alpha"]))
+        print(kind, "tib layers", len(rec["tib_alpha"]), "loss", rec["tib_loss"][:3].tolist(), "...", rec["tib_loss"][-2:].tolist())
+        out["models"][kind] = rec
+    torch.save(out, os.path.join(HERE, "recon_trace.pt"))
+    print("recon_trace.pt written")
+
+
 def unet_keys():
     """state_dict keys / shapes of the REFERENCE UNetModel for every supported LDM config (meta device: no weights are
     materialised), and the module list of the reference QuantModel on the small transformer UNet."""
@@ -578,6 +653,8 @@ if __name__ == "__main__":
         unet_keys()
     if "plms" in what:
         plms_golden()
+    if "recon" in what:
+        recon_golden()
     for full in ("sd_v14", "cin256"):
         if full in what:
             full_size_golden(full)

@@ -135,3 +135,77 @@ def test_cali_model_spatial_transformer_unet(dev):
     out, _ = DDIMSampler(q2, ckpt=ckpt).sample(2, 2, (4, 16, 16), conditioning=c, unconditional_conditioning=uc,
                                               unconditional_guidance_scale=3.0, x_T=x)
     assert torch.isfinite(out).all() and out.shape == x.shape
+
+
+@pytest.mark.parametrize("kind", ["cifar", "sdmini"])
+def test_reconstruction_trace_matches_the_reference(dev, kind):
+    """50 iterations of `tib_reconstruction` and `block_reconstruction` with a fixed torch seed against the trace of
+    the reference's own functions (quant/reconstruction.py:86-318, run on the CPU by tests/golden/make_golden.py::recon_golden):
+    the loss of every iteration and the learned alpha of every layer.  Same sequence as cali_model: weight-quantiser
+    initialisation, exemptions, TIB, then the blocks (whose asymmetric input cache sees the reconstructed TIB).
+    cifar: DDIM-flavour TIB + an AttnBlock; sdmini: LDM-flavour TIB + a ResBlock + a BasicTransformerBlock."""
+    import tfmq_b200.quant.reconstruction as R
+    from tfmq_b200.quant.adaptive_rounding import AdaRoundQuantizer
+    from tfmq_b200.quant.quant_layer import QMODE, QuantLayer, Scaler
+    from tfmq_b200.quant.quant_model import QuantModel
+    from tfmq_b200.quant.reconstruction_util import RLOSS
+    g = load_golden("recon_trace.pt")
+    rec = g["models"][kind]
+    torch.backends.cudnn.allow_tf32 = False          # the unit's forward / backward through torch stays fp32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    wq = dict(bits=4, channel_wise=True, scaler=Scaler.MINMAX)
+    aq = dict(bits=8, channel_wise=False, scaler=Scaler.MINMAX, leaf_param=True)
+    qnn = QuantModel(fp_model(kind, g["seed"]).to(dev), wq, aq, cali=True, softmax_a_bit=8,
+                     aq_mode=[QMODE.NORMAL.value, QMODE.QDIFF.value]).eval()
+    if kind == "cifar":
+        cali = (synth.latents((32, 3, 32, 32), 71),
+                torch.randint(0, 1000, (32,), generator=torch.Generator().manual_seed(72)).float())
+    else:
+        cali = (synth.latents((32, 4, 16, 16), 73),
+                torch.randint(0, 1000, (32,), generator=torch.Generator().manual_seed(74)).float(),
+                synth.latents((32, 7, 96), 75))
+    qnn.set_quant_state(True, False)
+    with torch.no_grad():
+        qnn(*(d[:8].to(dev) for d in cali))
+    qnn.disable_out_quantization()
+    kw = dict(g["kw"], opt_mode=RLOSS.MSE)
+
+    def compare(tag, trace, want_trace, alphas, want_alphas):
+        trace = torch.tensor(trace)
+        assert trace.shape == want_trace.shape
+        rel = ((trace - want_trace).abs() / want_trace.abs().clamp_min(1e-6)).max().item()
+        worst, worst_frac = 0.0, 0.0
+        for name, (sample, s1, s2) in want_alphas.items():
+            a = alphas[name].detach().float().cpu()
+            d = (a.flatten()[::g["stride"]] - sample).abs()
+            # Adam divides by sqrt(v): where a gradient sits at the fp32 noise floor the update direction is chance, so a few
+            # elements may end a couple of learning-rate steps (1e-3 each) apart; the rest agrees to fp32 accuracy
+            frac_far = (d > 1e-3).float().mean().item()
+            worst, worst_frac = max(worst, d.max().item()), max(worst_frac, frac_far)
+            assert frac_far < 2e-3 and d.max().item() < 0.05, (tag, name, frac_far, d.max().item())
+            assert abs(float(a.double().sum()) - s1) <= 2e-4 * max(1.0, s2), (tag, name)
+        print(f"[{kind} {tag}] {len(trace)} iterations: loss trace max relative deviation {rel:.3e} (first {want_trace[0]:.5f}, "
+              f"last {want_trace[-1]:.2f}); alpha of {len(want_alphas)} layers: worst element deviation {worst:.3e}, at most "
+              f"{worst_frac:.1e} of a layer beyond 1e-3")
+        assert rel < 2e-3, (tag, rel)
+
+    R.LOSS_TRACE = []
+    try:
+        torch.manual_seed(0)
+        R.tib_reconstruction(qnn.tib, cali_data=cali, **kw)
+        tib_trace, R.LOSS_TRACE = R.LOSS_TRACE, []
+        mods = dict(qnn.model.named_modules())
+        alphas = {nm: m.wqtizer.alpha for nm, m in mods.items()
+                  if isinstance(m, QuantLayer) and isinstance(m.wqtizer, AdaRoundQuantizer)}
+        assert sorted(alphas) == sorted(rec["tib_alpha"])
+        compare("tib_reconstruction", tib_trace, rec["tib_loss"], alphas, rec["tib_alpha"])
+        for i, (bn, want) in enumerate(rec["blocks"].items()):
+            R.LOSS_TRACE = []
+            torch.manual_seed(1 + i)
+            R.block_reconstruction(qnn, mods[bn], cali_data=cali, **kw)
+            blk_alphas = {nm: m.wqtizer.alpha for nm, m in mods[bn].named_modules()
+                          if isinstance(m, QuantLayer) and not m.quant_emb}
+            assert sorted(blk_alphas) == sorted(want["alpha"])
+            compare("block_reconstruction " + bn, R.LOSS_TRACE, want["loss"], blk_alphas, want["alpha"])
+    finally:
+        R.LOSS_TRACE = None

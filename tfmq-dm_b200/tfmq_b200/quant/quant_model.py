@@ -96,9 +96,16 @@ class QuantModel(nn.Module):
         initialise lazily and track running statistics): the calibration-time graph of quant/calibration.py,
         quant/reconstruction.py and quant/data_utill.py.  Leaving it drops the step engine (the state has changed)."""
         self._cali_depth += 1
+        # the calibration-time graph borrows torch's conv / matmul kernels: keep them in true fp32 (torch enables TF32 for
+        # cuDNN convolutions by default), so that weight-quantiser initialisation, cached block inputs / outputs and the
+        # FSC activation ranges are those of the fp32 reference path
+        saved = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
         try:
             yield self
         finally:
+            torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = saved
             self._cali_depth -= 1
             self.invalidate_engine()
 

@@ -28,6 +28,10 @@ from .reconstruction_util import RLOSS, LinearTempDecay, print_freq, unit_layers
 
 logger = logging.getLogger(__name__)
 
+# Test hook: when set to a list, every iteration appends its total loss (reconstruction + rounding regulariser,
+# what the reference's LossFunc returns) -- one host sync per iteration, so it stays None outside the parity tests.
+LOSS_TRACE = None
+
 
 class _LayerState:
     def __init__(self, layer: QuantLayer):
@@ -94,11 +98,13 @@ def _adaround_loop(forward, layers: List[QuantLayer], cached_inputs, cached_outp
             grads = allreduce_flat_(grads)
         b = decay(it) if it >= loss_start else 0.0
         log = it % print_freq == 0
-        if log:
+        if log or LOSS_TRACE is not None:
             round_acc.zero_()
         for s, g in zip(states, grads):
             ops.adaround_step(s.w2d, s.delta, s.zp, s.alpha.data, g.contiguous(), s.m, s.v, s.level, it, 1e-3,
                               float(b), float(w) * world, round_acc)
+        if LOSS_TRACE is not None:
+            LOSS_TRACE.append(float(rec) + float(round_acc) / world)
         if log:
             logger.info("Total loss:\t{:.8f} (rec:{:.8f}, round:{:.8f})\tb={:.2f}\tcount={}".format(
                 float(rec) + float(round_acc) / world, float(rec), float(round_acc) / world, b, it))
