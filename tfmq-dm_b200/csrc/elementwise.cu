@@ -95,19 +95,27 @@ __device__ __forceinline__ float silu_f(float v) { return v * rcp_approx(1.f + _
 // case and only then the correctly rounded division is evaluated.
 // Rounding and the float -> integer move use the 1.5*2^23 / 2^23 add tricks (full-rate FADD, round-half-even
 // like rintf) instead of FRND / F2I, which share the quarter-rate pipe with the SiLU's EX2 / RCP.
-__device__ __noinline__ float quant_slow(float t, float delta) { return rintf(__fdiv_rn(t, delta)); }
+// This version folds zero point and clamp in before the rounding: r = clamp(fma(t, 1/delta, zp), 0, 255) differs from
+// RN(t / delta) + zp by < 1e-4 inside the code range (and both saturate outside it), the 1.5*2^23 add rounds it half-even
+// and leaves the code in the low mantissa byte; 7 full-rate instructions per element instead of 14.
+__device__ __noinline__ float quant_slow(float t, float delta, float zp) {
+  const float code = fminf(fmaxf(rintf(__fdiv_rn(t, delta)) + zp, 0.f), 255.f);
+  return __fadd_rn(code, 12582912.f);
+}
+// returns a word whose LOW BYTE is the code
 __device__ __forceinline__ uint32_t quant1(float t, float delta, float inv, float zp) {
-  const float q = fminf(fmaxf(t * inv, -1024.f), 1024.f);   // beyond +-1024 steps the code saturates either way
-  float nq = __fsub_rn(__fadd_rn(q, 12582912.f), 12582912.f);
-  // |q| <= 1024: both t * inv and RN(t / delta) lie within 1.3e-4 of the real quotient, so their roundings can only
-  // differ when q is within 2.6e-4 of a half-integer; 5e-4 of margin sends 0.1 % of the elements to the exact path
-  if (fabsf(q - nq) > 0.4995f) nq = quant_slow(t, delta);
-  const float code = fminf(fmaxf(nq + zp, 0.f), 255.f);
-  return __float_as_uint(__fadd_rn(code, 8388608.f)) & 0xFFu;
+  const float r = fminf(fmaxf(fmaf(t, inv, zp), 0.f), 255.f);
+  float m = __fadd_rn(r, 12582912.f);                    // 1.5 * 2^23: the sum's low mantissa bits are rint(r)
+  const float nr = __fsub_rn(m, 12582912.f);
+  // r is within 1e-4 of the reference's pre-rounding value: the two roundings can only differ when r is within that of a
+  // half-integer; 5e-4 of margin sends 0.1 % of the elements to the exact path
+  if (fabsf(r - nr) > 0.4995f) m = quant_slow(t, delta, zp);
+  return __float_as_uint(m);
 }
 __device__ __forceinline__ uint32_t quant4(const float (&t)[4], float delta, float inv, float zp) {
-  return quant1(t[0], delta, inv, zp) | (quant1(t[1], delta, inv, zp) << 8) | (quant1(t[2], delta, inv, zp) << 16) |
-         (quant1(t[3], delta, inv, zp) << 24);
+  const uint32_t lo = __byte_perm(quant1(t[0], delta, inv, zp), quant1(t[1], delta, inv, zp), 0x0040);
+  const uint32_t hi = __byte_perm(quant1(t[2], delta, inv, zp), quant1(t[3], delta, inv, zp), 0x0040);
+  return __byte_perm(lo, hi, 0x5410);
 }
 
 // v = hi + lo (+ O(2^-22 |v|)): hi = half(v), lo = half(v - hi); saturating, so an out-of-range value cannot become inf
@@ -285,6 +293,151 @@ __global__ void __launch_bounds__(ACT_THREADS) act_prepare_kernel(const ActParam
   }
 }
 
+// ------------------------------------------------- the same producer, flattened (GroupNorm / no normalisation)
+// The warp-per-pixel kernel above spends ~40 issue slots per element at the LDM-4 shapes (ncu: issue-bound at a third of the
+// DRAM rate): the per-pixel decode (division by the row length, border test, 64-bit addresses) is amortised over only
+// c / 128 vectors per lane, a quarter of the lanes idle when c / 4 is not a multiple of 32, the SiLU's __expf carries a
+// denormal-range fix-up and every element has its own branch to the exact-rounding path.  Here a thread owns float4 VECTORS of
+// the flattened [destination pixels x c / 4] space: two multiply-high divisions per vector recover (pixel, channel vector),
+// all lanes work, the exponential is one ex2.approx.ftz, the exact-rounding path is tested once per vector, and ACT_UNROLL
+// vectors per thread are in flight.  The zero-point halo is filled by a separate short loop over the border pixels.
+constexpr int ACT_UNROLL = 2;
+
+struct ActFlatParams {
+  tfmq_act_desc d;
+  int out_h, out_w;
+  int nvec;                  // c / 4
+  uint32_t nvec_magic;       // ceil(2^32 / nvec): idx / nvec = umulhi(idx, magic) for idx * nvec < 2^32
+  uint32_t ow_magic;         // the same for out_w
+  unsigned vec_per_cta;      // flattened vectors per CTA (a multiple of ACT_THREADS * ACT_UNROLL)
+  unsigned vec_total;        // out_h * out_w * nvec
+  int border_per_cta;        // halo pixels per CTA
+  double inv_cnt;
+};
+
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// x * sigmoid(x) = x / (1 + 2^(-x log2 e)); a result of the exponential below the normal range flushes to 0 (sigmoid = 1)
+__device__ __forceinline__ float silu_fast(float v) { return v * rcp_approx(1.f + ex2_ftz(v * -1.4426950408889634f)); }
+
+template <bool GN, bool SILU, int OUT>
+__global__ void __launch_bounds__(ACT_THREADS) act_flat_kernel(const ActFlatParams P) {
+  extern __shared__ float sp[];  // [c] a = rstd*gamma, [c] b = beta - a*mean
+  griddep_launch_dependents();
+  griddep_wait();
+  const tfmq_act_desc& d = P.d;
+  const int n = blockIdx.y;
+  const int c = d.c;
+  if (GN) {
+    __shared__ float sg[2 * 64];
+    const int cpg = c / d.groups;
+    for (int g = threadIdx.x; g < d.groups; g += ACT_THREADS) {
+      const double su = d.gn_stats[((long long)n * d.groups + g) * 2];
+      const double sq = d.gn_stats[((long long)n * d.groups + g) * 2 + 1];
+      const double mean = su * P.inv_cnt;
+      double var = fma(-mean, mean, sq * P.inv_cnt);
+      if (var < 0) var = 0;
+      sg[2 * g] = 1.f / sqrtf((float)var + d.eps);
+      sg[2 * g + 1] = (float)mean;
+    }
+    __syncthreads();
+    for (int ch = threadIdx.x; ch < c; ch += ACT_THREADS) {
+      const int g = ch / cpg;
+      const float a = sg[2 * g] * d.gamma[ch];
+      sp[ch] = a;
+      sp[c + ch] = -a * sg[2 * g + 1] + d.beta[ch];
+    }
+    __syncthreads();
+  }
+  float delta = 1.f, zp = 0.f;
+  if (OUT == ACT_OUT_U8) delta = d.aq[0], zp = d.aq[1];
+  const float inv = __frcp_rn(delta);
+  const int halo = (OUT == ACT_OUT_U8) ? d.halo : 0;
+  const int Wp = P.out_w + 2 * halo;
+  const int npix = Wp * (P.out_h + 2 * halo);
+  const int nvec = P.nvec;
+  const int up = d.upsample ? 1 : 0;
+  const float* src_img = d.src + (long long)n * d.h * d.w * d.src_ld;
+  const unsigned v_begin = blockIdx.x * P.vec_per_cta;
+  const unsigned v_end = min(v_begin + P.vec_per_cta, P.vec_total);
+  for (unsigned base = v_begin + threadIdx.x; base < v_end; base += ACT_THREADS * ACT_UNROLL) {
+    float4 f[ACT_UNROLL];
+    int vch[ACT_UNROLL];
+    long long dpix[ACT_UNROLL];
+    bool ok[ACT_UNROLL];
+#pragma unroll
+    for (int u = 0; u < ACT_UNROLL; ++u) {
+      const unsigned idx = base + u * ACT_THREADS;
+      ok[u] = idx < v_end;
+      const unsigned pix = __umulhi(idx, P.nvec_magic);          // destination interior pixel (row-major oy, ox)
+      vch[u] = (int)(idx - pix * (unsigned)nvec);
+      const unsigned oy = __umulhi(pix, P.ow_magic);
+      const unsigned ox = pix - oy * (unsigned)P.out_w;
+      dpix[u] = (long long)n * npix + (long long)(oy + halo) * Wp + (ox + halo);
+      const long long soff = ((long long)(oy >> up) * d.w + (ox >> up)) * d.src_ld + vch[u] * 4;
+      f[u] = ok[u] ? *reinterpret_cast<const float4*>(src_img + soff) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < ACT_UNROLL; ++u) {
+      float t[4] = {f[u].x, f[u].y, f[u].z, f[u].w};
+      if (GN) {
+        const float4 a = *reinterpret_cast<const float4*>(sp + vch[u] * 4), b = *reinterpret_cast<const float4*>(sp + c + vch[u] * 4);
+        t[0] = fmaf(t[0], a.x, b.x), t[1] = fmaf(t[1], a.y, b.y), t[2] = fmaf(t[2], a.z, b.z), t[3] = fmaf(t[3], a.w, b.w);
+      }
+      if (SILU) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) t[j] = silu_fast(t[j]);
+      }
+      if (!ok[u]) continue;
+      if (OUT == ACT_OUT_U8) {
+        // fast rounding of the four codes; ONE test whether any of them sits within 2e-4 of a rounding boundary (the fast
+        // value is within 1e-4 of the reference's pre-rounding value), and only then the exact divisions
+        float m[4];
+        bool slow = false;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float r = fminf(fmaxf(fmaf(t[j], inv, zp), 0.f), 255.f);
+          m[j] = __fadd_rn(r, 12582912.f);
+          slow |= fabsf(r - __fsub_rn(m[j], 12582912.f)) > 0.4998f;
+        }
+        if (slow) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) m[j] = quant_slow(t[j], delta, zp);
+        }
+        const uint32_t lo = __byte_perm(__float_as_uint(m[0]), __float_as_uint(m[1]), 0x0040);
+        const uint32_t hi = __byte_perm(__float_as_uint(m[2]), __float_as_uint(m[3]), 0x0040);
+        *reinterpret_cast<uint32_t*>(d.dst_u8 + dpix[u] * d.dst_c + d.dst_c_off + vch[u] * 4) = __byte_perm(lo, hi, 0x5410);
+      } else if (OUT == ACT_OUT_H16) {
+        uint2 h, l;
+        split_h16x4(t, h, l);
+        *reinterpret_cast<uint2*>(static_cast<__half*>(d.dst_hi) + dpix[u] * d.dst_h_ld + vch[u] * 4) = h;
+        *reinterpret_cast<uint2*>(static_cast<__half*>(d.dst_lo) + dpix[u] * d.dst_h_ld + vch[u] * 4) = l;
+      } else {
+        *reinterpret_cast<float4*>(d.dst_f32 + dpix[u] * d.dst_ld + vch[u] * 4) = make_float4(t[0], t[1], t[2], t[3]);
+      }
+    }
+  }
+  if (OUT == ACT_OUT_U8 && halo) {
+    // zero-point border: pixel b of the ring, b in [0, 2 Wp + 2 out_h): top row, bottom row, left column, right column
+    const int nborder = 2 * Wp + 2 * P.out_h;
+    const int b0 = blockIdx.x * P.border_per_cta, b1 = min(b0 + P.border_per_cta, nborder);
+    const uint32_t zfill = (uint32_t)zp * 0x01010101u;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int b = b0 + warp; b < b1; b += ACT_THREADS / 32) {
+      int yy, xx;
+      if (b < Wp) yy = 0, xx = b;
+      else if (b < 2 * Wp) yy = P.out_h + 1, xx = b - Wp;
+      else if (b < 2 * Wp + P.out_h) yy = b - 2 * Wp + 1, xx = 0;
+      else yy = b - 2 * Wp - P.out_h + 1, xx = Wp - 1;
+      uint32_t* o8 = reinterpret_cast<uint32_t*>(d.dst_u8 + ((long long)n * npix + (long long)yy * Wp + xx) * d.dst_c + d.dst_c_off);
+      for (int v = lane; v < nvec; v += 32) o8[v] = zfill;
+    }
+  }
+}
+
 // ---------------------------------------------------------------- DDIM update
 __global__ void ddim_update_kernel(const float* __restrict__ x, const float* __restrict__ e,
                                    const float* __restrict__ noise, const float* __restrict__ coef, long long count,
@@ -436,6 +589,53 @@ extern "C" int tfmq_act_prepare(tfmq_ctx* ctx, const tfmq_act_desc* d, void* str
     TFMQ_REQUIRE(!d->upsample, TFMQ_ERR_ARG, "act_prepare: GN with upsample unsupported");
   }
   if (d->n == 0) return TFMQ_OK;
+  static const bool flat_env = !(getenv("TFMQ_ACT_FLAT") && atoi(getenv("TFMQ_ACT_FLAT")) == 0);   // 0: the warp-per-pixel kernel
+  const long long out_pix = (long long)(d->upsample ? 4 : 1) * d->h * d->w;
+  // (the multiply-high divisions are exact while dividend * divisor < 2^32)
+  // measured (tools/microbench_act.py, LDM-4 shapes): the flattened kernel is 13-20 % faster for the fp16-split / fp32
+  // outputs; with u8 output both kernels sit at the same ~3.1 TB/s (bound by the per-launch latency chain, not by issue
+  // slots), so the u8 path keeps the warp-per-pixel kernel whose halo fill is part of the same loop
+  static const int flat_u8 = getenv("TFMQ_ACT_FLAT_U8") ? atoi(getenv("TFMQ_ACT_FLAT_U8")) : 0;
+  if (flat_env && (!d->dst_u8 || flat_u8) && !d->ln_gamma && !d->geglu && out_pix * (d->c / 4) * (d->c / 4) < (1ll << 32) &&
+      out_pix * (d->upsample ? 2 * d->w : d->w) < (1ll << 32)) {
+    ActFlatParams F;
+    F.d = *d;
+    F.out_h = d->upsample ? 2 * d->h : d->h;
+    F.out_w = d->upsample ? 2 * d->w : d->w;
+    F.nvec = d->c / 4;
+    F.nvec_magic = (uint32_t)(((1ull << 32) + F.nvec - 1) / F.nvec);
+    F.ow_magic = (uint32_t)(((1ull << 32) + F.out_w - 1) / F.out_w);
+    // umulhi(x, ceil(2^32 / k)) == x / k holds while x * k < 2^32 (the error term x * (k - 2^32 mod k) / 2^32 stays below 1)
+    F.vec_total = (unsigned)(out_pix * F.nvec);
+    static const int flat_mult = getenv("TFMQ_ACT_CTAS") ? atoi(getenv("TFMQ_ACT_CTAS")) : 8;
+    int chunks = (ctx->sm_count * flat_mult + d->n - 1) / d->n;
+    const unsigned gran = ACT_THREADS * ACT_UNROLL;
+    unsigned vpc = (F.vec_total + chunks - 1) / chunks;
+    vpc = (vpc + gran - 1) / gran * gran;
+    chunks = (int)((F.vec_total + vpc - 1) / vpc);
+    F.vec_per_cta = vpc;
+    const int halo_f = d->dst_u8 ? d->halo : 0;
+    const int nborder = halo_f ? 2 * (F.out_w + 2) + 2 * F.out_h : 0;
+    F.border_per_cta = (nborder + chunks - 1) / chunks;
+    F.inv_cnt = d->gn_stats ? 1.0 / ((double)(d->c / d->groups) * d->h * d->w) : 0.0;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(chunks, d->n), cfg.blockDim = dim3(ACT_THREADS);
+    cfg.dynamicSmemBytes = d->gn_stats ? 2 * (size_t)d->c * sizeof(float) : 0, cfg.stream = tfmq_stream(stream);
+    cudaLaunchAttribute attr[1];
+    cfg.attrs = attr, cfg.numAttrs = (unsigned)tfmq_pdl_attr(&attr[0]);
+    const int out = d->dst_u8 ? ACT_OUT_U8 : d->dst_hi ? ACT_OUT_H16 : ACT_OUT_F32;
+    cudaError_t e;
+#define FLAT_BY_OUT(GN, SILU)                                                                        \
+  (out == ACT_OUT_U8 ? cudaLaunchKernelEx(&cfg, act_flat_kernel<GN, SILU, ACT_OUT_U8>, F)           \
+   : out == ACT_OUT_H16 ? cudaLaunchKernelEx(&cfg, act_flat_kernel<GN, SILU, ACT_OUT_H16>, F)       \
+                        : cudaLaunchKernelEx(&cfg, act_flat_kernel<GN, SILU, ACT_OUT_F32>, F))
+    if (d->gn_stats) e = d->silu ? FLAT_BY_OUT(true, true) : FLAT_BY_OUT(true, false);
+    else e = d->silu ? FLAT_BY_OUT(false, true) : FLAT_BY_OUT(false, false);
+#undef FLAT_BY_OUT
+    if (e != cudaSuccess) return tfmq_fail(ctx, TFMQ_ERR_CUDA, "act_prepare: launch: %s", cudaGetErrorString(e));
+    TFMQ_LAUNCH_CHECK("act_prepare");
+    return TFMQ_OK;
+  }
   ActParams P;
   P.d = *d;
   P.out_h = d->upsample ? 2 * d->h : d->h;
