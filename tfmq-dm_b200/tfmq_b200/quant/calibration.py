@@ -228,7 +228,7 @@ def act_tables_from_ckpt(ckpt: dict) -> list:
 
 def cali_model_multi(gpu: int, dist_backend: str, world_size: int, dist_url: str, rank: int, ngpus_per_node: int,
                      model, use_aq: bool, path: str, w_cali_data, a_cali_data, interval: int, running_stat: bool,
-                     kwargs: dict) -> None:
+                     kwargs: dict):
     """Data-parallel calibration, one process per GPU (reference :228-389): every rank takes a
     1/world slice of each per-timestep interval; AdaRound alpha gradients are SUM-all-reduced each
     iteration (one flat bucket per unit, reconstruction.py), activation deltas are averaged; rank 0 saves."""
@@ -239,7 +239,7 @@ def cali_model_multi(gpu: int, dist_backend: str, world_size: int, dist_url: str
     if dist_backend == "nccl":
         torch.cuda.set_device(gpu)
     dev = torch.device("cuda", gpu) if torch.cuda.is_available() else torch.device("cpu")
-    qnn = QuantModel(model, kwargs.pop("wq_params"), kwargs.pop("aq_params"), cali=True,
+    qnn = QuantModel(model.to(dev), kwargs.pop("wq_params"), kwargs.pop("aq_params"), cali=True,
                      softmax_a_bit=kwargs.pop("softmax_a_bit", 8), aq_mode=kwargs.pop("aq_mode", [2])).to(dev)
     qnn.eval()
 
@@ -258,6 +258,7 @@ def cali_model_multi(gpu: int, dist_backend: str, world_size: int, dist_url: str
             ckpt = _fsc_multi(qnn, a_shard, interval // world_size, running_stat, ckpt)
     if rank == 0 and path:
         torch.save(ckpt, path)
+    return ckpt          # (the reference returns None; every rank's dict is returned so callers can check rank consistency)
 
 
 def _fsc_multi(qnn, a_cali_data, interval, running_stat, ckpt):

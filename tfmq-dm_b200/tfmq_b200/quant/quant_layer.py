@@ -241,6 +241,16 @@ class QuantLayer(nn.Module):
             b = b.to(x.device)
         return self.act_func(self.kwd_func(x, w, b, **self.fwd_kwargs))
 
+    def _apply(self, fn, *a, **kw):
+        """`.to()` / `.cuda()` also move the FP copies.  The reference keeps `original_w` as a plain tensor attribute and
+        re-copies it to the input's device on every forward (quant/quant_layer.py:333-335); a QuantModel built on the CPU and
+        moved afterwards (cali_model_multi) would otherwise initialise AdaRound's alpha from a CPU tensor."""
+        out = super()._apply(fn, *a, **kw)
+        self.original_w = fn(self.original_w)
+        if isinstance(self.original_b, torch.Tensor):
+            self.original_b = fn(self.original_b)
+        return out
+
     def set_quant_state(self, use_wq: bool = False, use_aq: bool = False) -> None:
         self.use_wq = use_wq if not self.ignore_recon else False
         self.use_aq = use_aq if not self.ignore_recon else False
