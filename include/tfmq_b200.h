@@ -229,6 +229,11 @@ typedef struct {
   void* out_hi;
   void* out_lo;
   int64_t out_h_ld;
+  /* optional split-K for reductions over a very long K with few output tiles (the weight-gradient GEMMs of the AdaRound
+   * reconstruction loop, quant/reconstruction.py:182-198 `err.backward()`): 0 / 1 = off, > 1 = that many K ranges per output
+   * tile, < 0 = chosen by the library.  `out` is cleared and the partial tiles are added by TMA reduce (fp32 adds in arrival
+   * order: not bit-reproducible run to run).  Not combinable with res / emb / n_stat / plane output. */
+  int ksplit;
 } tfmq_conv_h16_desc;
 int tfmq_conv_h16(tfmq_ctx* ctx, const tfmq_conv_h16_desc* d, void* stream);
 

@@ -137,15 +137,29 @@ def test_cali_model_spatial_transformer_unet(dev):
     assert torch.isfinite(out).all() and out.shape == x.shape
 
 
+@pytest.mark.parametrize("tc", [True, False], ids=["own-kernels", "torch-kernels"])
 @pytest.mark.parametrize("kind", ["cifar", "sdmini"])
-def test_reconstruction_trace_matches_the_reference(dev, kind):
+def test_reconstruction_trace_matches_the_reference(dev, kind, tc, monkeypatch):
     """50 iterations of `tib_reconstruction` and `block_reconstruction` with a fixed torch seed against the trace of
     the reference's own functions (quant/reconstruction.py:86-318, run on the CPU by tests/golden/make_golden.py::recon_golden):
     the loss of every iteration and the learned alpha of every layer.  Same sequence as cali_model: weight-quantiser
     initialisation, exemptions, TIB, then the blocks (whose asymmetric input cache sees the reconstructed TIB).
     cifar: DDIM-flavour TIB + an AttnBlock; sdmini: LDM-flavour TIB + a ResBlock + a BasicTransformerBlock."""
+    import tfmq_b200.quant.quant_layer as QL
     import tfmq_b200.quant.reconstruction as R
     from tfmq_b200.quant.adaptive_rounding import AdaRoundQuantizer
+    # tc: the unit's contractions (forward, dgrad, wgrad) on this library's tcgen05 kernels (quant/tc_autograd.py, the
+    # default) or on torch's fp32 kernels
+    monkeypatch.setattr(QL, "TC_RECONSTRUCTION", tc)
+    # Adam divides by sqrt(v): where a gradient sits at the fp32 noise floor its sign, and so the direction of the 1e-3 step, is
+    # chance.  torch's fp32 kernels happen to round like the reference's CPU kernels (no element moves); the tcgen05 path (fp16
+    # split, 3 products) rounds differently, and up to ~1 % of a layer's elements end one or two steps apart.  Gates: the loss
+    # trace, a bound on the largest deviation in steps, the fraction of elements beyond one step, and the sum of alpha.
+    # (the loss responds to those elements: its trace follows the reference to 3e-3 with the own kernels, to 5e-6 with torch's)
+    # measured with the own kernels: <= 1.1 % of a conv layer, 6-14 % of the self-attention output projection of the transformer
+    # block (during the 10 warm-up iterations there is no rounding regulariser, and the reconstruction gradient of that layer
+    # is mostly at the noise floor) beyond one step, never more than 6 of the 50 steps
+    far_frac, far_max, trace_tol = (0.20, 1e-2, 5e-3) if tc else (2e-3, 5e-3, 1e-4)
     from tfmq_b200.quant.quant_layer import QMODE, QuantLayer, Scaler
     from tfmq_b200.quant.quant_model import QuantModel
     from tfmq_b200.quant.reconstruction_util import RLOSS
@@ -178,16 +192,14 @@ def test_reconstruction_trace_matches_the_reference(dev, kind):
         for name, (sample, s1, s2) in want_alphas.items():
             a = alphas[name].detach().float().cpu()
             d = (a.flatten()[::g["stride"]] - sample).abs()
-            # Adam divides by sqrt(v): where a gradient sits at the fp32 noise floor the update direction is chance, so a few
-            # elements may end a couple of learning-rate steps (1e-3 each) apart; the rest agrees to fp32 accuracy
             frac_far = (d > 1e-3).float().mean().item()
             worst, worst_frac = max(worst, d.max().item()), max(worst_frac, frac_far)
-            assert frac_far < 2e-3 and d.max().item() < 0.05, (tag, name, frac_far, d.max().item())
-            assert abs(float(a.double().sum()) - s1) <= 2e-4 * max(1.0, s2), (tag, name)
-        print(f"[{kind} {tag}] {len(trace)} iterations: loss trace max relative deviation {rel:.3e} (first {want_trace[0]:.5f}, "
+            assert frac_far < far_frac and d.max().item() < far_max, (tag, name, frac_far, d.max().item())
+            assert abs(float(a.double().sum()) - s1) <= 5e-4 * max(1.0, s2), (tag, name)
+        print(f"[{kind} {'own' if tc else 'torch'} kernels, {tag}] {len(trace)} iterations: loss trace max relative deviation {rel:.3e} (first {want_trace[0]:.5f}, "
               f"last {want_trace[-1]:.2f}); alpha of {len(want_alphas)} layers: worst element deviation {worst:.3e}, at most "
               f"{worst_frac:.1e} of a layer beyond 1e-3")
-        assert rel < 2e-3, (tag, rel)
+        assert rel < trace_tol, (tag, rel)
 
     R.LOSS_TRACE = []
     try:
@@ -209,3 +221,47 @@ def test_reconstruction_trace_matches_the_reference(dev, kind):
             compare("block_reconstruction " + bn, R.LOSS_TRACE, want["loss"], blk_alphas, want["alpha"])
     finally:
         R.LOSS_TRACE = None
+
+
+@pytest.mark.parametrize("xs,ws,kw,gscale", [
+    ((8, 32, 16, 16), (64, 32, 3, 3), dict(stride=(1, 1), padding=(1, 1)), 1e-4),
+    ((4, 224, 32, 32), (224, 224, 3, 3), dict(stride=(1, 1), padding=(1, 1)), 1e-6),
+    ((8, 64, 16, 16), (128, 64, 1, 1), dict(stride=(1, 1), padding=(0, 0)), 1e-3),
+    ((8, 256, 96), (384, 96), {}, 1e-5),
+    ((32, 128), (512, 128), {}, 1.0),
+], ids=["conv3x3-32-64", "conv3x3-224-224", "conv1x1-64-128", "linear-tokens", "linear-tib"])
+def test_tc_autograd_forward_dgrad_wgrad_against_float64(dev, xs, ws, kw, gscale):
+    """The three contractions of a reconstructed layer on the library's tcgen05 kernel (quant/tc_autograd.py: forward, dgrad on
+    the flipped / transposed weights, wgrad as a pixel-reduction GEMM) against torch in float64 -- what `out_quant = block(...)`
+    and `err.backward()` (quant/reconstruction.py:182-198) compute for a QuantLayer.  Gradients as small as 1e-6 (the scale of
+    back-propagated reconstruction errors) must keep fp32-class accuracy: tolerance 3e-5 of the tensor's largest magnitude
+    (measured 1e-7 ... 1e-5, the same band as torch's own fp32 kernels with TF32 off; tools/precision_tc_autograd.py)."""
+    import torch.nn.functional as F
+    from tfmq_b200.quant.tc_autograd import tc_conv
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(xs, generator=g).to(dev)
+    w = (torch.randn(ws, generator=g) * 0.05).to(dev)
+    b = torch.randn(ws[0], generator=g).to(dev)
+    xx, ww, bb = (t.detach().double().requires_grad_(True) for t in (x, w, b))
+    y64 = F.conv2d(xx, ww, bb, **kw) if len(ws) == 4 else F.linear(xx, ww, bb)
+    gy = (torch.randn(y64.shape, generator=g) * gscale).to(dev)
+    want = (y64.detach(),) + torch.autograd.grad(y64, (xx, ww, bb), gy.double())
+    x1, w1, b1 = (t.detach().requires_grad_(True) for t in (x, w, b))
+    y = tc_conv(x1, w1, b1, kw)
+    assert y is not None
+    got = (y.detach(),) + torch.autograd.grad(y, (x1, w1, b1), gy)
+    for name, a, r in zip(("y", "dx", "dW", "db"), got, want):
+        err = ((a.double() - r).abs().max() / r.abs().max()).item()
+        assert err < 3e-5, (name, err)
+
+
+def test_tc_autograd_declines_unsupported_shapes(dev):
+    """Stride-2 down-sampling convs, channel counts that are not a multiple of 16 and non power-of-two maps stay on torch's op:
+    tc_conv returns None and QuantLayer.forward falls through."""
+    from tfmq_b200.quant.tc_autograd import tc_conv
+    x = torch.randn(2, 32, 16, 16, device=dev)
+    assert tc_conv(x, torch.randn(32, 32, 3, 3, device=dev), None, dict(stride=(2, 2), padding=(1, 1))) is None
+    assert tc_conv(torch.randn(2, 3, 16, 16, device=dev), torch.randn(32, 3, 3, 3, device=dev), None,
+                   dict(stride=(1, 1), padding=(1, 1))) is None
+    assert tc_conv(torch.randn(2, 32, 12, 12, device=dev), torch.randn(32, 32, 3, 3, device=dev), None,
+                   dict(stride=(1, 1), padding=(1, 1))) is None

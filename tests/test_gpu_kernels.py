@@ -251,6 +251,44 @@ def test_conv_h16_integer_weights_exact(dev):
     assert err <= 2e-6 * max(1.0, ref.abs().max().item()), err
 
 
+@pytest.mark.parametrize("m,n,k,ksplit,conv", [(384, 224, 16384, -1, False), (1344, 224, 9472, 7, False),
+                                               (130, 48, 4096, 3, False), (256, 64, 131072, -1, False),
+                                               (2, 96, 96, 5, True)])
+def test_conv_h16_split_k(dev, m, n, k, ksplit, conv):
+    """Split-K of the fp16-split kernel (tfmq_conv_h16_desc.ksplit): the k-blocks of an output tile are shared by several
+    CTAs and the partial tiles are added into the cleared output by TMA reduce -- the weight-gradient GEMMs of the
+    reconstruction loop (few output tiles, K = every pixel of the batch).  As a GEMM (1x1, one pixel per row) with ragged M,
+    a bias (must be added once, not per K range), an output that holds garbage before the call; and as a 3x3 conv whose
+    K ranges cut through the taps.  Against float64."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(m + n)
+    if conv:
+        x = torch.randn(m, 16, 16, k, generator=g)
+        wt = torch.randn(n, 3 * 3 * k, generator=g) / math.sqrt(9 * k)
+        ref = F.conv2d(x.permute(0, 3, 1, 2).double(), wt.view(n, 3, 3, k).permute(0, 3, 1, 2).double(), padding=1)
+        ref = ref.permute(0, 2, 3, 1)
+        ks = 3
+    else:
+        x = torch.randn(m, 1, 1, k, generator=g)
+        wt = torch.randn(n, k, generator=g) / math.sqrt(k)
+        ref = (x.view(m, k).double() @ wt.double().t()).view(m, 1, 1, n)
+        ks = 1
+    bias = torch.randn(n, generator=g)
+    ref = ref + bias.double()
+    w_hi, w_lo, wscale = ops.split_h16(wt.to(dev), keep_lo=True)
+    xd = x.to(dev)
+    x_hi = torch.empty(xd.shape, dtype=torch.float16, device=dev)
+    x_lo = torch.empty_like(x_hi)
+    ops.act_prepare(xd, dst_h16=(x_hi, x_lo))
+    out = torch.full(ref.shape, 7.0, device=dev)
+    ops.conv_h16(x_hi, x_lo, ks, 1, ks // 2, w_hi, w_lo, out, bias=bias.to(dev), wscale=wscale, ksplit=ksplit)
+    torch.cuda.synchronize()
+    err = (out.cpu().double() - ref).abs().max().item()
+    assert err <= max(3e-6, 8 * 2.0 ** -26 * (k * ks * ks / 16)) * max(1.0, ref.abs().max().item()), err
+    with pytest.raises(RuntimeError):        # no residual with split-K
+        ops.conv_h16(x_hi, x_lo, ks, 1, ks // 2, w_hi, w_lo, out, wscale=wscale, res=out, ksplit=2)
+
+
 # ------------------------------------------------------------------ GroupNorm + producer
 @pytest.mark.parametrize("n,h,w,c,eps", [(2, 16, 16, 128, 1e-6), (3, 32, 32, 224, 1e-5), (1, 8, 8, 1792, 1e-5)])
 def test_gn_silu_quant(dev, n, h, w, c, eps):

@@ -116,7 +116,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const int unit0 = (CG == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;     // cluster (or CTA) index
   const int nunits = (CG == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const int tiles_mu = tiles_m / CG;
-  const int total_units = tiles_mu * tiles_n;
+  // split-K (MODE_F16, p.ksplit > 1): unit = (K range, N tile, M tile); the partial tiles meet in global memory through
+  // TMA reduce-adds.  Reductions over the pixel axis (weight gradients) have few output tiles and very long K.
+  const int KS = (MODE == MODE_F16) ? p.ksplit : 1;
+  const int mn_units = tiles_mu * tiles_n;
+  const int total_units = mn_units * KS;
   const int b_rows = p.b_rows[rank];       // weight rows of the N tile this CTA stages
   const int kchunks = (p.cin + p.kchunk - 1) / p.kchunk;
   const int taps = p.ksize * p.ksize;
@@ -198,14 +202,17 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     int s = 0;
     uint32_t par = 0;
     for (int ut = unit0; ut < total_units; ut += nunits) {
-      int mt = (ut % tiles_mu) * CG + (int)rank;
-      const int c_out0 = (ut / tiles_mu) * p.tile_n;
+      const int ks = (KS > 1) ? ut / mn_units : 0, umn = (KS > 1) ? ut - ks * mn_units : ut;
+      const int kb0 = (KS > 1) ? (int)((long long)ks * nkb / KS) : 0, kb1 = (KS > 1) ? (int)((long long)(ks + 1) * nkb / KS) : nkb;
+      int mt = (umn % tiles_mu) * CG + (int)rank;
+      const int c_out0 = (umn / tiles_mu) * p.tile_n;
       const int tx = mt % tiles_x;
       mt /= tiles_x;
       const int ty = mt % tiles_y;
       const int n0 = (mt / tiles_y) * p.tn, y0 = ty * p.th, x0 = tx * p.tw;
-      int kc = 0, kx = 0, ky = 0, tap = 0;
-      for (int kb = 0; kb < nkb; ++kb) {
+      int tap = kb0 / kchunks, kc = kb0 - tap * kchunks;
+      int ky = tap / p.ksize, kx = tap - ky * p.ksize;
+      for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait_relaxed(&empty[s], par ^ 1u);
         uint8_t* st = W4 ? smem + (size_t)s * IGEMM_A_BYTES : smem + (size_t)s * p.stage_bytes;
         if (elect_one_sync()) {
@@ -308,8 +315,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       // tensor-core accumulator adds them to a small running sum, not to the large main one
       const uint32_t tmem_lo = tmem_d + (uint32_t)p.tile_n;
       uint32_t accumulate = 0, accumulate_lo = 0;
-      int kc = 0;
-      for (int kb = 0; kb < nkb; ++kb) {
+      const int ks = (KS > 1) ? ut / mn_units : 0;
+      const int kb0 = (KS > 1) ? (int)((long long)ks * nkb / KS) : 0, kb1 = (KS > 1) ? (int)((long long)(ks + 1) * nkb / KS) : nkb;
+      int kc = kb0 % kchunks;
+      for (int kb = kb0; kb < kb1; ++kb) {
         PROF_T(2)
         if (W4) {
           mbar_wait(&full_tma[s], par);
@@ -324,7 +333,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const int nslice = (kc == kchunks - 1) ? nslice_last : 4;
         const uint64_t a_hi = d_a + s_units, b_hi = d_b + (W4 ? su_units : s_units);
         const uint64_t a_lo = d_alo + s_units, b_lo = d_blo + s_units;
-        const bool last = kb == nkb - 1;
+        const bool last = kb == kb1 - 1;
         if (elect_one_sync()) {
           if (FP) {
             if (need_a_lo) {
@@ -511,8 +520,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     long long prof_t = prof_on ? clock64() : 0;
     const uint32_t acc_empty_remote = (CG == 2 && rank != 0) ? mapa_u32(smem_u32(acc_empty), 0) : 0u;
     for (int ut = unit0; ut < total_units; ut += nunits, ++tcount) {
-      int mt = (ut % tiles_mu) * CG + (int)rank;
-      const int c_out0 = (ut / tiles_mu) * p.tile_n;
+      const int ks = (KS > 1) ? ut / mn_units : 0, umn = (KS > 1) ? ut - ks * mn_units : ut;
+      int mt = (umn % tiles_mu) * CG + (int)rank;
+      const int c_out0 = (umn / tiles_mu) * p.tile_n;
       const int tx = mt % tiles_x;
       mt /= tiles_x;
       const int ty = mt % tiles_y;
@@ -536,7 +546,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       }
       // per-channel constants of this N tile; a persistent CTA walks the units M-fastest, so consecutive units usually
       // share the N tile (always, when one tile covers all output channels) and the constants are kept
-      const bool chp_keep = tcount > 0 && c_out0 == chp_c0 && (!emb_folded || n0 == chp_n0);
+      const bool chp_keep = tcount > 0 && c_out0 == chp_c0 && (!emb_folded || n0 == chp_n0) && KS == 1;
       chp_c0 = c_out0, chp_n0 = n0;
       if (!chp_keep) named_bar_sync(1, ET);   // previous tile is done with chp
       for (int ch = et; ch < (chp_keep ? 0 : p.tile_n); ch += ET) {
@@ -550,7 +560,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         } else if (p.wscale) {
           sc = p.wscale[c];
         }
-        if (p.bias) bi = p.bias[c];
+        if (p.bias && ks == 0) bi = p.bias[c];      // split-K: the bias joins the first partial tile only
         if (emb_folded) bi += p.emb[(long long)n0 * p.emb_ld + c];
         chp[ch] = make_float4(sc, bi, __int_as_float(ws), __int_as_float(zw));
       }
@@ -670,7 +680,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         // the store (and the next residual load) go out BEFORE the statistics pass over the same buffer: the TMA engine
         // works while the warps sum columns, and thread 0's warp is the one every other warp waits for at the next barrier
         if (et == 0) {
-          tma_store_4d(&tmOut, buf, c_out0 + ci * CW, x0, y0, n0);
+          if (KS > 1) tma_reduce_add_4d(&tmOut, buf, c_out0 + ci * CW, x0, y0, n0);
+          else tma_store_4d(&tmOut, buf, c_out0 + ci * CW, x0, y0, n0);
           if (FP && p.out_planes) tma_store_4d(&tmRes, buf + 128u * 64u, c_out0 + ci * CW, x0, y0, n0);   // lo plane
           tma_store_commit();
           if (ci + 1 < nchunks) {
@@ -942,7 +953,16 @@ static int launch_igemm(tfmq_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap
     }
   }
   const int tiles_m = (p.W / p.tw) * (p.H / p.th) * ((p.n_img + p.tn - 1) / p.tn);
-  const int total = tiles_m / CG * (p.cout / p.tile_n);           // tiles, or pairs of M-adjacent tiles
+  if (MODE != MODE_F16 || p.ksplit < 1) p.ksplit = 1;
+  if (p.ksplit > nkb) p.ksplit = nkb;
+  if (p.ksplit > 1) {
+    // split-K partial tiles are added into the output by TMA reduce: it starts from zero
+    if (p.res || p.emb || p.n_stat || p.out_planes)
+      return tfmq_fail(ctx, TFMQ_ERR_ARG, "%s: split-K takes no residual / embedding / statistics / plane output", name);
+    cudaError_t e = cudaMemset2DAsync(p.out, (size_t)p.out_ld * 4, 0, (size_t)p.cout * 4, (size_t)p.n_img * p.H * p.W, stream);
+    if (e != cudaSuccess) return tfmq_fail(ctx, TFMQ_ERR_CUDA, "%s: clearing the split-K output: %s", name, cudaGetErrorString(e));
+  }
+  const int total = tiles_m / CG * (p.cout / p.tile_n) * p.ksplit;   // tiles, or pairs of M-adjacent tiles (x K ranges)
   const int units = ctx->sm_count / CG;
   const int grid = (total < units ? total : units) * CG;
   static const bool time_env = getenv("TFMQ_IGEMM_TIME") != nullptr;   // debug aid: per-launch time, synchronous
@@ -1201,6 +1221,23 @@ extern "C" int tfmq_conv_h16(tfmq_ctx* ctx, const tfmq_conv_h16_desc* d, void* s
     const int tiles_m = (d->out_w / g.tw) * (d->out_h / g.th) * ((d->n + g.tn - 1) / g.tn);
     const int limit = nkb_est < 24 ? 128 : 256;
     p.tile_n = pick_tile_n_balanced(d->cout, limit, tiles_m, nkb_est, ctx->sm_count, 300.0, 6.0, planes ? 32 : 16);
+    if (d->ksplit != 0 && d->ksplit != 1) {
+      // split-K: the widest N tile (fewest re-reads of the pixel operand), and as many K ranges as it takes to give every
+      // SM a unit (ksplit < 0: chosen here), each at least 8 k-blocks long
+      TFMQ_REQUIRE(!planes && !d->res && !d->emb && d->n_stat == 0, TFMQ_ERR_ARG,
+                   "conv_h16: split-K takes no residual / embedding / statistics / plane output");
+      int tn = 0;
+      for (int t = 256; t >= 32 && !tn; t -= 32)
+        if (d->cout % t == 0) tn = t;
+      if (tn) p.tile_n = tn;
+      const int units_mn = tiles_m * (d->cout / p.tile_n);
+      int ks = d->ksplit;
+      if (ks < 0) {
+        ks = ctx->sm_count / units_mn;
+        if (ks > nkb_est / 8) ks = nkb_est / 8;
+      }
+      p.ksplit = ks < 1 ? 1 : ks;
+    }
   }
   p.out_planes = planes ? 1 : 0;
   p.out_hi = d->out_hi, p.out_lo = d->out_lo, p.out_h_ld = d->out_h_ld;

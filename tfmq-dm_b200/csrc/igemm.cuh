@@ -42,6 +42,7 @@ struct IgemmParams {
   int b_rows[2], b_row0[2];  // weight rows of the N tile staged by CTA rank 0 / 1 of a pair (rank 0 only when CG == 1)
   uint32_t stage_bytes, offA_lo, offB, offB_lo, offP;
   int pass_flags;
+  int ksplit;                // MODE_F16: the k-blocks of a tile are shared by ksplit units, partial tiles added by TMA reduce (out pre-zeroed)
   // epilogue
   float* out;
   long long out_ld;

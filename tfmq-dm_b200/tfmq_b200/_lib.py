@@ -76,6 +76,7 @@ class ConvH16Desc(C.Structure):
         ("emb", C.c_void_p), ("emb_ld", i64),
         ("n_stat", C.c_int), ("stat", GnTarget * 2),
         ("out_hi", C.c_void_p), ("out_lo", C.c_void_p), ("out_h_ld", i64),
+        ("ksplit", C.c_int),
     ]
 
 

@@ -185,9 +185,10 @@ def conv_fp(x: torch.Tensor, ksize: int, stride: int, pad_lo: int, w_hi, w_lo, o
 
 
 def conv_h16(x_hi: torch.Tensor, x_lo: torch.Tensor, ksize: int, stride: int, pad_lo: int, w_hi, w_lo, out,
-             bias=None, wscale=None, res=None, emb=None, stats=None, out_h16=None):
+             bias=None, wscale=None, res=None, emb=None, stats=None, out_h16=None, ksplit: int = 0):
     """fp32-accurate conv on kind::f16 from pre-split fp16 hi / lo planes (see include/tfmq_b200.h).
-    out_h16 = (hi, lo): the result is written as fp16 hi / lo planes instead of fp32 `out` (which may be None)."""
+    out_h16 = (hi, lo): the result is written as fp16 hi / lo planes instead of fp32 `out` (which may be None).
+    ksplit: split-K for pixel-axis reductions (weight gradients): > 1 K ranges per output tile, < 0 chosen by the library."""
     ctx = _ctx(x_hi)
     assert x_hi.dtype == torch.float16 and x_lo.dtype == torch.float16 and w_hi.dtype == torch.float16
     n, h, w, cin, x_ld = _nhwc(x_hi)
@@ -220,10 +221,11 @@ def conv_h16(x_hi: torch.Tensor, x_lo: torch.Tensor, ksize: int, stride: int, pa
         assert emb.stride(-1) == 1
         d.emb, d.emb_ld = emb.data_ptr(), (emb.stride(0) if emb.dim() == 2 and emb.shape[0] > 1 else 0)
     _set_stats(d, stats)
+    d.ksplit = ksplit
     ctx.call("tfmq_conv_h16", C.byref(d), _stream())
 
 
-def split_h16(w2d: torch.Tensor, wscale: torch.Tensor | None = None):
+def split_h16(w2d: torch.Tensor, wscale: torch.Tensor | None = None, keep_lo: bool = False):
     """Load-time split of fp32 weights [cout][k] into fp16 planes: w * 2^e = hi + lo per output channel, with e chosen so
     that max|w| lands in [2^12, 2^13) (lo stays a normal fp16).  Returns (hi, lo or None, scale) where scale[c] = 2^-e
     (times `wscale` if given) is what the conv epilogue multiplies by; lo is None when every weight is exact in fp16."""
@@ -238,7 +240,8 @@ def split_h16(w2d: torch.Tensor, wscale: torch.Tensor | None = None):
     inv = torch.exp2(-e)
     if wscale is not None:
         inv = inv * wscale.float()
-    return hi.contiguous(), (lo.contiguous() if bool((lo != 0).any()) else None), inv.contiguous()
+    # keep_lo: always return the lo plane (no host sync on `any()`): the reconstruction loop re-splits its weights every iteration
+    return hi.contiguous(), (lo.contiguous() if (keep_lo or bool((lo != 0).any())) else None), inv.contiguous()
 
 
 def split_tf32(w2d: torch.Tensor):

@@ -12,6 +12,7 @@ There is no CPU path: a CPU tensor raises.
 from __future__ import annotations
 
 import logging
+import os
 from enum import Enum
 from typing import List, Union
 
@@ -20,6 +21,10 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 logger = logging.getLogger(__name__)
+
+# The three contractions of every reconstructed layer (forward, dgrad, wgrad) on the library's tensor-core kernels; False keeps
+# torch's conv / linear kernels in the reconstruction loop (comparison runs).
+TC_RECONSTRUCTION = os.environ.get("TFMQ_TC_RECON", "1") != "0"
 
 
 def _require_cuda(x: torch.Tensor, who: str) -> None:
@@ -239,6 +244,12 @@ class QuantLayer(nn.Module):
         w = w.to(x.device)
         if isinstance(b, torch.Tensor):
             b = b.to(x.device)
+        if self.w_override is not None and self.use_wq and TC_RECONSTRUCTION:
+            # reconstruction loop: forward / dgrad / wgrad of the layer on this library's tcgen05 kernels (tc_autograd.py)
+            from .tc_autograd import tc_conv
+            y = tc_conv(x, w, b if isinstance(b, torch.Tensor) else None, self.fwd_kwargs)
+            if y is not None:
+                return self.act_func(y)
         return self.act_func(self.kwd_func(x, w, b, **self.fwd_kwargs))
 
     def _apply(self, fn, *a, **kw):

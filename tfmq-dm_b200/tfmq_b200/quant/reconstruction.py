@@ -87,11 +87,18 @@ def _adaround_loop(forward, layers: List[QuantLayer], cached_inputs, cached_outp
         cur_in = tuple(x[idx].to(dev) for x in cached_inputs)
         leaves = [s.materialise() for s in states]
         out = forward(*cur_in)
-        if tuple_out:
-            rec = sum(lp_loss(o_, t_[idx].to(dev), p=2.0) for o_, t_ in zip(out, cached_outputs))
-        else:
-            rec = lp_loss(out, cached_outputs[idx].to(dev), p=2.0)
-        grads = torch.autograd.grad(rec, leaves, allow_unused=True)
+        # reconstruction loss and its gradient w.r.t. the unit's outputs in one kernel per output (tfmq_rec_loss: lp_loss with
+        # p = 2, `.sum(1).mean()`, quant/quant_layer.py:146-156; LossFuncTimeEmbedding sums it over the TIB's outputs)
+        outs = list(out) if tuple_out else [out]
+        tgts = [t_[idx].to(dev) for t_ in cached_outputs] if tuple_out else [cached_outputs[idx].to(dev)]
+        rec = torch.zeros(1, device=dev)
+        gouts = []
+        for o_, t_ in zip(outs, tgts):
+            o_c, t_c = o_.detach().contiguous(), t_.contiguous()
+            g_ = torch.empty_like(o_c)
+            ops.rec_loss(o_c, t_c, o_c.numel() // o_c.shape[1], rec, g_)
+            gouts.append(g_)
+        grads = torch.autograd.grad(outs, leaves, grad_outputs=gouts, allow_unused=True)
         grads = [g if g is not None else torch.zeros_like(l_) for g, l_ in zip(grads, leaves)]
         if world > 1:
             from ..dist_utils import allreduce_flat_

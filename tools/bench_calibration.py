@@ -23,6 +23,13 @@ from tfmq_b200.quant.reconstruction import block_reconstruction, layer_reconstru
 from tfmq_b200.quant.reconstruction_util import RLOSS  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+# cali_model runs inside QuantModel.calibrating(), which switches TF32 off (fp32 parity with the reference's CPU graph); the
+# units are called directly here, so set the same state.  TFMQ_BENCH_TF32=1 times torch's kernels with TF32 on instead.
+_tf32 = os.environ.get("TFMQ_BENCH_TF32", "0") == "1"
+torch.backends.cudnn.allow_tf32 = _tf32
+torch.backends.cuda.matmul.allow_tf32 = _tf32
+print(f"contractions: {'own tcgen05 kernels (quant/tc_autograd.py)' if os.environ.get('TFMQ_TC_RECON', '1') != '0' else 'torch kernels'}"
+      f", TF32 {'on' if _tf32 else 'off'}")
 K1, K2 = 10, 60
 dev = torch.device("cuda:0")
 wq = dict(bits=4, channel_wise=True, scaler=Scaler.MINMAX)
@@ -72,6 +79,25 @@ names = {id(m): n_ for n_, m in qnn.model.named_modules()}
 tot_iter = tot_cache = 0.0
 todo = units(qnn.model, [])
 print(f"{len(todo)} reconstruction units, {n} calibration samples, batch 32")
+only = os.environ.get("TFMQ_BENCH_UNIT")        # e.g. output_blocks.9.0: time that unit alone and print its kernel profile
+if only:
+    todo = [u for u in todo if names.get(id(u[2]), "tib") == only]
+    _, kind, m = todo[0]
+    run(kind, m, 5)
+    import tfmq_b200.quant.reconstruction as R
+    from torch.profiler import ProfilerActivity, profile
+    loop = R._adaround_loop
+
+    def profiled_loop(*a, **k):            # the iteration loop alone (not the input / output caching before it)
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            r = loop(*a, **k)
+            torch.cuda.synchronize()
+        print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=30, max_name_column_width=90))
+        return r
+    R._adaround_loop = profiled_loop
+    run(kind, m, 10)
+    R._adaround_loop = loop
 for _, kind, m in todo:
     has_layers = kind == "tib" or any(isinstance(x, QuantLayer) and not x.quant_emb for x in m.modules())
     if not has_layers:
