@@ -147,7 +147,8 @@ typedef struct {
   int n, h, w, cin, cout;
   int ksize;            /* 1 or 3 */
   const uint8_t* packed; /* tfmq_pack_w4 output, [cout][ksize*ksize*cin/2] */
-  const uint8_t* wzp;    /* [cout] weight zero points as u8 */
+  const int32_t* wzp;    /* [cout] weight zero points; any integer: Scaler.MSE does not force the range to contain 0
+                          * (quant/quant_layer.py:38-64), so a channel whose weights share one sign has zp < 0 or > 15 */
   const float* wdelta;   /* [cout] */
   const int32_t* wsum;   /* [cout] */
   const float* bias;     /* [cout] or NULL */
@@ -332,7 +333,9 @@ int tfmq_attention_h16(tfmq_ctx* ctx, const tfmq_attn_h16_desc* d, void* stream)
  * 196-212), elementwise on [count] floats:
  *   x0 = (x - e*sqrt(1-a_t)) / sqrt(a_t);   x_prev = sqrt(a_prev)*x0 + c1*noise + c2*e
  * coef = device float[4] {sqrt(a_t), sqrt(1-a_t), sqrt(a_prev), c2}; c1*noise is
- * added when noise != NULL with c1 = coef[4].  x0_out may be NULL.
+ * added when noise != NULL (eta > 0), and coef is then float[6]: c1 = coef[4], and coef[5] != 0 selects the LDM sampler's
+ * summation order (sqrt(a_prev)*x0 + c2*e) + c1*noise (ldm/models/diffusion/ddim.py:205-211; sigma_t * randn there)
+ * instead of the DDIM runner's (sqrt(a_prev)*x0 + c1*noise) + c2*e.  x0_out may be NULL.
  * ------------------------------------------------------------------------- */
 int tfmq_ddim_update(tfmq_ctx* ctx, const float* x, const float* e, const float* noise, const float* coef,
                      int64_t count, float* x_prev, float* x0_out, void* stream);

@@ -519,6 +519,15 @@ def plms_golden():
                                unconditional_conditioning=uc, unconditional_guidance_scale=3.0)
         s4, _ = cls(m).sample(S=10, batch_size=2, shape=[4, 8, 8], eta=0.0, x_T=x_T.clone(), verbose=False, untill_fake_t=5)
         out[name] = dict(full=s10, guided=s10c, stop5=s4)
+    # stochastic DDIM (eta = 1, the README's lsun / ffhq commands): sigma_t * noise_like(...) per step from the global CPU
+    # generator, seeded here; the test feeds the product the same stream
+    out["eta_seed"] = 77
+    torch.manual_seed(out["eta_seed"])
+    e1, _ = DDIMSampler(m).sample(S=10, batch_size=2, shape=[4, 8, 8], eta=1.0, x_T=x_T.clone(), verbose=False)
+    torch.manual_seed(out["eta_seed"])
+    e1c, _ = DDIMSampler(m).sample(S=10, batch_size=2, shape=[4, 8, 8], eta=1.0, x_T=x_T.clone(), verbose=False, conditioning=c,
+                                   unconditional_conditioning=uc, unconditional_guidance_scale=3.0)
+    out["ddim"]["eta1"], out["ddim"]["eta1_guided"] = e1, e1c
     torch.save(out, os.path.join(HERE, "samplers_stub.pt"))
     print("samplers_stub.pt written", {k: (v["full"].abs().max().item() if isinstance(v, dict) else None) for k, v in out.items()
                                         if isinstance(v, dict)})

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in the header but not exported"
     assert sorted(_lib.EXPORTS) == names, "ctypes binding and header disagree"
-    assert lib.tfmq_abi_version() == 5
+    assert lib.tfmq_abi_version() == 6
 
 
 def test_struct_layouts_match_c():

@@ -300,7 +300,7 @@ def test_conditional_ddim_sampler_with_guidance(dev):
         e = eng.forward(torch.cat([xx, xx]), torch.full((2 * B,), ts[k]), cc)
         e_u, e_c = e[:B], e[B:]
         e = e_u + scale * (e_c - e_u)
-        sa, s1, sn, c2, _ = (torch.tensor(v, device=dev) for v in rows[k])
+        sa, s1, sn, c2 = (torch.tensor(v, device=dev) for v in rows[k][:4])
         x0 = (xx - e * s1) / sa
         xx = sn * x0 + c2 * e
     d = (out - xx).abs().max().item()
@@ -441,6 +441,71 @@ def test_sampler_update_rules_match_the_reference_samplers(dev, name):
         err = (got.cpu() - ref).abs().max().item()
         print(f"[{name}] {tag}: max-abs {err:.3e} (|x| max {ref.abs().max():.2f})")
         assert err <= 1e-5 * max(1.0, ref.abs().max().item())
+
+
+def test_stochastic_ddim_eta1_matches_the_reference_sampler(dev, monkeypatch):
+    """eta > 0 (the README's `-e 1.0` commands): DDIMSampler's sigma_t * noise_like(...) term, plain and with guidance,
+    against trajectories of the reference's own DDIMSampler at eta = 1 driven by the stand-in UNet.  The reference drew its
+    noise from the seeded global CPU generator; the product's one draw per step (`samplers._randn`) is fed the same stream."""
+    import tfmq_b200.samplers as S
+    g = load_golden("samplers_stub.pt")
+    x_T, c, uc = g["x_T"].to(dev), g["c"].to(dev), g["uc"].to(dev)
+    mk = lambda: S.DDIMSampler(_stub_eps, linear_start=g["linear_start"], linear_end=g["linear_end"])  # noqa: E731
+    for tag, kw in (("eta1", {}), ("eta1_guided", dict(conditioning=c, unconditional_conditioning=uc,
+                                                        unconditional_guidance_scale=3.0))):
+        gen = torch.Generator().manual_seed(g["eta_seed"])
+        monkeypatch.setattr(S, "_randn", lambda shape, device: torch.randn(tuple(shape), generator=gen).to(device))
+        got, _ = mk().sample(10, 2, (4, 8, 8), x_T=x_T, eta=1.0, **kw)
+        ref = g["ddim"][tag]
+        err = (got.cpu() - ref).abs().max().item()
+        print(f"[ddim eta=1] {tag}: max-abs {err:.3e} (|x| max {ref.abs().max():.2f}); differs from eta=0 by "
+              f"{(ref - g['ddim']['full']).abs().max():.2f}")
+        assert err <= 1e-5 * max(1.0, ref.abs().max().item())
+    with pytest.raises(ValueError):
+        S.PLMSSampler(_stub_eps, linear_start=g["linear_start"], linear_end=g["linear_end"]).sample(
+            10, 2, (4, 8, 8), x_T=x_T, eta=1.0)
+
+
+def test_stochastic_step_through_the_engine(dev, monkeypatch):
+    """generalized_steps with eta = 1 on a QuantModel (ddim/functions/denoising.py:31-37): the engine's resident noise buffer
+    and the c1 column of its step table.  Every step's x_next must equal, bit for bit, the reference expression evaluated
+    with torch on the engine's own eps / x0 of that step and the same draw."""
+    import tfmq_b200.samplers as S
+    from tfmq_b200.quant.quant_layer import QMODE, Scaler
+    from tfmq_b200.quant.quant_model import QuantModel
+    wq = dict(bits=4, channel_wise=True, scaler=Scaler.MINMAX)
+    aq = dict(bits=8, channel_wise=False, scaler=Scaler.MINMAX, leaf_param=True)
+    qnn = QuantModel(fp_model("cifar").to(dev), wq, aq, cali=False, softmax_a_bit=8,
+                     aq_mode=[QMODE.NORMAL.value, QMODE.QDIFF.value]).eval()
+    x = synth.latents((2, 3, 32, 32), 44).to(dev)
+    qnn.set_quant_state(True, True)
+    with torch.no_grad():
+        qnn(x, torch.full((2,), 900.0, device=dev))          # lazy quantiser initialisation through the module graph
+        qnn.disable_out_quantization()
+    betas = synth.ddim_betas().to(dev)
+    seq = [0, 300, 600, 900]
+    draws = []
+    gen = torch.Generator().manual_seed(5)
+
+    def randn(shape, device):
+        draws.append(torch.randn(tuple(shape), generator=gen).to(device))
+        return draws[-1]
+    monkeypatch.setattr(S, "_randn", randn)
+    xs, x0s, _, _ = S.generalized_steps(x, seq, qnn, betas, eta=1.0, keep_trajectory=True)
+    assert len(draws) == len(seq) and len(xs) == len(seq) + 1
+    rows = S.ddim_coefficients(seq, betas, 1.0)
+    assert all(r[4] > 0 for r in rows[:-1])
+    for k in range(len(seq)):
+        sa, s1ma, sap, c2, c1 = (torch.tensor(v, dtype=torch.float32) for v in rows[k])
+        xt, x0 = xs[k].cpu().float(), x0s[k].cpu().float()
+        et = (xt - x0 * sa) / s1ma                              # eps of the step, to fp32 rounding
+        want = sap * x0 + c1 * draws[k].cpu() + c2 * et
+        err = (xs[k + 1].cpu() - want).abs().max().item()
+        assert err <= 2e-5 * max(1.0, want.abs().max().item()), (k, err)
+    # and eta = 0 afterwards drops the term again (the captured step graph is rebuilt without the noise pointer)
+    xs0, _, _, _ = S.generalized_steps(x, seq, qnn, betas, eta=0.0)
+    xs0b, _, _, _ = S.generalized_steps(x, seq, qnn, betas, eta=0.0)
+    assert torch.equal(xs0[-1], xs0b[-1]) and not torch.equal(xs0[-1], xs[-1].cpu())
 
 
 def test_fp_engine_and_calibration_data_generation(dev):

@@ -98,7 +98,7 @@ def _w4a8_case(dev, n, h, w, cin, cout, ksize, use_emb, use_res, seed, ld_extra=
         out.copy_(nhwc(res).to(dev))   # residual aliases the output, as in the engine
         res_d = out
     aq = torch.tensor([delta_a.item(), zp_a.item()], dtype=torch.float32, device=dev)
-    ops.conv_w4a8(act.to(dev), ksize, packed, zp_w.reshape(-1).to(torch.uint8).to(dev),
+    ops.conv_w4a8(act.to(dev), ksize, packed, zp_w.reshape(-1).to(torch.int32).to(dev),
                   delta_w.reshape(-1).contiguous().to(dev), wsum, bias.to(dev), aq, out,
                   emb=emb.to(dev) if use_emb else None, res=res_d)
     torch.cuda.synchronize()
@@ -130,6 +130,42 @@ def _w4a8_case(dev, n, h, w, cin, cout, ksize, use_emb, use_res, seed, ld_extra=
 ])
 def test_conv_w4a8_exact(dev, n, h, w, cin, cout, ks, emb, res):
     _w4a8_case(dev, n, h, w, cin, cout, ks, emb, res, seed=n * 1000 + cin + cout + ks)
+
+
+def test_conv_w4a8_zero_points_outside_the_code_range(dev):
+    """Scaler.MSE does not force the weight range to contain 0 (quant/quant_layer.py:38-64): a channel whose weights share one
+    sign gets a zero point below 0 or above 15.  The reference handles it through clamp(round(w / d) + zp, 0, 15) and
+    d * (q - zp); here the codes stay in [0, 15] and the epilogue folds zp in as int32.  Exact against float64."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(12)
+    n, h, w, cin, cout = 2, 16, 16, 64, 32
+    wt = torch.randn(cout, cin, 3, 3, generator=g) * 0.05
+    wt[0] = wt[0].abs() + 0.5            # all positive, far from 0: zp << 0
+    wt[1] = -wt[1].abs() - 0.2           # all negative: zp >> 15
+    wt[2] = wt[2].abs() + 0.01
+    w2 = wt.reshape(cout, -1)
+    lo, hi = w2.min(1).values, w2.max(1).values
+    delta = (hi - lo) / 15
+    zp = torch.round(-lo / delta)
+    assert zp[0] < 0 and zp[1] > 15
+    codes = torch.clamp(torch.round(wt / delta.view(-1, 1, 1, 1)) + zp.view(-1, 1, 1, 1), 0, 15)
+    x = torch.randn(n, cin, h, w, generator=g)
+    da, za = (x.max() - x.min()) / 255, torch.round(-x.min() / ((x.max() - x.min()) / 255))
+    qa = torch.clamp(torch.round(x / da) + za, 0, 255)
+    ref = F.conv2d((qa - za).double(), (codes - zp.view(-1, 1, 1, 1)).double(), padding=1) * (
+        da.double() * delta.double().view(1, -1, 1, 1))
+    act = torch.full((n, h + 2, w + 2, cin), int(za.item()), dtype=torch.uint8)
+    act[:, 1:-1, 1:-1, :] = nhwc(qa).to(torch.uint8)
+    got_codes, packed, wsum = ops.pack_w4(to_ohwi(wt).to(dev), delta.to(dev), zp.to(dev))
+    assert torch.equal(got_codes.cpu().float().view(cout, 3, 3, cin).permute(0, 3, 1, 2), codes)
+    assert torch.equal(wsum.cpu().double(), (codes - zp.view(-1, 1, 1, 1)).double().sum((1, 2, 3)))
+    out = torch.zeros((n, h, w, cout), device=dev)
+    aq = torch.tensor([da.item(), za.item()], device=dev)
+    ops.conv_w4a8(act.to(dev), 3, packed, zp.to(torch.int32).to(dev), delta.contiguous().to(dev), wsum,
+                  torch.zeros(cout, device=dev), aq, out)
+    torch.cuda.synchronize()
+    err = (out.cpu().permute(0, 3, 1, 2).double() - ref).abs().max().item()
+    assert err <= 2e-6 * ref.abs().max().item() + 1e-6, err
 
 
 def test_conv_w4a8_strided_output(dev):
@@ -495,6 +531,15 @@ def test_ddim_update_and_embedding(dev):
     ops.ddim_update(x.to(dev), e.to(dev), coef, xp, x0d)
     assert (x0d.cpu() - x0).abs().max().item() <= 1e-6
     assert (xp.cpu() - ref).abs().max().item() <= 1e-6
+    # eta > 0: c1 * noise, in the DDIM runner's order (coef[5] = 0) and the LDM sampler's (coef[5] = 1), bit for bit
+    nz = torch.randn(2, 3, 32, 32, generator=g)
+    c1 = 0.8 * ((1 - at / an) * (1 - an) / (1 - at)).abs().sqrt()
+    c2n = ((1 - an) - c1 ** 2).sqrt()
+    x0f = (x - e * (1 - at).sqrt()) / at.sqrt()
+    for order, want in ((0.0, an.sqrt() * x0f + c1 * nz + c2n * e), (1.0, an.sqrt() * x0f + c2n * e + c1 * nz)):
+        coef6 = torch.stack([at.sqrt(), (1 - at).sqrt(), an.sqrt(), c2n, c1, torch.tensor(order)]).to(dev)
+        ops.ddim_update(x.to(dev), e.to(dev), coef6, xp, x0d, noise=nz.to(dev))
+        assert torch.equal(xp.cpu(), want), order
     t = torch.tensor([999.0, 500.0, 1.0])
     for style, dim in ((0, 128), (1, 224)):
         out = torch.empty((3, dim), device=dev)
@@ -705,7 +750,7 @@ def test_conv_epilogue_gn_stats(dev, n, h, w, cin, cout, cpg, ch_off, groups):
     out = torch.zeros((n, h, w, cout), device=dev)
     aq = torch.tensor([delta_a.item(), zp_a.item()], device=dev)
     stats = torch.zeros((n, groups, 2), dtype=torch.float64, device=dev)
-    ops.conv_w4a8(act.to(dev), 3, packed, zp_w.reshape(-1).to(torch.uint8).to(dev),
+    ops.conv_w4a8(act.to(dev), 3, packed, zp_w.reshape(-1).to(torch.int32).to(dev),
                   delta_w.reshape(-1).contiguous().to(dev), wsum, bias.to(dev), aq, out, stats=[(stats, cpg, ch_off)])
     torch.cuda.synchronize()
     o = out.cpu().double()                                   # [n,h,w,cout]

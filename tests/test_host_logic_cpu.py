@@ -83,7 +83,7 @@ def test_ldm_ddim_schedule_matches_reference_formulas():
     assert abs(float(s.ddim_alphas[0]) - ac[1]) < 1e-7 and abs(float(s.ddim_alphas_prev[0]) - ac[0]) < 1e-7
     rows = s.coefficient_rows()
     assert len(rows) == 200
-    sa, s1, sp, c2, c1 = rows[0]                       # first sampling step = largest t
+    sa, s1, sp, c2, c1, order = rows[0]                # first sampling step = largest t; order 1 = the LDM summation order
     assert abs(sa - math.sqrt(ac[996])) < 1e-6 and abs(s1 - math.sqrt(1 - ac[996])) < 1e-6
     assert abs(sp - math.sqrt(ac[991])) < 1e-6 and abs(c2 - math.sqrt(1 - ac[991])) < 1e-6 and c1 == 0.0
     assert list(make_ddim_timesteps(50)) == [i + 1 for i in range(0, 1000, 20)]

@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(256) pack_w4_kernel(const float* __restrict__ 
 
 }  // namespace tfmq
 
-extern "C" int tfmq_abi_version(void) { return 5; }   // 4: tfmq_attention_h16, tfmq_conv_h16_desc.out_hi / out_lo; 5: tfmq_conv_h16_desc.ksplit
+extern "C" int tfmq_abi_version(void) { return 6; }   // 4: tfmq_attention_h16, tfmq_conv_h16_desc.out_hi / out_lo; 5: tfmq_conv_h16_desc.ksplit; 6: int32 weight zero points, ddim_update coef[5]
 
 extern "C" int tfmq_create(tfmq_ctx** out, int device) {
   if (!out) return TFMQ_ERR_ARG;

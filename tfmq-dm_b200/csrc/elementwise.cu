@@ -444,6 +444,9 @@ __global__ void ddim_update_kernel(const float* __restrict__ x, const float* __r
                                    float* __restrict__ x_prev, float* __restrict__ x0_out) {
   const float sa = coef[0], s1ma = coef[1], sap = coef[2], c2 = coef[3];
   const float c1 = noise ? coef[4] : 0.f;
+  // coef[5] != 0 (read only with noise): the LDM sampler's order  (sqrt(a') x0 + c2 e) + c1 noise  (ddim.py:205-211) instead of
+  // the DDIM runner's  (sqrt(a') x0 + c1 noise) + c2 e  (denoising.py:31-37)
+  const bool dir_first = noise && coef[5] != 0.f;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count;
        i += (long long)gridDim.x * blockDim.x) {
     const float ev = e[i];
@@ -451,8 +454,12 @@ __global__ void ddim_update_kernel(const float* __restrict__ x, const float* __r
     // ddim/functions/denoising.py:31-37 so the fp32 roundings agree; no FMA contraction
     const float x0 = __fdiv_rn(__fsub_rn(x[i], __fmul_rn(ev, s1ma)), sa);
     float r = __fmul_rn(sap, x0);
-    if (noise) r = __fadd_rn(r, __fmul_rn(c1, noise[i]));
-    r = __fadd_rn(r, __fmul_rn(c2, ev));
+    if (dir_first) {
+      r = __fadd_rn(__fadd_rn(r, __fmul_rn(c2, ev)), __fmul_rn(c1, noise[i]));
+    } else {
+      if (noise) r = __fadd_rn(r, __fmul_rn(c1, noise[i]));
+      r = __fadd_rn(r, __fmul_rn(c2, ev));
+    }
     x_prev[i] = r;
     if (x0_out) x0_out[i] = x0;
   }

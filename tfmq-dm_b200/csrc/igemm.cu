@@ -556,7 +556,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (MODE == MODE_W4A8) {
           sc = a_scale * p.wscale[c];
           ws = za * p.wsum[c];
-          zw = (int)p.wzp[c];
+          zw = p.wzp[c];
         } else if (p.wscale) {
           sc = p.wscale[c];
         }

@@ -49,7 +49,7 @@ struct IgemmParams {
   const float* bias;
   const float* wscale;  // [cout] per-channel scale (delta_w) or null
   const int32_t* wsum;
-  const uint8_t* wzp;
+  const int32_t* wzp;
   const float* aq;  // (delta_a, zp_a) or null
   const float* emb;
   long long emb_ld;

@@ -70,7 +70,7 @@ def engine_constants(eng) -> List[torch.Tensor]:
     """Every device constant a sampling rank needs from rank 0."""
     out = [eng.table] if eng.table is not None else []
     for q in eng.ql.values():
-        for name in ("packed", "codes", "wdelta", "wzp_f", "wzp_u8", "wsum", "bias", "w_hi", "w_lo", "w_f32", "w_oihw",
+        for name in ("packed", "codes", "wdelta", "wzp_f", "wzp_i32", "wsum", "bias", "w_hi", "w_lo", "w_f32", "w_oihw",
                      "h_hi", "h_lo", "h_scale"):
             t = getattr(q, name, None)
             if torch.is_tensor(t):

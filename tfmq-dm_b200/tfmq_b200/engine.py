@@ -108,9 +108,8 @@ class _QL:
             self.codes, self.packed, self.wsum = ops.pack_w4(w2d, delta, zp, alpha)
             self.wdelta, self.wzp_f = delta.contiguous(), zp.contiguous()
             # Scaler.MSE does not force the range to contain 0 (quant/quant_layer.py:38-64): a row whose weights share one
-            # sign gets a zero point outside [0, 255], which the u8 zero-point vector of the int8 epilogue cannot carry
-            self.wzp_in_range = bool(((zp >= 0) & (zp <= 255)).all())
-            self.wzp_u8 = zp.clamp(0, 255).to(torch.uint8).contiguous()
+            # sign gets a zero point below 0 or above 15; the int8 epilogue carries zero points as int32
+            self.wzp_i32 = zp.round().to(torch.int32).contiguous()
         else:
             self.w_f32 = w2d
         self._fp_ready = False
@@ -229,7 +228,8 @@ class StepEngine:
 
         timesteps[k]: the t fed to the UNet at sampling step k.  act_tables[k]: the reference's
         `act_k` dict ('model.<layer>.aqtizer.delta' / '.zero_point', quant/calibration.py:147-152) or
-        None to keep the current values.  ddim_coefs[k] = (sqrt(a_t), sqrt(1-a_t), sqrt(a_prev), c2, c1)."""
+        None to keep the current values.  ddim_coefs[k] = (sqrt(a_t), sqrt(1-a_t), sqrt(a_prev), c2, c1[, order]); c1 is
+        used only with a noise tensor (`set_noise`, eta > 0), order != 0 = the LDM sampler's summation order."""
         steps = len(timesteps) if timesteps is not None else len(act_tables)
         tab = self.cur.detach().cpu().repeat(steps, 1)
         if act_tables is not None:
@@ -246,9 +246,24 @@ class StepEngine:
             tab[:, self.off_emb:self.off_emb + self.emb_dim] = self.timestep_embedding_cpu(ts)
             self.timesteps = [float(t) for t in timesteps]
         if ddim_coefs is not None:
-            tab[:, self.off_coef:self.off_coef + 5] = torch.tensor(ddim_coefs, dtype=torch.float64).float()
+            rows = torch.tensor(ddim_coefs, dtype=torch.float64).float()
+            tab[:, self.off_coef:self.off_coef + 6] = 0.0
+            tab[:, self.off_coef:self.off_coef + rows.shape[1]] = rows
         self.table = tab.to(self.dev)
         self.select_step(0)
+
+    def set_noise(self, noise: Optional[torch.Tensor]):
+        """eta > 0: the standard-normal draw of the coming step (`torch.randn_like(x)` of denoising.py:36 / `noise_like` of
+        ddim.py:209), one per step; copied into a resident buffer the update kernel reads.  None switches the term off.
+        With guidance the draw has the shape of one half of the batch."""
+        if noise is None:
+            if self.noise is not None:
+                self.noise, self.g_upd = None, None
+            return
+        if self.noise is None or self.noise.shape != noise.shape:
+            self.noise = torch.empty_like(noise, device=self.dev)
+            self.g_upd = None                 # the captured step graph holds the pointer
+        self.noise.copy_(noise, non_blocking=True)
 
     def select_step(self, k: int):
         self.cur.copy_(self.table[k], non_blocking=True)
@@ -309,10 +324,6 @@ class StepEngine:
             tok["geglu"] = True
         if out is None:
             out = self._new(x.n, oh, ow, q.cout)
-        if q.quant_w and q.aq_index is not None and not q.wzp_in_range:
-            raise NotImplementedError(
-                f"StepEngine: layer {q.name} has a weight zero point outside [0, 255] (a channel whose weights share one sign "
-                "under Scaler.MSE); the w4a8 epilogue carries zero points as u8 -- refusing to run it with a wrapped value")
         if q.quant_w and q.aq_index is not None:
             halo = 1 if q.ksize == 3 else 0
             u8 = torch.empty((x.n, oh + 2 * halo, ow + 2 * halo, q.cin), dtype=torch.uint8, device=self.dev)
@@ -330,7 +341,7 @@ class StepEngine:
                     # conv inputs are recorded [b, c, h, w], token / context inputs [b, tokens, c]
                     forced = forced.permute(0, 2, 3, 1) if forced.dim() == 4 else forced.reshape(u8.shape)
                     (u8[:, 1:-1, 1:-1] if halo else u8).copy_(forced)
-                ops.conv_w4a8(u8, q.ksize, q.packed, q.wzp_u8, q.wdelta, q.wsum, q.bias, aq, out.view, emb=emb,
+                ops.conv_w4a8(u8, q.ksize, q.packed, q.wzp_i32, q.wdelta, q.wsum, q.bias, aq, out.view, emb=emb,
                               res=res.view if res is not None else None, stats=self._stats_of(rec))
             self.ops.append(run)
         else:

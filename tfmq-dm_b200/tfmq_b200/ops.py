@@ -131,7 +131,7 @@ def act_prepare(src: torch.Tensor, *, aq: torch.Tensor | None = None, dst_u8: to
 
 
 # --------------------------------------------------------------------------- tensor-core convs
-def conv_w4a8(act: torch.Tensor, ksize: int, packed, wzp_u8, wdelta, wsum, bias, aq, out: torch.Tensor,
+def conv_w4a8(act: torch.Tensor, ksize: int, packed, wzp_i32, wdelta, wsum, bias, aq, out: torch.Tensor,
               emb: torch.Tensor | None = None, res: torch.Tensor | None = None, stats=None):
     """act: u8 [N, H+2h, W+2h, Cin] (h = 1 for 3x3, 0 for 1x1); out: fp32 NHWC view [N,H,W,Cout]."""
     ctx = _ctx(out)
@@ -142,7 +142,8 @@ def conv_w4a8(act: torch.Tensor, ksize: int, packed, wzp_u8, wdelta, wsum, bias,
     d = ConvW4A8Desc()
     d.act = act.data_ptr()
     d.n, d.h, d.w, d.cin, d.cout, d.ksize = n, h, w, act.shape[3], cout, ksize
-    d.packed, d.wzp, d.wdelta, d.wsum = packed.data_ptr(), wzp_u8.data_ptr(), wdelta.data_ptr(), wsum.data_ptr()
+    assert wzp_i32.dtype == torch.int32, "weight zero points are int32 (ABI 6)"
+    d.packed, d.wzp, d.wdelta, d.wsum = packed.data_ptr(), wzp_i32.data_ptr(), wdelta.data_ptr(), wsum.data_ptr()
     d.bias = bias.data_ptr() if bias is not None else None
     d.aq = aq.data_ptr()
     if emb is not None:

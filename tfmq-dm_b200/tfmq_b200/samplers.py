@@ -24,6 +24,12 @@ def compute_alpha(beta: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
     return (1 - beta).cumprod(dim=0).index_select(0, t + 1).view(-1, 1, 1, 1)
 
 
+def _randn(shape, device) -> torch.Tensor:
+    """One standard-normal draw of a stochastic (eta > 0) step, from the same generator, in the same order and with the same
+    shape as the reference's `torch.randn_like(x)` (denoising.py:36) / `noise_like(x.shape, device)` (ddim.py:209)."""
+    return torch.randn(tuple(shape), device=device)
+
+
 def ddim_coefficients(seq: Sequence[int], betas: torch.Tensor, eta: float = 0.0):
     """Per sampling step (sqrt(a_t), sqrt(1-a_t), sqrt(a_next), c2, c1) as fp32 values computed with the
     same tensor ops as the reference loop (denoising.py:19-36), so the device update reproduces it."""
@@ -52,8 +58,6 @@ def generalized_steps(x, seq, model, b, **kwargs):
     untill_fake_t.  Returns (xs, x0_preds, xt, t) with xs[0] = x and xs[-1] the denoised sample
     (intermediates are kept only with keep_trajectory=True)."""
     eta = kwargs.get("eta", 0)
-    if eta != 0:
-        raise NotImplementedError("eta > 0 (stochastic DDIM) is not part of the benchmarked path yet")
     dev = next(model.parameters()).device
     n = x.size(0)
     seq = list(seq)
@@ -74,6 +78,7 @@ def generalized_steps(x, seq, model, b, **kwargs):
             xt = eng.x_in.clone()
         if stop is not None and k == stop - 1:
             break
+        eng.set_noise(_randn(x.shape, dev) if eta != 0 else None)      # c1 * randn_like(x), denoising.py:36
         eng.step(k)
         if keep:
             xs.append(eng.x_in.to("cpu"))
@@ -156,18 +161,16 @@ class DDIMSampler:
             a_t, a_prev = self.ddim_alphas[index], self.ddim_alphas_prev[index]
             sigma = self.ddim_sigmas[index]
             rows.append([a_t.sqrt().item(), self.ddim_sqrt_one_minus_alphas[index].item(), a_prev.sqrt().item(),
-                         (1.0 - a_prev - sigma ** 2).sqrt().item(), sigma.item()])
+                         (1.0 - a_prev - sigma ** 2).sqrt().item(), sigma.item(), 1.0])   # 1.0: (x0 term + dir_xt) + noise
         return rows
 
     @torch.no_grad()
     def sample(self, S, batch_size, shape, conditioning=None, eta=0.0, x_T=None, verbose=False,
                unconditional_guidance_scale=1.0, unconditional_conditioning=None, untill_fake_t=None, **kwargs):
-        if eta != 0:
-            raise NotImplementedError("eta > 0")
         self.make_schedule(S, eta)
         if not hasattr(self.model, "build_engine"):
             return self._sample_callable(S, batch_size, shape, conditioning, x_T, unconditional_guidance_scale,
-                                         unconditional_conditioning, untill_fake_t)
+                                         unconditional_conditioning, untill_fake_t, eta=eta)
         dev = next(self.model.parameters()).device
         C, H, W = shape
         img = torch.randn((batch_size, C, H, W), device=dev) if x_T is None else x_T.to(dev)
@@ -193,6 +196,8 @@ class DDIMSampler:
         eng.x_in.copy_(torch.cat([img, img], dim=0) if cfg else img)
         n_run = S if not untill_fake_t else min(S, untill_fake_t - 1)
         for k in range(n_run):
+            # sigma_t * noise_like(x.shape, device) (ddim.py:209): one draw per step, of the un-doubled batch
+            eng.set_noise(_randn((batch_size, C, H, W), dev) if eta != 0 else None)
             eng.step(k)
         out = eng.x_in[:batch_size].clone()
         return out, {"x_inter": [img, out], "pred_x0": [img, eng.x0_pred[:batch_size].clone()]}
@@ -213,7 +218,7 @@ def _callable_eps(model, batch_size, ctx, cfg, scale):
     return fn
 
 
-def _sample_callable(self, S, batch_size, shape, conditioning, x_T, scale, uncond, untill_fake_t):
+def _sample_callable(self, S, batch_size, shape, conditioning, x_T, scale, uncond, untill_fake_t, eta=0.0):
     """DDIM with a plain callable as the UNet (update-rule parity tests): same kernels for guidance and the update."""
     from . import ops
     dev = x_T.device
@@ -227,7 +232,8 @@ def _sample_callable(self, S, batch_size, shape, conditioning, x_T, scale, uncon
     ts = [float(t) for t in np.flip(self.ddim_timesteps)]
     x0 = torch.empty_like(img)
     for k in range(S if not untill_fake_t else min(S, untill_fake_t - 1)):
-        ops.ddim_update(img, eps_fn(img, ts[k], k).contiguous(), rows[k], img, x0)
+        e = eps_fn(img, ts[k], k).contiguous()
+        ops.ddim_update(img, e, rows[k], img, x0, noise=_randn(img.shape, dev) if eta != 0 else None)
     return img, {"x_inter": [x_T, img], "pred_x0": [x_T, x0]}
 
 

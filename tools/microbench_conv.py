@@ -42,7 +42,7 @@ def w4a8(n, h, w, cin, cout, ks, res, emb, stats):
     bias = torch.zeros(cout, device=dev)
     e = torch.zeros((n, cout), device=dev) if emb else None
     st = [(torch.zeros((n, 32, 2), dtype=torch.float64, device=dev), cout // 32, 0)] if stats else None
-    fn = lambda: ops.conv_w4a8(act, ks, packed, zp.to(torch.uint8), delta, wsum, bias, aq, out, emb=e,  # noqa: E731
+    fn = lambda: ops.conv_w4a8(act, ks, packed, zp.to(torch.int32), delta, wsum, bias, aq, out, emb=e,  # noqa: E731
                                res=out if res else None, stats=st)
     us = timeit(fn)
     gop = 2 * n * h * w * cout * ks * ks * cin / 1e9
