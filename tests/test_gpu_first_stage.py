@@ -107,6 +107,14 @@ def test_decoder_engine_matches_oracle_and_reference(dev, kind):
         eng.decode(z)                      # CPU latent
     with pytest.raises(RuntimeError):
         eng.decode(z[:1].to(dev))          # other batch than the program was built for
+    # a scale_factor assigned after the first decode (the scripts set it on the LatentDiffusion object) must not replay the
+    # graph captured with the old value
+    if cfg["n_embed"] is None:
+        old = m.scale_factor
+        m.scale_factor = 2.0 * old
+        img_half = m.decode_first_stage((2.0 * z).to(dev)).cpu()       # (2 z) / (2 s) = z / s, power-of-two scaling is exact
+        m.scale_factor = old
+        assert torch.equal(img_half, img)
 
 
 def test_full_size_vq_f4_decode(dev):

@@ -333,7 +333,9 @@ class DecoderEngine(StepEngine):
         if not self.use_graph:
             self._run(quantize, scale)
             return self.image.clone()
-        key = (quantize, scale)
+        # 1 / scale_factor is a kernel argument baked into the captured graph, and `decode_first_stage` callers may assign
+        # `fs.scale_factor` between calls: its value is part of the key
+        key = (quantize, scale, float(self.fs.scale_factor) if scale else None)
         g = self._graphs.get(key)
         if g is None:
             s = torch.cuda.Stream(self.dev)
