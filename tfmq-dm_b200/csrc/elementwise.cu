@@ -17,42 +17,70 @@ namespace tfmq {
 constexpr int GN_THREADS = 256;
 constexpr int GN_MAXVEC = 2;  // c <= 2048
 
+// When c / 4 <= 256 the threads form a (channel vector tv, pixel lane tp) grid of tvn x k: with one pixel row per CTA pass a
+// 224-channel tensor kept 56 of the 256 threads busy, one load in flight each (64 us for 59 MB); the k pixel lanes' fp32
+// partials meet in shared memory and are added in a fixed order.
 __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const float* __restrict__ x, long long ld, int hw, int c,
                                                               int groups, int pix_per_cta,
-                                                              double* __restrict__ stats, int cpg, int ch_off) {
+                                                              double* __restrict__ stats, int cpg, int ch_off, int tvn, int k) {
   extern __shared__ double sm[];  // [c] sum, [c] sumsq
+  __shared__ float part[GN_THREADS * 8];   // [tp][sum x4 | sumsq x4][tv]
   const int n = blockIdx.y;
   const int p0 = blockIdx.x * pix_per_cta;
   int p1 = p0 + pix_per_cta;
   if (p1 > hw) p1 = hw;
   const int nvec = c >> 2;
+  const int tv = threadIdx.x % tvn, tp = threadIdx.x / tvn;
   float s[GN_MAXVEC][4], ss[GN_MAXVEC][4];
 #pragma unroll
   for (int v = 0; v < GN_MAXVEC; ++v)
 #pragma unroll
     for (int j = 0; j < 4; ++j) s[v][j] = ss[v][j] = 0.f;
   const float* base = x + ((long long)n * hw) * ld;
-  for (int p = p0; p < p1; ++p) {
-    const float4* row = reinterpret_cast<const float4*>(base + (long long)p * ld);
+  if (tp < k) {
+    for (int p = p0 + tp; p < p1; p += k) {
+      const float4* row = reinterpret_cast<const float4*>(base + (long long)p * ld);
+#pragma unroll
+      for (int v = 0; v < GN_MAXVEC; ++v) {
+        const int iv = tv + v * GN_THREADS;
+        if (iv < nvec) {
+          const float4 f = row[iv];
+          s[v][0] += f.x, s[v][1] += f.y, s[v][2] += f.z, s[v][3] += f.w;
+          ss[v][0] += f.x * f.x, ss[v][1] += f.y * f.y, ss[v][2] += f.z * f.z, ss[v][3] += f.w * f.w;
+        }
+      }
+    }
+  }
+  if (k == 1) {
 #pragma unroll
     for (int v = 0; v < GN_MAXVEC; ++v) {
       const int iv = threadIdx.x + v * GN_THREADS;
       if (iv < nvec) {
-        const float4 f = row[iv];
-        s[v][0] += f.x, s[v][1] += f.y, s[v][2] += f.z, s[v][3] += f.w;
-        ss[v][0] += f.x * f.x, ss[v][1] += f.y * f.y, ss[v][2] += f.z * f.z, ss[v][3] += f.w * f.w;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          sm[iv * 4 + j] = (double)s[v][j];
+          sm[c + iv * 4 + j] = (double)ss[v][j];
+        }
       }
     }
-  }
-#pragma unroll
-  for (int v = 0; v < GN_MAXVEC; ++v) {
-    const int iv = threadIdx.x + v * GN_THREADS;
-    if (iv < nvec) {
+  } else {
+    if (tp < k) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        sm[iv * 4 + j] = (double)s[v][j];
-        sm[c + iv * 4 + j] = (double)ss[v][j];
+        part[(tp * 8 + j) * tvn + tv] = s[0][j];
+        part[(tp * 8 + 4 + j) * tvn + tv] = ss[0][j];
       }
+    }
+    __syncthreads();
+    for (int ch = threadIdx.x; ch < c; ch += GN_THREADS) {
+      const int iv = ch >> 2, j = ch & 3;
+      double a = 0.0, b = 0.0;
+      for (int t = 0; t < k; ++t) {
+        a += (double)part[(t * 8 + j) * tvn + iv];
+        b += (double)part[(t * 8 + 4 + j) * tvn + iv];
+      }
+      sm[ch] = a;
+      sm[c + ch] = b;
     }
   }
   __syncthreads();
@@ -301,7 +329,7 @@ __global__ void __launch_bounds__(ACT_THREADS) act_prepare_kernel(const ActParam
 // the flattened [destination pixels x c / 4] space: two multiply-high divisions per vector recover (pixel, channel vector),
 // all lanes work, the exponential is one ex2.approx.ftz, the exact-rounding path is tested once per vector, and ACT_UNROLL
 // vectors per thread are in flight.  The zero-point halo is filled by a separate short loop over the border pixels.
-constexpr int ACT_UNROLL = 2;
+constexpr int ACT_UNROLL_DEFAULT = 2;
 
 struct ActFlatParams {
   tfmq_act_desc d;
@@ -323,7 +351,7 @@ __device__ __forceinline__ float ex2_ftz(float x) {
 // x * sigmoid(x) = x / (1 + 2^(-x log2 e)); a result of the exponential below the normal range flushes to 0 (sigmoid = 1)
 __device__ __forceinline__ float silu_fast(float v) { return v * rcp_approx(1.f + ex2_ftz(v * -1.4426950408889634f)); }
 
-template <bool GN, bool SILU, int OUT>
+template <bool GN, bool SILU, int OUT, int ACT_UNROLL>
 __global__ void __launch_bounds__(ACT_THREADS) act_flat_kernel(const ActFlatParams P) {
   extern __shared__ float sp[];  // [c] a = rstd*gamma, [c] b = beta - a*mean
   griddep_launch_dependents();
@@ -433,6 +461,159 @@ __global__ void __launch_bounds__(ACT_THREADS) act_flat_kernel(const ActFlatPara
       else if (b < 2 * Wp + P.out_h) yy = b - 2 * Wp + 1, xx = 0;
       else yy = b - 2 * Wp - P.out_h + 1, xx = Wp - 1;
       uint32_t* o8 = reinterpret_cast<uint32_t*>(d.dst_u8 + ((long long)n * npix + (long long)yy * Wp + xx) * d.dst_c + d.dst_c_off);
+      for (int v = lane; v < nvec; v += 32) o8[v] = zfill;
+    }
+  }
+}
+
+
+// ------------------------------------------------- the same producer with VECTOR-STATIONARY threads
+// Both kernels above spend more than half of their issue slots on addressing (SASS of the flattened u8 kernel: ~55 of ~105
+// instructions per float4 vector are multiply-high divisions, 64-bit IMAD.WIDE chains and the reload of the GroupNorm constants
+// from shared memory), and the kernel is issue-bound at 2.9 TB/s.  Here blockDim.x = TV * k with TV = (c / 4) / R: a thread owns
+// the SAME R channel vectors for its whole life and walks pixels with stride k.  Its GroupNorm constants are loaded once into
+// registers, the (pixel, row) pair advances by additions, all offsets are 32-bit relative to per-image base pointers, and two
+// pixels are in flight per thread.
+struct ActStatParams {
+  tfmq_act_desc d;
+  int out_h, out_w;
+  int tv;                    // threads along the channel-vector axis: (c / 4) / R
+  int k;                     // pixels per CTA pass (blockDim.x = tv * k)
+  int pix_per_cta;           // interior destination pixels per CTA
+  int border_per_cta;        // halo pixels per CTA
+  double inv_cnt;
+};
+
+template <bool GN, bool SILU, int OUT, int R, int U>
+__global__ void __launch_bounds__(ACT_THREADS) act_stat_kernel(const ActStatParams P) {
+  extern __shared__ float sp[];  // [c] a = rstd*gamma, [c] b = beta - a*mean
+  griddep_launch_dependents();
+  griddep_wait();
+  const tfmq_act_desc& d = P.d;
+  const int n = blockIdx.y;
+  const int c = d.c;
+  const int tv = threadIdx.x % P.tv, tp = threadIdx.x / P.tv;
+  float4 ga[R], gb[R];
+  if (GN) {
+    __shared__ float sg[2 * 64];
+    const int cpg = c / d.groups;
+    for (int g = threadIdx.x; g < d.groups; g += blockDim.x) {
+      const double su = d.gn_stats[((long long)n * d.groups + g) * 2];
+      const double sq = d.gn_stats[((long long)n * d.groups + g) * 2 + 1];
+      const double mean = su * P.inv_cnt;
+      double var = fma(-mean, mean, sq * P.inv_cnt);
+      if (var < 0) var = 0;
+      sg[2 * g] = 1.f / sqrtf((float)var + d.eps);
+      sg[2 * g + 1] = (float)mean;
+    }
+    __syncthreads();
+    for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+      const int g = ch / cpg;
+      const float a = sg[2 * g] * d.gamma[ch];
+      sp[ch] = a;
+      sp[c + ch] = -a * sg[2 * g + 1] + d.beta[ch];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      ga[j] = *reinterpret_cast<const float4*>(sp + (tv + j * P.tv) * 4);
+      gb[j] = *reinterpret_cast<const float4*>(sp + c + (tv + j * P.tv) * 4);
+    }
+  }
+  float delta = 1.f, zp = 0.f;
+  if (OUT == ACT_OUT_U8) delta = d.aq[0], zp = d.aq[1];
+  const float inv = __frcp_rn(delta);
+  const int halo = (OUT == ACT_OUT_U8) ? d.halo : 0;
+  const int W = P.out_w, Wp = W + 2 * halo;
+  const int npix_dst = Wp * (P.out_h + 2 * halo);
+  const int up = d.upsample ? 1 : 0;
+  // per-image bases; everything below is a 32-bit offset from them
+  const float* src_img = d.src + (long long)n * d.h * d.w * d.src_ld + tv * 4;
+  uint8_t* dst8 = (OUT == ACT_OUT_U8) ? d.dst_u8 + (long long)n * npix_dst * d.dst_c + d.dst_c_off + tv * 4 : nullptr;
+  __half* dsth = (OUT == ACT_OUT_H16) ? static_cast<__half*>(d.dst_hi) + (long long)n * npix_dst * d.dst_h_ld + tv * 4 : nullptr;
+  __half* dstl = (OUT == ACT_OUT_H16) ? static_cast<__half*>(d.dst_lo) + (long long)n * npix_dst * d.dst_h_ld + tv * 4 : nullptr;
+  float* dstf = (OUT == ACT_OUT_F32) ? d.dst_f32 + (long long)n * npix_dst * d.dst_ld + tv * 4 : nullptr;
+  const unsigned src_ld = (unsigned)d.src_ld, vstep = (unsigned)P.tv * 4u;
+  const int p0 = blockIdx.x * P.pix_per_cta;
+  const int p1 = min(p0 + P.pix_per_cta, P.out_h * W);
+  const int k = P.k;
+  int pix = p0 + tp;
+  int oy = pix / W, ox = pix - oy * W;
+  for (; pix < p1; pix += U * k) {
+    float4 f[U][R];
+    unsigned doff[U];
+    bool ok[U];
+    int oy_u = oy, ox_u = ox;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      ok[u] = pix + u * k < p1;
+      const unsigned spix = up ? (unsigned)((oy_u >> 1) * d.w + (ox_u >> 1)) : (unsigned)(pix + u * k);
+      const unsigned dpix = (unsigned)((oy_u + halo) * Wp + ox_u + halo);
+      doff[u] = OUT == ACT_OUT_U8 ? dpix * (unsigned)d.dst_c : OUT == ACT_OUT_H16 ? dpix * (unsigned)d.dst_h_ld : dpix * (unsigned)d.dst_ld;
+#pragma unroll
+      for (int j = 0; j < R; ++j)
+        f[u][j] = ok[u] ? *reinterpret_cast<const float4*>(src_img + spix * src_ld + j * vstep) : make_float4(0.f, 0.f, 0.f, 0.f);
+      ox_u += k;
+      while (ox_u >= W) ox_u -= W, ++oy_u;
+    }
+    oy = oy_u, ox = ox_u;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+        float t[4] = {f[u][j].x, f[u][j].y, f[u][j].z, f[u][j].w};
+        if (GN) {
+          t[0] = fmaf(t[0], ga[j].x, gb[j].x), t[1] = fmaf(t[1], ga[j].y, gb[j].y);
+          t[2] = fmaf(t[2], ga[j].z, gb[j].z), t[3] = fmaf(t[3], ga[j].w, gb[j].w);
+        }
+        if (SILU) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) t[e] = silu_fast(t[e]);
+        }
+        if (!ok[u]) continue;
+        if (OUT == ACT_OUT_U8) {
+          // fast rounding of the four codes; ONE test whether any of them sits within 2e-4 of a rounding boundary (the fast
+          // value is within 1e-4 of the reference's pre-rounding value), and only then the exact divisions
+          float m[4];
+          bool slow = false;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float r = fminf(fmaxf(fmaf(t[e], inv, zp), 0.f), 255.f);
+            m[e] = __fadd_rn(r, 12582912.f);
+            slow |= fabsf(r - __fsub_rn(m[e], 12582912.f)) > 0.4998f;
+          }
+          if (slow) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) m[e] = quant_slow(t[e], delta, zp);
+          }
+          const uint32_t lo = __byte_perm(__float_as_uint(m[0]), __float_as_uint(m[1]), 0x0040);
+          const uint32_t hi = __byte_perm(__float_as_uint(m[2]), __float_as_uint(m[3]), 0x0040);
+          *reinterpret_cast<uint32_t*>(dst8 + doff[u] + j * vstep) = __byte_perm(lo, hi, 0x5410);
+        } else if (OUT == ACT_OUT_H16) {
+          uint2 h, l;
+          split_h16x4(t, h, l);
+          *reinterpret_cast<uint2*>(dsth + doff[u] + j * vstep) = h;
+          *reinterpret_cast<uint2*>(dstl + doff[u] + j * vstep) = l;
+        } else {
+          *reinterpret_cast<float4*>(dstf + doff[u] + j * vstep) = make_float4(t[0], t[1], t[2], t[3]);
+        }
+      }
+    }
+  }
+  if (OUT == ACT_OUT_U8 && halo) {
+    // zero-point border: pixel b of the ring, b in [0, 2 Wp + 2 out_h): top row, bottom row, left column, right column
+    const int nborder = 2 * Wp + 2 * P.out_h;
+    const int b0 = blockIdx.x * P.border_per_cta, b1 = min(b0 + P.border_per_cta, nborder);
+    const uint32_t zfill = (uint32_t)zp * 0x01010101u;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = (blockDim.x + 31) >> 5;
+    const int nvec = c >> 2;
+    for (int b = b0 + warp; b < b1; b += nwarp) {
+      int yy, xx;
+      if (b < Wp) yy = 0, xx = b;
+      else if (b < 2 * Wp) yy = P.out_h + 1, xx = b - Wp;
+      else if (b < 2 * Wp + P.out_h) yy = b - 2 * Wp + 1, xx = 0;
+      else yy = b - 2 * Wp - P.out_h + 1, xx = Wp - 1;
+      uint32_t* o8 = reinterpret_cast<uint32_t*>(d.dst_u8 + ((long long)n * npix_dst + (long long)yy * Wp + xx) * d.dst_c + d.dst_c_off);
       for (int v = lane; v < nvec; v += 32) o8[v] = zfill;
     }
   }
@@ -560,8 +741,10 @@ extern "C" int tfmq_gn_stats_part(tfmq_ctx* ctx, const float* x, int64_t ld, int
   if (chunks < 1) chunks = 1;
   const int ppc = (hw + chunks - 1) / chunks;
   chunks = (hw + ppc - 1) / ppc;
+  const int nvec = c / 4;
+  const int tvn = nvec < GN_THREADS ? nvec : GN_THREADS, k = nvec < GN_THREADS ? GN_THREADS / nvec : 1;   // thread grid tvn x k
   gn_stats_kernel<<<dim3(chunks, n), GN_THREADS, 2 * c * sizeof(double), tfmq_stream(stream)>>>(
-      x, ld, hw, c, groups, ppc, stats, target->cpg, target->ch_off);
+      x, ld, hw, c, groups, ppc, stats, target->cpg, target->ch_off, tvn, k);
   TFMQ_LAUNCH_CHECK("gn_stats");
   return TFMQ_OK;
 }
@@ -596,6 +779,58 @@ extern "C" int tfmq_act_prepare(tfmq_ctx* ctx, const tfmq_act_desc* d, void* str
     TFMQ_REQUIRE(!d->upsample, TFMQ_ERR_ARG, "act_prepare: GN with upsample unsupported");
   }
   if (d->n == 0) return TFMQ_OK;
+  // vector-stationary kernel: c / 4 = R * tv with tv <= 256 threads along the channel axis, R in {1, 2}; every offset inside
+  // one image must fit 32 bits
+  static const bool stat_env = !(getenv("TFMQ_ACT_STAT") && atoi(getenv("TFMQ_ACT_STAT")) == 0);
+  {
+    const int nvec = d->c / 4;
+    const int R = nvec <= ACT_THREADS ? 1 : 2;
+    const long long out_h = d->upsample ? 2 * d->h : d->h, out_w = d->upsample ? 2 * d->w : d->w;
+    const int halo_s = d->dst_u8 ? d->halo : 0;
+    const long long dst_pitch = d->dst_u8 ? d->dst_c : d->dst_hi ? d->dst_h_ld : d->dst_ld;
+    const bool fits = (long long)d->h * d->w * d->src_ld < (1ll << 31) &&
+                      (out_h + 2 * halo_s) * (out_w + 2 * halo_s) * dst_pitch < (1ll << 31);
+    if (stat_env && !d->ln_gamma && !d->geglu && nvec % R == 0 && nvec / R <= ACT_THREADS && fits) {
+      ActStatParams S;
+      S.d = *d;
+      S.out_h = (int)out_h, S.out_w = (int)out_w;
+      S.tv = nvec / R;
+      S.k = ACT_THREADS / S.tv;
+      const int threads = S.tv * S.k;
+      static const int stat_mult = getenv("TFMQ_ACT_CTAS") ? atoi(getenv("TFMQ_ACT_CTAS")) : 4;   // measured best of 3..8 (tools/microbench_act.py)
+      const int npix_s = (int)(out_h * out_w);
+      int chunks = (ctx->sm_count * stat_mult + d->n - 1) / d->n;
+      int ppc = (npix_s + chunks - 1) / chunks;
+      static const int stat_u = getenv("TFMQ_ACT_INFLIGHT") ? atoi(getenv("TFMQ_ACT_INFLIGHT")) : 4;
+      const int U = (R == 1 && stat_u == 4) ? 4 : 2;               // pixels in flight per thread
+      ppc = (ppc + U * S.k - 1) / (U * S.k) * (U * S.k);           // whole passes of U k pixels
+      chunks = (npix_s + ppc - 1) / ppc;
+      S.pix_per_cta = ppc;
+      const int nborder = halo_s ? 2 * (S.out_w + 2) + 2 * S.out_h : 0;
+      S.border_per_cta = (nborder + chunks - 1) / chunks;
+      S.inv_cnt = d->gn_stats ? 1.0 / ((double)(d->c / d->groups) * d->h * d->w) : 0.0;
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(chunks, d->n), cfg.blockDim = dim3(threads);
+      cfg.dynamicSmemBytes = d->gn_stats ? 2 * (size_t)d->c * sizeof(float) : 0, cfg.stream = tfmq_stream(stream);
+      cudaLaunchAttribute attr[1];
+      cfg.attrs = attr, cfg.numAttrs = (unsigned)tfmq_pdl_attr(&attr[0]);
+      const int out = d->dst_u8 ? ACT_OUT_U8 : d->dst_hi ? ACT_OUT_H16 : ACT_OUT_F32;
+      cudaError_t e;
+#define STAT_BY_OUT_R(GN, SILU, RR, UU)                                                                \
+  (out == ACT_OUT_U8 ? cudaLaunchKernelEx(&cfg, act_stat_kernel<GN, SILU, ACT_OUT_U8, RR, UU>, S)     \
+   : out == ACT_OUT_H16 ? cudaLaunchKernelEx(&cfg, act_stat_kernel<GN, SILU, ACT_OUT_H16, RR, UU>, S) \
+                        : cudaLaunchKernelEx(&cfg, act_stat_kernel<GN, SILU, ACT_OUT_F32, RR, UU>, S))
+#define STAT_BY_OUT(GN, SILU) \
+  (R == 2 ? STAT_BY_OUT_R(GN, SILU, 2, 2) : U == 4 ? STAT_BY_OUT_R(GN, SILU, 1, 4) : STAT_BY_OUT_R(GN, SILU, 1, 2))
+      if (d->gn_stats) e = d->silu ? STAT_BY_OUT(true, true) : STAT_BY_OUT(true, false);
+      else e = d->silu ? STAT_BY_OUT(false, true) : STAT_BY_OUT(false, false);
+#undef STAT_BY_OUT
+#undef STAT_BY_OUT_R
+      if (e != cudaSuccess) return tfmq_fail(ctx, TFMQ_ERR_CUDA, "act_prepare: launch: %s", cudaGetErrorString(e));
+      TFMQ_LAUNCH_CHECK("act_prepare");
+      return TFMQ_OK;
+    }
+  }
   static const bool flat_env = !(getenv("TFMQ_ACT_FLAT") && atoi(getenv("TFMQ_ACT_FLAT")) == 0);   // 0: the warp-per-pixel kernel
   const long long out_pix = (long long)(d->upsample ? 4 : 1) * d->h * d->w;
   // (the multiply-high divisions are exact while dividend * divisor < 2^32)
@@ -616,7 +851,9 @@ extern "C" int tfmq_act_prepare(tfmq_ctx* ctx, const tfmq_act_desc* d, void* str
     F.vec_total = (unsigned)(out_pix * F.nvec);
     static const int flat_mult = getenv("TFMQ_ACT_CTAS") ? atoi(getenv("TFMQ_ACT_CTAS")) : 8;
     int chunks = (ctx->sm_count * flat_mult + d->n - 1) / d->n;
-    const unsigned gran = ACT_THREADS * ACT_UNROLL;
+    static const int unroll_env = getenv("TFMQ_ACT_UNROLL") ? atoi(getenv("TFMQ_ACT_UNROLL")) : ACT_UNROLL_DEFAULT;
+    const int unroll = unroll_env == 4 ? 4 : 2;                  // float4 vectors in flight per thread
+    const unsigned gran = ACT_THREADS * (unsigned)unroll;
     unsigned vpc = (F.vec_total + chunks - 1) / chunks;
     vpc = (vpc + gran - 1) / gran * gran;
     chunks = (int)((F.vec_total + vpc - 1) / vpc);
@@ -632,13 +869,15 @@ extern "C" int tfmq_act_prepare(tfmq_ctx* ctx, const tfmq_act_desc* d, void* str
     cfg.attrs = attr, cfg.numAttrs = (unsigned)tfmq_pdl_attr(&attr[0]);
     const int out = d->dst_u8 ? ACT_OUT_U8 : d->dst_hi ? ACT_OUT_H16 : ACT_OUT_F32;
     cudaError_t e;
-#define FLAT_BY_OUT(GN, SILU)                                                                        \
-  (out == ACT_OUT_U8 ? cudaLaunchKernelEx(&cfg, act_flat_kernel<GN, SILU, ACT_OUT_U8>, F)           \
-   : out == ACT_OUT_H16 ? cudaLaunchKernelEx(&cfg, act_flat_kernel<GN, SILU, ACT_OUT_H16>, F)       \
-                        : cudaLaunchKernelEx(&cfg, act_flat_kernel<GN, SILU, ACT_OUT_F32>, F))
+#define FLAT_BY_OUT_U(GN, SILU, U)                                                                   \
+  (out == ACT_OUT_U8 ? cudaLaunchKernelEx(&cfg, act_flat_kernel<GN, SILU, ACT_OUT_U8, U>, F)        \
+   : out == ACT_OUT_H16 ? cudaLaunchKernelEx(&cfg, act_flat_kernel<GN, SILU, ACT_OUT_H16, U>, F)    \
+                        : cudaLaunchKernelEx(&cfg, act_flat_kernel<GN, SILU, ACT_OUT_F32, U>, F))
+#define FLAT_BY_OUT(GN, SILU) (unroll == 4 ? FLAT_BY_OUT_U(GN, SILU, 4) : FLAT_BY_OUT_U(GN, SILU, 2))
     if (d->gn_stats) e = d->silu ? FLAT_BY_OUT(true, true) : FLAT_BY_OUT(true, false);
     else e = d->silu ? FLAT_BY_OUT(false, true) : FLAT_BY_OUT(false, false);
 #undef FLAT_BY_OUT
+#undef FLAT_BY_OUT_U
     if (e != cudaSuccess) return tfmq_fail(ctx, TFMQ_ERR_CUDA, "act_prepare: launch: %s", cudaGetErrorString(e));
     TFMQ_LAUNCH_CHECK("act_prepare");
     return TFMQ_OK;
