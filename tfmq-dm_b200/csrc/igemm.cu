@@ -45,9 +45,10 @@ __device__ __forceinline__ float2 chunk_col_partial(const uint8_t* buf, int et) 
   return make_float2(s1, s2);
 }
 
-template <int MODE>
+template <int MODE, int CG>
 __device__ __forceinline__ void umma_fp(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-  if (MODE == MODE_F16) umma_f16(tmem_d, adesc, bdesc, idesc, acc);
+  if (MODE == MODE_F16 && CG == 2) umma_f16_2cta(tmem_d, adesc, bdesc, idesc, acc);
+  else if (MODE == MODE_F16) umma_f16(tmem_d, adesc, bdesc, idesc, acc);
   else umma_tf32(tmem_d, adesc, bdesc, idesc, acc);
 }
 
@@ -111,7 +112,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const int tiles_n = p.cout / p.tile_n;
   // CG == 2: a cluster of two CTAs (one TPC) works on two M-adjacent tiles of the same N tile with
   // tcgen05.mma.cta_group::2 (M = 256): every CTA stages its own 128 pixels of A but only HALF of the N rows of B.
-  static_assert(CG == 1 || MODE == MODE_W4A8, "the CTA-pair path exists for the w4a8 mode");
+  // (the fp16-split mode as a pair: each CTA's TMA producer loads its own A planes and HALF of the weight rows of both B planes;
+  //  the UMMAs then read 7.5 KB instead of 11 KB of shared memory per K = 16 step and CTA)
+  static_assert(CG == 1 || MODE == MODE_W4A8 || MODE == MODE_F16, "the CTA-pair path exists for the w4a8 and fp16-split modes");
   const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
   const int unit0 = (CG == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;     // cluster (or CTA) index
   const int nunits = (CG == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
@@ -142,7 +145,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       }
     } else {
       for (int s = 0; s < S; ++s) {
-        mbar_init(&full_tma[s], 1);
+        mbar_init(&full_tma[s], (CG == 2 && rank == 0) ? 2 : 1);   // own TMA (+ the peer's "my tiles landed" arrive)
         mbar_init(&full_xf[s], IGEMM_XF_WARPS);
         mbar_init(&empty[s], 1);
       }
@@ -197,7 +200,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     // (whole warp convergent, one elected lane issues: coordinates and addresses stay warp-uniform)
     uint32_t tx_bytes = IGEMM_A_BYTES;          // w4a8: the A tile only (B comes through the transform warps)
     if (MODE == MODE_I8) tx_bytes += (uint32_t)p.tile_n * 128u;
-    if (FP) tx_bytes += (uint32_t)p.tile_n * 128u * (need_b_lo ? 2u : 1u);
+    if (FP) tx_bytes += (uint32_t)b_rows * 128u * (need_b_lo ? 2u : 1u);     // CTA pair: this CTA's half of the weight rows
     if (MODE == MODE_F16 && need_a_lo) tx_bytes += IGEMM_A_BYTES;
     int s = 0;
     uint32_t par = 0;
@@ -226,8 +229,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               tma_load_4d(st + p.offA_lo, &tmA2, &full_tma[s], kc * p.kchunk, x0 * p.stride + kx + p.off,
                           y0 * p.stride + ky + p.off, n0);
             if (!W4) {
-              tma_load_2d(st + p.offB, &tmB, &full_tma[s], tap * p.cin + kc * p.kchunk, c_out0);
-              if (need_b_lo) tma_load_2d(st + p.offB_lo, &tmB2, &full_tma[s], tap * p.cin + kc * p.kchunk, c_out0);
+              tma_load_2d(st + p.offB, &tmB, &full_tma[s], tap * p.cin + kc * p.kchunk, c_out0 + p.b_row0[rank]);
+              if (need_b_lo)
+                tma_load_2d(st + p.offB_lo, &tmB2, &full_tma[s], tap * p.cin + kc * p.kchunk, c_out0 + p.b_row0[rank]);
             }
           }
         }
@@ -286,7 +290,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     // without a per-instruction register shuffle; the tensor pipe starves on anything slower.
     const uint32_t umma_n = (uint32_t)p.tile_n + (W4 ? 16u : 0u);
     const uint32_t idesc = (MODE == MODE_TF32)  ? idesc_tf32(128, umma_n)
-                           : (MODE == MODE_F16) ? idesc_f16(128, umma_n)
+                           : (MODE == MODE_F16) ? idesc_f16(128 * CG, umma_n)
                                                 : idesc_i8_u8s8(128 * CG, umma_n);
     const uint32_t smem_base = smem_u32(smem);
     const uint64_t d_a = smem_desc_sw128(smem_base);
@@ -339,17 +343,17 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             if (need_a_lo) {
 #pragma unroll
               for (int k = 0; k < 4; ++k)
-                if (k < nslice) umma_fp<MODE>(tmem_lo, a_lo + 2 * k, b_hi + 2 * k, idesc, (k > 0) | accumulate_lo);
+                if (k < nslice) umma_fp<MODE, CG>(tmem_lo, a_lo + 2 * k, b_hi + 2 * k, idesc, (k > 0) | accumulate_lo);
             }
             if (need_b_lo) {
 #pragma unroll
               for (int k = 0; k < 4; ++k)
                 if (k < nslice)
-                  umma_fp<MODE>(tmem_lo, a_hi + 2 * k, b_lo + 2 * k, idesc, (k > 0) | accumulate_lo | (need_a_lo ? 1u : 0u));
+                  umma_fp<MODE, CG>(tmem_lo, a_hi + 2 * k, b_lo + 2 * k, idesc, (k > 0) | accumulate_lo | (need_a_lo ? 1u : 0u));
             }
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              if (k < nslice) umma_fp<MODE>(tmem_d, a_hi + 2 * k, b_hi + 2 * k, idesc, (k > 0) | accumulate);
+              if (k < nslice) umma_fp<MODE, CG>(tmem_d, a_hi + 2 * k, b_hi + 2 * k, idesc, (k > 0) | accumulate);
           } else {
 #pragma unroll
             for (int k = 0; k < 4; ++k)
@@ -360,7 +364,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           }
           if (CG == 2) {          // slot / accumulator hand-over goes to the same barrier of both CTAs
             umma_commit_2cta(&empty[s], 3);
-            umma_commit_2cta(&empty_u[su], 3);
+            if (W4) umma_commit_2cta(&empty_u[su], 3);
             if (last) umma_commit_2cta(&acc_full[as], 3);
           } else {
             umma_commit(&empty[s]);
@@ -874,7 +878,7 @@ static int launch_igemm(tfmq_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap
     p.stage_bytes = IGEMM_A_BYTES;
     smem = (size_t)stages * IGEMM_A_BYTES + (size_t)p.u_stages * p.u_bytes + (size_t)p.p_stages * p.p_bytes + extra;
   } else {
-    const uint32_t bB = (uint32_t)p.tile_n * 128u;
+    const uint32_t bB = (uint32_t)(CG == 2 ? p.b_rows[0] : p.tile_n) * 128u;   // CTA pair: half of the weight rows per CTA
     uint32_t off = IGEMM_A_BYTES;
     constexpr bool FPM = (MODE == MODE_TF32 || MODE == MODE_F16);
     if (FPM && (p.pass_flags & PASS_LO_HI)) {
@@ -1216,11 +1220,15 @@ extern "C" int tfmq_conv_h16(tfmq_ctx* ctx, const tfmq_conv_h16_desc* d, void* s
   p.ksize = d->ksize, p.stride = d->stride, p.off = d->ksize == 3 ? -d->pad_lo : 0;
   p.th = g.th, p.tw = g.tw, p.tn = g.tn;
   const int nkb_est = d->ksize * d->ksize * ((d->cin + 63) / 64);
+  // CTA pairs (cta_group::2, M = 256) whenever the M tiles pair up and split-K is off; TFMQ_IGEMM_F16_CG=1 forces single CTAs
+  static const int f16_cg_env = getenv("TFMQ_IGEMM_F16_CG") ? atoi(getenv("TFMQ_IGEMM_F16_CG")) : 2;
+  int cg = 1;
   {
     // two accumulator stages (each main + small-terms) need tile_n <= 128
     const int tiles_m = (d->out_w / g.tw) * (d->out_h / g.th) * ((d->n + g.tn - 1) / g.tn);
     const int limit = nkb_est < 24 ? 128 : 256;
-    p.tile_n = pick_tile_n_balanced(d->cout, limit, tiles_m, nkb_est, ctx->sm_count, 300.0, 6.0, planes ? 32 : 16);
+    if (f16_cg_env == 2 && tiles_m % 2 == 0 && ctx->sm_count % 2 == 0 && (d->ksplit == 0 || d->ksplit == 1)) cg = 2;
+    p.tile_n = pick_tile_n_balanced(d->cout, limit, tiles_m / cg, nkb_est, ctx->sm_count / cg, 300.0, 6.0, planes ? 32 : 16);
     if (d->ksplit != 0 && d->ksplit != 1) {
       // split-K: the widest N tile (fewest re-reads of the pixel operand), and as many K ranges as it takes to give every
       // SM a unit (ksplit < 0: chosen here), each at least 8 k-blocks long
@@ -1278,13 +1286,15 @@ extern "C" int tfmq_conv_h16(tfmq_ctx* ctx, const tfmq_conv_h16_desc* d, void* s
     }
     cuuint64_t dims[2] = {kk, (cuuint64_t)d->cout};
     cuuint64_t str[1] = {kk * 2};
-    cuuint32_t box[2] = {64, (cuuint32_t)p.tile_n};
+    cuuint32_t box[2] = {64, (cuuint32_t)(p.tile_n / cg)};       // CTA pair: each CTA loads half of the weight rows
     cuuint32_t es[2] = {1, 1};
     int rc = encode(ctx, i ? &tmB2 : &tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, w, dims, str, box, es,
                     CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
-  int rc = launch_igemm<MODE_F16, 1>(ctx, tmA, tmA2, tmB, tmB2, p, tfmq_stream(stream), "conv_h16");
+  if (cg == 2) p.b_rows[0] = p.b_rows[1] = p.tile_n / 2, p.b_row0[0] = 0, p.b_row0[1] = p.tile_n / 2;
+  int rc = cg == 2 ? launch_igemm<MODE_F16, 2>(ctx, tmA, tmA2, tmB, tmB2, p, tfmq_stream(stream), "conv_h16")
+                   : launch_igemm<MODE_F16, 1>(ctx, tmA, tmA2, tmB, tmB2, p, tfmq_stream(stream), "conv_h16");
   for (int i = 0; rc == TFMQ_OK && !fuse_stats && i < d->n_stat; ++i)
     rc = tfmq_gn_stats_part(ctx, d->out, d->out_ld, d->n, d->out_h * d->out_w, d->cout, &d->stat[i], stream);
   return rc;
