@@ -1227,7 +1227,12 @@ extern "C" int tfmq_conv_h16(tfmq_ctx* ctx, const tfmq_conv_h16_desc* d, void* s
     // two accumulator stages (each main + small-terms) need tile_n <= 128
     const int tiles_m = (d->out_w / g.tw) * (d->out_h / g.th) * ((d->n + g.tn - 1) / g.tn);
     const int limit = nkb_est < 24 ? 128 : 256;
-    if (f16_cg_env == 2 && tiles_m % 2 == 0 && ctx->sm_count % 2 == 0 && (d->ksplit == 0 || d->ksplit == 1)) cg = 2;
+    // measured per layer (profiles/r2l_conv_layers.md): pairs win where the main loop dominates (3x3 convs, K >= 896, the wide
+    // qkv projections: 74 -> 67 us) and lose 5-15 % on the epilogue-bound 1x1 convs with K <= 672 and N <= 672
+    static const int f16_cg_kb = getenv("TFMQ_IGEMM_F16_CG_KB") ? atoi(getenv("TFMQ_IGEMM_F16_CG_KB")) : 14;
+    if (f16_cg_env == 2 && tiles_m % 2 == 0 && ctx->sm_count % 2 == 0 && (d->ksplit == 0 || d->ksplit == 1) &&
+        (nkb_est >= f16_cg_kb || d->cout >= 1344))
+      cg = 2;
     p.tile_n = pick_tile_n_balanced(d->cout, limit, tiles_m / cg, nkb_est, ctx->sm_count / cg, 300.0, 6.0, planes ? 32 : 16);
     if (d->ksplit != 0 && d->ksplit != 1) {
       // split-K: the widest N tile (fewest re-reads of the pixel operand), and as many K ranges as it takes to give every
