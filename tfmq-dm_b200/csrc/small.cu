@@ -126,10 +126,13 @@ __global__ void __launch_bounds__(LIN_THREADS) linear_grouped_kernel(const tfmq_
   linear_small_body<LIN_GROUP_OUT_PER_CTA>(d, blockIdx.x - cta_start[l], blockIdx.y, xs);
 }
 
-// conv_in: NCHW (cin<=4) -> NHWC, 3x3 pad 1.  CTA = 16 pixels x 16 channel groups; weights transposed in
-// smem as ws[tap*cin][cout] so each thread reads float4 of 4 consecutive output channels.
-constexpr int CIN_PIX = 16;
-constexpr int CIN_GROUPS = 8;     // pixel groups per CTA: the transposed weight staging is shared by 128 pixels
+// conv_in: NCHW (cin<=4) -> NHWC, 3x3 pad 1.  Weights transposed in smem as ws[tap*cin][cout] so a thread reads float4 of 4
+// consecutive output channels.  A thread owns FOUR consecutive pixels of an image row x 4 output channels per pass: one
+// weight float4 feeds 16 FMAs (with one pixel per thread the kernel was bound by shared-memory bandwidth: 27 LDS.128 per 108
+// FMAs, four wavefronts each: 97 us for a 59 MB output), the 3 x 6 input window of the four pixels lives in registers.
+constexpr int CIN_PIX = 16;       // pixel quads per CTA pass (x 16 channel groups = 256 threads)
+constexpr int CIN_GROUPS = 4;     // passes per CTA: the transposed weight staging is shared by 256 pixels
+constexpr int CIN_Q = 4;          // pixels per thread
 __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                       const float* __restrict__ bias, int n, int h, int wd, int cin,
                                                       int cout, float* __restrict__ out, long long out_ld) {
@@ -140,45 +143,57 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ 
     ws[k * cout + co] = w[i];
   }
   __syncthreads();
-  const long long total = (long long)n * h * wd;
+  const int qpr = (wd + CIN_Q - 1) / CIN_Q;                     // pixel quads per image row
+  const long long total_q = (long long)n * h * qpr;
   const int cg = threadIdx.x & 15;
   for (int grp = 0; grp < CIN_GROUPS; ++grp) {
-  const long long pix = ((long long)blockIdx.x * CIN_GROUPS + grp) * CIN_PIX + (threadIdx.x >> 4);
-  if (pix >= total) return;
-  const int xx = (int)(pix % wd);
-  const int yy = (int)((pix / wd) % h);
-  const int nn = (int)(pix / ((long long)wd * h));
-  float in[36];
+    const long long q = ((long long)blockIdx.x * CIN_GROUPS + grp) * CIN_PIX + (threadIdx.x >> 4);
+    if (q >= total_q) return;
+    const int x0 = (int)(q % qpr) * CIN_Q;
+    const int yy = (int)((q / qpr) % h);
+    const int nn = (int)(q / ((long long)qpr * h));
+    float in[4][3][CIN_Q + 2];                  // [ci][ky][column x0 - 1 ... x0 + 4]
 #pragma unroll
-  for (int k = 0; k < 36; ++k) in[k] = 0.f;
-#pragma unroll
-  for (int ci = 0; ci < 4; ++ci) {
-    if (ci < cin) {
-      const float* xp = x + ((long long)nn * cin + ci) * h * wd;
+    for (int ci = 0; ci < 4; ++ci) {
+      const float* xp = x + ((long long)nn * cin + (ci < cin ? ci : 0)) * h * wd;
 #pragma unroll
       for (int ky = 0; ky < 3; ++ky) {
         const int y = yy + ky - 1;
 #pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-          const int xq = xx + kx - 1;
-          if (y >= 0 && y < h && xq >= 0 && xq < wd) in[ci * 9 + ky * 3 + kx] = xp[(long long)y * wd + xq];
+        for (int j = 0; j < CIN_Q + 2; ++j) {
+          const int xq = x0 + j - 1;
+          in[ci][ky][j] = (ci < cin && y >= 0 && y < h && xq >= 0 && xq < wd) ? xp[(long long)y * wd + xq] : 0.f;
         }
       }
     }
-  }
-  for (int co = cg * 4; co < cout; co += 64) {
-    float4 acc = bias ? *reinterpret_cast<const float4*>(bias + co) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const long long pix0 = ((long long)nn * h + yy) * wd + x0;
+    for (int co = cg * 4; co < cout; co += 64) {
+      const float4 b4 = bias ? *reinterpret_cast<const float4*>(bias + co) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 acc[CIN_Q];
 #pragma unroll
-    for (int k = 0; k < 36; ++k) {
-      if (k < K) {
-        const float4 w4 = *reinterpret_cast<const float4*>(ws + k * cout + co);
-        const float v = in[k];
-        acc.x = fmaf(v, w4.x, acc.x), acc.y = fmaf(v, w4.y, acc.y);
-        acc.z = fmaf(v, w4.z, acc.z), acc.w = fmaf(v, w4.w, acc.w);
+      for (int p = 0; p < CIN_Q; ++p) acc[p] = b4;
+#pragma unroll
+      for (int ci = 0; ci < 4; ++ci) {
+        if (ci < cin) {
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+              const float4 w4 = *reinterpret_cast<const float4*>(ws + (ci * 9 + ky * 3 + kx) * cout + co);
+#pragma unroll
+              for (int p = 0; p < CIN_Q; ++p) {
+                const float v = in[ci][ky][p + kx];
+                acc[p].x = fmaf(v, w4.x, acc[p].x), acc[p].y = fmaf(v, w4.y, acc[p].y);
+                acc[p].z = fmaf(v, w4.z, acc[p].z), acc[p].w = fmaf(v, w4.w, acc[p].w);
+              }
+            }
+          }
+        }
       }
+#pragma unroll
+      for (int p = 0; p < CIN_Q; ++p)
+        if (x0 + p < wd) *reinterpret_cast<float4*>(out + (pix0 + p) * out_ld + co) = acc[p];
     }
-    *reinterpret_cast<float4*>(out + pix * out_ld + co) = acc;
-  }
   }
 }
 
@@ -257,17 +272,21 @@ __global__ void __launch_bounds__(256) conv_out_row8_kernel(const float* __restr
   float4 acc[8];
 #pragma unroll
   for (int p = 0; p < 8; ++p) acc[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+  // (addressing in 32-bit offsets from one 64-bit row pointer, bounds tests only on the two edge columns: the version with a
+  //  64-bit multiply and two compares per load executed ~410 instructions per (row, channel) step for 96 FMAs)
+  const int ld = (int)x_ld;
+  const bool left = x0 > 0, right = x0 + 8 < wd;
   for (int ky = 0; ky < 3; ++ky) {
     const int y = yy + ky - 1;
     if (y < 0 || y >= h) continue;
-    const float* row = x + (((long long)nn * h + y) * wd) * x_ld;
+    const float* row = x + (((long long)nn * h + y) * wd + x0) * x_ld;      // column x0 of the input row
     for (int ci = lane; ci < cin; ci += 32) {
+      const float* pc = row + ci;
       float v[10];
+      v[0] = left ? pc[-ld] : 0.f;
 #pragma unroll
-      for (int j = 0; j < 10; ++j) {
-        const int xq = x0 + j - 1;
-        v[j] = (xq >= 0 && xq < wd) ? row[(long long)xq * x_ld + ci] : 0.f;
-      }
+      for (int j = 1; j < 9; ++j) v[j] = pc[(j - 1) * ld];
+      v[9] = right ? pc[8 * ld] : 0.f;
 #pragma unroll
       for (int kx = 0; kx < 3; ++kx) {
         const float4 w4 = w4s[(ky * 3 + kx) * cin + ci];
@@ -425,7 +444,8 @@ extern "C" int tfmq_conv_in(tfmq_ctx* ctx, const float* x_nchw, const float* w, 
                "conv_in: out / bias must be 16-byte aligned");
   const long long total = (long long)n * h * wd;
   if (total == 0) return TFMQ_OK;
-  conv_in_kernel<<<(unsigned)((total + CIN_PIX * CIN_GROUPS - 1) / (CIN_PIX * CIN_GROUPS)), 256, smem_in,
+  const long long total_q = (long long)n * h * ((wd + CIN_Q - 1) / CIN_Q);       // pixel quads
+  conv_in_kernel<<<(unsigned)((total_q + CIN_PIX * CIN_GROUPS - 1) / (CIN_PIX * CIN_GROUPS)), 256, smem_in,
                    tfmq_stream(stream)>>>(x_nchw, w, bias, n, h, wd, cin, cout, out, out_ld);
   TFMQ_LAUNCH_CHECK("conv_in");
   return TFMQ_OK;
