@@ -136,12 +136,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         mbar_init(&empty[s], 1);
       }
       for (int s = 0; s < SU; ++s) {
-        mbar_init(&full_xf[s], IGEMM_XF_GROUP_WARPS * CG);         // one transform group, of both CTAs of a pair
+        mbar_init(&full_xf[s], p.xf_gw * CG);                      // one transform group, of both CTAs of a pair
         mbar_init(&empty_u[s], 1);
       }
       for (int s = 0; s < SP; ++s) {
         mbar_init(&full_p[s], 1);
-        mbar_init(&empty_p[s], IGEMM_XF_GROUP_WARPS);
+        mbar_init(&empty_p[s], p.xf_gw);
       }
     } else {
       for (int s = 0; s < S; ++s) {
@@ -396,16 +396,21 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       // warps work on alternate k-blocks (ring depths are even, so a group sees consecutive phases of every barrier
       // it waits on).  Codes stay unsigned (0..15): two ANDs and a shift per word; the zero point is folded out
       // through the ones row.  Thread tg of a group owns pieces (row (tg >> 2) + 16 i, K slice tg & 3).
-      constexpr int NP = (CG == 2) ? 8 : 15;            // pieces per thread: ceil(max rows / 16)
-      const int grp = (warp - IGEMM_WARP_XF0) / IGEMM_XF_GROUP_WARPS;
-      const int tg = threadIdx.x - (IGEMM_WARP_XF0 + grp * IGEMM_XF_GROUP_WARPS) * 32;
+      // Group width GW (p.xf_gw): two warps per group for wide tiles; for narrow tiles (<= 64 weight rows per CTA) FOUR groups
+      // of one warp each take every fourth k-block -- a k-block of a 64-wide tile is a latency chain (wait for the packed tile,
+      // LDS, wait for a free s8 slot, STS, proxy fence, arrive) of ~1000 clocks per group, so the number of groups in flight,
+      // not the unpack work, sets the k-block rate of the small-map layers.  A group pass covers RP = 8 GW rows.
+      constexpr int NP = (CG == 2) ? 8 : 15;            // pieces per thread: ceil(max rows / RP)
+      const int GW = p.xf_gw, RP = 8 * GW;
+      const int grp = (warp - IGEMM_WARP_XF0) / GW;
+      const int tg = threadIdx.x - (IGEMM_WARP_XF0 + grp * GW) * 32;
       const int sub = tg & 3, row0 = tg >> 2;
       const uint32_t swz = (uint32_t)(row0 & 7);
       const uint32_t rd0 = (uint32_t)row0 * 64u + (uint32_t)sub * 16u;
       const uint32_t wr_lo = (uint32_t)row0 * 128u + (((2u * sub) ^ swz) << 4);
       const uint32_t wr_hi = (uint32_t)row0 * 128u + (((2u * sub + 1u) ^ swz) << 4);
       const uint32_t xf_remote = (CG == 2 && rank != 0) ? mapa_u32(smem_u32(full_xf), 0) : 0u;
-      constexpr int NG = IGEMM_XF_WARPS / IGEMM_XF_GROUP_WARPS;
+      const int NG = IGEMM_XF_WARPS / GW;
       uint32_t it = 0;                                   // k-blocks of this CTA so far (all units)
       int su = 0, sp = 0;
       uint32_t pu = 0, pp = 0;
@@ -422,7 +427,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             if (active) {
 #pragma unroll
               for (int i = 0; i < NP; ++i)
-                if (row0 + 16 * i < b_rows) pk[i] = *reinterpret_cast<const uint4*>(src + i * 1024);
+                if (row0 + RP * i < b_rows) pk[i] = *reinterpret_cast<const uint4*>(src + i * RP * 64);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_p[sp]);    // release: the reads above are ordered before it
@@ -431,14 +436,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             if (active) {
 #pragma unroll
               for (int i = 0; i < NP; ++i) {
-                if (row0 + 16 * i < b_rows) {
+                if (row0 + RP * i < b_rows) {
                   const uint4 k4 = pk[i];
                   uint4 lo, hi;
                   lo.x = k4.x & 0x0F0F0F0Fu, lo.y = k4.y & 0x0F0F0F0Fu, lo.z = k4.z & 0x0F0F0F0Fu, lo.w = k4.w & 0x0F0F0F0Fu;
                   hi.x = (k4.x >> 4) & 0x0F0F0F0Fu, hi.y = (k4.y >> 4) & 0x0F0F0F0Fu;
                   hi.z = (k4.z >> 4) & 0x0F0F0F0Fu, hi.w = (k4.w >> 4) & 0x0F0F0F0Fu;
-                  *reinterpret_cast<uint4*>(dst + wr_lo + i * 2048) = lo;
-                  *reinterpret_cast<uint4*>(dst + wr_hi + i * 2048) = hi;
+                  *reinterpret_cast<uint4*>(dst + wr_lo + i * RP * 128) = lo;
+                  *reinterpret_cast<uint4*>(dst + wr_hi + i * RP * 128) = hi;
                 }
               }
             }
@@ -862,6 +867,14 @@ static int launch_igemm(tfmq_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap
     if (p.u_stages < 2 || p.u_stages > 8 || (p.u_stages & 1) || p.p_stages < 1 || p.p_stages > 8)
       return tfmq_fail(ctx, TFMQ_ERR_ARG, "%s: ring depths (s8 B %d: even, 2..8; packed %d: 1..8)", name, p.u_stages, p.p_stages);
     p.deep_bars = (p.u_stages > 4 || p.p_stages > 4) ? 1 : 0;
+    {
+      // transform groups: four single-warp groups when a pass of 8 rows x NP pieces covers this CTA's weight rows
+      static const int gw_env = getenv("TFMQ_IGEMM_XFGW") ? atoi(getenv("TFMQ_IGEMM_XFGW")) : 0;
+      const int rows = CG == 2 ? (p.b_rows[0] > p.b_rows[1] ? p.b_rows[0] : p.b_rows[1]) : p.tile_n;
+      const int np = CG == 2 ? 8 : 15;
+      p.xf_gw = (rows <= 8 * np && p.u_stages % 4 == 0 && p.p_stages % 4 == 0) ? 1 : 2;
+      if (gw_env == 2) p.xf_gw = 2;
+    }
     deep_extra = p.deep_bars ? 512u : 0u;             // second block of 64 barrier slots
     extra += deep_extra;
     const long long left = (long long)ctx->max_smem_optin - extra - (long long)p.u_stages * p.u_bytes -

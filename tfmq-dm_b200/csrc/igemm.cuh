@@ -35,6 +35,7 @@ struct IgemmParams {
   int epi_bufs;              // epilogue chunk buffers (2, or 3: residual loads two chunks ahead)
   int deep_bars;             // w4a8: ring barrier arrays of 8 slots in a second barrier block (ring depths > 4)
   int kchunk, kslice;  // channels per k-block / per UMMA
+  int xf_gw;                 // w4a8: warps per transform group (2, or 1 for narrow tiles: four groups in flight)
   int u_stages;              // w4a8: slots of the s8 B ring
   uint32_t u_bytes;          // w4a8: bytes per s8 B slot
   int p_stages;              // w4a8: slots of the packed int4 ring
