@@ -303,8 +303,8 @@ def time_w4a8_kernels(eng):
 
 
 def ncu_traffic():
-    """DRAM bytes per launch of the w4a8 conv kernel from the committed `ncu --set full` capture
-    (profiles/r1j_ncu_full_igemm.csv: dram__bytes_read.sum + dram__bytes_write.sum, mean over the captured launches)."""
+    """DRAM bytes per launch of the w4a8 conv kernel from the committed ncu capture (profiles/r2_ncu_full_igemm.csv: every conv
+    launch of one step; dram__bytes_read.sum + dram__bytes_write.sum, mean over the 46 w4a8 launches)."""
     import csv
     name = next((n for n in ("r2_ncu_full_igemm.csv", "r1j_ncu_full_igemm.csv", "r1f_ncu_full_igemm.csv")
                  if os.path.exists(os.path.join(ROOT, "profiles", n))), None)
@@ -317,7 +317,13 @@ def ncu_traffic():
     vals = [(float(x[r]) + float(x[w])) * 1e6 for x in rows[2:] if "igemm_kernel<0" in x[k]]
     if not vals:
         return None, "capture holds no w4a8 launch"
-    return sum(vals) / len(vals), f"mean over {len(vals)} captured w4a8 launches (profiles/{name})"
+    note = f"mean over {len(vals)} captured w4a8 launches (profiles/{name})"
+    if name.startswith("r2_"):
+        note += ("; all 46 launches of one step, the same set algorithmic_bytes_per_launch averages over; DRAM traffic is BELOW the "
+                 "algorithmic bytes because a layer's fp32 output (<= 59 MB) and its u8 input stay in the 126 MB L2 between "
+                 "producer and consumer -- the kernel's memory-side load is its L2 traffic, 293 MB per launch (lts__t_bytes: every "
+                 "A tile is fetched once per tap and per N tile), see DESIGN 7.1")
+    return sum(vals) / len(vals), note
 
 
 def int8_cublas_tops(dev):
