@@ -454,6 +454,42 @@ def recon_golden(iters=50):
     print("recon_trace.pt written")
 
 
+def inout_golden():
+    """The reference's own `save_inout` (quant/data_utill.py:13-55, GetLayerInpOut :109-169) on the small SpatialTransformer
+    UNet after weight-quantiser initialisation: cached inputs and FP outputs of a ResBlock (x, emb), a BasicTransformerBlock
+    (x, context) and the TIB-facing time-embedding layer, symmetric (FP inputs) and asymmetric (inputs seen with the preceding
+    layers weight-quantised), as strided samples + sums."""
+    from ldm.modules.diffusionmodules.openaimodel import UNetModel
+    from quant.data_utill import save_inout
+    from tfmq_b200.host.ldm_unet import sd_mini_config
+    fp = UNetModel(**sd_mini_config()).eval()
+    synth.fill_state_dict(fp, SEED)
+    wq, aq = wq_aq()
+    qnn = QuantModel(fp, wq, aq, cali=True, softmax_a_bit=8, aq_mode=[QMODE.NORMAL.value, QMODE.QDIFF.value])
+    qnn.eval()
+    cali = (synth.latents((16, 4, 16, 16), 173),
+            torch.randint(0, 1000, (16,), generator=torch.Generator().manual_seed(174)).float(), synth.latents((16, 7, 96), 175))
+    qnn.set_quant_state(True, False)
+    with torch.no_grad():
+        qnn(*(d[:8] for d in cali))
+    qnn.disable_out_quantization()
+    stride = 53
+    mods = dict(qnn.model.named_modules())
+
+    def pack(t):
+        t = t.detach().float()
+        return tuple(t.shape), t.flatten()[::stride].clone(), float(t.double().sum()), float(t.double().abs().sum())
+    out = dict(seed=SEED, stride=stride, units={})
+    for name in ("input_blocks.1.0", "input_blocks.1.1.transformer_blocks.0", "middle_block.0", "output_blocks.0.0"):
+        for asym in (False, True):
+            ins, outs = save_inout(qnn, mods[name], cali, asym=asym, use_act=False, batch_size=8, keep_gpu=True)
+            outs = outs if isinstance(outs, tuple) else (outs,)
+            out["units"][(name, asym)] = dict(ins=[pack(t) for t in ins], outs=[pack(t) for t in outs])
+            print(name, "asym" if asym else "sym", [tuple(t.shape) for t in ins], "->", [tuple(t.shape) for t in outs])
+    torch.save(out, os.path.join(HERE, "inout_sdmini.pt"))
+    print("inout_sdmini.pt written")
+
+
 def unet_keys():
     """state_dict keys / shapes of the REFERENCE UNetModel for every supported LDM config (meta device: no weights are
     materialised), and the module list of the reference QuantModel on the small transformer UNet."""
@@ -664,6 +700,8 @@ if __name__ == "__main__":
         plms_golden()
     if "recon" in what:
         recon_golden()
+    if "inout" in what:
+        inout_golden()
     for full in ("sd_v14", "cin256"):
         if full in what:
             full_size_golden(full)

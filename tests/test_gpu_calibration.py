@@ -265,3 +265,43 @@ def test_tc_autograd_declines_unsupported_shapes(dev):
                    dict(stride=(1, 1), padding=(1, 1))) is None
     assert tc_conv(torch.randn(2, 32, 12, 12, device=dev), torch.randn(32, 32, 3, 3, device=dev), None,
                    dict(stride=(1, 1), padding=(1, 1))) is None
+
+
+def test_save_inout_matches_the_reference(dev):
+    """`save_inout` / `GetLayerInpOut` (quant/data_utill.py:13-55, :109-169) -- the cached inputs and FP targets of
+    a reconstruction unit -- against the reference's own function on the same model and data (tests/golden/inout_sdmini.pt, made
+    on the CPU by make_golden.py::inout_golden): a ResBlock (x, emb), a BasicTransformerBlock (x, context), the middle block and
+    an output block over a skip concatenation; symmetric (FP inputs) and asymmetric (inputs seen through the weight-quantised
+    layers before the unit).  Tolerance 2e-5 of the tensor's largest magnitude on every sampled element (fp32 accumulation
+    order of GPU vs CPU kernels; TF32 is off inside QuantModel.calibrating), 1e-6 relative on the sums."""
+    from tfmq_b200.quant.data_utill import save_inout
+    from tfmq_b200.quant.quant_layer import QMODE, Scaler
+    from tfmq_b200.quant.quant_model import QuantModel
+    g = load_golden("inout_sdmini.pt")
+    wq = dict(bits=4, channel_wise=True, scaler=Scaler.MINMAX)
+    aq = dict(bits=8, channel_wise=False, scaler=Scaler.MINMAX, leaf_param=True)
+    qnn = QuantModel(fp_model("sdmini", g["seed"]).to(dev), wq, aq, cali=True, softmax_a_bit=8,
+                     aq_mode=[QMODE.NORMAL.value, QMODE.QDIFF.value]).eval()
+    cali = (synth.latents((16, 4, 16, 16), 173),
+            torch.randint(0, 1000, (16,), generator=torch.Generator().manual_seed(174)).float(), synth.latents((16, 7, 96), 175))
+    qnn.set_quant_state(True, False)
+    with torch.no_grad():
+        qnn(*(d[:8].to(dev) for d in cali))
+    qnn.disable_out_quantization()
+    mods = dict(qnn.model.named_modules())
+    worst = 0.0
+    for (name, asym), want in g["units"].items():
+        ins, outs = save_inout(qnn, mods[name], cali, asym=asym, use_act=False, batch_size=8)
+        outs = outs if isinstance(outs, tuple) else (outs,)
+        assert len(ins) == len(want["ins"]) and len(outs) == len(want["outs"]), (name, asym)
+        for tag, got, ref in [("in", a, b) for a, b in zip(ins, want["ins"])] + [("out", a, b) for a, b in zip(outs, want["outs"])]:
+            shape, sample, s1, s2 = ref
+            t = got.detach().float().cpu()
+            assert tuple(t.shape) == shape, (name, asym, tag, tuple(t.shape), shape)
+            scale = max(sample.abs().max().item(), 1e-6)
+            err = (t.flatten()[::g["stride"]] - sample).abs().max().item() / scale
+            worst = max(worst, err)
+            assert err < 2e-5, (name, asym, tag, err)
+            assert abs(float(t.double().sum()) - s1) <= 1e-6 * max(1.0, s2), (name, asym, tag)
+    print(f"[save_inout] {len(g['units'])} (unit, asym) cases against the reference: worst sampled deviation {worst:.2e} of the "
+          "tensor's largest magnitude")
