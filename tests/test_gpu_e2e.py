@@ -443,6 +443,30 @@ def test_sampler_update_rules_match_the_reference_samplers(dev, name):
         assert err <= 1e-5 * max(1.0, ref.abs().max().item())
 
 
+def test_engine_refuses_hand_set_quantised_attention(dev):
+    """the attention-core quantisers hang on the block's own `use_aq`, which nothing in the reference (or here) ever
+    sets; the step program implements the fp32 attention core.  A block whose flag was set by hand must raise, not be computed
+    differently."""
+    from tfmq_b200.quant.quant_block import QuantAttnBlock
+    from tfmq_b200.quant.quant_layer import QMODE, Scaler
+    from tfmq_b200.quant.quant_model import QuantModel
+    qnn = QuantModel(fp_model("cifar").to(dev), dict(bits=4, channel_wise=True, scaler=Scaler.MINMAX),
+                     dict(bits=8, channel_wise=False, scaler=Scaler.MINMAX, leaf_param=True), cali=False,
+                     aq_mode=[QMODE.NORMAL.value, QMODE.QDIFF.value]).eval()
+    qnn.set_quant_state(True, True)
+    x, t = synth.latents((1, 3, 32, 32), 3).to(dev), torch.zeros(1, device=dev)
+    blocks = [m for m in qnn.model.modules() if isinstance(m, QuantAttnBlock)]
+    assert blocks and not any(b.use_aq for b in blocks)            # set_quant_state(True, True) leaves the block flag alone
+    with torch.no_grad():
+        qnn(x, t)
+        qnn.disable_out_quantization()
+        qnn(x, t)                                                  # the engine runs: fp32 attention core
+        blocks[0].use_aq = True
+        qnn._engine = None
+        with pytest.raises(NotImplementedError, match="use_aq"):
+            qnn(x, t)
+
+
 def test_stochastic_ddim_eta1_matches_the_reference_sampler(dev, monkeypatch):
     """eta > 0 (the README's `-e 1.0` commands): DDIMSampler's sigma_t * noise_like(...) term, plain and with guidance,
     against trajectories of the reference's own DDIMSampler at eta = 1 driven by the stand-in UNet.  The reference drew its

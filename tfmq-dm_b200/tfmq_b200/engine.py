@@ -130,6 +130,19 @@ class _QL:
         self._fp_ready = True
 
 
+def _refuse_quantised_attention(mod, name: str) -> None:
+    """The q / k / v / softmax quantisers of the attention blocks (quant/quant_block.py:226,240,318,350,487,496) are switched by
+    the BLOCK's own `use_aq`, which `set_quant_state` never touches and none of the reference's entry points sets (SURVEY F3);
+    the step program evaluates the attention core in fp32 like the reference then does.  A block on which a caller has set the
+    flag by hand would be computed differently here, so that is an error, not a silent difference."""
+    from .quant.quant_layer import QuantLayer
+    if any(bool(getattr(m, "use_aq", False)) for m in mod.modules() if not isinstance(m, QuantLayer)):
+        raise NotImplementedError(
+            f"StepEngine: attention block {name} has use_aq set (quantised q / k / v / softmax, SURVEY F3); the sm_100a step "
+            "program implements the fp32 attention core the reference's entry points run -- that branch exists in the module "
+            "graph only (`with qnn.calibrating():`)")
+
+
 class StepEngine:
     def __init__(self, qnn, batch: int, act_tables: Optional[Sequence[Dict[str, torch.Tensor]]] = None,
                  timesteps: Optional[Sequence[int]] = None, fp_passes: int = 3, device=None, use_graph: bool = True,
@@ -526,6 +539,7 @@ class StepEngine:
             return out
 
         def attnblock(blk: QuantAttnBlock, x: T) -> T:
+            _refuse_quantised_attention(blk, self._names.get(id(blk), "attn"))
             gn = self._gn(x, blk.norm)
             q = self._qconv(blk.q, x, gn=gn)
             k = self._qconv(blk.k, x, gn=gn)
@@ -610,6 +624,7 @@ class StepEngine:
             return out
 
         def attnblock(blk: QuantAttentionBlock, x: T) -> T:
+            _refuse_quantised_attention(blk, self._names.get(id(blk), "attention"))
             gn = self._gn(x, blk.norm)
             xn = self._fp_input(x, gn)
             heads = blk.num_heads
@@ -656,6 +671,7 @@ class StepEngine:
             """quant_block.cross_attn_forward (reference :212-245) on tokens = NHWC pixels: LayerNorm + quantise feeds the
             q (and, for self-attention, k / v) projections; the attention core is fp32 (the block's own quantisers
             are inert); to_out adds the residual in its epilogue."""
+            _refuse_quantised_attention(att, "cross_attn_forward")
             qt = self._qconv(att.to_q, tok, ln=norm)
             if ctx is None:
                 kt, vt = self._qconv(att.to_k, tok, ln=norm), self._qconv(att.to_v, tok, ln=norm)
