@@ -24,7 +24,7 @@ __device__ __forceinline__ int warp_sum_i(int v) {
 constexpr int LIN_THREADS = 256;
 constexpr int LIN_OUT_PER_CTA = 8;   // one output per warp: many small CTAs, short dependent-load chains
 constexpr int LIN_ROWS = 8;
-constexpr int LIN_GROUP_OUT_PER_CTA = 32;   // grouped launch: the input transform of a CTA is shared by 32 outputs
+constexpr int LIN_GROUP_OUT_PER_CTA = 64;   // grouped launch: the input transform of a CTA (SiLU + exact quantiser: two thirds of the kernel at 32) is shared by 64 outputs
 
 template <int OPC>
 __device__ __forceinline__ void linear_small_body(const tfmq_linear_desc& d, const int bx, const int by, float* xs) {
