@@ -535,7 +535,7 @@ def run_ours(args):
         sampler.join(timeout=2)
 
     shard = {}
-    if world == 8 and not args.no_extra:
+    if (world == 8 or os.environ.get("TFMQ_BENCH_SHARDS") == "1") and not args.no_extra:     # the env switch: dry runs at other N
         # BASELINE configs[2] (SD v1.4 batch 8 over 8 GPUs: 1 prompt x 2 guidance halves per GPU, 50 steps) and configs[4]
         # (cin256 batch 64 over 8 GPUs: 8 classes x 2 per GPU, 250 steps): every rank times its share, max over ranks
         for nm, nb, nsteps in (("sd_v14", 2, 50), ("cin256", 16, 250)):
@@ -545,7 +545,8 @@ def run_ours(args):
                 ms_x, l_x = float("nan"), -1
                 print(f"[rank {rank}] {nm} shard failed: {exc}", file=sys.stderr)
             tt = torch.tensor([ms_x], device=dev)
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             shard[nm] = {"ms_per_step_max_over_ranks": tt.item(), "launches_per_step": l_x, "batch_per_gpu": nb,
                          "images_per_s_8gpu": 8 * (nb // 2) / (nsteps * tt.item() * 1e-3), "steps_per_image": nsteps}
     if rank == 0:
