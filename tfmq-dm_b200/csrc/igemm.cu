@@ -123,7 +123,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   // TMA reduce-adds.  Reductions over the pixel axis (weight gradients) have few output tiles and very long K.
   const int KS = (MODE == MODE_F16) ? p.ksplit : 1;
   const int mn_units = tiles_mu * tiles_n;
-  const int total_units = mn_units * KS;
+  const int total_units = (p.dbg & 64) ? 0 : mn_units * KS;     // dbg 64: timing experiment, prologue + teardown only
   const int b_rows = p.b_rows[rank];       // weight rows of the N tile this CTA stages
   const int kchunks = (p.cin + p.kchunk - 1) / p.kchunk;
   const int taps = p.ksize * p.ksize;
@@ -650,7 +650,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           *reinterpret_cast<uint4*>(rl + pa) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
           *reinterpret_cast<uint4*>(rl + pb) = make_uint4(lw[4], lw[5], lw[6], lw[7]);
         }
-        const bool fold_f32 = !(FP && p.out_planes);
+        const bool fold_f32 = !(FP && p.out_planes) && !(p.dbg & 32);   // dbg 32: timing experiment without the fold
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           if (k < npiece && fold_f32) {
@@ -689,7 +689,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         // the store (and the next residual load) go out BEFORE the statistics pass over the same buffer: the TMA engine
         // works while the warps sum columns, and thread 0's warp is the one every other warp waits for at the next barrier
         if (et == 0) {
-          if (KS > 1) tma_reduce_add_4d(&tmOut, buf, c_out0 + ci * CW, x0, y0, n0);
+          if (p.dbg & 16) {
+            // timing experiment: no store
+          } else if (KS > 1) tma_reduce_add_4d(&tmOut, buf, c_out0 + ci * CW, x0, y0, n0);
           else tma_store_4d(&tmOut, buf, c_out0 + ci * CW, x0, y0, n0);
           if (FP && p.out_planes) tma_store_4d(&tmRes, buf + 128u * 64u, c_out0 + ci * CW, x0, y0, n0);   // lo plane
           tma_store_commit();

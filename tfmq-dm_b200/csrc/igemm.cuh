@@ -64,7 +64,8 @@ struct IgemmParams {
   int n_stat;        // fused GroupNorm statistics of the output
   int stat_imgs;     // images a tile spans when statistics are fused (tn), else 1
   tfmq_gn_target stat[2];
-  int dbg;           // debug: bit0 = producer skips the TMA loads (timing experiments only, TFMQ_IGEMM_DBG)
+  int dbg;           // debug, timing experiments only (TFMQ_IGEMM_DBG): 1 = no TMA loads of A, 8 = no int4 unpack, 16 = no TMA store,
+                     // 32 = no epilogue fold, 64 = prologue + teardown only (tools/epi_probe.py)
   long long* prof;   // debug: per-CTA phase cycle counters [grid][16] (TFMQ_IGEMM_PROF=1), else null
 };
 

@@ -16,18 +16,32 @@ PROF = os.environ.get("TFMQ_IGEMM_PROF") is not None   # kernel prints its phase
 
 
 def timeit(fn, iters=20):
+    """GPU time per call: `iters` calls captured in a CUDA graph and replayed (a Python-side launch of these kernels costs
+    more CPU time than the kernel runs, so back-to-back eager launches measure the host, not the device)."""
     if PROF:
-        iters = 1
-    for _ in range(1 if PROF else 3):
         fn()
+        torch.cuda.synchronize()
+        fn()
+        torch.cuda.synchronize()
+        return 0.0
+    for _ in range(2):
+        fn()
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(graph, stream=side):
+            for _ in range(iters):
+                fn()
+    graph.replay()
     torch.cuda.synchronize()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()
-    for _ in range(iters):
-        fn()
+    for _ in range(3):
+        graph.replay()
     e.record()
     torch.cuda.synchronize()
-    return s.elapsed_time(e) / iters * 1e3
+    return s.elapsed_time(e) / (3 * iters) * 1e3
 
 
 def w4a8(n, h, w, cin, cout, ks, res, emb, stats):
