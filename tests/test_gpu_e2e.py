@@ -181,6 +181,12 @@ def test_cifar_unet_step_and_ddim_trajectory(dev):
     with torch.no_grad():
         e2 = qnn(g["eps"][0][0].to(dev), g["eps"][0][1].to(dev)).cpu()
     assert torch.equal(e2, eng.forward(g["eps"][0][0].to(dev), g["eps"][0][1]).cpu())
+    # a scheduled timestep takes its embedding row from the resident step table; the host-computed upload is bit-identical
+    assert eng._sched_index.get(float(g["eps"][0][1].reshape(-1)[0])) is not None
+    saved, eng._sched_index = eng._sched_index, {}
+    e3 = eng.forward(g["eps"][0][0].to(dev), g["eps"][0][1]).cpu()
+    eng._sched_index = saved
+    assert torch.equal(e2, e3)
     # 50-step DDIM trajectory, eta = 0
     xl = eng.sample(g["x_T"].to(dev)).cpu()
     err = (xl - g["xs_last"]).abs().max().item()

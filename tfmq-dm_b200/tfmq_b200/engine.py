@@ -192,6 +192,7 @@ class StepEngine:
         self.cur[0:2 * L:2] = 1.0
         self.table = None
         self.timesteps = None
+        self._sched_index = {}      # timestep value -> first row of the step table that carries its embedding
 
         # ---- trace the program
         N = batch
@@ -258,6 +259,9 @@ class StepEngine:
             ts = torch.tensor([float(t) for t in timesteps])
             tab[:, self.off_emb:self.off_emb + self.emb_dim] = self.timestep_embedding_cpu(ts)
             self.timesteps = [float(t) for t in timesteps]
+            self._sched_index = {t: k for k, t in reversed(list(enumerate(self.timesteps)))}
+        else:
+            self._sched_index = {}      # the rows carry the current embedding, not one per timestep
         if ddim_coefs is not None:
             rows = torch.tensor(ddim_coefs, dtype=torch.float64).float()
             tab[:, self.off_coef:self.off_coef + 6] = 0.0
@@ -834,7 +838,13 @@ class StepEngine:
             t = torch.as_tensor(t, dtype=torch.float32, device=self.dev).reshape(-1)
             t = t.expand(self.batch) if t.numel() == 1 else t
             tc = t.detach().cpu()
-            self.emb_rows.copy_(self.timestep_embedding_cpu(tc).to(self.dev))
+            # a timestep of the installed schedule: its embedding row is already resident in the step table (computed by the same
+            # host function), so the per-call host sin / cos and the pageable upload are skipped
+            k = self._sched_index.get(float(tc[0])) if bool((tc == tc[0]).all()) else None
+            if k is not None and self.table is not None:
+                self.emb_rows.copy_(self.table[k, self.off_emb:self.off_emb + self.emb_dim].reshape(1, -1).expand(self.batch, -1))
+            else:
+                self.emb_rows.copy_(self.timestep_embedding_cpu(tc).to(self.dev))
         else:
             self._emb_rows_from_cur()
         self._launch(with_update=False)

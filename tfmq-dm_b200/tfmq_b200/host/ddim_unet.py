@@ -18,12 +18,25 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 
+_FREQ: dict = {}
+
+
+def _frequencies(half: int, device) -> torch.Tensor:
+    """The frequency row, evaluated on the host as the reference does and kept per device: no pageable upload per call (a
+    captured reconstruction iteration, quant/reconstruction.py, could not contain one)."""
+    key = (half, str(device))
+    f = _FREQ.get(key)
+    if f is None:
+        f = torch.exp(torch.arange(half, dtype=torch.float32) * -(math.log(10000) / (half - 1))).to(device)
+        _FREQ[key] = f
+    return f
+
+
 def get_timestep_embedding(timesteps: torch.Tensor, embedding_dim: int) -> torch.Tensor:
     """[sin | cos] sinusoid with frequencies exp(-ln(1e4) i / (half-1)) (ddim/models/diffusion.py:6-24)."""
     assert timesteps.dim() == 1
     half = embedding_dim // 2
-    freq = torch.exp(torch.arange(half, dtype=torch.float32) * -(math.log(10000) / (half - 1)))
-    arg = timesteps.float()[:, None] * freq.to(timesteps.device)[None, :]
+    arg = timesteps.float()[:, None] * _frequencies(half, timesteps.device)[None, :]
     emb = torch.cat([arg.sin(), arg.cos()], dim=1)
     return F.pad(emb, (0, 1, 0, 0)) if embedding_dim % 2 == 1 else emb
 

@@ -24,13 +24,26 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 
+_FREQ: dict = {}
+
+
+def _frequencies(half: int, max_period: int, device) -> torch.Tensor:
+    """The frequency row, evaluated on the host as the reference does and kept per device: no pageable upload per call (a
+    captured reconstruction iteration, quant/reconstruction.py, could not contain one)."""
+    key = (half, max_period, str(device))
+    f = _FREQ.get(key)
+    if f is None:
+        f = torch.exp(-math.log(max_period) * torch.arange(0, half, dtype=torch.float32) / half).to(device)
+        _FREQ[key] = f
+    return f
+
+
 def timestep_embedding(timesteps: torch.Tensor, dim: int, max_period: int = 10000, repeat_only: bool = False):
     """[cos | sin] sinusoid, frequencies exp(-ln(max_period) i / half) (ldm/.../util.py:151-171)."""
     if repeat_only:
         return timesteps[:, None].expand(-1, dim)
     half = dim // 2
-    freqs = torch.exp(-math.log(max_period) * torch.arange(0, half, dtype=torch.float32) / half)
-    args = timesteps[:, None].float() * freqs.to(timesteps.device)[None]
+    args = timesteps[:, None].float() * _frequencies(half, max_period, timesteps.device)[None]
     emb = torch.cat([args.cos(), args.sin()], dim=-1)
     if dim % 2:
         emb = torch.cat([emb, torch.zeros_like(emb[:, :1])], dim=-1)

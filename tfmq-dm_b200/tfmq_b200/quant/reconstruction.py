@@ -15,6 +15,7 @@ regulariser by world_size, which is reproduced through lambda * world_size).
 from __future__ import annotations
 
 import logging
+import os
 from typing import List
 
 import torch
@@ -31,6 +32,10 @@ logger = logging.getLogger(__name__)
 # Test hook: when set to a list, every iteration appends its total loss (reconstruction + rounding regulariser,
 # what the reference's LossFunc returns) -- one host sync per iteration, so it stays None outside the parity tests.
 LOSS_TRACE = None
+
+# The iteration body (soft weights, unit forward, loss, backward) as one captured CUDA graph.  TFMQ_RECON_GRAPH=0 runs it eagerly
+# (debugging; same kernels, same order, same results).
+RECON_GRAPH = os.environ.get("TFMQ_RECON_GRAPH", "1") != "0"
 
 
 class _LayerState:
@@ -72,6 +77,8 @@ def _adaround_loop(forward, layers: List[QuantLayer], cached_inputs, cached_outp
     states = [_LayerState(m) for m in layers]
     if not states:
         return
+    from .tc_autograd import trim_buffers
+    trim_buffers()
     dev = states[0].w2d.device
     decay = LinearTempDecay(iters, warmup, b_range[0], b_range[1])
     loss_start = iters * warmup
@@ -82,16 +89,29 @@ def _adaround_loop(forward, layers: List[QuantLayer], cached_inputs, cached_outp
     round_acc = torch.zeros(1, device=dev)
     tuple_out = isinstance(cached_outputs, (tuple, list))
     n = cached_inputs[0].size(0)
-    for it in range(1, iters + 1):
-        idx = torch.randperm(n)[:batch_size].to(cached_inputs[0].device)
-        cur_in = tuple(x[idx].to(dev) for x in cached_inputs)
+    tgt_src = list(cached_outputs) if tuple_out else [cached_outputs]
+    bs = min(batch_size, n)
+    # resident batch buffers: the sampled rows of the cached inputs / targets are gathered into them every iteration, so the
+    # forward / loss / backward of the unit is one fixed sequence of launches on fixed addresses -- captured ONCE as a CUDA graph
+    # and replayed (the module graph + autograd engine cost ~3x the GPU time of an iteration in host time when run eagerly)
+    cur_in = tuple(torch.empty((bs,) + tuple(x.shape[1:]), dtype=x.dtype, device=dev) for x in cached_inputs)
+    tgts = [torch.empty((bs,) + tuple(t_.shape[1:]), dtype=t_.dtype, device=dev) for t_ in tgt_src]
+    rec = torch.zeros(1, device=dev)
+
+    def gather(it_idx):
+        for buf, x in zip(cur_in, cached_inputs):
+            buf.copy_(x[it_idx.to(x.device)], non_blocking=True)
+        for buf, t_ in zip(tgts, tgt_src):
+            buf.copy_(t_[it_idx.to(t_.device)], non_blocking=True)
+
+    def body():
+        """soft weights -> unit forward -> reconstruction loss and its output gradient -> dL/dW_soft of every layer"""
         leaves = [s.materialise() for s in states]
         out = forward(*cur_in)
         # reconstruction loss and its gradient w.r.t. the unit's outputs in one kernel per output (tfmq_rec_loss: lp_loss with
         # p = 2, `.sum(1).mean()`, quant/quant_layer.py:146-156; LossFuncTimeEmbedding sums it over the TIB's outputs)
         outs = list(out) if tuple_out else [out]
-        tgts = [t_[idx].to(dev) for t_ in cached_outputs] if tuple_out else [cached_outputs[idx].to(dev)]
-        rec = torch.zeros(1, device=dev)
+        rec.zero_()
         gouts = []
         for o_, t_ in zip(outs, tgts):
             o_c, t_c = o_.detach().contiguous(), t_.contiguous()
@@ -99,7 +119,30 @@ def _adaround_loop(forward, layers: List[QuantLayer], cached_inputs, cached_outp
             ops.rec_loss(o_c, t_c, o_c.numel() // o_c.shape[1], rec, g_)
             gouts.append(g_)
         grads = torch.autograd.grad(outs, leaves, grad_outputs=gouts, allow_unused=True)
-        grads = [g if g is not None else torch.zeros_like(l_) for g, l_ in zip(grads, leaves)]
+        return [g.contiguous() if g is not None else torch.zeros_like(l_) for g, l_ in zip(grads, leaves)]
+
+    graph, graph_grads = None, None
+    for it in range(1, iters + 1):
+        idx = torch.randperm(n)[:batch_size]
+        gather(idx)
+        if not RECON_GRAPH or dev.type != "cuda":
+            grads = body()
+        elif graph is None:
+            # warm-up on a side stream (lazy module / attribute initialisation, cached plane buffers), then capture; the body
+            # does not change the optimiser state, so running it more than once for the first batch is harmless
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                body()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                graph_grads = body()
+            graph.replay()
+            grads = graph_grads
+        else:
+            graph.replay()
+            grads = graph_grads
         if world > 1:
             from ..dist_utils import allreduce_flat_
             grads = allreduce_flat_(grads)
@@ -115,6 +158,7 @@ def _adaround_loop(forward, layers: List[QuantLayer], cached_inputs, cached_outp
         if log:
             logger.info("Total loss:\t{:.8f} (rec:{:.8f}, round:{:.8f})\tb={:.2f}\tcount={}".format(
                 float(rec) + float(round_acc) / world, float(rec), float(round_acc) / world, b, it))
+    del graph, graph_grads
     for s in states:
         s.finish()
 

@@ -93,10 +93,15 @@ def _wgrad_buffers(dev, ci: int, co: int, n: int, h: int, w: int):
         b = dict(hp=hp, wp=wp, q=q, guard=guard,
                  x=torch.zeros((2, 3, ci, guard + q + guard), dtype=torch.float16, device=dev),
                  g=torch.zeros((2, co, q), dtype=torch.float16, device=dev))
-        if len(_WG_BUF) > 8:
-            _WG_BUF.clear()
         _WG_BUF[key] = b
     return b
+
+
+def trim_buffers(keep: int = 8) -> None:
+    """Drop the cached weight-gradient plane buffers once more than `keep` shapes have accumulated.  Called between units
+    (reconstruction.py), never inside one: a captured iteration graph holds the addresses of the buffers it was captured with."""
+    if len(_WG_BUF) > keep:
+        _WG_BUF.clear()
 
 
 def _flat_planes(t: torch.Tensor):
