@@ -33,6 +33,10 @@ logger = logging.getLogger(__name__)
 # what the reference's LossFunc returns) -- one host sync per iteration, so it stays None outside the parity tests.
 LOSS_TRACE = None
 
+# Bench hook: called with the iteration number at the end of every iteration (tools/bench_calibration.py stamps two of them to
+# time the steady state without the caching before the loop and the graph capture of its first iteration).
+ITER_HOOK = None
+
 # The iteration body (soft weights, unit forward, loss, backward) as one captured CUDA graph.  TFMQ_RECON_GRAPH=0 runs it eagerly
 # (debugging; same kernels, same order, same results).
 RECON_GRAPH = os.environ.get("TFMQ_RECON_GRAPH", "1") != "0"
@@ -155,6 +159,8 @@ def _adaround_loop(forward, layers: List[QuantLayer], cached_inputs, cached_outp
                               float(b), float(w) * world, round_acc)
         if LOSS_TRACE is not None:
             LOSS_TRACE.append(float(rec) + float(round_acc) / world)
+        if ITER_HOOK is not None:
+            ITER_HOOK(it)
         if log:
             logger.info("Total loss:\t{:.8f} (rec:{:.8f}, round:{:.8f})\tb={:.2f}\tcount={}".format(
                 float(rec) + float(round_acc) / world, float(rec), float(round_acc) / world, b, it))

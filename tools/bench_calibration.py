@@ -1,7 +1,7 @@
 """Wall-clock of the PTQ weight-reconstruction phase (BASELINE configs[3]: TIAR + AdaRound block reconstruction) on one
 B200: every reconstruction unit of the LDM-4 UNet (22 QuantResBlocks + 3 upsample convs + the Temporal Information Block)
-is run through `block_/layer_/tib_reconstruction` twice with small iteration counts; the difference gives the time per
-iteration, the intercept the input/output caching.  The reference runs 20 000 iterations per unit
+is run through `block_/layer_/tib_reconstruction` for K2 iterations; device-synchronised stamps at iterations K1 and K2 give the
+steady-state time per iteration, the rest of the run is the input/output caching (+ the graph capture).  The reference runs 20 000 iterations per unit
 (sample_diffusion_ldm.py:506-538), so  sum(per-iteration) x 20 000 + caching  is the projected W1 wall-clock.
 
   python tools/bench_calibration.py [n_calibration_samples=256]
@@ -30,7 +30,7 @@ torch.backends.cudnn.allow_tf32 = _tf32
 torch.backends.cuda.matmul.allow_tf32 = _tf32
 print(f"contractions: {'own tcgen05 kernels (quant/tc_autograd.py)' if os.environ.get('TFMQ_TC_RECON', '1') != '0' else 'torch kernels'}"
       f", TF32 {'on' if _tf32 else 'off'}")
-K1, K2 = 10, 60
+K1, K2 = (int(v) for v in os.environ.get("TFMQ_BENCH_ITERS", "20,220").split(","))     # iterations of the two runs per unit
 dev = torch.device("cuda:0")
 wq = dict(bits=4, channel_wise=True, scaler=Scaler.MINMAX)
 aq = dict(bits=8, channel_wise=False, scaler=Scaler.MINMAX, leaf_param=True)
@@ -62,6 +62,22 @@ def units(model, out):
     return out
 
 
+import tfmq_b200.quant.reconstruction as _R  # noqa: E402
+
+_stamp = {}
+
+
+def _hook(it):
+    """device-synchronised wall-clock stamps at iterations K1 and K2 of a run: the steady state of the loop, without the input /
+    output caching before it and the CUDA-graph capture of its first iteration"""
+    if it in (K1, K2):
+        torch.cuda.synchronize()
+        _stamp[it] = time.time()
+
+
+_R.ITER_HOOK = _hook
+
+
 def run(kind, m, iters):
     torch.cuda.synchronize()
     t0 = time.time()
@@ -84,7 +100,7 @@ if only:
     todo = [u for u in todo if names.get(id(u[2]), "tib") == only]
     _, kind, m = todo[0]
     run(kind, m, 5)
-    import tfmq_b200.quant.reconstruction as R
+    R = _R
     from torch.profiler import ProfilerActivity, profile
     loop = R._adaround_loop
 
@@ -102,10 +118,9 @@ for _, kind, m in todo:
     has_layers = kind == "tib" or any(isinstance(x, QuantLayer) and not x.quant_emb for x in m.modules())
     if not has_layers:
         continue
-    a = run(kind, m, K1)
-    b = run(kind, m, K2)
-    per = (b - a) / (K2 - K1)
-    cache = max(a - K1 * per, 0.0)
+    total = run(kind, m, K2)
+    per = (_stamp[K2] - _stamp[K1]) / (K2 - K1)
+    cache = max(total - K2 * per, 0.0)   # input / output caching (+ the graph capture)
     tot_iter += per
     tot_cache += cache
     print(f"  {names.get(id(m), 'tib'):28s} {kind:5s} {per * 1e3:7.2f} ms / iteration   caching {cache:5.2f} s", flush=True)
