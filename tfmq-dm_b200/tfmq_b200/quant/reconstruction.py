@@ -14,6 +14,7 @@ regulariser by world_size, which is reproduced through lambda * world_size).
 """
 from __future__ import annotations
 
+import contextlib
 import logging
 import os
 from typing import List
@@ -169,6 +170,33 @@ def _adaround_loop(forward, layers: List[QuantLayer], cached_inputs, cached_outp
         s.finish()
 
 
+@contextlib.contextmanager
+def _plain_convs_on_own_kernels(unit):
+    """The convolutions of a unit that are NOT QuantLayers (a ResBlock's 1x1 skip_connection: shortcuts are never quantised,
+    quant/quant_model.py:57-58) run in fp32 on cuDNN's SIMT kernel in the reference.  Inside the iteration loop they go through
+    the same fp32-accurate tcgen05 kernel as the reconstructed layers (forward only: neither their weights nor the unit's input
+    receive a gradient) -- 0.95 ms of a 9 ms iteration on the 64x64 blocks otherwise.  Shapes the kernel does not take keep
+    torch's op."""
+    from .quant_layer import TC_RECONSTRUCTION
+    from .tc_autograd import tc_conv
+    patched = []
+    if TC_RECONSTRUCTION:
+        for m in unit.modules():
+            if type(m) is torch.nn.Conv2d and m.weight.is_cuda and m.padding_mode == "zeros":
+                kw = dict(stride=m.stride, padding=m.padding, dilation=m.dilation, groups=m.groups)
+
+                def fwd(x, m=m, kw=kw):
+                    y = tc_conv(x, m.weight.detach(), m.bias.detach() if m.bias is not None else None, kw)
+                    return y if y is not None else torch.nn.Conv2d.forward(m, x)
+                m.forward = fwd
+                patched.append(m)
+    try:
+        yield
+    finally:
+        for m in patched:
+            del m.forward            # back to the class's forward
+
+
 def _common(model, unit, cali_data, batch_size, iters, w, opt_mode, asym, include_act_func, b_range, warmup, use_aq,
             p, multi_gpu, keep_gpu, layers, forward, cache_model):
     if use_aq:
@@ -181,7 +209,8 @@ def _common(model, unit, cali_data, batch_size, iters, w, opt_mode, asym, includ
         org, unit.act_func = unit.act_func, StraightThrough()
     if layers:
         ins, outs = save_inout(cache_model, unit, cali_data, asym, use_aq, batch_size, keep_gpu)
-        _adaround_loop(forward, layers, ins, outs, batch_size, iters, w, b_range, warmup, multi_gpu, p)
+        with _plain_convs_on_own_kernels(unit):
+            _adaround_loop(forward, layers, ins, outs, batch_size, iters, w, b_range, warmup, multi_gpu, p)
     if org is not None:
         unit.act_func = org
 
