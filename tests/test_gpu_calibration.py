@@ -267,6 +267,64 @@ def test_tc_autograd_declines_unsupported_shapes(dev):
                    dict(stride=(1, 1), padding=(1, 1))) is None
 
 
+def test_plain_convs_of_a_unit_run_on_the_own_kernel_inside_the_loop(dev):
+    """A ResBlock's skip_connection is a plain nn.Conv2d (never a QuantLayer): inside the reconstruction loop its forward goes
+    through the fp32-accurate tcgen05 kernel (forward only), outside it is torch's op again -- also after an exception."""
+    from tfmq_b200.quant.reconstruction import _plain_convs_on_own_kernels
+    torch.manual_seed(0)
+    unit = torch.nn.Sequential(torch.nn.Conv2d(64, 32, 1), torch.nn.Conv2d(32, 32, 3, stride=2, padding=1)).to(dev)
+    x = torch.randn(4, 64, 16, 16, device=dev)
+    with torch.no_grad():
+        want = torch.nn.functional.conv2d(x.double(), unit[0].weight.double(), unit[0].bias.double()).float()
+        with _plain_convs_on_own_kernels(unit):
+            assert "forward" in unit[0].__dict__ and "forward" in unit[1].__dict__
+            got = unit[0](x)
+            y2 = unit[1](got)                      # stride 2: the kernel declines, torch's op answers
+        assert (got - want).abs().max().item() < 3e-5 * want.abs().max().item()
+        assert y2.shape == (4, 32, 8, 8)
+    assert "forward" not in unit[0].__dict__ and "forward" not in unit[1].__dict__
+    with pytest.raises(RuntimeError):
+        with _plain_convs_on_own_kernels(unit):
+            raise RuntimeError("boom")
+    assert "forward" not in unit[0].__dict__
+
+
+def test_reconstruction_graph_replay_equals_the_eager_loop(dev, monkeypatch):
+    """The captured iteration graph runs the same kernels in the same order as the eager loop: identical loss trace and alpha."""
+    import tfmq_b200.quant.reconstruction as R
+    from tfmq_b200.quant.reconstruction_util import RLOSS
+    w_cali = (synth.latents((64, 3, 32, 32), 51),
+              torch.randint(0, 1000, (64,), generator=torch.Generator().manual_seed(2)).float())
+    res = {}
+    for mode in (True, False):
+        qnn = _qnn(dev, cali=True)
+        qnn.set_quant_state(True, False)
+        with torch.no_grad():
+            qnn(*(d[:8].to(dev) for d in w_cali))
+        qnn.disable_out_quantization()
+        blk = qnn.model.down[1].block[0]
+        blk.dropout.p = 0.0      # the unit runs in train() mode (data_utill.py:72): eager and replayed masks come from different
+        #                          positions of the generator stream, everything else is the same arithmetic
+        monkeypatch.setattr(R, "RECON_GRAPH", mode)
+        trace = []
+        monkeypatch.setattr(R, "LOSS_TRACE", trace)
+        torch.manual_seed(0)
+        R.block_reconstruction(qnn, blk, w_cali, batch_size=32, iters=30, w=0.01, opt_mode=RLOSS.MSE, asym=False,
+                               b_range=(20, 2), warmup=0.2, multi_gpu=False)
+        alphas = [m.wqtizer.alpha.detach().clone() for m in blk.modules() if hasattr(m, "wqtizer") and hasattr(m.wqtizer, "alpha")]
+        res[mode] = (trace, alphas)
+    tr_g, al_g = res[True]
+    tr_e, al_e = res[False]
+    assert len(tr_g) == len(tr_e) == 30
+    # split-K weight gradients are reduced by TMA adds in arrival order, so single runs differ in the last bits
+    assert max(abs(a - b) for a, b in zip(tr_g, tr_e)) <= 1e-3 * max(abs(v) for v in tr_e)
+    moved = sum(int(((a - b).abs() > 2.5e-3).sum()) for a, b in zip(al_g, al_e))
+    total = sum(a.numel() for a in al_g)
+    print(f"graph vs eager: loss trace max diff {max(abs(a - b) for a, b in zip(tr_g, tr_e)):.3e}; alpha elements more than two "
+          f"Adam steps apart: {moved} of {total}")
+    assert moved <= 0.02 * total
+
+
 def test_save_inout_matches_the_reference(dev):
     """`save_inout` / `GetLayerInpOut` (quant/data_utill.py:13-55, :109-169) -- the cached inputs and FP targets of
     a reconstruction unit -- against the reference's own function on the same model and data (tests/golden/inout_sdmini.pt, made

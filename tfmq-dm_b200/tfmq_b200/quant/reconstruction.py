@@ -126,6 +126,8 @@ def _adaround_loop(forward, layers: List[QuantLayer], cached_inputs, cached_outp
         grads = torch.autograd.grad(outs, leaves, grad_outputs=gouts, allow_unused=True)
         return [g.contiguous() if g is not None else torch.zeros_like(l_) for g, l_ in zip(grads, leaves)]
 
+    # (random ops of the unit -- the reference leaves the model in train() mode after caching, so CIFAR's ResnetBlocks draw
+    # dropout masks, data_utill.py:72 -- are captured with torch's graph-safe generator state: every replay draws fresh masks)
     graph, graph_grads = None, None
     for it in range(1, iters + 1):
         idx = torch.randperm(n)[:batch_size]
