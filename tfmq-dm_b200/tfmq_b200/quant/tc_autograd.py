@@ -45,13 +45,19 @@ def supported(x: torch.Tensor, w: torch.Tensor, fwd_kwargs: dict) -> bool:
             and grp == 1 and w.shape[1] % 16 == 0 and w.shape[0] % 16 == 0 and _pow2(x.shape[2]) and _pow2(x.shape[3]))
 
 
+def _absmax(t: torch.Tensor) -> torch.Tensor:
+    """max |t| as a device scalar in ONE pass over t (`t.abs().amax()` writes |t| out and reads it back: three passes)."""
+    mn, mx = torch.aminmax(t)
+    return torch.maximum(-mn, mx)
+
+
 def _planes(t_nhwc: torch.Tensor, autoscale: bool = False):
     """fp16 hi / lo planes of an NHWC tensor.  autoscale (gradients): the tensor is first multiplied by the power of two that
     brings its largest magnitude to [2^10, 2^11) -- back-propagated errors of 1e-6 would sit in fp16's subnormal range --
     and the inverse is returned as a device scalar for the caller to fold into the kernel's per-channel output scale."""
     inv = None
     if autoscale:
-        amax = t_nhwc.abs().amax().clamp_min(1e-30)
+        amax = _absmax(t_nhwc).clamp_min(1e-30)
         s = torch.exp2(10.0 - torch.floor(torch.log2(amax)))
         t_nhwc = t_nhwc * s
         inv = 1.0 / s
@@ -170,7 +176,7 @@ class _TcConv(torch.autograd.Function):
             k, ci = w.shape[2], w.shape[1]
             # back-propagated errors of 1e-6 would sit in fp16's subnormal range: scale by the power of two that brings the
             # largest magnitude to [2^10, 2^11); the inverse goes into the kernels' per-channel output scale
-            g_s = torch.exp2(10.0 - torch.floor(torch.log2(gy.abs().amax().clamp_min(1e-30))))
+            g_s = torch.exp2(10.0 - torch.floor(torch.log2(_absmax(gy).clamp_min(1e-30))))
             g_inv = 1.0 / g_s
             gs = gy * g_s
             if ctx.needs_input_grad[0]:
