@@ -351,3 +351,38 @@ def test_quant_model_engine_invalidation_and_calibration_context():
     with qnn.calibrating():
         pass
     assert qnn._engine is None
+
+
+def test_timestep_embedding_frequency_rows_are_cached_and_unchanged():
+    """The frequency row of the sinusoidal embedding is evaluated on the host exactly as the reference does (ldm util.py:151-171,
+    ddim/models/diffusion.py:6-24) and kept per device, so a captured reconstruction iteration contains no pageable upload."""
+    from tfmq_b200.host import ddim_unet, ldm_unet
+    t = torch.tensor([0.0, 1.0, 500.0, 999.0])
+    half = 64
+    f_ldm = torch.exp(-math.log(10000) * torch.arange(0, half, dtype=torch.float32) / half)
+    a = t[:, None].float() * f_ldm[None]
+    assert torch.equal(ldm_unet.timestep_embedding(t, 2 * half), torch.cat([a.cos(), a.sin()], dim=-1))
+    assert ldm_unet._frequencies(half, 10000, t.device) is ldm_unet._frequencies(half, 10000, t.device)
+    f_ddim = torch.exp(torch.arange(half, dtype=torch.float32) * -(math.log(10000) / (half - 1)))
+    b = t.float()[:, None] * f_ddim[None, :]
+    assert torch.equal(ddim_unet.get_timestep_embedding(t, 2 * half), torch.cat([b.sin(), b.cos()], dim=1))
+    assert ddim_unet._frequencies(half, t.device) is ddim_unet._frequencies(half, t.device)
+    # odd widths keep the reference's zero padding
+    assert ldm_unet.timestep_embedding(t, 2 * half + 1).shape == (4, 2 * half + 1)
+    assert ddim_unet.get_timestep_embedding(t, 2 * half + 1).shape == (4, 2 * half + 1)
+
+
+def test_weight_gradient_buffers_are_trimmed_between_units_only():
+    """A captured iteration graph holds the addresses of the cached plane buffers: the cache never shrinks inside a unit
+    (`_wgrad_buffers`), only through `trim_buffers` at the start of the next one."""
+    from tfmq_b200.quant import tc_autograd as T
+    T._WG_BUF.clear()
+    for i in range(12):
+        T._wgrad_buffers(torch.device("cpu"), 16, 16, 1, 4, 4 + 4 * i)
+    assert len(T._WG_BUF) == 12
+    first = T._wgrad_buffers(torch.device("cpu"), 16, 16, 1, 4, 4)
+    assert first is T._wgrad_buffers(torch.device("cpu"), 16, 16, 1, 4, 4)
+    T.trim_buffers(keep=16)
+    assert len(T._WG_BUF) == 12
+    T.trim_buffers()
+    assert len(T._WG_BUF) == 0
