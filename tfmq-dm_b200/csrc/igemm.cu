@@ -339,7 +339,21 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const uint64_t a_lo = d_alo + s_units, b_lo = d_blo + s_units;
         const bool last = kb == kb1 - 1;
         if (elect_one_sync()) {
-          if (FP) {
+          if (FP && nslice == 4) {
+            // full channel chunk: unpredicated UMMAs, descriptors advanced in uniform registers (see the w4a8 branch below; with
+            // three products the predicated form issues a k-block in ~1070 clocks against 672 of tensor-pipe time at N = 112)
+            if (need_a_lo) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) umma_fp<MODE, CG>(tmem_lo, a_lo + 2 * k, b_hi + 2 * k, idesc, (k > 0) | accumulate_lo);
+            }
+            if (need_b_lo) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_fp<MODE, CG>(tmem_lo, a_hi + 2 * k, b_lo + 2 * k, idesc, (k > 0) | accumulate_lo | (need_a_lo ? 1u : 0u));
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_fp<MODE, CG>(tmem_d, a_hi + 2 * k, b_hi + 2 * k, idesc, (k > 0) | accumulate);
+          } else if (FP) {
             if (need_a_lo) {
 #pragma unroll
               for (int k = 0; k < 4; ++k)
@@ -354,6 +368,15 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #pragma unroll
             for (int k = 0; k < 4; ++k)
               if (k < nslice) umma_fp<MODE, CG>(tmem_d, a_hi + 2 * k, b_hi + 2 * k, idesc, (k > 0) | accumulate);
+          } else if (nslice == 4) {
+            // full channel chunk (every k-block when cin is a multiple of 128): four unpredicated UMMAs, descriptors advanced in
+            // uniform registers -- the predicated form below re-materialises both descriptors per UMMA (25 R2UR per k-block),
+            // and the issue loop is what bounds the narrow tiles of the small maps (profiles/r2w_epilogue_probes.md)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              if (CG == 2) umma_i8_2cta(tmem_d, a_hi + 2 * k, b_hi + 2 * k, idesc, (k > 0) | accumulate);
+              else umma_i8(tmem_d, a_hi + 2 * k, b_hi + 2 * k, idesc, (k > 0) | accumulate);
+            }
           } else {
 #pragma unroll
             for (int k = 0; k < 4; ++k)
